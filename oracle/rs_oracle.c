@@ -1,0 +1,1077 @@
+/*
+ * rs_oracle.c -- CPU restatement (double precision, plain C) of the reference's
+ * World::step hot path.  TEST INFRASTRUCTURE ONLY: nothing under oracle/ is
+ * imported, linked or executed by the product path (roboschool_b200/); only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs use it, as the checker / reported CPU baseline.
+ *
+ * PARITY UNPINNED.  The arithmetic of the path lives in a third-party dependency
+ * that is NOT under /root/reference: github.com/olegklimov/bullet3, branch
+ * roboschool_self_collision (Bullet 2.87, built -DUSE_DOUBLE_PRECISION=1;
+ * install_bullet.sh:8-11,27).  The reference has no golden vectors for it
+ * (docker_test_wheel.sh:6 only checks gym.make does not crash).  This file
+ * restates Bullet's published algorithm as recalled from upstream bullet3 2.87,
+ * anchored on the reference's own call sites:
+ *   - step:        World::bullet_step          physics-bullet.cpp:358-412
+ *                  (gravity, 5 iterations, contactERP 0.9, dt*skip, skip sub-steps :368-376;
+ *                   CONTROL_MODE_TORQUE re-sent each step :379-391; StepSimulation :396-397)
+ *   - readback:    World::query_body_position  physics-bullet.cpp:440-495
+ *   - rel. joints: Joint::joint_current_relative_position physics-bullet.cpp:547-566
+ *   - contacts:    World::bullet_contact_list  physics-bullet.cpp:596-637
+ *   - reset:       Joint::reset_current_position :568-577, World::robot_move :583-594
+ *   - obs/reward:  RoboschoolForwardWalker.calc_state/step gym_forward_walker.py:45-133,
+ *                  alive_bonus gym_mujoco_walkers.py:22-23,69-70,135-136,
+ *                  Pose::rpy python-binding.cpp:60-73
+ * Each function below names the upstream Bullet routine it restates.
+ *
+ * What IS pinned (tests/): the obs/reward epilogue against the reference's own
+ * Python run in-container over a stub cpp_household (tests/golden/), the MLP
+ * against the shipped .weights known answers, and closed-form physics
+ * (free fall, pendulum period, energy/momentum conservation).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include "../include/rs_model.h"
+
+#define ML RS_MAX_LINKS
+#define MAXROWS 256
+#define MAXDOF (6 + RS_MAX_LINKS)
+#define MANIFOLD_CACHE_SIZE 4
+#define WARMSTART 0 /* "disable warmstarting for btMultiBody, it has issues gaining energy" (btMultiBodyConstraintSolver.cpp, 2.87) */
+
+typedef struct { double w[3], v[3]; } sv6;   /* motion: w=angular v=linear ; force: w=torque v=force */
+
+typedef struct {
+    double localA[3], localB[3];
+    double normal[3];      /* world, on B, pointing B -> A */
+    double posA[3], posB[3];
+    double dist;
+    double friction;
+    double imp_n, imp_f1, imp_f2; /* applied impulses of the last solve (reported, not warm-started) */
+    int lifetime;
+} cpoint;
+
+typedef struct {
+    int n;
+    cpoint p[MANIFOLD_CACHE_SIZE];
+} manifold;
+
+typedef struct {
+    /* generalized state */
+    double base_pos[3], base_quat[4]; /* quat x,y,z,w rotating base coords -> world */
+    double base_w[3], base_v[3];      /* world frame */
+    double q[ML], qd[ML];
+    double tau[ML];                   /* joint torques, persist over the sub-steps of one env step */
+    manifold *man;                    /* [n_geoms floor manifolds][n_pairs pair manifolds] */
+    /* episode bookkeeping (gym_forward_walker.py) */
+    double potential;
+    double initial_z;
+    double feet_contact[RS_MAX_FEET];
+    int frame;
+    int done_latch;
+    uint32_t episode;
+    /* outputs of the last env step */
+    double obs[8 + 2 * RS_MAX_ACT + RS_MAX_FEET];
+    double reward, rewards5[5];
+    int done;
+    int n_rows_last, n_contacts_last;
+    /* kinematics cache (valid after kinematics()) */
+    double Rpl[ML][9];   /* rot parent -> link coords                     */
+    double rvec[ML][3];  /* parent COM -> link COM in link coords          */
+    double Rwl[ML + 1][9];  /* rot world -> link coords, [0]=base           */
+    double pos[ML + 1][3];  /* world COM position, [0]=base                 */
+    sv6 S[ML];           /* joint motion subspace in link coords            */
+    /* ABA cache for constraint-response passes */
+    sv6 h[ML];
+    double invD[ML];
+    double Ibase_inv[36];
+    sv6 vel[ML + 1];     /* spatial velocity, link coords                   */
+} oenv;
+
+typedef struct oracle_world {
+    rs_model_desc m;
+    int n_envs;
+    int nman;
+    oenv *env;
+} oracle_world;
+
+/* ---------------- small vector helpers ---------------- */
+static inline void v3set(double *a, double x, double y, double z) { a[0] = x; a[1] = y; a[2] = z; }
+static inline void v3cpy(double *a, const double *b) { a[0] = b[0]; a[1] = b[1]; a[2] = b[2]; }
+static inline double v3dot(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static inline void v3cross(double *o, const double *a, const double *b) {
+    double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+static inline void v3sub(double *o, const double *a, const double *b) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; }
+static inline void v3add(double *o, const double *a, const double *b) { o[0] = a[0] + b[0]; o[1] = a[1] + b[1]; o[2] = a[2] + b[2]; }
+static inline void v3axpy(double *o, double s, const double *a) { o[0] += s * a[0]; o[1] += s * a[1]; o[2] += s * a[2]; }
+static inline double v3len(const double *a) { return sqrt(v3dot(a, a)); }
+static inline void m3mulv(double *o, const double *M, const double *v) {
+    double x = M[0] * v[0] + M[1] * v[1] + M[2] * v[2];
+    double y = M[3] * v[0] + M[4] * v[1] + M[5] * v[2];
+    double z = M[6] * v[0] + M[7] * v[1] + M[8] * v[2];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+static inline void m3tmulv(double *o, const double *M, const double *v) {
+    double x = M[0] * v[0] + M[3] * v[1] + M[6] * v[2];
+    double y = M[1] * v[0] + M[4] * v[1] + M[7] * v[2];
+    double z = M[2] * v[0] + M[5] * v[1] + M[8] * v[2];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+static inline void m3mul(double *o, const double *A, const double *B) {
+    double t[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) t[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+    memcpy(o, t, sizeof t);
+}
+/* rotation matrix of a unit quaternion (x,y,z,w): v_out = R v_in rotates by the quaternion */
+static void quat_to_mat(double *R, const double *q) {
+    double x = q[0], y = q[1], z = q[2], w = q[3];
+    R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w);     R[2] = 2 * (x * z + y * w);
+    R[3] = 2 * (x * y + z * w);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+    R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
+}
+static void quat_mul(double *o, const double *a, const double *b) { /* o = a*b, (x,y,z,w) */
+    double x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+    double y = a[3] * b[1] - a[0] * b[2] + a[1] * b[3] + a[2] * b[0];
+    double z = a[3] * b[2] + a[0] * b[1] - a[1] * b[0] + a[2] * b[3];
+    double w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+    o[0] = x; o[1] = y; o[2] = z; o[3] = w;
+}
+
+/* btPlaneSpace1 (LinearMath/btVector3.h) */
+static void plane_space(const double *n, double *p, double *q) {
+    if (fabs(n[2]) > 0.7071067811865475244008443621048490) {
+        double a = n[1] * n[1] + n[2] * n[2];
+        double k = 1.0 / sqrt(a);
+        p[0] = 0; p[1] = -n[2] * k; p[2] = n[1] * k;
+        q[0] = a * k; q[1] = -n[0] * p[2]; q[2] = n[0] * p[1];
+    } else {
+        double a = n[0] * n[0] + n[1] * n[1];
+        double k = 1.0 / sqrt(a);
+        p[0] = -n[1] * k; p[1] = n[0] * k; p[2] = 0;
+        q[0] = -n[2] * p[1]; q[1] = n[2] * p[0]; q[2] = a * k;
+    }
+}
+
+/* ---------------- spatial transforms (btSpatialTransformationMatrix) ---------------- */
+/* motion parent -> child: w' = R w ; v' = R v - r x (R w) */
+static void xf_motion(sv6 *o, const double *R, const double *r, const sv6 *in) {
+    double w[3], v[3], c[3];
+    m3mulv(w, R, in->w);
+    m3mulv(v, R, in->v);
+    v3cross(c, r, w);
+    v3sub(v, v, c);
+    v3cpy(o->w, w); v3cpy(o->v, v);
+}
+/* force child -> parent (transformInverse): f' = R^T f ; t' = R^T (t + r x f) */
+static void xf_force_inv(sv6 *o, const double *R, const double *r, const sv6 *in) {
+    double t[3], c[3];
+    v3cross(c, r, in->v);
+    v3add(t, in->w, c);
+    m3tmulv(o->w, R, t);
+    m3tmulv(o->v, R, in->v);
+}
+static inline double sv_dot(const sv6 *m, const sv6 *f) { return v3dot(m->w, f->w) + v3dot(m->v, f->v); }
+/* 6x6 matrix (row-major, order [w;v]) times motion -> force */
+static void m6mulv(sv6 *o, const double *I, const sv6 *a) {
+    double x[6] = {a->w[0], a->w[1], a->w[2], a->v[0], a->v[1], a->v[2]}, y[6];
+    for (int i = 0; i < 6; i++) {
+        double s = 0;
+        for (int j = 0; j < 6; j++) s += I[i * 6 + j] * x[j];
+        y[i] = s;
+    }
+    v3set(o->w, y[0], y[1], y[2]); v3set(o->v, y[3], y[4], y[5]);
+}
+/* build the 6x6 motion transform X (parent->child) */
+static void build_X(double *X, const double *R, const double *r) {
+    /* [w';v'] = [[R,0],[-[r]x R, R]] [w;v] */
+    double rx[9] = {0, -r[2], r[1], r[2], 0, -r[0], -r[1], r[0], 0}, rxR[9];
+    m3mul(rxR, rx, R);
+    memset(X, 0, 36 * sizeof(double));
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            X[i * 6 + j] = R[i * 3 + j];
+            X[(i + 3) * 6 + j] = -rxR[i * 3 + j];
+            X[(i + 3) * 6 + j + 3] = R[i * 3 + j];
+        }
+}
+/* Ip += X^T Ic X */
+static void inertia_to_parent_add(double *Ip, const double *Ic, const double *X) {
+    double T[36];
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) {
+            double s = 0;
+            for (int k = 0; k < 6; k++) s += Ic[i * 6 + k] * X[k * 6 + j];
+            T[i * 6 + j] = s;
+        }
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) {
+            double s = 0;
+            for (int k = 0; k < 6; k++) s += X[k * 6 + i] * T[k * 6 + j];
+            Ip[i * 6 + j] += s;
+        }
+}
+/* dense symmetric-positive 6x6 inverse by Gauss-Jordan with partial pivoting
+ * (btMultiBody::solveImatrix does the same job block-wise) */
+static int inv6(double *out, const double *in) {
+    double a[6][12];
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) { a[i][j] = in[i * 6 + j]; a[i][j + 6] = (i == j); }
+    for (int c = 0; c < 6; c++) {
+        int p = c;
+        for (int r = c + 1; r < 6; r++) if (fabs(a[r][c]) > fabs(a[p][c])) p = r;
+        if (fabs(a[p][c]) < 1e-300) return -1;
+        if (p != c) for (int j = 0; j < 12; j++) { double t = a[c][j]; a[c][j] = a[p][j]; a[p][j] = t; }
+        double inv = 1.0 / a[c][c];
+        for (int j = 0; j < 12; j++) a[c][j] *= inv;
+        for (int r = 0; r < 6; r++) if (r != c) {
+            double f = a[r][c];
+            if (f != 0) for (int j = 0; j < 12; j++) a[r][j] -= f * a[c][j];
+        }
+    }
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) out[i * 6 + j] = a[i][j + 6];
+    return 0;
+}
+
+/* ---------------- kinematics (btMultiBody: rot_from_parent / cachedRVector / forwardKinematics) ---------------- */
+static void kinematics(const rs_model_desc *m, oenv *e) {
+    /* base: Bullet stores m_baseQuat as world->base; we store base->world and transpose */
+    double Rbw[9];
+    quat_to_mat(Rbw, e->base_quat);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) e->Rwl[0][i * 3 + j] = Rbw[j * 3 + i];
+    v3cpy(e->pos[0], e->base_pos);
+    for (int i = 0; i < m->n_links; i++) {
+        int p = m->parent[i];
+        double R0[9];
+        quat_to_mat(R0, m->zero_rot[i]); /* parent coords -> link coords at q=0 */
+        const double *ax = m->axis[i];
+        if (m->jtype[i] == RS_JOINT_REVOLUTE) {
+            /* m_cachedRotParentToThis = btQuaternion(axis, -q) * m_zeroRotParentToThis */
+            double half = -0.5 * e->q[m->dof_idx[i]];
+            double s = sin(half), qa[4] = {ax[0] * s, ax[1] * s, ax[2] * s, cos(half)}, Ra[9];
+            quat_to_mat(Ra, qa);
+            m3mul(e->Rpl[i], Ra, R0);
+            /* m_cachedRVector = quatRotate(cachedRot, eVector) + dVector */
+            m3mulv(e->rvec[i], e->Rpl[i], m->e_vec[i]);
+            v3add(e->rvec[i], e->rvec[i], m->d_vec[i]);
+            v3cpy(e->S[i].w, ax);
+            v3cross(e->S[i].v, ax, m->d_vec[i]);   /* axis_bottom = axis x dVector */
+        } else if (m->jtype[i] == RS_JOINT_PRISMATIC) {
+            memcpy(e->Rpl[i], R0, sizeof R0);
+            m3mulv(e->rvec[i], R0, m->e_vec[i]);
+            v3add(e->rvec[i], e->rvec[i], m->d_vec[i]);
+            v3axpy(e->rvec[i], e->q[m->dof_idx[i]], ax);
+            v3set(e->S[i].w, 0, 0, 0);
+            v3cpy(e->S[i].v, ax);
+        } else {
+            memcpy(e->Rpl[i], R0, sizeof R0);
+            m3mulv(e->rvec[i], R0, m->e_vec[i]);
+            v3add(e->rvec[i], e->rvec[i], m->d_vec[i]);
+            v3set(e->S[i].w, 0, 0, 0); v3set(e->S[i].v, 0, 0, 0);
+        }
+        m3mul(e->Rwl[i + 1], e->Rpl[i], e->Rwl[p + 1]);
+        double rw[3];
+        m3tmulv(rw, e->Rwl[i + 1], e->rvec[i]);
+        v3add(e->pos[i + 1], e->pos[p + 1], rw);
+    }
+}
+
+/* spatial velocities of all links in link coords (first sweep of the ABA) */
+static void velocities(const rs_model_desc *m, oenv *e) {
+    if (m->fixed_base) { memset(&e->vel[0], 0, sizeof(sv6)); }
+    else { m3mulv(e->vel[0].w, e->Rwl[0], e->base_w); m3mulv(e->vel[0].v, e->Rwl[0], e->base_v); }
+    for (int i = 0; i < m->n_links; i++) {
+        int p = m->parent[i];
+        xf_motion(&e->vel[i + 1], e->Rpl[i], e->rvec[i], &e->vel[p + 1]);
+        if (m->dof_idx[i] >= 0) {
+            double qd = e->qd[m->dof_idx[i]];
+            v3axpy(e->vel[i + 1].w, qd, e->S[i].w);
+            v3axpy(e->vel[i + 1].v, qd, e->S[i].v);
+        }
+    }
+}
+
+/* ---------------- btMultiBody::computeAccelerationsArticulatedBodyAlgorithmMultiDof ----------------
+ * Gravity enters as an applied force m*g on every link (btMultiBodyDynamicsWorld::solveConstraints),
+ * velocity damping k*v*(1+|v|) and the gyroscopic term are part of the zero-acceleration force.
+ * Result: accelerations applied to the velocities (applyDeltaVeeMultiDof(output, dt), with the
+ * m_maxCoordinateVelocity clamp). */
+static void clamp_vel(const rs_model_desc *m, oenv *e) {
+    double c = m->max_coord_vel;
+    if (!m->fixed_base)
+        for (int k = 0; k < 3; k++) {
+            if (e->base_w[k] > c) e->base_w[k] = c; if (e->base_w[k] < -c) e->base_w[k] = -c;
+            if (e->base_v[k] > c) e->base_v[k] = c; if (e->base_v[k] < -c) e->base_v[k] = -c;
+        }
+    for (int d = 0; d < m->n_dof; d++) { if (e->qd[d] > c) e->qd[d] = c; if (e->qd[d] < -c) e->qd[d] = -c; }
+}
+
+static void aba(const rs_model_desc *m, oenv *e, double dt) {
+    int n = m->n_links;
+    static const double zero3[3] = {0, 0, 0};
+    double IA[ML + 1][36];
+    sv6 Z[ML + 1], c[ML], acc[ML + 1];
+    double Y[ML];
+    double gw[3] = {0, 0, -m->gravity};
+    velocities(m, e);
+    for (int b = 0; b <= n; b++) {
+        double mass = b == 0 ? m->base_mass : m->mass[b - 1];
+        const double *I3 = b == 0 ? m->base_inertia : m->inertia[b - 1];
+        const sv6 *v = &e->vel[b];
+        /* applied force: gravity (world) rotated into link coords; no applied torque */
+        double fl[3], fw[3] = {gw[0] * mass, gw[1] * mass, gw[2] * mass};
+        m3mulv(fl, e->Rwl[b], fw);
+        double wn = v3len(v->w), vn = v3len(v->v);
+        double Iw[3] = {I3[0] * v->w[0], I3[1] * v->w[1], I3[2] * v->w[2]};
+        double ka = m->ang_damping * (1.0 + wn), kl = m->lin_damping * (1.0 + vn);
+        for (int k = 0; k < 3; k++) {
+            Z[b].w[k] = Iw[k] * ka;
+            Z[b].v[k] = -fl[k] + mass * v->v[k] * kl;
+        }
+        if (m->use_gyro != 0.0) { double g[3]; v3cross(g, v->w, Iw); v3add(Z[b].w, Z[b].w, g); }
+        { double g[3]; v3cross(g, v->w, v->v); v3axpy(Z[b].v, mass, g); }
+        if (b == 0 && m->fixed_base) { memset(&Z[0], 0, sizeof(sv6)); }
+        memset(IA[b], 0, sizeof IA[b]);
+        IA[b][0] = I3[0]; IA[b][7] = I3[1]; IA[b][14] = I3[2];
+        IA[b][21] = IA[b][28] = IA[b][35] = mass;
+        if (b > 0) {
+            int i = b - 1;
+            if (m->dof_idx[i] >= 0) {
+                /* spatCoriolisAcc = spatVel x spatJointVel */
+                double qd = e->qd[m->dof_idx[i]];
+                sv6 jv; for (int k = 0; k < 3; k++) { jv.w[k] = qd * e->S[i].w[k]; jv.v[k] = qd * e->S[i].v[k]; }
+                double t1[3], t2[3];
+                v3cross(c[i].w, v->w, jv.w);
+                v3cross(t1, v->w, jv.v); v3cross(t2, v->v, jv.w);
+                v3add(c[i].v, t1, t2);
+            } else { v3cpy(c[i].w, zero3); v3cpy(c[i].v, zero3); }
+        }
+    }
+    /* leaves -> base */
+    for (int i = n - 1; i >= 0; i--) {
+        int p = m->parent[i];
+        double X[36];
+        build_X(X, e->Rpl[i], e->rvec[i]);
+        sv6 Zt;
+        if (m->dof_idx[i] >= 0) {
+            int d = m->dof_idx[i];
+            m6mulv(&e->h[i], IA[i + 1], &e->S[i]);
+            double D = sv_dot(&e->S[i], &e->h[i]);
+            Y[i] = e->tau[d] - sv_dot(&e->S[i], &Z[i + 1]) - sv_dot(&c[i], &e->h[i]);
+            e->invD[i] = 1.0 / D;
+            double Ia[36], hh[6] = {e->h[i].w[0], e->h[i].w[1], e->h[i].w[2], e->h[i].v[0], e->h[i].v[1], e->h[i].v[2]};
+            for (int a = 0; a < 6; a++) for (int b2 = 0; b2 < 6; b2++) Ia[a * 6 + b2] = IA[i + 1][a * 6 + b2] - hh[a] * hh[b2] * e->invD[i];
+            inertia_to_parent_add(IA[p + 1], Ia, X);
+            sv6 Ic; m6mulv(&Ic, IA[i + 1], &c[i]);
+            double k = e->invD[i] * Y[i];
+            for (int a = 0; a < 3; a++) { Zt.w[a] = Z[i + 1].w[a] + Ic.w[a] + e->h[i].w[a] * k; Zt.v[a] = Z[i + 1].v[a] + Ic.v[a] + e->h[i].v[a] * k; }
+        } else {
+            inertia_to_parent_add(IA[p + 1], IA[i + 1], X);
+            Zt = Z[i + 1];
+            e->invD[i] = 0; Y[i] = 0; memset(&e->h[i], 0, sizeof(sv6));
+        }
+        sv6 Zp; xf_force_inv(&Zp, e->Rpl[i], e->rvec[i], &Zt);
+        v3add(Z[p + 1].w, Z[p + 1].w, Zp.w); v3add(Z[p + 1].v, Z[p + 1].v, Zp.v);
+    }
+    /* base acceleration */
+    if (m->fixed_base) { memset(&acc[0], 0, sizeof(sv6)); memset(e->Ibase_inv, 0, sizeof e->Ibase_inv); }
+    else {
+        inv6(e->Ibase_inv, IA[0]);
+        sv6 r; m6mulv(&r, e->Ibase_inv, &Z[0]);
+        for (int k = 0; k < 3; k++) { acc[0].w[k] = -r.w[k]; acc[0].v[k] = -r.v[k]; }
+    }
+    double qdd[ML];
+    for (int i = 0; i < n; i++) {
+        int p = m->parent[i];
+        xf_motion(&acc[i + 1], e->Rpl[i], e->rvec[i], &acc[p + 1]);
+        if (m->dof_idx[i] >= 0) {
+            double a = e->invD[i] * (Y[i] - sv_dot(&acc[i + 1], &e->h[i]));
+            qdd[m->dof_idx[i]] = a;
+            for (int k = 0; k < 3; k++) { acc[i + 1].w[k] += c[i].w[k] + a * e->S[i].w[k]; acc[i + 1].v[k] += c[i].v[k] + a * e->S[i].v[k]; }
+        }
+    }
+    /* apply: base accelerations back in the world frame (+ omega x v for the linear part) */
+    if (!m->fixed_base) {
+        double wd[3], vd[3], t[3], wxv[3];
+        m3tmulv(wd, e->Rwl[0], acc[0].w);
+        v3cross(wxv, e->vel[0].w, e->vel[0].v);
+        v3add(t, acc[0].v, wxv);
+        m3tmulv(vd, e->Rwl[0], t);
+        v3axpy(e->base_w, dt, wd); v3axpy(e->base_v, dt, vd);
+    }
+    for (int d = 0; d < m->n_dof; d++) e->qd[d] += dt * qdd[d];
+    clamp_vel(m, e);
+}
+
+/* ---------------- btMultiBody::calcAccelerationDeltasMultiDof ----------------
+ * force: [base torque(3, world) base force(3, world) joint forces(ndof)], out same layout. */
+static void accel_deltas(const rs_model_desc *m, const oenv *e, const double *force, double *out) {
+    int n = m->n_links;
+    sv6 Z[ML + 1], acc[ML + 1];
+    double Y[ML];
+    memset(Z, 0, sizeof(sv6) * (n + 1));
+    if (!m->fixed_base) {
+        double t[3];
+        m3mulv(t, e->Rwl[0], force);     Z[0].w[0] = -t[0]; Z[0].w[1] = -t[1]; Z[0].w[2] = -t[2];
+        m3mulv(t, e->Rwl[0], force + 3); Z[0].v[0] = -t[0]; Z[0].v[1] = -t[1]; Z[0].v[2] = -t[2];
+    }
+    for (int i = n - 1; i >= 0; i--) {
+        int p = m->parent[i];
+        sv6 Zt = Z[i + 1];
+        if (m->dof_idx[i] >= 0) {
+            Y[i] = force[6 + m->dof_idx[i]] - sv_dot(&e->S[i], &Z[i + 1]);
+            double k = e->invD[i] * Y[i];
+            v3axpy(Zt.w, k, e->h[i].w); v3axpy(Zt.v, k, e->h[i].v);
+        }
+        sv6 Zp; xf_force_inv(&Zp, e->Rpl[i], e->rvec[i], &Zt);
+        v3add(Z[p + 1].w, Z[p + 1].w, Zp.w); v3add(Z[p + 1].v, Z[p + 1].v, Zp.v);
+    }
+    if (m->fixed_base) memset(&acc[0], 0, sizeof(sv6));
+    else {
+        sv6 r; m6mulv(&r, e->Ibase_inv, &Z[0]);
+        for (int k = 0; k < 3; k++) { acc[0].w[k] = -r.w[k]; acc[0].v[k] = -r.v[k]; }
+    }
+    for (int i = 0; i < n; i++) {
+        int p = m->parent[i];
+        xf_motion(&acc[i + 1], e->Rpl[i], e->rvec[i], &acc[p + 1]);
+        if (m->dof_idx[i] >= 0) {
+            double a = e->invD[i] * (Y[i] - sv_dot(&acc[i + 1], &e->h[i]));
+            out[6 + m->dof_idx[i]] = a;
+            v3axpy(acc[i + 1].w, a, e->S[i].w); v3axpy(acc[i + 1].v, a, e->S[i].v);
+        }
+    }
+    if (m->fixed_base) { for (int k = 0; k < 6; k++) out[k] = 0; }
+    else { m3tmulv(out, e->Rwl[0], acc[0].w); m3tmulv(out + 3, e->Rwl[0], acc[0].v); }
+}
+
+/* ---------------- btMultiBody::fillContactJacobianMultiDof ----------------
+ * jac . [w_base v_base qd] = n . (velocity of world point p rigidly attached to body b)  (b: 0=base, i+1=link i) */
+static void contact_jacobian(const rs_model_desc *m, const oenv *e, int b, const double *p, const double *n, double *jac) {
+    memset(jac, 0, sizeof(double) * (6 + m->n_dof));
+    if (!m->fixed_base) {
+        double r[3]; v3sub(r, p, e->pos[0]);
+        v3cross(jac, r, n);
+        v3cpy(jac + 3, n);
+    }
+    int l = b - 1;
+    while (l >= 0) {
+        if (m->dof_idx[l] >= 0) {
+            double aw[3];
+            m3tmulv(aw, e->Rwl[l + 1], m->axis[l]);      /* axis in world */
+            if (m->jtype[l] == RS_JOINT_REVOLUTE) {
+                /* pivot = link COM - R^T d */
+                double dw[3], piv[3], r[3], c[3];
+                m3tmulv(dw, e->Rwl[l + 1], m->d_vec[l]);
+                v3sub(piv, e->pos[l + 1], dw);
+                v3sub(r, p, piv);
+                v3cross(c, r, n);
+                jac[6 + m->dof_idx[l]] = v3dot(aw, c);
+            } else jac[6 + m->dof_idx[l]] = v3dot(aw, n);
+        }
+        l = m->parent[l];
+    }
+}
+
+/* ---------------- narrowphase + persistent manifolds ---------------- */
+static void link_to_world(const oenv *e, int b, const double *local, double *w) {
+    double t[3]; m3tmulv(t, e->Rwl[b], local); v3add(w, e->pos[b], t);
+}
+static void world_to_link(const oenv *e, int b, const double *w, double *local) {
+    double t[3]; v3sub(t, w, e->pos[b]); m3mulv(local, e->Rwl[b], t);
+}
+
+/* btPersistentManifold::sortCachedPoints (gContactCalcArea3Points = true) */
+static int sort_cached_points(const manifold *mf, const cpoint *pt) {
+    int maxPenetrationIndex = -1;
+    double maxPenetration = pt->dist;
+    for (int i = 0; i < 4; i++) if (mf->p[i].dist < maxPenetration) { maxPenetrationIndex = i; maxPenetration = mf->p[i].dist; }
+    double res[4] = {0, 0, 0, 0}, a[3], b[3], c[3];
+    if (maxPenetrationIndex != 0) { v3sub(a, pt->localA, mf->p[1].localA); v3sub(b, mf->p[3].localA, mf->p[2].localA); v3cross(c, a, b); res[0] = v3dot(c, c); }
+    if (maxPenetrationIndex != 1) { v3sub(a, pt->localA, mf->p[0].localA); v3sub(b, mf->p[3].localA, mf->p[2].localA); v3cross(c, a, b); res[1] = v3dot(c, c); }
+    if (maxPenetrationIndex != 2) { v3sub(a, pt->localA, mf->p[0].localA); v3sub(b, mf->p[3].localA, mf->p[1].localA); v3cross(c, a, b); res[2] = v3dot(c, c); }
+    if (maxPenetrationIndex != 3) { v3sub(a, pt->localA, mf->p[0].localA); v3sub(b, mf->p[2].localA, mf->p[1].localA); v3cross(c, a, b); res[3] = v3dot(c, c); }
+    /* btVector4::closestAxis4 -> absolute().maxAxis4(): first strict maximum */
+    int best = -1; double mv = -1e300;
+    for (int i = 0; i < 4; i++) if (fabs(res[i]) > mv) { mv = fabs(res[i]); best = i; }
+    return best;
+}
+
+/* btManifoldResult::addContactPoint + btPersistentManifold::getCacheEntry/addManifoldPoint/replaceContactPoint */
+static void manifold_add(manifold *mf, const oenv *e, int bA, int bB, const double *n, const double *pOnB, double depth,
+                         double thresh, double friction) {
+    if (depth > thresh) return;
+    cpoint np; memset(&np, 0, sizeof np);
+    double pA[3] = {pOnB[0] + n[0] * depth, pOnB[1] + n[1] * depth, pOnB[2] + n[2] * depth};
+    world_to_link(e, bA, pA, np.localA);
+    if (bB >= 0) world_to_link(e, bB, pOnB, np.localB); else v3cpy(np.localB, pOnB);
+    v3cpy(np.normal, n); v3cpy(np.posA, pA); v3cpy(np.posB, pOnB);
+    np.dist = depth; np.friction = friction;
+    double shortest = thresh * thresh; int nearest = -1;
+    for (int i = 0; i < mf->n; i++) {
+        double d[3]; v3sub(d, mf->p[i].localA, np.localA);
+        double dd = v3dot(d, d);
+        if (dd < shortest) { shortest = dd; nearest = i; }
+    }
+    if (nearest >= 0) {
+        /* replaceContactPoint: keeps lifetime and applied impulses */
+        np.lifetime = mf->p[nearest].lifetime;
+        np.imp_n = mf->p[nearest].imp_n; np.imp_f1 = mf->p[nearest].imp_f1; np.imp_f2 = mf->p[nearest].imp_f2;
+        mf->p[nearest] = np;
+    } else {
+        int idx = mf->n;
+        if (idx == MANIFOLD_CACHE_SIZE) idx = sort_cached_points(mf, &np); else mf->n++;
+        mf->p[idx] = np;
+    }
+}
+
+/* btPersistentManifold::refreshContactPoints */
+static void manifold_refresh(manifold *mf, const oenv *e, int bA, int bB, double thresh) {
+    for (int i = mf->n - 1; i >= 0; i--) {
+        cpoint *p = &mf->p[i];
+        link_to_world(e, bA, p->localA, p->posA);
+        if (bB >= 0) link_to_world(e, bB, p->localB, p->posB); else v3cpy(p->posB, p->localB);
+        double d[3]; v3sub(d, p->posA, p->posB);
+        p->dist = v3dot(d, p->normal);
+        p->lifetime++;
+    }
+    for (int i = mf->n - 1; i >= 0; i--) {
+        cpoint *p = &mf->p[i];
+        int remove = 0;
+        if (!(p->dist <= thresh)) remove = 1;
+        else {
+            double proj[3], diff[3];
+            for (int k = 0; k < 3; k++) proj[k] = p->posA[k] - p->normal[k] * p->dist;
+            v3sub(diff, p->posB, proj);
+            if (v3dot(diff, diff) > thresh * thresh) remove = 1;
+        }
+        if (remove) { mf->p[i] = mf->p[mf->n - 1]; mf->n--; }
+    }
+}
+
+/* closest points between segments [p1,q1] and [p2,q2] (the analytic answer GJK converges to
+ * for btMultiSphereShape capsules) */
+static void seg_seg_closest(const double *p1, const double *q1, const double *p2, const double *q2, double *c1, double *c2) {
+    double d1[3], d2[3], r[3];
+    v3sub(d1, q1, p1); v3sub(d2, q2, p2); v3sub(r, p1, p2);
+    double a = v3dot(d1, d1), e = v3dot(d2, d2), f = v3dot(d2, r), s, t;
+    const double EPS = 1e-12;
+    if (a <= EPS && e <= EPS) { s = t = 0; }
+    else if (a <= EPS) { s = 0; t = f / e; t = t < 0 ? 0 : (t > 1 ? 1 : t); }
+    else {
+        double c = v3dot(d1, r);
+        if (e <= EPS) { t = 0; s = -c / a; s = s < 0 ? 0 : (s > 1 ? 1 : s); }
+        else {
+            double b = v3dot(d1, d2), denom = a * e - b * b;
+            if (denom > EPS * a * e) { s = (b * f - c * e) / denom; s = s < 0 ? 0 : (s > 1 ? 1 : s); } else s = 0;
+            t = (b * s + f) / e;
+            if (t < 0) { t = 0; s = -c / a; s = s < 0 ? 0 : (s > 1 ? 1 : s); }
+            else if (t > 1) { t = 1; s = (b - c) / a; s = s < 0 ? 0 : (s > 1 ? 1 : s); }
+        }
+    }
+    for (int k = 0; k < 3; k++) { c1[k] = p1[k] + d1[k] * s; c2[k] = p2[k] + d2[k] * t; }
+}
+
+static void collide(const rs_model_desc *m, oenv *e) {
+    /* floor: btConvexPlaneCollisionAlgorithm::collideSingleContact -- one support vertex per geom per
+     * sub-step into that (geom, plane) manifold, then refreshContactPoints */
+    const double nz[3] = {0, 0, 1};
+    for (int g = 0; g < m->n_geoms; g++) {
+        manifold *mf = &e->man[g];
+        if (!m->g_floor[g]) { mf->n = 0; continue; }
+        int b = m->g_link[g] + 1;
+        double thr = m->break_thresh[b]; /* min(link compound, plane=huge) */
+        double c0[3], c1[3];
+        link_to_world(e, b, m->g_p0[g], c0);
+        const double *c = c0;
+        if (m->g_type[g] == RS_GEOM_CAPSULE) {
+            link_to_world(e, b, m->g_p1[g], c1);
+            if (c1[2] < c0[2]) c = c1;   /* support in -n: first sphere wins ties */
+        }
+        double vtx[3] = {c[0], c[1], c[2] - m->g_radius[g]};
+        double dist = vtx[2];
+        if (dist < thr) {
+            double pOnB[3] = {vtx[0], vtx[1], 0.0};
+            manifold_add(mf, e, b, -1, nz, pOnB, dist, thr, m->g_friction[g] * m->floor_friction);
+        }
+        if (mf->n) manifold_refresh(mf, e, b, -1, thr);
+    }
+    /* self collision: closest points between sphere/capsule cores */
+    for (int k = 0; k < m->n_pairs; k++) {
+        manifold *mf = &e->man[m->n_geoms + k];
+        int ga = m->pair_a[k], gb = m->pair_b[k];
+        int bA = m->g_link[ga] + 1, bB = m->g_link[gb] + 1;
+        double thr = m->break_thresh[bA] < m->break_thresh[bB] ? m->break_thresh[bA] : m->break_thresh[bB];
+        double a0[3], a1[3], b0[3], b1[3], cA[3], cB[3];
+        link_to_world(e, bA, m->g_p0[ga], a0); link_to_world(e, bA, m->g_p1[ga], a1);
+        link_to_world(e, bB, m->g_p0[gb], b0); link_to_world(e, bB, m->g_p1[gb], b1);
+        seg_seg_closest(a0, a1, b0, b1, cA, cB);
+        double d[3]; v3sub(d, cA, cB);
+        double len = v3len(d), rA = m->g_radius[ga], rB = m->g_radius[gb];
+        double dist = len - rA - rB;
+        int both_spheres = m->g_type[ga] == RS_GEOM_SPHERE && m->g_type[gb] == RS_GEOM_SPHERE;
+        /* btSphereSphereCollisionAlgorithm only reports penetrating pairs; GJK pairs report up to the breaking threshold */
+        int hit = both_spheres ? (dist <= 0.0) : (dist < thr);
+        if (hit) {
+            double n[3] = {1, 0, 0};
+            if (len > 1e-12) { n[0] = d[0] / len; n[1] = d[1] / len; n[2] = d[2] / len; }
+            double pOnB[3] = {cB[0] + n[0] * rB, cB[1] + n[1] * rB, cB[2] + n[2] * rB};
+            manifold_add(mf, e, bA, bB, n, pOnB, dist, thr, m->g_friction[ga] * m->g_friction[gb]);
+        }
+        if (mf->n) manifold_refresh(mf, e, bA, bB, thr);
+    }
+}
+
+/* ---------------- constraint rows: btMultiBodyConstraintSolver ---------------- */
+typedef struct {
+    double jac[MAXDOF];     /* jacA + jacB (both act on the same multibody) */
+    double unit[MAXDOF];    /* deltaVelocitiesUnitImpulse (A + B)           */
+    double inv_denom, rhs, lo, hi, applied, friction;
+    int friction_index;     /* friction rows: index of their normal row     */
+    cpoint *cp; int which;  /* write-back target                            */
+} crow;
+
+static double row_finish(const rs_model_desc *m, const oenv *e, crow *r, const double *jA, const double *jB, int nd) {
+    /* fillMultiBodyConstraint / setupMultiBodyContactConstraint: unit-impulse responses per body side,
+     * denom = jA.uA + jB.uB (Bullet treats the two sides independently even on one multibody) */
+    double uA[MAXDOF], uB[MAXDOF], denom = 0, relvel = 0;
+    double vel[MAXDOF];
+    for (int k = 0; k < 3; k++) { vel[k] = e->base_w[k]; vel[3 + k] = e->base_v[k]; }
+    for (int d = 0; d < m->n_dof; d++) vel[6 + d] = e->qd[d];
+    accel_deltas(m, e, jA, uA);
+    for (int k = 0; k < nd; k++) { denom += jA[k] * uA[k]; relvel += jA[k] * vel[k]; r->jac[k] = jA[k]; r->unit[k] = uA[k]; }
+    if (jB) {
+        accel_deltas(m, e, jB, uB);
+        for (int k = 0; k < nd; k++) { denom += jB[k] * uB[k]; relvel += jB[k] * vel[k]; r->jac[k] += jB[k]; r->unit[k] += uB[k]; }
+    }
+    /* "disable the constraint row to handle singularity/redundant constraint" (d > SIMD_EPSILON);
+     * FLT_EPSILON is used in both the oracle and the fp32 CUDA path (planar robots: exact 0) */
+    r->inv_denom = denom > 1.1920929e-07 ? 1.0 / denom : 0.0;   /* relaxation 1, cfm 0 */
+    r->applied = 0;
+    return relvel;
+}
+
+static int setup_rows(const rs_model_desc *m, oenv *e, double dt, crow *nc, int *n_nc, crow *cn, int *n_cn, crow *cf, int *n_cf) {
+    int nd = 6 + m->n_dof;
+    *n_nc = *n_cn = *n_cf = 0;
+    /* btMultiBodyJointLimitConstraint::createConstraintRows: row 0 lower, row 1 upper, only when violated */
+    for (int i = 0; i < m->n_links; i++) {
+        if (!m->has_limit[i] || m->dof_idx[i] < 0) continue;
+        int d = m->dof_idx[i];
+        for (int row = 0; row < 2; row++) {
+            double pen = row == 0 ? e->q[d] - m->lim_lo[i] : m->lim_hi[i] - e->q[d];
+            if (pen > 0) continue;
+            double jA[MAXDOF]; memset(jA, 0, sizeof jA);
+            jA[6 + d] = row == 0 ? 1.0 : -1.0;
+            crow *r = &nc[(*n_nc)++];
+            double relvel = row_finish(m, e, r, jA, NULL, nd);
+            double erp = m->erp2;
+            if (pen > m->split_thresh) erp = m->erp;   /* m_splitImpulse is on by default */
+            double posErr = -pen * erp / dt, velErr = -relvel;
+            if (pen > m->split_thresh) r->rhs = (posErr + velErr) * r->inv_denom;
+            else r->rhs = velErr * r->inv_denom;        /* m_rhsPenetration is never used for multibodies */
+            r->lo = 0; r->hi = m->max_limit_impulse; r->cp = NULL; r->friction_index = -1;
+        }
+    }
+    /* contacts: btMultiBodyConstraintSolver::convertMultiBodyContact, manifold order, point order */
+    int nman = m->n_geoms + m->n_pairs;
+    for (int k = 0; k < nman; k++) {
+        manifold *mf = &e->man[k];
+        int bA, bB;
+        if (k < m->n_geoms) { bA = m->g_link[k] + 1; bB = -1; }
+        else { bA = m->g_link[m->pair_a[k - m->n_geoms]] + 1; bB = m->g_link[m->pair_b[k - m->n_geoms]] + 1; }
+        for (int pi = 0; pi < mf->n; pi++) {
+            cpoint *cp = &mf->p[pi];
+            if (*n_cn >= MAXROWS / 4) continue;
+            double dirs[3][3];
+            v3cpy(dirs[0], cp->normal);
+            plane_space(cp->normal, dirs[1], dirs[2]);
+            int normal_index = *n_cn;
+            for (int w = 0; w < 3; w++) {
+                double jA[MAXDOF], jB[MAXDOF], nneg[3] = {-dirs[w][0], -dirs[w][1], -dirs[w][2]};
+                contact_jacobian(m, e, bA, cp->posA, dirs[w], jA);
+                if (bB >= 0) contact_jacobian(m, e, bB, cp->posB, nneg, jB);
+                crow *r = w == 0 ? &cn[(*n_cn)++] : &cf[(*n_cf)++];
+                double relvel = row_finish(m, e, r, jA, bB >= 0 ? jB : NULL, nd);
+                r->cp = cp; r->which = w; r->friction = cp->friction;
+                if (w == 0) {
+                    double pen = cp->dist;     /* + m_linearSlop (0) */
+                    double erp = m->erp2;
+                    if (pen > m->split_thresh) erp = m->erp;
+                    double posErr = 0, velErr = -relvel;   /* restitution 0 */
+                    if (pen > 0) velErr -= pen / dt; else posErr = -pen * erp / dt;
+                    if (pen > m->split_thresh) r->rhs = (posErr + velErr) * r->inv_denom;
+                    else r->rhs = velErr * r->inv_denom;
+                    r->lo = 0; r->hi = 1e10; r->friction_index = -1;
+                } else {
+                    r->rhs = -relvel * r->inv_denom;
+                    r->lo = -cp->friction; r->hi = cp->friction; r->friction_index = normal_index;
+                }
+            }
+        }
+    }
+    return *n_nc + *n_cn + *n_cf;
+}
+
+/* resolveSingleConstraintRowGeneric */
+static inline void resolve_row(crow *c, double *dv, int nd) {
+    double dimp = c->rhs, dot = 0;        /* - applied*cfm (cfm 0) */
+    for (int k = 0; k < nd; k++) dot += c->jac[k] * dv[k];
+    dimp -= dot * c->inv_denom;
+    double sum = c->applied + dimp;
+    if (sum < c->lo) { dimp = c->lo - c->applied; c->applied = c->lo; }
+    else if (sum > c->hi) { dimp = c->hi - c->applied; c->applied = c->hi; }
+    else c->applied = sum;
+    for (int k = 0; k < nd; k++) dv[k] += c->unit[k] * dimp;
+}
+
+static void solve(const rs_model_desc *m, oenv *e, double dt) {
+    static __thread crow nc[2 * ML], cn[MAXROWS / 4], cf[MAXROWS / 2];
+    int n_nc, n_cn, n_cf, nd = 6 + m->n_dof;
+    int total = setup_rows(m, e, dt, nc, &n_nc, cn, &n_cn, cf, &n_cf);
+    e->n_rows_last = total; e->n_contacts_last = n_cn;
+    if (!total) return;
+    double dv[MAXDOF]; memset(dv, 0, sizeof dv);
+    /* btMultiBodyConstraintSolver::solveSingleIteration */
+    for (int it = 0; it < m->n_iter; it++) {
+        for (int j = 0; j < n_nc; j++) { int idx = (it & 1) ? j : n_nc - 1 - j; resolve_row(&nc[idx], dv, nd); }
+        for (int j = 0; j < n_cn; j++) resolve_row(&cn[j], dv, nd);
+        for (int j = 0; j < n_cf; j++) {
+            double tot = cn[cf[j].friction_index].applied;
+            if (tot > 0) { cf[j].lo = -cf[j].friction * tot; cf[j].hi = cf[j].friction * tot; resolve_row(&cf[j], dv, nd); }
+        }
+    }
+    /* write back: velocities += deltaV ; applied impulses -> manifold points */
+    if (!m->fixed_base) for (int k = 0; k < 3; k++) { e->base_w[k] += dv[k]; e->base_v[k] += dv[3 + k]; }
+    for (int d = 0; d < m->n_dof; d++) e->qd[d] += dv[6 + d];
+    clamp_vel(m, e);
+    for (int j = 0; j < n_cn; j++) cn[j].cp->imp_n = cn[j].applied;
+    for (int j = 0; j < n_cf; j++) { if (cf[j].which == 1) cf[j].cp->imp_f1 = cf[j].applied; else cf[j].cp->imp_f2 = cf[j].applied; }
+}
+
+/* ---------------- btMultiBody::stepPositionsMultiDof ---------------- */
+static void integrate(const rs_model_desc *m, oenv *e, double dt) {
+    if (!m->fixed_base) {
+        v3axpy(e->base_pos, dt, e->base_v);
+        /* pQuatUpdateFun, baseBody branch, restated for a base->world quaternion: q <- dq(omega_world) * q */
+        double ang = v3len(e->base_w), axis[3];
+        if (ang * dt > 0.7853981633974483) ang = 0.5 * 1.5707963267948966 / dt; /* ANGULAR_MOTION_THRESHOLD */
+        double k;
+        if (ang < 0.001) k = 0.5 * dt - dt * dt * dt * 0.020833333333 * ang * ang;
+        else k = sin(0.5 * ang * dt) / ang;
+        for (int i = 0; i < 3; i++) axis[i] = e->base_w[i] * k;
+        double dq[4] = {axis[0], axis[1], axis[2], cos(ang * dt * 0.5)}, nq[4];
+        quat_mul(nq, dq, e->base_quat);
+        double nn = sqrt(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]);
+        for (int i = 0; i < 4; i++) e->base_quat[i] = nq[i] / nn;
+    }
+    for (int d = 0; d < m->n_dof; d++) e->q[d] += dt * e->qd[d];
+}
+
+static void substep(const rs_model_desc *m, oenv *e) {
+    double dt = m->timestep;
+    kinematics(m, e);
+    collide(m, e);      /* performDiscreteCollisionDetection */
+    aba(m, e, dt);      /* solveConstraints: forward dynamics ... */
+    solve(m, e, dt);    /* ... then the multibody constraint solver */
+    integrate(m, e, dt);
+}
+
+/* ---------------- state readback: query_body_position (physics-bullet.cpp:440-495) ---------------- */
+static void mat_to_quat(const double *R, double *q) { /* R rotates local->world ; (x,y,z,w) */
+    double t = R[0] + R[4] + R[8];
+    if (t > 0) { double s = sqrt(t + 1.0) * 2; q[3] = 0.25 * s; q[0] = (R[7] - R[5]) / s; q[1] = (R[2] - R[6]) / s; q[2] = (R[3] - R[1]) / s; }
+    else if (R[0] > R[4] && R[0] > R[8]) { double s = sqrt(1.0 + R[0] - R[4] - R[8]) * 2; q[3] = (R[7] - R[5]) / s; q[0] = 0.25 * s; q[1] = (R[1] + R[3]) / s; q[2] = (R[2] + R[6]) / s; }
+    else if (R[4] > R[8]) { double s = sqrt(1.0 + R[4] - R[0] - R[8]) * 2; q[3] = (R[2] - R[6]) / s; q[0] = (R[1] + R[3]) / s; q[1] = 0.25 * s; q[2] = (R[5] + R[7]) / s; }
+    else { double s = sqrt(1.0 + R[8] - R[0] - R[4]) * 2; q[3] = (R[3] - R[1]) / s; q[0] = (R[2] + R[6]) / s; q[1] = (R[5] + R[7]) / s; q[2] = 0.25 * s; }
+}
+static void body_pose(const oenv *e, int b, double *pos, double *quat, double *linvel) {
+    v3cpy(pos, e->pos[b]);
+    double Rlw[9];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Rlw[i * 3 + j] = e->Rwl[b][j * 3 + i];
+    if (b == 0) memcpy(quat, e->base_quat, 4 * sizeof(double)); else mat_to_quat(Rlw, quat);
+    m3tmulv(linvel, e->Rwl[b], e->vel[b].v);
+}
+
+/* Pose::rpy  (python-binding.cpp:60-73) */
+static void quat_rpy(const double *q, double *r, double *p, double *y) {
+    double qx = q[0], qy = q[1], qz = q[2], qw = q[3];
+    double sqw = qw * qw, sqx = qx * qx, sqy = qy * qy, sqz = qz * qz;
+    double t2 = -2.0 * (qx * qz - qy * qw) / (sqx + sqy + sqz + sqw);
+    *y = atan2(2.0 * (qx * qy + qz * qw), (sqx - sqy - sqz + sqw));
+    *r = atan2(2.0 * (qy * qz + qx * qw), (-sqx - sqy + sqz + sqw));
+    t2 = t2 > 1.0 ? 1.0 : t2; t2 = t2 < -1.0 ? -1.0 : t2;
+    *p = asin(t2);
+}
+
+/* foot contact flags: World::bullet_contact_list(foot) -> names (gym_forward_walker.py:106-112) */
+static void foot_contacts(const rs_model_desc *m, const oenv *e, int foot, int *ground, int *other) {
+    *ground = *other = 0;
+    int fb = m->foot_link[foot] + 1;
+    for (int g = 0; g < m->n_geoms; g++) if (m->g_link[g] + 1 == fb && e->man[g].n > 0) *ground = 1;
+    for (int k = 0; k < m->n_pairs; k++) {
+        int bA = m->g_link[m->pair_a[k]] + 1, bB = m->g_link[m->pair_b[k]] + 1;
+        if ((bA == fb || bB == fb) && e->man[m->n_geoms + k].n > 0) *other = 1;
+    }
+}
+
+/* calc_state (gym_forward_walker.py:45-76), float32 squeezes where the reference has them */
+static void calc_state(const rs_model_desc *m, oenv *e, double *body_xy_dist) {
+    kinematics(m, e); velocities(m, e);
+    int A = m->n_act;
+    float j[2 * RS_MAX_ACT];
+    int at_limit = 0;
+    for (int k = 0; k < A; k++) {
+        int d = m->act_dof[k], li = -1;
+        for (int i = 0; i < m->n_links; i++) if (m->dof_idx[i] == d) li = i;
+        float pos = (float)e->q[d], spd = (float)e->qd[d];        /* Joint::joint_current_position is a float */
+        float l1 = (float)m->lim_lo[li], l2 = (float)m->lim_hi[li];
+        if (l1 < l2) { float mid = (float)(0.5 * (l1 + l2)); pos = 2 * (pos - mid) / (l2 - l1); }
+        if (m->max_vel[li] > 0) spd /= (float)m->max_vel[li];
+        else spd *= (m->jtype[li] == RS_JOINT_REVOLUTE) ? 0.1f : 0.5f;
+        j[2 * k] = pos; j[2 * k + 1] = spd;
+        if (fabsf(pos) > 0.99f) at_limit++;
+    }
+    e->rewards5[3] = m->joints_at_limit_cost * at_limit;
+    double bp[3], bq[4], bv[3];
+    body_pose(e, m->body_link + 1, bp, bq, bv);
+    double mx = 0, my = 0;
+    for (int k = 0; k < m->n_parts; k++) { mx += e->pos[m->part_link[k] + 1][0]; my += e->pos[m->part_link[k] + 1][1]; }
+    mx /= m->n_parts; my /= m->n_parts;
+    double z = bp[2], r, p, yaw;
+    quat_rpy(bq, &r, &p, &yaw);
+    if (e->initial_z < 0) e->initial_z = z;
+    double theta = atan2(m->walk_target_y - my, m->walk_target_x - mx);
+    double dy = m->walk_target_y - my, dx = m->walk_target_x - mx;
+    *body_xy_dist = sqrt(dy * dy + dx * dx);
+    double ang = theta - yaw;
+    double cy = cos(-yaw), sy = sin(-yaw);
+    double vx = cy * bv[0] - sy * bv[1], vy = sy * bv[0] + cy * bv[1], vz = bv[2];
+    float more[8] = {(float)(z - e->initial_z), (float)sin(ang), (float)cos(ang), (float)(0.3 * vx), (float)(0.3 * vy), (float)(0.3 * vz), (float)r, (float)p};
+    int o = 0;
+    for (int k = 0; k < 8; k++) e->obs[o++] = more[k];
+    for (int k = 0; k < 2 * A; k++) e->obs[o++] = j[k];
+    for (int k = 0; k < m->n_feet; k++) e->obs[o++] = (float)e->feet_contact[k];
+    for (int k = 0; k < o; k++) { if (e->obs[k] > 5) e->obs[k] = 5; if (e->obs[k] < -5) e->obs[k] = -5; }
+    /* keep pitch for alive_bonus */
+    e->rewards5[0] = p; /* temporarily */
+}
+
+/* RoboschoolForwardWalker.step epilogue (gym_forward_walker.py:94-133) */
+static void epilogue(const rs_model_desc *m, oenv *e, const double *a) {
+    double dist;
+    calc_state(m, e, &dist);
+    double pitch = e->rewards5[0];
+    double z = e->obs[0] + e->initial_z;   /* state[0]+initial_z, state already float32 & clipped */
+    double alive;
+    if (m->alive_rule == RS_ALIVE_Z_AND_PITCH) alive = (z > m->alive_z && fabs(pitch) < 1.0) ? m->alive_bonus : -1;
+    else if (m->alive_rule == RS_ALIVE_Z) alive = (z > m->alive_z) ? m->alive_bonus : -1;
+    else alive = m->alive_bonus;
+    int done = alive < 0;
+    for (int k = 0; k < m->obs_dim; k++) if (!isfinite(e->obs[k])) done = 1;
+    double pot_old = e->potential;
+    e->potential = -dist / m->dt_env;
+    double progress = e->potential - pot_old;
+    double feet_cost = 0;
+    for (int f = 0; f < m->n_feet; f++) {
+        int g, o; foot_contacts(m, e, f, &g, &o);
+        e->feet_contact[f] = g ? 1.0 : 0.0;
+        if (o) feet_cost += m->foot_collision_cost;
+    }
+    int A = m->n_act;
+    double s1 = 0, s2 = 0;
+    for (int k = 0; k < A; k++) { double sp = e->obs[8 + 2 * k + 1]; /* joint_speeds are pre-clip in the reference */
+        s1 += fabs(a[k] * sp); s2 += a[k] * a[k]; }
+    (void)s1;
+    /* joint_speeds = j[1::2] BEFORE np.clip: recompute unclipped */
+    s1 = 0;
+    for (int k = 0; k < A; k++) {
+        int d = m->act_dof[k], li = -1;
+        for (int i = 0; i < m->n_links; i++) if (m->dof_idx[i] == d) li = i;
+        float spd = (float)e->qd[d];
+        if (m->max_vel[li] > 0) spd /= (float)m->max_vel[li]; else spd *= (m->jtype[li] == RS_JOINT_REVOLUTE) ? 0.1f : 0.5f;
+        s1 += fabs(a[k] * (double)spd);
+    }
+    double elec = m->electricity_cost * (s1 / A) + m->stall_torque_cost * (s2 / A);
+    double jl = e->rewards5[3];
+    e->rewards5[0] = alive; e->rewards5[1] = progress; e->rewards5[2] = elec; e->rewards5[3] = jl; e->rewards5[4] = feet_cost;
+    e->reward = alive + progress + elec + jl + feet_cost;
+    e->done = done;
+    e->frame++;
+}
+
+/* counter-based RNG shared bit-for-bit with the CUDA path (integer hash -> 24-bit uniform) */
+static uint32_t rs_hash(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    uint32_t h = 0x9E3779B9u ^ a;
+    h = (h ^ (h >> 16)) * 0x85EBCA6Bu; h ^= b + 0x9E3779B9u + (h << 6) + (h >> 2);
+    h = (h ^ (h >> 13)) * 0xC2B2AE35u; h ^= c + 0x9E3779B9u + (h << 6) + (h >> 2);
+    h = (h ^ (h >> 16)) * 0x85EBCA6Bu; h ^= d + 0x9E3779B9u + (h << 6) + (h >> 2);
+    h = (h ^ (h >> 13)) * 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+static double rs_uniform(uint32_t seed, uint32_t env, uint32_t episode, uint32_t k) {
+    return (double)(rs_hash(seed, env, episode, k) >> 8) * (1.0 / 16777216.0);
+}
+
+/* reset: reference reset distribution (gym_forward_walker.py:24-30, gym_mujoco_walkers.py:106-128) */
+static void env_reset(const rs_model_desc *m, oenv *e, int nman, uint32_t seed, uint32_t env_id) {
+    e->episode++;
+    memset(e->q, 0, sizeof e->q); memset(e->qd, 0, sizeof e->qd); memset(e->tau, 0, sizeof e->tau);
+    for (int k = 0; k < m->n_act; k++) {
+        double u = rs_uniform(seed, env_id, e->episode, (uint32_t)k);
+        e->q[m->act_dof[k]] = (double)(float)(m->reset_joint_spread * (2.0 * u - 1.0)); /* reset_current_position(float,..) */
+    }
+    v3cpy(e->base_pos, m->reset_base_pos);
+    memcpy(e->base_quat, m->reset_base_quat, sizeof e->base_quat);
+    if (m->reset_set_base && m->reset_yaw_spread > 0) {
+        double u = rs_uniform(seed, env_id, e->episode, 1000u);
+        double yaw = m->reset_yaw_spread * (2.0 * u - 1.0);
+        /* Pose::set_rpy(0,0,yaw) python-binding.cpp:42-55 */
+        e->base_quat[0] = 0; e->base_quat[1] = 0; e->base_quat[2] = sin(0.5 * yaw); e->base_quat[3] = cos(0.5 * yaw);
+    }
+    v3set(e->base_w, 0, 0, 0); v3set(e->base_v, 0, 0, 0);
+    for (int k = 0; k < nman; k++) e->man[k].n = 0;
+    memset(e->feet_contact, 0, sizeof e->feet_contact);
+    e->initial_z = m->initial_z;
+    e->frame = 0; e->done = 0;
+    double dist;
+    calc_state(m, e, &dist);
+    e->potential = -dist / m->dt_env;
+}
+
+/* =========================== exported API =========================== */
+oracle_world *oracle_create(const rs_model_desc *m, int n_envs) {
+    oracle_world *w = (oracle_world *)calloc(1, sizeof *w);
+    w->m = *m; w->n_envs = n_envs; w->nman = m->n_geoms + m->n_pairs;
+    w->env = (oenv *)calloc((size_t)n_envs, sizeof(oenv));
+    for (int i = 0; i < n_envs; i++) {
+        w->env[i].man = (manifold *)calloc((size_t)(w->nman > 0 ? w->nman : 1), sizeof(manifold));
+        w->env[i].base_quat[3] = 1;
+        w->env[i].initial_z = m->initial_z;
+    }
+    return w;
+}
+void oracle_destroy(oracle_world *w) {
+    for (int i = 0; i < w->n_envs; i++) free(w->env[i].man);
+    free(w->env); free(w);
+}
+int oracle_state_dim(const oracle_world *w) { return (w->m.fixed_base ? 0 : 13) + 2 * w->m.n_dof; }
+/* state layout: [pos3 quat4(xyzw) omega3 vel3] (floating base only) q[ndof] qd[ndof] */
+void oracle_set_state(oracle_world *w, int env, const double *s, int clear_contacts) {
+    oenv *e = &w->env[env]; const rs_model_desc *m = &w->m;
+    if (!m->fixed_base) { v3cpy(e->base_pos, s); memcpy(e->base_quat, s + 3, 4 * sizeof(double)); v3cpy(e->base_w, s + 7); v3cpy(e->base_v, s + 10); s += 13; }
+    for (int d = 0; d < m->n_dof; d++) { e->q[d] = s[d]; e->qd[d] = s[m->n_dof + d]; }
+    if (clear_contacts) for (int k = 0; k < w->nman; k++) e->man[k].n = 0;
+    kinematics(m, e); velocities(m, e);
+}
+void oracle_get_state(const oracle_world *w, int env, double *s) {
+    const oenv *e = &w->env[env]; const rs_model_desc *m = &w->m;
+    if (!m->fixed_base) { v3cpy(s, e->base_pos); memcpy(s + 3, e->base_quat, 4 * sizeof(double)); v3cpy(s + 7, e->base_w); v3cpy(s + 10, e->base_v); s += 13; }
+    for (int d = 0; d < m->n_dof; d++) { s[d] = e->q[d]; s[m->n_dof + d] = e->qd[d]; }
+}
+void oracle_set_episode(oracle_world *w, int env, double potential, double initial_z, const double *feet_contact, int frame) {
+    oenv *e = &w->env[env];
+    e->potential = potential; e->initial_z = initial_z; e->frame = frame;
+    for (int k = 0; k < w->m.n_feet; k++) e->feet_contact[k] = feet_contact[k];
+}
+void oracle_get_episode(const oracle_world *w, int env, double *potential, double *initial_z, double *feet_contact, int *frame) {
+    const oenv *e = &w->env[env];
+    *potential = e->potential; *initial_z = e->initial_z; *frame = e->frame;
+    for (int k = 0; k < w->m.n_feet; k++) feet_contact[k] = e->feet_contact[k];
+}
+void oracle_reset(oracle_world *w, int env, uint32_t seed, uint32_t env_id) { env_reset(&w->m, &w->env[env], w->nman, seed, env_id); }
+void oracle_reset_all(oracle_world *w, uint32_t seed, uint32_t env_id0) {
+    for (int i = 0; i < w->n_envs; i++) env_reset(&w->m, &w->env[i], w->nman, seed, env_id0 + (uint32_t)i);
+}
+/* raw torques (physics-only tests): tau[ndof] */
+void oracle_set_tau(oracle_world *w, int env, const double *tau) { for (int d = 0; d < w->m.n_dof; d++) w->env[env].tau[d] = tau[d]; }
+void oracle_substeps(oracle_world *w, int env, int n) {
+    oenv *e = &w->env[env];
+    for (int s = 0; s < n; s++) substep(&w->m, e);
+    kinematics(&w->m, e); velocities(&w->m, e);
+}
+/* one full env step for all envs: apply_action -> frame_skip sub-steps -> calc_state/reward/done (-> auto reset) */
+static void step_one(oracle_world *w, int i, const double *actions, int auto_reset, uint32_t seed, uint32_t env_id0) {
+    const rs_model_desc *m = &w->m;
+    oenv *e = &w->env[i];
+    const double *a = actions + (size_t)i * m->n_act;
+    for (int d = 0; d < m->n_dof; d++) e->tau[d] = 0;
+    for (int k = 0; k < m->n_act; k++) {
+        double c = a[k] > 1 ? 1 : (a[k] < -1 ? -1 : a[k]);
+        e->tau[m->act_dof[k]] = (double)(float)(m->act_gain[k] * c);   /* set_motor_torque(float) */
+    }
+    /* applyJointDamping: once per stepSimulation, from the velocities at its start */
+    for (int l = 0; l < m->n_links; l++) if (m->dof_idx[l] >= 0 && m->jdamping[l] != 0) e->tau[m->dof_idx[l]] += -m->jdamping[l] * e->qd[m->dof_idx[l]];
+    for (int s = 0; s < m->frame_skip; s++) substep(m, e);
+    epilogue(m, e, a);
+    if (auto_reset && (e->done || e->frame >= m->max_episode_steps)) {
+        /* obs returned for a finished env is the first obs of the next episode (vector-env convention) */
+        double rew = e->reward;
+        env_reset(m, e, w->nman, seed, env_id0 + (uint32_t)i);
+        e->done = 1; e->reward = rew;
+    }
+}
+typedef struct { oracle_world *w; const double *actions; int auto_reset; uint32_t seed, env_id0; int lo, hi; } step_job;
+static void *step_worker(void *arg) {
+    step_job *j = (step_job *)arg;
+    for (int i = j->lo; i < j->hi; i++) step_one(j->w, i, j->actions, j->auto_reset, j->seed, j->env_id0);
+    return NULL;
+}
+void oracle_step(oracle_world *w, const double *actions, int auto_reset, uint32_t seed, uint32_t env_id0, int n_threads) {
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > w->n_envs) n_threads = w->n_envs;
+    if (n_threads > 256) n_threads = 256;
+    if (n_threads == 1) { for (int i = 0; i < w->n_envs; i++) step_one(w, i, actions, auto_reset, seed, env_id0); return; }
+    pthread_t th[256]; step_job jobs[256];
+    for (int t = 0; t < n_threads; t++) {
+        jobs[t] = (step_job){w, actions, auto_reset, seed, env_id0, (int)((long)w->n_envs * t / n_threads), (int)((long)w->n_envs * (t + 1) / n_threads)};
+        pthread_create(&th[t], NULL, step_worker, &jobs[t]);
+    }
+    for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+}
+void oracle_get_obs(const oracle_world *w, double *obs, double *rew, int *done) {
+    for (int i = 0; i < w->n_envs; i++) {
+        for (int k = 0; k < w->m.obs_dim; k++) obs[(size_t)i * w->m.obs_dim + k] = w->env[i].obs[k];
+        rew[i] = w->env[i].reward; done[i] = w->env[i].done;
+    }
+}
+void oracle_get_rewards5(const oracle_world *w, int env, double *r5) { memcpy(r5, w->env[env].rewards5, 5 * sizeof(double)); }
+/* (1+L) x {pos3, quat4, linvel3}: what query_body_position caches into Thingy */
+void oracle_link_poses(oracle_world *w, int env, double *out) {
+    oenv *e = &w->env[env];
+    kinematics(&w->m, e); velocities(&w->m, e);
+    for (int b = 0; b <= w->m.n_links; b++) body_pose(e, b, out + b * 10, out + b * 10 + 3, out + b * 10 + 7);
+}
+/* contact rows: per live manifold point {manifold_id, slot, dist, nx,ny,nz, posA xyz, imp_n, lifetime}; returns count */
+int oracle_get_contacts(const oracle_world *w, int env, double *out, int max_pts) {
+    const oenv *e = &w->env[env]; int c = 0;
+    for (int k = 0; k < w->nman; k++)
+        for (int p = 0; p < e->man[k].n && c < max_pts; p++) {
+            const cpoint *cp = &e->man[k].p[p]; double *o = out + c * 12;
+            o[0] = k; o[1] = p; o[2] = cp->dist; v3cpy(o + 3, cp->normal); v3cpy(o + 6, cp->posA); o[9] = cp->imp_n; o[10] = cp->lifetime; o[11] = cp->friction;
+            c++;
+        }
+    return c;
+}
+void oracle_counts(const oracle_world *w, int env, int *n_rows, int *n_contacts) { *n_rows = w->env[env].n_rows_last; *n_contacts = w->env[env].n_contacts_last; }
+/* mechanical energy (kinetic + potential), for conservation tests */
+double oracle_energy(oracle_world *w, int env) {
+    const rs_model_desc *m = &w->m; oenv *e = &w->env[env];
+    kinematics(m, e); velocities(m, e);
+    double E = 0;
+    for (int b = 0; b <= m->n_links; b++) {
+        double mass = b == 0 ? m->base_mass : m->mass[b - 1];
+        const double *I3 = b == 0 ? m->base_inertia : m->inertia[b - 1];
+        if (b == 0 && m->fixed_base) continue;
+        const sv6 *v = &e->vel[b];
+        E += 0.5 * mass * v3dot(v->v, v->v) + 0.5 * (I3[0] * v->w[0] * v->w[0] + I3[1] * v->w[1] * v->w[1] + I3[2] * v->w[2] * v->w[2]);
+        E += mass * m->gravity * e->pos[b][2];
+    }
+    return E;
+}
+uint32_t oracle_hash(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return rs_hash(a, b, c, d); }

@@ -1,0 +1,132 @@
+"""Per-environment task constants layered on a compiled model.
+
+Restates the class attributes / constructor arguments of
+roboschool/gym_mujoco_walkers.py:14-136, gym_forward_walker.py:11-22,83-87,
+gym_pendulums.py:70-127 and the gym registration in roboschool/__init__.py:11-110.
+"""
+import math
+import os
+
+import numpy as np
+
+from .model import (ModelDesc, RS_MAX_ACT, RS_MAX_FEET, RS_MAX_PARTS)
+from . import mjcf
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+MODEL_DIR = os.path.join(_HERE, "models")
+
+RS_ALIVE_Z_AND_PITCH, RS_ALIVE_Z, RS_ALIVE_ALWAYS = 0, 1, 2
+
+ENV_SPECS = {
+    # id: xml, robot_name, A, O, power, foot_list, alive rule/params, per-joint coef overrides
+    "RoboschoolHopper-v1": dict(
+        xml="hopper.xml", robot="torso", A=3, O=15, power=0.75, feet=["foot"],
+        alive_rule=RS_ALIVE_Z_AND_PITCH, alive_z=0.8, alive_bonus=1.0, cost_scale=1.0,
+        initial_z=None, coef={}, reward_threshold=2500.0),
+    "RoboschoolWalker2d-v1": dict(
+        xml="walker2d.xml", robot="torso", A=6, O=22, power=0.40, feet=["foot", "foot_left"],
+        alive_rule=RS_ALIVE_Z_AND_PITCH, alive_z=0.8, alive_bonus=1.0, cost_scale=1.0,
+        initial_z=None, coef={"foot_joint": 30.0, "foot_left_joint": 30.0}, reward_threshold=2500.0),
+    "RoboschoolAnt-v1": dict(
+        xml="ant.xml", robot="torso", A=8, O=28, power=2.5,
+        feet=["front_left_foot", "front_right_foot", "left_back_foot", "right_back_foot"],
+        alive_rule=RS_ALIVE_Z, alive_z=0.26, alive_bonus=1.0, cost_scale=1.0,
+        initial_z=None, coef={}, reward_threshold=2500.0),
+    "RoboschoolHumanoid-v1": dict(
+        xml="humanoid_symmetric.xml", robot="torso", A=17, O=44, power=0.41,
+        feet=["right_foot", "left_foot"],
+        alive_rule=RS_ALIVE_Z, alive_z=0.78, alive_bonus=2.0, cost_scale=4.25,
+        initial_z=0.8,
+        coef={"abdomen_z": 100, "abdomen_y": 100, "abdomen_x": 100,
+              "right_hip_x": 100, "right_hip_z": 100, "right_hip_y": 300, "right_knee": 200,
+              "left_hip_x": 100, "left_hip_z": 100, "left_hip_y": 300, "left_knee": 200,
+              "right_shoulder1": 75, "right_shoulder2": 75, "right_elbow": 75,
+              "left_shoulder1": 75, "left_shoulder2": 75, "left_elbow": 75},
+        reset_base=dict(z=1.4, yaw_spread=math.pi / 16), reward_threshold=3500.0),
+    # plumbing config (BASELINE.json configs[0]); obs/reward computed by the Python facade
+    "RoboschoolInvertedPendulum-v1": dict(
+        xml="inverted_pendulum.xml", robot="cart", A=1, O=5, power=1.0, feet=[],
+        alive_rule=RS_ALIVE_ALWAYS, alive_z=0.0, alive_bonus=0.0, cost_scale=1.0,
+        initial_z=None, coef={"slider": 100.0}, no_floor=True, timestep=0.0165, frame_skip=1,
+        act_joints=["slider"], reward_threshold=950.0),
+}
+
+
+def apply_task(m: ModelDesc, spec: dict) -> ModelDesc:
+    """Fill the task section of the descriptor from an ENV_SPECS entry."""
+    jn = m.meta["joint_names"]
+    ln = m.meta["link_names"]
+    # ordered_joints: non-"ignore" joints in link order (gym_mujoco_xml_env.py:63-70)
+    if "act_joints" in spec:
+        ordered = [jn.index(n) for n in spec["act_joints"]]
+    else:
+        ordered = [i for i, n in enumerate(jn) if n is not None and not n.startswith("ignore")]
+    assert len(ordered) == spec["A"], (len(ordered), spec["A"])
+    m.n_act = spec["A"]
+    for k, li in enumerate(ordered):
+        m.act_dof[k] = m.dof_idx[li]
+        m.act_gain[k] = spec["power"] * float(spec["coef"].get(jn[li], 100.0))
+    m.meta["ordered_joints"] = [jn[li] for li in ordered]
+    m.meta["ordered_joint_links"] = ordered
+    # feet
+    m.n_feet = len(spec["feet"])
+    for k, f in enumerate(spec["feet"]):
+        m.foot_link[k] = ln.index(f)
+    # parts dict de-duplicates by name (gym_mujoco_xml_env.py:57-62); root_part is NOT in parts
+    seen, parts = set(), []
+    for i, n in enumerate(ln):
+        if n in seen:
+            parts = [p for p in parts if ln[p] != n]
+        seen.add(n)
+        parts.append(i)
+    m.n_parts = len(parts)
+    for k, p in enumerate(parts):
+        m.part_link[k] = p
+    # robot body
+    if m.meta["base_name"] == spec["robot"] and spec["robot"] not in ln:
+        m.body_link = -1
+    else:
+        m.body_link = ln.index(spec["robot"])
+    m.obs_dim = spec["O"]
+    m.alive_rule = spec["alive_rule"]
+    m.alive_z = spec["alive_z"]
+    m.alive_bonus = spec["alive_bonus"]
+    m.electricity_cost = -2.0 * spec["cost_scale"]       # gym_forward_walker.py:83, gym_mujoco_walkers.py:86
+    m.stall_torque_cost = -0.1 * spec["cost_scale"]      # :84 / :87
+    m.foot_collision_cost = -1.0                         # :85
+    m.joints_at_limit_cost = -0.2                        # :87
+    m.initial_z = -1.0 if spec["initial_z"] is None else spec["initial_z"]
+    m.walk_target_x, m.walk_target_y = 1e3, 0.0          # gym_forward_walker.py:13-14
+    m.reset_joint_spread = 0.1                           # gym_forward_walker.py:26
+    rb = spec.get("reset_base")
+    if rb:
+        m.reset_set_base = 1
+        m.arr("reset_base_pos")[:] = [0.0, 0.0, rb["z"]]
+        m.arr("reset_base_quat")[:] = [0, 0, 0, 1]
+        m.reset_yaw_spread = rb["yaw_spread"]
+    m.max_episode_steps = 1000
+    m.meta["env_id"] = spec.get("env_id", "")
+    m.meta["reward_threshold"] = spec.get("reward_threshold")
+    return m
+
+
+def compile_env(env_id, assets_dir, **kw):
+    """MJCF (from a roboschool ``mujoco_assets`` dir) -> full descriptor for ``env_id``."""
+    spec = dict(ENV_SPECS[env_id], env_id=env_id)
+    m = mjcf.compile_mjcf(os.path.join(assets_dir, spec["xml"]),
+                          has_floor=not spec.get("no_floor", False),
+                          timestep=spec.get("timestep", 0.0165 / 4),
+                          frame_skip=spec.get("frame_skip", 4), **kw)
+    return apply_task(m, spec)
+
+
+def load_env_model(env_id):
+    """Load the pre-compiled descriptor shipped in ``roboschool_b200/models``.
+
+    Generated by ``tools/compile_models.py`` from the reference's MJCF files; the
+    GPU box has no /root/reference, so the compiled descriptors travel instead.
+    """
+    path = os.path.join(MODEL_DIR, env_id + ".json")
+    if not os.path.exists(path):
+        raise FileNotFoundError("no compiled model for %s (run tools/compile_models.py)" % env_id)
+    return ModelDesc.load(path)
