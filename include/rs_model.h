@@ -59,7 +59,7 @@ typedef struct rs_model_desc {
     int alive_rule;
     int body_link;    /* link whose pose/speed is robot_body (-1 = base)                 */
     int max_episode_steps;
-    int pad0;
+    int max_contacts; /* capacity of the per-env live contact-point pool (points beyond it are dropped, in manifold order) */
 
     /* ---- base ---- */
     double base_mass;

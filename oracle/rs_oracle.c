@@ -625,6 +625,13 @@ static void collide(const rs_model_desc *m, oenv *e) {
         }
         if (mf->n) manifold_refresh(mf, e, bA, bB, thr);
     }
+    /* bounded live-point pool shared with the CUDA path: points beyond max_contacts are dropped in manifold order */
+    int total = 0;
+    for (int k = 0; k < m->n_geoms + m->n_pairs; k++) {
+        manifold *mf = &e->man[k];
+        if (total + mf->n > m->max_contacts) mf->n = m->max_contacts - total;
+        total += mf->n;
+    }
 }
 
 /* ---------------- constraint rows: btMultiBodyConstraintSolver ---------------- */

@@ -1,0 +1,1067 @@
+// rs_core.cuh -- per-env articulated-rigid-body step, fp32, one env per thread (lane = env).
+//
+// This is the device-side replacement for what the reference does inside
+//   World::bullet_step -> b3InitStepSimulationCommand        (physics-bullet.cpp:358-412)
+//   World::query_body_position                                (physics-bullet.cpp:440-495)
+//   RoboschoolForwardWalker.calc_state / step                 (gym_forward_walker.py:45-133)
+// for ONE env.  The kernels in rs_step.cu map 32 consecutive envs onto the 32 lanes of a warp;
+// every per-env quantity is either a register, a thread-private scratch array or a
+// [field][env] SoA slot, so all lanes execute the same instruction stream on coalesced data.
+//
+// The functions are __host__ __device__ so that tests/ can run the SAME fp32 code on the CPU
+// (tests/host_emul) when no GPU is present; the product path only ever launches them on the GPU.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include "../../include/rs_model.h"
+
+#ifdef __CUDACC__
+#define RS_HD __host__ __device__ __forceinline__
+#define RS_HDN __host__ __device__ __noinline__
+#else
+#define RS_HD inline
+#define RS_HDN
+#endif
+
+namespace rs {
+
+constexpr int ML = RS_MAX_LINKS;
+constexpr int MG = RS_MAX_GEOMS;
+constexpr int MP = RS_MAX_PAIRS;
+constexpr int MA = RS_MAX_ACT;
+constexpr int MF = RS_MAX_FEET;
+constexpr int MPT = RS_MAX_PARTS;
+constexpr float RS_FLT_EPS = 1.1920929e-07f;
+constexpr int CDAT = 10;  // floats per cached contact point: localA3 localB3 normal3 dist
+
+// ---------------------------------------------------------------------------------------------
+// float, GPU-ready image of rs_model_desc (+ derived tables). Lives in __constant__ memory.
+// ---------------------------------------------------------------------------------------------
+struct DevModel {
+    int n_links, n_dof, fixed_base, n_geoms, n_pairs, n_act, n_feet, n_parts;
+    int obs_dim, has_floor, n_iter, frame_skip, alive_rule, body_link, max_episode_steps, max_contacts;
+    float base_mass, base_inertia[3];
+    int parent[ML], jtype[ML], dof_idx[ML], has_limit[ML], dof_link[ML];
+    float Sw[ML][3], Sv[ML][3];       // joint motion subspace in link coords (axis ; axis x d)
+    float R0[ML][9];                  // parent coords -> link coords at q=0
+    float axis[ML][3], e_vec[ML][3], d_vec[ML][3];
+    float mass[ML], inertia[ML][3];
+    float lim_lo[ML], lim_hi[ML], jdamping[ML], max_vel[ML];
+    float break_thresh[ML + 1];
+    int g_link[MG], g_type[MG], g_floor[MG];
+    float g_p0[MG][3], g_p1[MG][3], g_radius[MG], g_fric_floor[MG];
+    unsigned char pair_a[MP], pair_b[MP], pair_ss[MP];
+    float pair_thresh[MP], pair_friction[MP];
+    float gravity, timestep, lin_damping, ang_damping, max_coord_vel, erp, erp2, split_thresh, max_limit_impulse, use_gyro;
+    int act_dof[MA];
+    float act_gain[MA];
+    int foot_link[MF], part_link[MPT];
+    float alive_z, alive_bonus, electricity_cost, stall_torque_cost, joints_at_limit_cost, foot_collision_cost, initial_z;
+    double walk_target_x, walk_target_y, dt_env;
+    float reset_joint_spread, reset_yaw_spread, reset_base_pos[3], reset_base_quat[4];
+    int reset_set_base;
+};
+
+// ---------------------------------------------------------------------------------------------
+// small math
+// ---------------------------------------------------------------------------------------------
+RS_HD float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+RS_HD void cross3(float* o, const float* a, const float* b) {
+    float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+RS_HD void mulv(float* o, const float* M, const float* v) {  // o = M v
+    float x = M[0] * v[0] + M[1] * v[1] + M[2] * v[2];
+    float y = M[3] * v[0] + M[4] * v[1] + M[5] * v[2];
+    float z = M[6] * v[0] + M[7] * v[1] + M[8] * v[2];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+RS_HD void tmulv(float* o, const float* M, const float* v) {  // o = M^T v
+    float x = M[0] * v[0] + M[3] * v[1] + M[6] * v[2];
+    float y = M[1] * v[0] + M[4] * v[1] + M[7] * v[2];
+    float z = M[2] * v[0] + M[5] * v[1] + M[8] * v[2];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+RS_HD void mul33(float* o, const float* A, const float* B) {
+    float t[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) t[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+#pragma unroll
+    for (int i = 0; i < 9; i++) o[i] = t[i];
+}
+RS_HD void quat_to_mat(float* R, float x, float y, float z, float w) {
+    R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w);     R[2] = 2 * (x * z + y * w);
+    R[3] = 2 * (x * y + z * w);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+    R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
+}
+// btPlaneSpace1
+RS_HD void plane_space(const float* n, float* p, float* q) {
+    if (fabsf(n[2]) > 0.70710678f) {
+        float a = n[1] * n[1] + n[2] * n[2];
+        float k = 1.0f / sqrtf(a);
+        p[0] = 0; p[1] = -n[2] * k; p[2] = n[1] * k;
+        q[0] = a * k; q[1] = -n[0] * p[2]; q[2] = n[0] * p[1];
+    } else {
+        float a = n[0] * n[0] + n[1] * n[1];
+        float k = 1.0f / sqrtf(a);
+        p[0] = -n[1] * k; p[1] = n[0] * k; p[2] = 0;
+        q[0] = -n[2] * p[1]; q[1] = n[2] * p[0]; q[2] = a * k;
+    }
+}
+// spatial motion parent->child: w' = R w ; v' = R v - r x (R w)          (6-vectors: [w;v])
+RS_HD void xf_motion(float* o, const float* R, const float* r, const float* in) {
+    float w[3], v[3], c[3];
+    mulv(w, R, in); mulv(v, R, in + 3); cross3(c, r, w);
+    o[0] = w[0]; o[1] = w[1]; o[2] = w[2]; o[3] = v[0] - c[0]; o[4] = v[1] - c[1]; o[5] = v[2] - c[2];
+}
+// spatial force child->parent: f' = R^T f ; t' = R^T (t + r x f)             (6-vectors: [t;f])
+RS_HD void xf_force_inv_add(float* acc, const float* R, const float* r, const float* in) {
+    float c[3], t[3], o[3];
+    cross3(c, r, in + 3);
+    t[0] = in[0] + c[0]; t[1] = in[1] + c[1]; t[2] = in[2] + c[2];
+    tmulv(o, R, t); acc[0] += o[0]; acc[1] += o[1]; acc[2] += o[2];
+    tmulv(o, R, in + 3); acc[3] += o[0]; acc[4] += o[1]; acc[5] += o[2];
+}
+RS_HD float dot6(const float* a, const float* b) {
+    return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+}
+
+// articulated inertia as three 3x3 blocks: torque = A wd + B a ; force = B^T wd + Mm a
+// storage: A sym (6: xx xy xz yy yz zz), B full (9), Mm sym (6)  -> 21 floats
+RS_HD void sym_mulv(float* o, const float* S, const float* v) {
+    o[0] = S[0] * v[0] + S[1] * v[1] + S[2] * v[2];
+    o[1] = S[1] * v[0] + S[3] * v[1] + S[4] * v[2];
+    o[2] = S[2] * v[0] + S[4] * v[1] + S[5] * v[2];
+}
+RS_HD void inertia_mul(float* o, const float* I, const float* a) {  // o[6] = I * a[6]
+    float t[3], u[3];
+    sym_mulv(t, I, a); mulv(u, I + 6, a + 3);
+    o[0] = t[0] + u[0]; o[1] = t[1] + u[1]; o[2] = t[2] + u[2];
+    tmulv(t, I + 6, a); sym_mulv(u, I + 15, a + 3);
+    o[3] = t[0] + u[0]; o[4] = t[1] + u[1]; o[5] = t[2] + u[2];
+}
+RS_HD void sym_to_full(float* F, const float* S) {
+    F[0] = S[0]; F[1] = S[1]; F[2] = S[2]; F[3] = S[1]; F[4] = S[3]; F[5] = S[4]; F[6] = S[2]; F[7] = S[4]; F[8] = S[5];
+}
+// Ip += X^T Ic X  for X = motion transform parent->child (R, r)
+RS_HD void inertia_to_parent_add(float* Ip, const float* Ic, const float* R, const float* r) {
+    float A[9], B[9], M[9];
+    sym_to_full(A, Ic); sym_to_full(M, Ic + 15);
+#pragma unroll
+    for (int i = 0; i < 9; i++) B[i] = Ic[6 + i];
+    // shift to the parent origin (still child coords):  B' = B + r~ M ; A' = A - B r~ + r~ B'^T
+    float rx[9] = {0, -r[2], r[1], r[2], 0, -r[0], -r[1], r[0], 0};
+    float rM[9], Bp[9], Brx[9], BpT[9], rBpT[9];
+    mul33(rM, rx, M);
+#pragma unroll
+    for (int i = 0; i < 9; i++) Bp[i] = B[i] + rM[i];
+    mul33(Brx, B, rx);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) BpT[i * 3 + j] = Bp[j * 3 + i];
+    mul33(rBpT, rx, BpT);
+    float Ap[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) Ap[i] = A[i] - Brx[i] + rBpT[i];
+    // rotate into parent coords: X_p = R^T X R
+    float T[9], RT[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) RT[i * 3 + j] = R[j * 3 + i];
+    float Ar[9], Br[9], Mr[9];
+    mul33(T, Ap, R); mul33(Ar, RT, T);
+    mul33(T, Bp, R); mul33(Br, RT, T);
+    mul33(T, M, R);  mul33(Mr, RT, T);
+    Ip[0] += Ar[0]; Ip[1] += 0.5f * (Ar[1] + Ar[3]); Ip[2] += 0.5f * (Ar[2] + Ar[6]);
+    Ip[3] += Ar[4]; Ip[4] += 0.5f * (Ar[5] + Ar[7]); Ip[5] += Ar[8];
+#pragma unroll
+    for (int i = 0; i < 9; i++) Ip[6 + i] += Br[i];
+    Ip[15] += Mr[0]; Ip[16] += 0.5f * (Mr[1] + Mr[3]); Ip[17] += 0.5f * (Mr[2] + Mr[6]);
+    Ip[18] += Mr[4]; Ip[19] += 0.5f * (Mr[5] + Mr[7]); Ip[20] += Mr[8];
+}
+// Cholesky of the 6x6 SPD base articulated inertia; L packed lower-triangular row-major (21)
+RS_HD void chol6(float* L, const float* I) {
+    float a[6][6];
+    float A[9], M[9];
+    sym_to_full(A, I); sym_to_full(M, I + 15);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            a[i][j] = A[i * 3 + j]; a[i][j + 3] = I[6 + i * 3 + j]; a[i + 3][j] = I[6 + j * 3 + i]; a[i + 3][j + 3] = M[i * 3 + j];
+        }
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            float s = a[i][j];
+#pragma unroll
+            for (int p = 0; p < j; p++) s -= L[i * (i + 1) / 2 + p] * L[j * (j + 1) / 2 + p];
+            if (i == j) L[k] = sqrtf(s); else L[k] = s / L[j * (j + 1) / 2 + j];
+            k++;
+        }
+}
+RS_HD void chol6_solve(float* x, const float* L, const float* b) {  // x = (L L^T)^-1 b
+    float y[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        float s = b[i];
+#pragma unroll
+        for (int p = 0; p < i; p++) s -= L[i * (i + 1) / 2 + p] * y[p];
+        y[i] = s / L[i * (i + 1) / 2 + i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+        float s = y[i];
+#pragma unroll
+        for (int p = i + 1; p < 6; p++) s -= L[p * (p + 1) / 2 + i] * x[p];
+        x[i] = s / L[i * (i + 1) / 2 + i];
+    }
+}
+
+// counter-based RNG, bit-identical with oracle/rs_oracle.c rs_hash
+RS_HD uint32_t rs_hash(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    uint32_t h = 0x9E3779B9u ^ a;
+    h = (h ^ (h >> 16)) * 0x85EBCA6Bu; h ^= b + 0x9E3779B9u + (h << 6) + (h >> 2);
+    h = (h ^ (h >> 13)) * 0xC2B2AE35u; h ^= c + 0x9E3779B9u + (h << 6) + (h >> 2);
+    h = (h ^ (h >> 16)) * 0x85EBCA6Bu; h ^= d + 0x9E3779B9u + (h << 6) + (h >> 2);
+    h = (h ^ (h >> 13)) * 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+RS_HD float rs_uniform(uint32_t seed, uint32_t env, uint32_t episode, uint32_t k) {
+    return (float)(rs_hash(seed, env, episode, k) >> 8) * (1.0f / 16777216.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-thread working set.  NL/MC are capacities chosen per model family at launch.
+// ---------------------------------------------------------------------------------------------
+template <int NL, int MC>
+struct Work {
+    // generalized state
+    float bpos[3], bquat[4], bw[3], bv[3];
+    float q[NL], qd[NL], tau[NL];
+    // kinematics (valid after kinematics())
+    float Rpl[NL][9], rvec[NL][3];
+    float Rwl[NL + 1][9], pos[NL + 1][3];
+    // ABA cache for the unit-impulse response passes
+    float h[NL][6], invD[NL];
+    float Lb[21];
+    float vel[NL + 1][6];
+    // live contact points, double buffered (old list -> new list every sub-step)
+    int ckey[2][MC];             // manifold id (floor: geom index ; self pair: n_geoms + pair index)
+    float cdat[2][MC][CDAT];
+    int ccount[2];
+    int cur;
+    int n_rows, n_contacts;      // of the last solve (reported)
+};
+
+// row workspace: one record per constraint row, strided so that lane-adjacent envs are address-adjacent
+struct RowWS {
+    float* p;      // base pointer for this thread
+    int stride;    // distance (floats) between consecutive elements of one thread's record
+    RS_HD float& at(int row, int rec, int k) const { return p[(size_t)(row * rec + k) * stride]; }
+};
+// record layout: [0,nd) J ; [nd,2nd) unit response ; then the scalars below
+enum { R_RHS = 0, R_INVD, R_LO, R_HI, R_APPLIED, R_FRIC, R_FIDX, R_NSCALAR };
+
+// ---------------------------------------------------------------------------------------------
+// kinematics: rot_from_parent / cachedRVector / world transforms     (btMultiBody, forwardKinematics)
+// ---------------------------------------------------------------------------------------------
+template <int NL, int MC>
+RS_HD void kinematics(const DevModel& M, Work<NL, MC>& W) {
+    float Rbw[9];
+    quat_to_mat(Rbw, W.bquat[0], W.bquat[1], W.bquat[2], W.bquat[3]);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) W.Rwl[0][i * 3 + j] = Rbw[j * 3 + i];
+    W.pos[0][0] = W.bpos[0]; W.pos[0][1] = W.bpos[1]; W.pos[0][2] = W.bpos[2];
+    for (int i = 0; i < M.n_links; i++) {
+        int p = M.parent[i];
+        float R[9];
+        if (M.jtype[i] == RS_JOINT_REVOLUTE) {
+            // m_cachedRotParentToThis = btQuaternion(axis, -q) * m_zeroRotParentToThis
+            float half = -0.5f * W.q[M.dof_idx[i]];
+            float s = sinf(half), c = cosf(half), Ra[9];
+            quat_to_mat(Ra, M.axis[i][0] * s, M.axis[i][1] * s, M.axis[i][2] * s, c);
+            mul33(R, Ra, M.R0[i]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; k++) R[k] = M.R0[i][k];
+        }
+        float rv[3];
+        mulv(rv, R, M.e_vec[i]);
+        rv[0] += M.d_vec[i][0]; rv[1] += M.d_vec[i][1]; rv[2] += M.d_vec[i][2];
+        if (M.jtype[i] == RS_JOINT_PRISMATIC) {
+            float qq = W.q[M.dof_idx[i]];
+            rv[0] += qq * M.axis[i][0]; rv[1] += qq * M.axis[i][1]; rv[2] += qq * M.axis[i][2];
+        }
+#pragma unroll
+        for (int k = 0; k < 9; k++) W.Rpl[i][k] = R[k];
+        W.rvec[i][0] = rv[0]; W.rvec[i][1] = rv[1]; W.rvec[i][2] = rv[2];
+        mul33(W.Rwl[i + 1], R, W.Rwl[p + 1]);
+        float rw[3];
+        tmulv(rw, W.Rwl[i + 1], rv);
+        W.pos[i + 1][0] = W.pos[p + 1][0] + rw[0]; W.pos[i + 1][1] = W.pos[p + 1][1] + rw[1]; W.pos[i + 1][2] = W.pos[p + 1][2] + rw[2];
+    }
+}
+
+template <int NL, int MC>
+RS_HD void velocities(const DevModel& M, Work<NL, MC>& W) {
+    if (M.fixed_base) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) W.vel[0][k] = 0;
+    } else { mulv(W.vel[0], W.Rwl[0], W.bw); mulv(W.vel[0] + 3, W.Rwl[0], W.bv); }
+    for (int i = 0; i < M.n_links; i++) {
+        int p = M.parent[i];
+        xf_motion(W.vel[i + 1], W.Rpl[i], W.rvec[i], W.vel[p + 1]);
+        int d = M.dof_idx[i];
+        if (d >= 0) {
+            float qd = W.qd[d];
+#pragma unroll
+            for (int k = 0; k < 3; k++) { W.vel[i + 1][k] += qd * M.Sw[i][k]; W.vel[i + 1][3 + k] += qd * M.Sv[i][k]; }
+        }
+    }
+}
+
+template <int NL, int MC>
+RS_HD void clamp_vel(const DevModel& M, Work<NL, MC>& W) {
+    float c = M.max_coord_vel;
+    if (!M.fixed_base) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { W.bw[k] = fminf(fmaxf(W.bw[k], -c), c); W.bv[k] = fminf(fmaxf(W.bv[k], -c), c); }
+    }
+    for (int d = 0; d < M.n_dof; d++) W.qd[d] = fminf(fmaxf(W.qd[d], -c), c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// btMultiBody::computeAccelerationsArticulatedBodyAlgorithmMultiDof + applyDeltaVeeMultiDof(dt)
+// ---------------------------------------------------------------------------------------------
+template <int NL, int MC>
+RS_HD void aba(const DevModel& M, Work<NL, MC>& W, float dt) {
+    const int n = M.n_links;
+    float IA[NL + 1][21];
+    float Z[NL + 1][6], c[NL][6], Y[NL];
+    velocities(M, W);
+    for (int b = 0; b <= n; b++) {
+        float mass = b == 0 ? M.base_mass : M.mass[b - 1];
+        const float* I3 = b == 0 ? M.base_inertia : M.inertia[b - 1];
+        const float* v = W.vel[b];
+        float fw[3] = {0.f, 0.f, -M.gravity * mass}, fl[3];
+        mulv(fl, W.Rwl[b], fw);
+        float wn = sqrtf(dot3(v, v)), vn = sqrtf(dot3(v + 3, v + 3));
+        float Iw[3] = {I3[0] * v[0], I3[1] * v[1], I3[2] * v[2]};
+        float ka = M.ang_damping * (1.0f + wn), kl = M.lin_damping * (1.0f + vn);
+        float g1[3], g2[3];
+        cross3(g1, v, Iw); cross3(g2, v, v + 3);
+        float gy = M.use_gyro;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            Z[b][k] = Iw[k] * ka + gy * g1[k];
+            Z[b][3 + k] = -fl[k] + mass * v[3 + k] * kl + mass * g2[k];
+        }
+        if (b == 0 && M.fixed_base) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) Z[0][k] = 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 21; k++) IA[b][k] = 0;
+        IA[b][0] = I3[0]; IA[b][3] = I3[1]; IA[b][5] = I3[2];
+        IA[b][15] = mass; IA[b][18] = mass; IA[b][20] = mass;
+        if (b > 0) {
+            int i = b - 1, d = M.dof_idx[i];
+            if (d >= 0) {
+                float qd = W.qd[d], jw[3], jv[3], t1[3], t2[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) { jw[k] = qd * M.Sw[i][k]; jv[k] = qd * M.Sv[i][k]; }
+                cross3(c[i], v, jw);
+                cross3(t1, v, jv); cross3(t2, v + 3, jw);
+                c[i][3] = t1[0] + t2[0]; c[i][4] = t1[1] + t2[1]; c[i][5] = t1[2] + t2[2];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 6; k++) c[i][k] = 0;
+            }
+        }
+    }
+    for (int i = n - 1; i >= 0; i--) {
+        int p = M.parent[i], d = M.dof_idx[i];
+        float Zt[6];
+        if (d >= 0) {
+            float S[6] = {M.Sw[i][0], M.Sw[i][1], M.Sw[i][2], M.Sv[i][0], M.Sv[i][1], M.Sv[i][2]};
+            float h[6];
+            inertia_mul(h, IA[i + 1], S);
+            float D = dot6(S, h);
+            float y = W.tau[d] - dot6(S, Z[i + 1]) - dot6(c[i], h);
+            float invD = 1.0f / D;
+            Y[i] = y; W.invD[i] = invD;
+#pragma unroll
+            for (int k = 0; k < 6; k++) W.h[i][k] = h[k];
+            float Ic[6];
+            inertia_mul(Ic, IA[i + 1], c[i]);
+            float kk = invD * y;
+#pragma unroll
+            for (int k = 0; k < 6; k++) Zt[k] = Z[i + 1][k] + Ic[k] + h[k] * kk;
+            // Ia = IA - h h^T / D   (in place: IA[i+1] is not needed afterwards)
+            float* I = IA[i + 1];
+            I[0] -= h[0] * h[0] * invD; I[1] -= h[0] * h[1] * invD; I[2] -= h[0] * h[2] * invD;
+            I[3] -= h[1] * h[1] * invD; I[4] -= h[1] * h[2] * invD; I[5] -= h[2] * h[2] * invD;
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int b2 = 0; b2 < 3; b2++) I[6 + a * 3 + b2] -= h[a] * h[3 + b2] * invD;
+            I[15] -= h[3] * h[3] * invD; I[16] -= h[3] * h[4] * invD; I[17] -= h[3] * h[5] * invD;
+            I[18] -= h[4] * h[4] * invD; I[19] -= h[4] * h[5] * invD; I[20] -= h[5] * h[5] * invD;
+        } else {
+            Y[i] = 0; W.invD[i] = 0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) { W.h[i][k] = 0; Zt[k] = Z[i + 1][k]; }
+        }
+        inertia_to_parent_add(IA[p + 1], IA[i + 1], W.Rpl[i], W.rvec[i]);
+        xf_force_inv_add(Z[p + 1], W.Rpl[i], W.rvec[i], Zt);
+    }
+    float acc[NL + 1][6];
+    if (M.fixed_base) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) acc[0][k] = 0;
+    } else {
+        chol6(W.Lb, IA[0]);
+        float r[6];
+        chol6_solve(r, W.Lb, Z[0]);
+#pragma unroll
+        for (int k = 0; k < 6; k++) acc[0][k] = -r[k];
+    }
+    for (int i = 0; i < n; i++) {
+        int p = M.parent[i], d = M.dof_idx[i];
+        xf_motion(acc[i + 1], W.Rpl[i], W.rvec[i], acc[p + 1]);
+        if (d >= 0) {
+            float a = W.invD[i] * (Y[i] - dot6(acc[i + 1], W.h[i]));
+#pragma unroll
+            for (int k = 0; k < 3; k++) { acc[i + 1][k] += c[i][k] + a * M.Sw[i][k]; acc[i + 1][3 + k] += c[i][3 + k] + a * M.Sv[i][k]; }
+            W.qd[d] += dt * a;
+        }
+    }
+    if (!M.fixed_base) {
+        float wd[3], vd[3], t[3], wxv[3];
+        tmulv(wd, W.Rwl[0], acc[0]);
+        cross3(wxv, W.vel[0], W.vel[0] + 3);
+        t[0] = acc[0][3] + wxv[0]; t[1] = acc[0][4] + wxv[1]; t[2] = acc[0][5] + wxv[2];
+        tmulv(vd, W.Rwl[0], t);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { W.bw[k] += dt * wd[k]; W.bv[k] += dt * vd[k]; }
+    }
+    clamp_vel(M, W);
+}
+
+// ---------------------------------------------------------------------------------------------
+// unit-impulse response of a contact/limit direction, fused with the Jacobian fill:
+//   btMultiBody::fillContactJacobianMultiDof + calcAccelerationDeltasMultiDof.
+// A wrench (t,f) given in the coordinates of body b (about its COM) is walked to the root twice in
+// one sweep: `f` unchanged (its projections S.f are the Jacobian entries) and `Z` with the
+// articulated-body corrections; the second sweep distributes accelerations.  jtau: optional
+// generalized joint force (limit rows).  J and u are ACCUMULATED into the row record.
+// ---------------------------------------------------------------------------------------------
+template <int NL, int MC>
+RS_HD float row_response(const DevModel& M, const Work<NL, MC>& W, int body, const float* wrench, int jdof, float jdir,
+                         const RowWS& ws, int row, int rec, bool first) {
+    const int n = M.n_links, nd = 6 + M.n_dof;
+    float F[NL + 1][6], Z[NL + 1][6], Y[NL];
+    for (int b = 0; b <= n; b++) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) { F[b][k] = 0; Z[b][k] = 0; }
+    }
+    if (body >= 0) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) { F[body][k] = wrench[k]; Z[body][k] = -wrench[k]; }
+    }
+    float denom = 0.f;
+    for (int i = n - 1; i >= 0; i--) {
+        int p = M.parent[i], d = M.dof_idx[i];
+        float Zt[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) Zt[k] = Z[i + 1][k];
+        if (d >= 0) {
+            float S[6] = {M.Sw[i][0], M.Sw[i][1], M.Sw[i][2], M.Sv[i][0], M.Sv[i][1], M.Sv[i][2]};
+            float j = dot6(S, F[i + 1]) + (d == jdof ? jdir : 0.f);
+            float y = (d == jdof ? jdir : 0.f) - dot6(S, Z[i + 1]);
+            Y[i] = y;
+            float kk = W.invD[i] * y;
+#pragma unroll
+            for (int k = 0; k < 6; k++) Zt[k] += W.h[i][k] * kk;
+            float& J = ws.at(row, rec, 6 + d);
+            J = first ? j : J + j;
+        } else Y[i] = 0;
+        xf_force_inv_add(Z[p + 1], W.Rpl[i], W.rvec[i], Zt);
+        xf_force_inv_add(F[p + 1], W.Rpl[i], W.rvec[i], F[i + 1]);
+    }
+    float acc[NL + 1][6];
+    if (M.fixed_base) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) { acc[0][k] = 0; float& J = ws.at(row, rec, k); float& U = ws.at(row, rec, nd + k); if (first) { J = 0; U = 0; } }
+    } else {
+        // base Jacobian / response live in WORLD coordinates (Bullet's velocity vector convention)
+        float jw[3], jv[3], r[6], uw[3], uv[3];
+        tmulv(jw, W.Rwl[0], F[0]); tmulv(jv, W.Rwl[0], F[0] + 3);
+        chol6_solve(r, W.Lb, Z[0]);
+#pragma unroll
+        for (int k = 0; k < 6; k++) acc[0][k] = -r[k];
+        tmulv(uw, W.Rwl[0], acc[0]); tmulv(uv, W.Rwl[0], acc[0] + 3);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            float& J0 = ws.at(row, rec, k); float& J1 = ws.at(row, rec, 3 + k);
+            float& U0 = ws.at(row, rec, nd + k); float& U1 = ws.at(row, rec, nd + 3 + k);
+            if (first) { J0 = jw[k]; J1 = jv[k]; U0 = uw[k]; U1 = uv[k]; }
+            else { J0 += jw[k]; J1 += jv[k]; U0 += uw[k]; U1 += uv[k]; }
+            denom += jw[k] * uw[k] + jv[k] * uv[k];
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        int p = M.parent[i], d = M.dof_idx[i];
+        xf_motion(acc[i + 1], W.Rpl[i], W.rvec[i], acc[p + 1]);
+        if (d >= 0) {
+            float a = W.invD[i] * (Y[i] - dot6(acc[i + 1], W.h[i]));
+#pragma unroll
+            for (int k = 0; k < 3; k++) { acc[i + 1][k] += a * M.Sw[i][k]; acc[i + 1][3 + k] += a * M.Sv[i][k]; }
+            float& U = ws.at(row, rec, nd + 6 + d);
+            float S[6] = {M.Sw[i][0], M.Sw[i][1], M.Sw[i][2], M.Sv[i][0], M.Sv[i][1], M.Sv[i][2]};
+            float j = dot6(S, F[i + 1]) + (d == jdof ? jdir : 0.f);
+            U = first ? a : U + a;
+            denom += j * a;
+        }
+    }
+    return denom;   // j . u of THIS side (Bullet sums the two sides' denominators separately)
+}
+
+// wrench of a unit force along `dir` applied at world point `p`, in body b's coordinates about its COM
+template <int NL, int MC>
+RS_HD void unit_wrench(const Work<NL, MC>& W, int b, const float* p, const float* dir, float* out) {
+    float rw[3] = {p[0] - W.pos[b][0], p[1] - W.pos[b][1], p[2] - W.pos[b][2]}, rl[3], nl[3];
+    mulv(rl, W.Rwl[b], rw); mulv(nl, W.Rwl[b], dir);
+    cross3(out, rl, nl);
+    out[3] = nl[0]; out[4] = nl[1]; out[5] = nl[2];
+}
+
+// ---------------------------------------------------------------------------------------------
+// narrowphase + persistent manifolds (btConvexPlaneCollisionAlgorithm, GJK-equivalent closest
+// points for sphere/capsule pairs, btPersistentManifold add/replace/refresh)
+// ---------------------------------------------------------------------------------------------
+template <int NL, int MC>
+RS_HD void to_world(const Work<NL, MC>& W, int b, const float* l, float* w) {
+    float t[3]; tmulv(t, W.Rwl[b], l);
+    w[0] = W.pos[b][0] + t[0]; w[1] = W.pos[b][1] + t[1]; w[2] = W.pos[b][2] + t[2];
+}
+template <int NL, int MC>
+RS_HD void to_local(const Work<NL, MC>& W, int b, const float* w, float* l) {
+    float t[3] = {w[0] - W.pos[b][0], w[1] - W.pos[b][1], w[2] - W.pos[b][2]};
+    mulv(l, W.Rwl[b], t);
+}
+
+RS_HD void seg_seg_closest(const float* p1, const float* q1, const float* p2, const float* q2, float* c1, float* c2) {
+    float d1[3] = {q1[0] - p1[0], q1[1] - p1[1], q1[2] - p1[2]};
+    float d2[3] = {q2[0] - p2[0], q2[1] - p2[1], q2[2] - p2[2]};
+    float r[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+    float a = dot3(d1, d1), e = dot3(d2, d2), f = dot3(d2, r), s, t;
+    const float EPS = 1e-12f;
+    if (a <= EPS && e <= EPS) { s = t = 0; }
+    else if (a <= EPS) { s = 0; t = fminf(fmaxf(f / e, 0.f), 1.f); }
+    else {
+        float c = dot3(d1, r);
+        if (e <= EPS) { t = 0; s = fminf(fmaxf(-c / a, 0.f), 1.f); }
+        else {
+            float b = dot3(d1, d2), denom = a * e - b * b;
+            if (denom > EPS * a * e) s = fminf(fmaxf((b * f - c * e) / denom, 0.f), 1.f); else s = 0;
+            t = (b * s + f) / e;
+            if (t < 0) { t = 0; s = fminf(fmaxf(-c / a, 0.f), 1.f); }
+            else if (t > 1) { t = 1; s = fminf(fmaxf((b - c) / a, 0.f), 1.f); }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) { c1[k] = p1[k] + d1[k] * s; c2[k] = p2[k] + d2[k] * t; }
+}
+
+// one manifold (<=4 points) worth of cached points, processed in registers/scratch
+struct Manifold4 {
+    int n;
+    float d[4][CDAT];
+};
+
+RS_HD int sort_cached_points(const Manifold4& mf, const float* np) {
+    int maxi = -1; float maxp = np[9];
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (mf.d[i][9] < maxp) { maxi = i; maxp = mf.d[i][9]; }
+    float res[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        if (maxi == w) continue;
+        const int i0 = (w == 0) ? 1 : 0;
+        const int i1 = (w == 3) ? 2 : 3;
+        const int i2 = (w <= 1) ? 2 : 1;
+        float a[3] = {np[0] - mf.d[i0][0], np[1] - mf.d[i0][1], np[2] - mf.d[i0][2]};
+        float b[3] = {mf.d[i1][0] - mf.d[i2][0], mf.d[i1][1] - mf.d[i2][1], mf.d[i1][2] - mf.d[i2][2]};
+        float c[3]; cross3(c, a, b);
+        res[w] = dot3(c, c);
+    }
+    int best = -1; float mv = -1e30f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (fabsf(res[i]) > mv) { mv = fabsf(res[i]); best = i; }
+    return best;
+}
+
+template <int NL, int MC>
+RS_HD void manifold_add(Manifold4& mf, const Work<NL, MC>& W, int bA, int bB, const float* n, const float* pOnB, float depth, float thresh) {
+    if (depth > thresh) return;
+    float np[CDAT];
+    float pA[3] = {pOnB[0] + n[0] * depth, pOnB[1] + n[1] * depth, pOnB[2] + n[2] * depth};
+    to_local(W, bA, pA, np);
+    if (bB >= 0) to_local(W, bB, pOnB, np + 3); else { np[3] = pOnB[0]; np[4] = pOnB[1]; np[5] = pOnB[2]; }
+    np[6] = n[0]; np[7] = n[1]; np[8] = n[2]; np[9] = depth;
+    float shortest = thresh * thresh; int nearest = -1;
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (i < mf.n) {
+        float d[3] = {mf.d[i][0] - np[0], mf.d[i][1] - np[1], mf.d[i][2] - np[2]};
+        float dd = dot3(d, d);
+        if (dd < shortest) { shortest = dd; nearest = i; }
+    }
+    int idx = nearest;
+    if (idx < 0) { idx = mf.n; if (idx == 4) idx = sort_cached_points(mf, np); else mf.n++; }
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (i == idx) {
+#pragma unroll
+        for (int k = 0; k < CDAT; k++) mf.d[i][k] = np[k];
+    }
+}
+
+template <int NL, int MC>
+RS_HD void manifold_refresh(Manifold4& mf, const Work<NL, MC>& W, int bA, int bB, float thresh) {
+    bool rem[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        rem[i] = false;
+        if (i < mf.n) {
+            float pA[3], pB[3];
+            to_world(W, bA, mf.d[i], pA);
+            if (bB >= 0) to_world(W, bB, mf.d[i] + 3, pB); else { pB[0] = mf.d[i][3]; pB[1] = mf.d[i][4]; pB[2] = mf.d[i][5]; }
+            float df[3] = {pA[0] - pB[0], pA[1] - pB[1], pA[2] - pB[2]};
+            float dist = dot3(df, mf.d[i] + 6);
+            mf.d[i][9] = dist;
+            if (!(dist <= thresh)) rem[i] = true;
+            else {
+                float pd[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) pd[k] = pB[k] - (pA[k] - mf.d[i][6 + k] * dist);
+                if (dot3(pd, pd) > thresh * thresh) rem[i] = true;
+            }
+        }
+    }
+    // removeContactPoint(i) for i = n-1 .. 0 : swap with the last live point
+#pragma unroll
+    for (int i = 3; i >= 0; i--) if (i < mf.n && rem[i]) {
+        int last = mf.n - 1;
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (j == last && j != i) {
+#pragma unroll
+            for (int k = 0; k < CDAT; k++) mf.d[i][k] = mf.d[j][k];
+            rem[i] = rem[j];   // (already-visited higher slot: its flag is false by construction)
+        }
+        mf.n--;
+    }
+}
+
+template <int NL, int MC>
+RS_HD void collide(const DevModel& M, Work<NL, MC>& W) {
+    const int old = W.cur, nw = 1 - W.cur;
+    int oi = 0, no = 0;
+    const int nold = W.ccount[old];
+    const int nman = M.n_geoms + M.n_pairs;
+    for (int k = 0; k < nman; k++) {
+        Manifold4 mf; mf.n = 0;
+        while (oi < nold && W.ckey[old][oi] == k) {
+#pragma unroll
+            for (int s = 0; s < 4; s++) if (s == mf.n) {
+#pragma unroll
+                for (int j = 0; j < CDAT; j++) mf.d[s][j] = W.cdat[old][oi][j];
+            }
+            mf.n++; oi++;
+        }
+        if (k < M.n_geoms) {
+            if (!M.g_floor[k]) continue;
+            int b = M.g_link[k] + 1;
+            float thr = M.break_thresh[b];
+            float c0[3], c1[3];
+            to_world(W, b, M.g_p0[k], c0);
+            if (M.g_type[k] == RS_GEOM_CAPSULE) {
+                to_world(W, b, M.g_p1[k], c1);
+                if (c1[2] < c0[2]) { c0[0] = c1[0]; c0[1] = c1[1]; c0[2] = c1[2]; }
+            }
+            float dist = c0[2] - M.g_radius[k];
+            if (dist < thr) {
+                const float nz[3] = {0.f, 0.f, 1.f};
+                float pOnB[3] = {c0[0], c0[1], 0.f};
+                manifold_add(mf, W, b, -1, nz, pOnB, dist, thr);
+            }
+            if (mf.n) manifold_refresh(mf, W, b, -1, thr);
+        } else {
+            int pk = k - M.n_geoms;
+            int ga = M.pair_a[pk], gb = M.pair_b[pk];
+            int bA = M.g_link[ga] + 1, bB = M.g_link[gb] + 1;
+            float thr = M.pair_thresh[pk];
+            float a0[3], a1[3], b0[3], b1[3], cA[3], cB[3];
+            to_world(W, bA, M.g_p0[ga], a0); to_world(W, bA, M.g_p1[ga], a1);
+            to_world(W, bB, M.g_p0[gb], b0); to_world(W, bB, M.g_p1[gb], b1);
+            seg_seg_closest(a0, a1, b0, b1, cA, cB);
+            float d[3] = {cA[0] - cB[0], cA[1] - cB[1], cA[2] - cB[2]};
+            float len = sqrtf(dot3(d, d)), rB = M.g_radius[gb];
+            float dist = len - M.g_radius[ga] - rB;
+            bool hit = M.pair_ss[pk] ? (dist <= 0.f) : (dist < thr);
+            if (hit) {
+                float nn[3] = {1.f, 0.f, 0.f};
+                if (len > 1e-12f) { float il = 1.0f / len; nn[0] = d[0] * il; nn[1] = d[1] * il; nn[2] = d[2] * il; }
+                float pOnB[3] = {cB[0] + nn[0] * rB, cB[1] + nn[1] * rB, cB[2] + nn[2] * rB};
+                manifold_add(mf, W, bA, bB, nn, pOnB, dist, thr);
+            }
+            if (mf.n) manifold_refresh(mf, W, bA, bB, thr);
+        }
+#pragma unroll
+        for (int s = 0; s < 4; s++) if (s < mf.n && no < MC && no < M.max_contacts) {
+            W.ckey[nw][no] = k;
+#pragma unroll
+            for (int j = 0; j < CDAT; j++) W.cdat[nw][no][j] = mf.d[s][j];
+            no++;
+        }
+    }
+    W.ccount[nw] = no;
+    W.cur = nw;
+}
+
+// ---------------------------------------------------------------------------------------------
+// constraint rows + projected Gauss-Seidel (btMultiBodyConstraintSolver), Bullet's row order:
+// per iteration: non-contact rows (alternating direction), normal rows, friction rows.
+// ---------------------------------------------------------------------------------------------
+template <int NL, int MC>
+RS_HD void resolve_row(const RowWS& ws, int row, int rec, int nd, float* dv) {
+    float dot = 0.f;
+    for (int k = 0; k < nd; k++) dot += ws.at(row, rec, k) * dv[k];
+    float invd = ws.at(row, rec, 2 * nd + R_INVD);
+    float dimp = ws.at(row, rec, 2 * nd + R_RHS) - dot * invd;
+    float& applied = ws.at(row, rec, 2 * nd + R_APPLIED);
+    float lo = ws.at(row, rec, 2 * nd + R_LO), hi = ws.at(row, rec, 2 * nd + R_HI);
+    float sum = applied + dimp;
+    if (sum < lo) { dimp = lo - applied; applied = lo; }
+    else if (sum > hi) { dimp = hi - applied; applied = hi; }
+    else applied = sum;
+    for (int k = 0; k < nd; k++) dv[k] += ws.at(row, rec, nd + k) * dimp;
+}
+
+template <int NL, int MC>
+RS_HD void solve(const DevModel& M, Work<NL, MC>& W, float dt, const RowWS& ws) {
+    const int nd = 6 + M.n_dof, rec = 2 * nd + R_NSCALAR;
+    const int NC0 = 0, CN0 = NL, CF0 = NL + MC;    // row-index bases of the three groups
+    int n_nc = 0, n_cn = 0, n_cf = 0;
+    float vel[6 + NL];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { vel[k] = M.fixed_base ? 0.f : W.bw[k]; vel[3 + k] = M.fixed_base ? 0.f : W.bv[k]; }
+    for (int d = 0; d < M.n_dof; d++) vel[6 + d] = W.qd[d];
+    const float inv_dt = 1.0f / dt;
+    // joint limits: rows only when violated (btMultiBodyJointLimitConstraint::createConstraintRows)
+    for (int i = 0; i < M.n_links; i++) {
+        int d = M.dof_idx[i];
+        if (!M.has_limit[i] || d < 0) continue;
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            float pen = side == 0 ? W.q[d] - M.lim_lo[i] : M.lim_hi[i] - W.q[d];
+            if (pen > 0.f) continue;
+            float dir = side == 0 ? 1.f : -1.f;
+            int row = NC0 + n_nc++;
+            float denom = row_response(M, W, -1, nullptr, d, dir, ws, row, rec, true);
+            float invd = denom > RS_FLT_EPS ? 1.0f / denom : 0.f;
+            float relvel = dir * vel[6 + d];
+            float erp = pen > M.split_thresh ? M.erp : M.erp2;
+            float rhs = pen > M.split_thresh ? (-pen * erp * inv_dt - relvel) * invd : (-relvel) * invd;
+            ws.at(row, rec, 2 * nd + R_RHS) = rhs; ws.at(row, rec, 2 * nd + R_INVD) = invd;
+            ws.at(row, rec, 2 * nd + R_LO) = 0.f; ws.at(row, rec, 2 * nd + R_HI) = M.max_limit_impulse;
+            ws.at(row, rec, 2 * nd + R_APPLIED) = 0.f;
+        }
+    }
+    // contacts in pool order (manifold id, slot)
+    const int cur = W.cur, nc = W.ccount[cur];
+    for (int ci = 0; ci < nc; ci++) {
+        int key = W.ckey[cur][ci];
+        const float* cd = W.cdat[cur][ci];
+        int bA, bB; float fric;
+        if (key < M.n_geoms) { bA = M.g_link[key] + 1; bB = -1; fric = M.g_fric_floor[key]; }
+        else { int pk = key - M.n_geoms; bA = M.g_link[M.pair_a[pk]] + 1; bB = M.g_link[M.pair_b[pk]] + 1; fric = M.pair_friction[pk]; }
+        float pA[3], pB[3];
+        to_world(W, bA, cd, pA);
+        if (bB >= 0) to_world(W, bB, cd + 3, pB);
+        float dirs[3][3];
+        dirs[0][0] = cd[6]; dirs[0][1] = cd[7]; dirs[0][2] = cd[8];
+        plane_space(dirs[0], dirs[1], dirs[2]);
+        int nrow = CN0 + n_cn;
+        for (int w = 0; w < 3; w++) {
+            int row = (w == 0) ? CN0 + n_cn++ : CF0 + n_cf++;
+            float wr[6];
+            unit_wrench(W, bA, pA, dirs[w], wr);
+            float denom = row_response(M, W, bA, wr, -1, 0.f, ws, row, rec, true);
+            if (bB >= 0) {
+                float nneg[3] = {-dirs[w][0], -dirs[w][1], -dirs[w][2]};
+                unit_wrench(W, bB, pB, nneg, wr);
+                denom += row_response(M, W, bB, wr, -1, 0.f, ws, row, rec, false);
+            }
+            float invd = denom > RS_FLT_EPS ? 1.0f / denom : 0.f;
+            float relvel = 0.f;
+            for (int k = 0; k < nd; k++) relvel += ws.at(row, rec, k) * vel[k];
+            float rhs, lo, hi;
+            if (w == 0) {
+                float pen = cd[9];
+                float erp = pen > M.split_thresh ? M.erp : M.erp2;
+                float posErr = 0.f, velErr = -relvel;
+                if (pen > 0.f) velErr -= pen * inv_dt; else posErr = -pen * erp * inv_dt;
+                rhs = pen > M.split_thresh ? (posErr + velErr) * invd : velErr * invd;
+                lo = 0.f; hi = 1e10f;
+            } else { rhs = -relvel * invd; lo = -fric; hi = fric; }
+            ws.at(row, rec, 2 * nd + R_RHS) = rhs; ws.at(row, rec, 2 * nd + R_INVD) = invd;
+            ws.at(row, rec, 2 * nd + R_LO) = lo; ws.at(row, rec, 2 * nd + R_HI) = hi;
+            ws.at(row, rec, 2 * nd + R_APPLIED) = 0.f; ws.at(row, rec, 2 * nd + R_FRIC) = fric;
+            ws.at(row, rec, 2 * nd + R_FIDX) = (float)nrow;
+        }
+    }
+    W.n_rows = n_nc + n_cn + n_cf; W.n_contacts = n_cn;
+    if (W.n_rows == 0) return;
+    float dv[6 + NL];
+    for (int k = 0; k < nd; k++) dv[k] = 0.f;
+    for (int it = 0; it < M.n_iter; it++) {
+        for (int j = 0; j < n_nc; j++) { int idx = (it & 1) ? j : n_nc - 1 - j; resolve_row<NL, MC>(ws, NC0 + idx, rec, nd, dv); }
+        for (int j = 0; j < n_cn; j++) resolve_row<NL, MC>(ws, CN0 + j, rec, nd, dv);
+        for (int j = 0; j < n_cf; j++) {
+            int row = CF0 + j;
+            float tot = ws.at((int)ws.at(row, rec, 2 * nd + R_FIDX), rec, 2 * nd + R_APPLIED);
+            if (tot > 0.f) {
+                float fr = ws.at(row, rec, 2 * nd + R_FRIC);
+                ws.at(row, rec, 2 * nd + R_LO) = -fr * tot; ws.at(row, rec, 2 * nd + R_HI) = fr * tot;
+                resolve_row<NL, MC>(ws, row, rec, nd, dv);
+            }
+        }
+    }
+    if (!M.fixed_base) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { W.bw[k] += dv[k]; W.bv[k] += dv[3 + k]; }
+    }
+    for (int d = 0; d < M.n_dof; d++) W.qd[d] += dv[6 + d];
+    clamp_vel(M, W);
+}
+
+// ---------------------------------------------------------------------------------------------
+// btMultiBody::stepPositionsMultiDof
+// ---------------------------------------------------------------------------------------------
+template <int NL, int MC>
+RS_HD void integrate(const DevModel& M, Work<NL, MC>& W, float dt) {
+    if (!M.fixed_base) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) W.bpos[k] += dt * W.bv[k];
+        float ang = sqrtf(dot3(W.bw, W.bw));
+        if (ang * dt > 0.78539816f) ang = 0.5f * 1.57079633f / dt;
+        float kk;
+        if (ang < 0.001f) kk = 0.5f * dt - dt * dt * dt * 0.020833333333f * ang * ang;
+        else kk = sinf(0.5f * ang * dt) / ang;
+        float ax = W.bw[0] * kk, ay = W.bw[1] * kk, az = W.bw[2] * kk, aw = cosf(ang * dt * 0.5f);
+        float bx = W.bquat[0], by = W.bquat[1], bz = W.bquat[2], bwq = W.bquat[3];
+        float x = aw * bx + ax * bwq + ay * bz - az * by;
+        float y = aw * by - ax * bz + ay * bwq + az * bx;
+        float z = aw * bz + ax * by - ay * bx + az * bwq;
+        float w = aw * bwq - ax * bx - ay * by - az * bz;
+        float inv = 1.0f / sqrtf(x * x + y * y + z * z + w * w);
+        W.bquat[0] = x * inv; W.bquat[1] = y * inv; W.bquat[2] = z * inv; W.bquat[3] = w * inv;
+    }
+    for (int d = 0; d < M.n_dof; d++) W.q[d] += dt * W.qd[d];
+}
+
+template <int NL, int MC>
+RS_HD void substep(const DevModel& M, Work<NL, MC>& W, const RowWS& ws) {
+    float dt = M.timestep;
+    kinematics(M, W);
+    collide(M, W);
+    aba(M, W, dt);
+    solve(M, W, dt, ws);
+    integrate(M, W, dt);
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogue: query_body_position + calc_state + reward/done  (gym_forward_walker.py:45-133)
+// ---------------------------------------------------------------------------------------------
+RS_HD void mat_to_quat(const float* R, float* q) {  // R: local->world
+    float t = R[0] + R[4] + R[8];
+    if (t > 0) { float s = sqrtf(t + 1.0f) * 2; q[3] = 0.25f * s; q[0] = (R[7] - R[5]) / s; q[1] = (R[2] - R[6]) / s; q[2] = (R[3] - R[1]) / s; }
+    else if (R[0] > R[4] && R[0] > R[8]) { float s = sqrtf(1.0f + R[0] - R[4] - R[8]) * 2; q[3] = (R[7] - R[5]) / s; q[0] = 0.25f * s; q[1] = (R[1] + R[3]) / s; q[2] = (R[2] + R[6]) / s; }
+    else if (R[4] > R[8]) { float s = sqrtf(1.0f + R[4] - R[0] - R[8]) * 2; q[3] = (R[2] - R[6]) / s; q[0] = (R[1] + R[3]) / s; q[1] = 0.25f * s; q[2] = (R[5] + R[7]) / s; }
+    else { float s = sqrtf(1.0f + R[8] - R[0] - R[4]) * 2; q[3] = (R[3] - R[1]) / s; q[0] = (R[2] + R[6]) / s; q[1] = (R[5] + R[7]) / s; q[2] = 0.25f * s; }
+}
+template <int NL, int MC>
+RS_HD void body_pose(const Work<NL, MC>& W, int b, float* pos, float* quat, float* linvel) {
+    pos[0] = W.pos[b][0]; pos[1] = W.pos[b][1]; pos[2] = W.pos[b][2];
+    if (b == 0) { quat[0] = W.bquat[0]; quat[1] = W.bquat[1]; quat[2] = W.bquat[2]; quat[3] = W.bquat[3]; }
+    else {
+        float Rlw[9];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) Rlw[i * 3 + j] = W.Rwl[b][j * 3 + i];
+        mat_to_quat(Rlw, quat);
+    }
+    tmulv(linvel, W.Rwl[b], W.vel[b] + 3);
+}
+
+struct Episode {
+    double potential;
+    float initial_z;
+    float feet_contact[MF];
+    int frame;
+    uint32_t episode;
+};
+
+struct StepOut {
+    float reward;
+    int done;
+    float rewards5[5];
+};
+
+// joint_current_relative_position (physics-bullet.cpp:547-566)
+RS_HD void rel_joint(const DevModel& M, int li, float q, float qd, float* pos, float* spd) {
+    float l1 = M.lim_lo[li], l2 = M.lim_hi[li];
+    if (l1 < l2) { float mid = 0.5f * (l1 + l2); q = 2.f * (q - mid) / (l2 - l1); }
+    if (M.max_vel[li] > 0.f) qd /= M.max_vel[li];
+    else qd *= (M.jtype[li] == RS_JOINT_REVOLUTE) ? 0.1f : 0.5f;
+    *pos = q; *spd = qd;
+}
+
+// writes obs[k*ostride]; returns walk_target_dist (double) and pitch
+template <int NL, int MC>
+RS_HD void calc_state(const DevModel& M, Work<NL, MC>& W, Episode& E, float* obs, int ostride, double* dist, float* pitch, int* at_limit) {
+    kinematics(M, W); velocities(M, W);
+    const int A = M.n_act;
+    int nlim = 0;
+    for (int k = 0; k < A; k++) {
+        int d = M.act_dof[k], li = M.dof_link[d];
+        float p, s;
+        rel_joint(M, li, W.q[d], W.qd[d], &p, &s);
+        if (fabsf(p) > 0.99f) nlim++;
+        obs[(8 + 2 * k) * ostride] = fminf(fmaxf(p, -5.f), 5.f);
+        obs[(8 + 2 * k + 1) * ostride] = fminf(fmaxf(s, -5.f), 5.f);
+    }
+    *at_limit = nlim;
+    float bp[3], bq[4], bv[3];
+    body_pose(W, M.body_link + 1, bp, bq, bv);
+    float mx = 0.f, my = 0.f;
+    for (int k = 0; k < M.n_parts; k++) { mx += W.pos[M.part_link[k] + 1][0]; my += W.pos[M.part_link[k] + 1][1]; }
+    mx /= (float)M.n_parts; my /= (float)M.n_parts;
+    // Pose::rpy (python-binding.cpp:60-73)
+    float qx = bq[0], qy = bq[1], qz = bq[2], qw = bq[3];
+    float sqw = qw * qw, sqx = qx * qx, sqy = qy * qy, sqz = qz * qz;
+    float t2 = -2.0f * (qx * qz - qy * qw) / (sqx + sqy + sqz + sqw);
+    float yaw = atan2f(2.0f * (qx * qy + qz * qw), (sqx - sqy - sqz + sqw));
+    float roll = atan2f(2.0f * (qy * qz + qx * qw), (-sqx - sqy + sqz + sqw));
+    t2 = fminf(fmaxf(t2, -1.0f), 1.0f);
+    float p = asinf(t2);
+    float z = bp[2];
+    if (E.initial_z < 0.f) E.initial_z = z;
+    // target bearing / distance: the target is 1 km away, so these run in double (a handful of ops)
+    double dy = M.walk_target_y - (double)my, dx = M.walk_target_x - (double)mx;
+    *dist = sqrt(dy * dy + dx * dx);
+    float ang = (float)(atan2(dy, dx) - (double)yaw);
+    float cy = cosf(-yaw), sy = sinf(-yaw);
+    float vx = cy * bv[0] - sy * bv[1], vy = sy * bv[0] + cy * bv[1], vz = bv[2];
+    float more[8] = {z - E.initial_z, sinf(ang), cosf(ang), 0.3f * vx, 0.3f * vy, 0.3f * vz, roll, p};
+#pragma unroll
+    for (int k = 0; k < 8; k++) obs[k * ostride] = fminf(fmaxf(more[k], -5.f), 5.f);
+    for (int k = 0; k < M.n_feet; k++) obs[(8 + 2 * A + k) * ostride] = E.feet_contact[k];
+    *pitch = p;
+}
+
+template <int NL, int MC>
+RS_HD void epilogue(const DevModel& M, Work<NL, MC>& W, Episode& E, const float* act, int astride, float* obs, int ostride, StepOut& out) {
+    double dist; float pitch; int at_limit;
+    calc_state(M, W, E, obs, ostride, &dist, &pitch, &at_limit);
+    float z = obs[0] + E.initial_z;
+    float alive;
+    if (M.alive_rule == RS_ALIVE_Z_AND_PITCH) alive = (z > M.alive_z && fabsf(pitch) < 1.0f) ? M.alive_bonus : -1.f;
+    else if (M.alive_rule == RS_ALIVE_Z) alive = (z > M.alive_z) ? M.alive_bonus : -1.f;
+    else alive = M.alive_bonus;
+    int done = alive < 0.f;
+    for (int k = 0; k < M.obs_dim; k++) if (!isfinite(obs[k * ostride])) done = 1;
+    double pot_old = E.potential;
+    E.potential = -dist / M.dt_env;
+    float progress = (float)(E.potential - pot_old);
+    // feet: World::bullet_contact_list(foot) -> floor / other parts (gym_forward_walker.py:106-112)
+    float feet_cost = 0.f;
+    const int cur = W.cur, nc = W.ccount[cur];
+    for (int f = 0; f < M.n_feet; f++) {
+        int fb = M.foot_link[f] + 1, g = 0, o = 0;
+        for (int ci = 0; ci < nc; ci++) {
+            int key = W.ckey[cur][ci];
+            if (key < M.n_geoms) { if (M.g_link[key] + 1 == fb) g = 1; }
+            else { int pk = key - M.n_geoms; if (M.g_link[M.pair_a[pk]] + 1 == fb || M.g_link[M.pair_b[pk]] + 1 == fb) o = 1; }
+        }
+        E.feet_contact[f] = g ? 1.f : 0.f;
+        if (o) feet_cost += M.foot_collision_cost;
+    }
+    const int A = M.n_act;
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < A; k++) {
+        int d = M.act_dof[k], li = M.dof_link[d];
+        float p, s, a = act[k * astride];
+        rel_joint(M, li, W.q[d], W.qd[d], &p, &s);
+        s1 += fabsf(a * s); s2 += a * a;
+    }
+    float elec = M.electricity_cost * (s1 / (float)A) + M.stall_torque_cost * (s2 / (float)A);
+    float jl = M.joints_at_limit_cost * (float)at_limit;
+    out.rewards5[0] = alive; out.rewards5[1] = progress; out.rewards5[2] = elec; out.rewards5[3] = jl; out.rewards5[4] = feet_cost;
+    out.reward = alive + progress + elec + jl + feet_cost;
+    out.done = done;
+    E.frame++;
+}
+
+// reset to the reference's reset distribution (gym_forward_walker.py:24-30, gym_mujoco_walkers.py:106-128)
+template <int NL, int MC>
+RS_HD void env_reset(const DevModel& M, Work<NL, MC>& W, Episode& E, uint32_t seed, uint32_t env_id, float* obs, int ostride) {
+    E.episode++;
+    for (int d = 0; d < M.n_dof; d++) { W.q[d] = 0.f; W.qd[d] = 0.f; W.tau[d] = 0.f; }
+    for (int k = 0; k < M.n_act; k++) {
+        float u = rs_uniform(seed, env_id, E.episode, (uint32_t)k);
+        W.q[M.act_dof[k]] = (float)((double)M.reset_joint_spread * (2.0 * (double)u - 1.0));
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) { W.bpos[k] = M.reset_base_pos[k]; W.bw[k] = 0.f; W.bv[k] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) W.bquat[k] = M.reset_base_quat[k];
+    if (M.reset_set_base && M.reset_yaw_spread > 0.f) {
+        float u = rs_uniform(seed, env_id, E.episode, 1000u);
+        double yaw = (double)M.reset_yaw_spread * (2.0 * (double)u - 1.0);
+        W.bquat[0] = 0.f; W.bquat[1] = 0.f; W.bquat[2] = (float)sin(0.5 * yaw); W.bquat[3] = (float)cos(0.5 * yaw);
+    }
+    W.ccount[0] = W.ccount[1] = 0; W.cur = 0;
+    for (int k = 0; k < M.n_feet; k++) E.feet_contact[k] = 0.f;
+    E.initial_z = M.initial_z;
+    E.frame = 0;
+    double dist; float pitch; int al;
+    calc_state(M, W, E, obs, ostride, &dist, &pitch, &al);
+    E.potential = -dist / M.dt_env;
+}
+
+// apply_action: torque = float(power*coef*clip(a,-1,1))  (gym_forward_walker.py:40-43; set_motor_torque(float))
+template <int NL, int MC>
+RS_HD void apply_action(const DevModel& M, Work<NL, MC>& W, const float* act, int astride) {
+    for (int d = 0; d < M.n_dof; d++) W.tau[d] = 0.f;
+    for (int k = 0; k < M.n_act; k++) {
+        float a = fminf(fmaxf(act[k * astride], -1.f), 1.f);
+        W.tau[M.act_dof[k]] = M.act_gain[k] * a;
+    }
+    for (int l = 0; l < M.n_links; l++) {
+        int d = M.dof_idx[l];
+        if (d >= 0 && M.jdamping[l] != 0.f) W.tau[d] += -M.jdamping[l] * W.qd[d];
+    }
+}
+
+}  // namespace rs

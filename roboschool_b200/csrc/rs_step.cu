@@ -1,0 +1,494 @@
+// rs_step.cu -- kernels + C ABI (include/roboschool_b200.h) of the batched stepper.
+//
+// Data layout in HBM (all fp32 unless noted), SoA with the env index fastest so that the 32 lanes of
+// a warp (= 32 consecutive envs) touch 128 contiguous bytes per field:
+//   state   [S][N]            S = 13*(floating base) + 2*ndof          (read once, written once per env step)
+//   ccount  [N] int32, ckey [MC][N] int32, cdat [MC][10][N]            (live contact points, persistent manifolds)
+//   episode: potential [N] f64, initial_z [N], feet [F][N], frame [N] i32, episode [N] u32
+//   rows    [MAXR*REC][N]     per-env PGS row workspace (J, M^-1 J^T, rhs, limits) -- scratch, L2 resident
+// actions/obs are the caller's row-major [N][A] / [N][O] tensors.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/roboschool_b200.h"
+#include "rs_devmodel.h"
+
+using namespace rs;
+
+static thread_local std::string g_err;
+static int fail(const std::string& s) { g_err = s; return 1; }
+int rs_set_error(const char* s) { g_err = s; return 1; }   // shared with rs_mlp.cu
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+extern "C" const char* rs_last_error(void) { return g_err.c_str(); }
+extern "C" int rs_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+
+struct DevBuf {
+    float* state; int* ccount; int* ckey; float* cdat;
+    double* potential; float* initial_z; float* feet; int* frame; uint32_t* episode;
+    float* rows; float* tau; float* rewards5; int* nrows; int* ncontacts;
+    int N, S, MCcap, rec, maxr;
+};
+
+struct rs_world {
+    rs_model_desc desc;
+    DevModel M;
+    DevBuf B;
+    int device, n, family;   // family: 0 (NL<=6), 1 (NL<=12), 2 (NL<=24)
+    cudaStream_t stream;
+    // pinned staging + device staging for the host-buffer entry point
+    float *h_act, *h_obs, *h_rew; uint8_t* h_done;
+    float *d_act, *d_obs, *d_rew; uint8_t* d_done;
+    double* d_stats;
+    uint32_t rollout_seed, env_id0;
+};
+
+// ----------------------------------------------------------------------------------------------
+template <int NL, int MC>
+__device__ __forceinline__ void load_env(const DevModel& M, const DevBuf& B, int e, Work<NL, MC>& W, Episode& E) {
+    const int N = B.N;
+    const float* s = B.state + e;
+    int f = 0;
+    if (!M.fixed_base) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) W.bpos[k] = s[(size_t)(f++) * N];
+#pragma unroll
+        for (int k = 0; k < 4; k++) W.bquat[k] = s[(size_t)(f++) * N];
+#pragma unroll
+        for (int k = 0; k < 3; k++) W.bw[k] = s[(size_t)(f++) * N];
+#pragma unroll
+        for (int k = 0; k < 3; k++) W.bv[k] = s[(size_t)(f++) * N];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { W.bpos[k] = 0; W.bw[k] = 0; W.bv[k] = 0; W.bquat[k] = 0; }
+        W.bquat[3] = 1.f;
+    }
+    for (int d = 0; d < M.n_dof; d++) W.q[d] = s[(size_t)(f + d) * N];
+    for (int d = 0; d < M.n_dof; d++) W.qd[d] = s[(size_t)(f + M.n_dof + d) * N];
+    int nc = B.ccount[e];
+    W.cur = 0; W.ccount[0] = nc; W.ccount[1] = 0;
+    for (int i = 0; i < nc; i++) {
+        W.ckey[0][i] = B.ckey[(size_t)i * N + e];
+#pragma unroll
+        for (int k = 0; k < CDAT; k++) W.cdat[0][i][k] = B.cdat[((size_t)i * CDAT + k) * N + e];
+    }
+    E.potential = B.potential[e]; E.initial_z = B.initial_z[e]; E.frame = B.frame[e]; E.episode = B.episode[e];
+    for (int k = 0; k < M.n_feet; k++) E.feet_contact[k] = B.feet[(size_t)k * N + e];
+    W.n_rows = 0; W.n_contacts = 0;
+}
+
+template <int NL, int MC>
+__device__ __forceinline__ void store_env(const DevModel& M, const DevBuf& B, int e, const Work<NL, MC>& W, const Episode& E) {
+    const int N = B.N;
+    float* s = B.state + e;
+    int f = 0;
+    if (!M.fixed_base) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) s[(size_t)(f++) * N] = W.bpos[k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) s[(size_t)(f++) * N] = W.bquat[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) s[(size_t)(f++) * N] = W.bw[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) s[(size_t)(f++) * N] = W.bv[k];
+    }
+    for (int d = 0; d < M.n_dof; d++) s[(size_t)(f + d) * N] = W.q[d];
+    for (int d = 0; d < M.n_dof; d++) s[(size_t)(f + M.n_dof + d) * N] = W.qd[d];
+    const int cur = W.cur, nc = W.ccount[cur];
+    B.ccount[e] = nc;
+    for (int i = 0; i < nc; i++) {
+        B.ckey[(size_t)i * N + e] = W.ckey[cur][i];
+#pragma unroll
+        for (int k = 0; k < CDAT; k++) B.cdat[((size_t)i * CDAT + k) * N + e] = W.cdat[cur][i][k];
+    }
+    B.potential[e] = E.potential; B.initial_z[e] = E.initial_z; B.frame[e] = E.frame; B.episode[e] = E.episode;
+    for (int k = 0; k < M.n_feet; k++) B.feet[(size_t)k * N + e] = E.feet_contact[k];
+    B.nrows[e] = W.n_rows; B.ncontacts[e] = W.n_contacts;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// One env step per thread.  actions == nullptr: uniform random actions from the counter-based RNG.
+template <int NL, int MC>
+__global__ void __launch_bounds__(64) k_step(const __grid_constant__ DevModel M, const DevBuf B, const float* __restrict__ actions,
+                                             float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
+                                             int auto_reset, uint32_t seed, uint32_t env_id0, double* __restrict__ stats) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    double st_rew = 0, st_ep = 0, st_len = 0, st_nf = 0, st_rows = 0, st_con = 0, st_steps = 0;
+    if (e < B.N) {
+        Work<NL, MC> W;
+        Episode E;
+        load_env(M, B, e, W, E);
+        float a[MA];
+        if (actions) { for (int k = 0; k < M.n_act; k++) a[k] = actions[(size_t)e * M.n_act + k]; }
+        else { for (int k = 0; k < M.n_act; k++) a[k] = 2.f * rs_uniform(seed ^ 0xA5A5A5A5u, env_id0 + e, E.episode * 1024u + (uint32_t)E.frame, (uint32_t)k) - 1.f; }
+        apply_action(M, W, a, 1);
+        RowWS ws{B.rows + e, B.N};
+        for (int s = 0; s < M.frame_skip; s++) substep(M, W, ws);
+        float* o = obs + (size_t)e * M.obs_dim;
+        StepOut out;
+        epilogue(M, W, E, a, 1, o, 1, out);
+        int dn = out.done;
+        bool finite = true;
+        for (int k = 0; k < M.obs_dim; k++) finite = finite && isfinite(o[k]);
+        int finished = dn || E.frame >= M.max_episode_steps;
+        st_rew = out.reward; st_rows = W.n_rows; st_con = W.n_contacts; st_steps = 1; st_nf = finite ? 0 : 1;
+        if (finished) { st_ep = 1; st_len = E.frame; }
+        if (auto_reset && finished) { env_reset(M, W, E, seed, env_id0 + e, o, 1); dn = 1; }
+        rew[e] = out.reward; done[e] = (uint8_t)dn;
+        if (B.rewards5) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) B.rewards5[(size_t)e * 5 + k] = out.rewards5[k];
+        }
+        store_env(M, B, e, W, E);
+    }
+    if (stats) {
+        st_rew = warp_sum(st_rew); st_ep = warp_sum(st_ep); st_len = warp_sum(st_len); st_nf = warp_sum(st_nf);
+        st_rows = warp_sum(st_rows); st_con = warp_sum(st_con); st_steps = warp_sum(st_steps);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(stats + 0, st_rew); atomicAdd(stats + 1, st_ep); atomicAdd(stats + 2, st_len); atomicAdd(stats + 3, st_nf);
+            atomicAdd(stats + 4, st_rows); atomicAdd(stats + 5, st_con); atomicAdd(stats + 6, st_steps);
+        }
+    }
+}
+
+template <int NL, int MC>
+__global__ void __launch_bounds__(64) k_reset(const __grid_constant__ DevModel M, const DevBuf B, const uint8_t* __restrict__ mask,
+                                              float* __restrict__ obs, uint32_t seed, uint32_t env_id0) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B.N) return;
+    if (mask && !mask[e]) return;
+    Work<NL, MC> W;
+    Episode E;
+    load_env(M, B, e, W, E);
+    float tmp[8 + 2 * MA + MF];
+    env_reset(M, W, E, seed, env_id0 + e, tmp, 1);
+    if (obs) for (int k = 0; k < M.obs_dim; k++) obs[(size_t)e * M.obs_dim + k] = tmp[k];
+    store_env(M, B, e, W, E);
+}
+
+template <int NL, int MC>
+__global__ void __launch_bounds__(64) k_substeps(const __grid_constant__ DevModel M, const DevBuf B, int nsub) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B.N) return;
+    Work<NL, MC> W;
+    Episode E;
+    load_env(M, B, e, W, E);
+    for (int d = 0; d < M.n_dof; d++) W.tau[d] = B.tau[(size_t)d * B.N + e];
+    RowWS ws{B.rows + e, B.N};
+    for (int s = 0; s < nsub; s++) substep(M, W, ws);
+    store_env(M, B, e, W, E);
+}
+
+template <int NL, int MC>
+__global__ void __launch_bounds__(64) k_link_poses(const __grid_constant__ DevModel M, const DevBuf B, float* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B.N) return;
+    Work<NL, MC> W;
+    Episode E;
+    load_env(M, B, e, W, E);
+    kinematics(M, W); velocities(M, W);
+    for (int b = 0; b <= M.n_links; b++) {
+        float p[3], q[4], v[3];
+        body_pose(W, b, p, q, v);
+        float* o = out + ((size_t)e * (M.n_links + 1) + b) * 10;
+        o[0] = p[0]; o[1] = p[1]; o[2] = p[2]; o[3] = q[0]; o[4] = q[1]; o[5] = q[2]; o[6] = q[3]; o[7] = v[0]; o[8] = v[1]; o[9] = v[2];
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+#define FAMILY_DISPATCH(w, CALL)                                   \
+    switch ((w)->family) {                                         \
+        case 0: { constexpr int NL = 6, MC = 8; CALL; } break;     \
+        case 1: { constexpr int NL = 12, MC = 16; CALL; } break;   \
+        default: { constexpr int NL = 20, MC = 16; CALL; } break;  \
+    }
+
+static int family_of(const rs_model_desc* m, int* NL, int* MC) {
+    if (m->n_links <= 6 && m->max_contacts <= 8) { *NL = 6; *MC = 8; return 0; }
+    if (m->n_links <= 12 && m->max_contacts <= 16) { *NL = 12; *MC = 16; return 1; }
+    if (m->n_links <= 20 && m->max_contacts <= 16) { *NL = 20; *MC = 16; return 2; }
+    return -1;
+}
+
+extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int device, rs_world** out) {
+    if (!model || !out || n_envs <= 0) return fail("rs_world_create: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("rs_world_create: no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail("rs_world_create: device index out of range");
+    CK(cudaSetDevice(device));
+    rs_world* w = new rs_world();
+    memset(w, 0, sizeof *w);
+    w->desc = *model;
+    const char* err = nullptr;
+    if (build_dev_model(model, &w->M, &err)) { delete w; return fail(std::string("rs_world_create: ") + err); }
+    int NL, MC;
+    w->family = family_of(model, &NL, &MC);
+    if (w->family < 0) { delete w; return fail("rs_world_create: model exceeds kernel capacity (links<=20, contacts<=16)"); }
+    w->device = device; w->n = n_envs;
+    DevBuf& B = w->B;
+    B.N = n_envs; B.S = (model->fixed_base ? 0 : 13) + 2 * model->n_dof; B.MCcap = MC;
+    B.rec = 2 * (6 + model->n_dof) + R_NSCALAR; B.maxr = NL + 3 * MC;
+    size_t N = (size_t)n_envs;
+    CK(cudaMalloc(&B.state, sizeof(float) * N * (B.S > 0 ? B.S : 1)));
+    CK(cudaMalloc(&B.ccount, sizeof(int) * N));
+    CK(cudaMalloc(&B.ckey, sizeof(int) * N * MC));
+    CK(cudaMalloc(&B.cdat, sizeof(float) * N * MC * CDAT));
+    CK(cudaMalloc(&B.potential, sizeof(double) * N));
+    CK(cudaMalloc(&B.initial_z, sizeof(float) * N));
+    CK(cudaMalloc(&B.feet, sizeof(float) * N * MF));
+    CK(cudaMalloc(&B.frame, sizeof(int) * N));
+    CK(cudaMalloc(&B.episode, sizeof(uint32_t) * N));
+    CK(cudaMalloc(&B.rows, sizeof(float) * N * B.rec * B.maxr));
+    CK(cudaMalloc(&B.tau, sizeof(float) * N * (model->n_dof > 0 ? model->n_dof : 1)));
+    CK(cudaMalloc(&B.rewards5, sizeof(float) * N * 5));
+    CK(cudaMalloc(&B.nrows, sizeof(int) * N));
+    CK(cudaMalloc(&B.ncontacts, sizeof(int) * N));
+    CK(cudaMemset(B.state, 0, sizeof(float) * N * (B.S > 0 ? B.S : 1)));
+    CK(cudaMemset(B.ccount, 0, sizeof(int) * N));
+    CK(cudaMemset(B.potential, 0, sizeof(double) * N));
+    CK(cudaMemset(B.feet, 0, sizeof(float) * N * MF));
+    CK(cudaMemset(B.frame, 0, sizeof(int) * N));
+    CK(cudaMemset(B.episode, 0, sizeof(uint32_t) * N));
+    CK(cudaMemset(B.tau, 0, sizeof(float) * N * (model->n_dof > 0 ? model->n_dof : 1)));
+    CK(cudaMemset(B.rewards5, 0, sizeof(float) * N * 5));
+    CK(cudaMemset(B.nrows, 0, sizeof(int) * N));
+    CK(cudaMemset(B.ncontacts, 0, sizeof(int) * N));
+    {   // identity base quaternion, initial_z from the model
+        std::vector<float> s((size_t)N * (B.S > 0 ? B.S : 1), 0.f), iz(N, (float)model->initial_z);
+        if (!model->fixed_base) for (size_t e = 0; e < N; e++) s[6 * N + e] = 1.f;
+        CK(cudaMemcpy(B.state, s.data(), sizeof(float) * s.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(B.initial_z, iz.data(), sizeof(float) * N, cudaMemcpyHostToDevice));
+    }
+    CK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+    int A = model->n_act > 0 ? model->n_act : 1, O = model->obs_dim > 0 ? model->obs_dim : 1;
+    CK(cudaMallocHost(&w->h_act, sizeof(float) * N * A));
+    CK(cudaMallocHost(&w->h_obs, sizeof(float) * N * O));
+    CK(cudaMallocHost(&w->h_rew, sizeof(float) * N));
+    CK(cudaMallocHost(&w->h_done, N));
+    CK(cudaMalloc(&w->d_act, sizeof(float) * N * A));
+    CK(cudaMalloc(&w->d_obs, sizeof(float) * N * O));
+    CK(cudaMalloc(&w->d_rew, sizeof(float) * N));
+    CK(cudaMalloc(&w->d_done, N));
+    CK(cudaMalloc(&w->d_stats, sizeof(double) * 8));
+    *out = w;
+    return 0;
+}
+
+extern "C" int rs_world_destroy(rs_world* w) {
+    if (!w) return 0;
+    cudaSetDevice(w->device);
+    DevBuf& B = w->B;
+    cudaFree(B.state); cudaFree(B.ccount); cudaFree(B.ckey); cudaFree(B.cdat); cudaFree(B.potential); cudaFree(B.initial_z);
+    cudaFree(B.feet); cudaFree(B.frame); cudaFree(B.episode); cudaFree(B.rows); cudaFree(B.tau); cudaFree(B.rewards5);
+    cudaFree(B.nrows); cudaFree(B.ncontacts);
+    cudaFreeHost(w->h_act); cudaFreeHost(w->h_obs); cudaFreeHost(w->h_rew); cudaFreeHost(w->h_done);
+    cudaFree(w->d_act); cudaFree(w->d_obs); cudaFree(w->d_rew); cudaFree(w->d_done); cudaFree(w->d_stats);
+    cudaStreamDestroy(w->stream);
+    delete w;
+    return 0;
+}
+
+extern "C" int rs_world_n_envs(const rs_world* w) { return w->n; }
+extern "C" int rs_world_state_dim(const rs_world* w) { return w->B.S; }
+extern "C" int rs_world_obs_dim(const rs_world* w) { return w->desc.obs_dim; }
+extern "C" int rs_world_act_dim(const rs_world* w) { return w->desc.n_act; }
+extern "C" int rs_world_state_dev(rs_world* w, float** p) { *p = w->B.state; return 0; }
+
+static inline int nblocks(int n) { return (n + 63) / 64; }
+
+extern "C" int rs_world_reset(rs_world* w, uint32_t seed, uint32_t env_id0, const uint8_t* mask_dev, float* obs_dev, void* stream) {
+    CK(cudaSetDevice(w->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    FAMILY_DISPATCH(w, (k_reset<NL, MC><<<nblocks(w->n), 64, 0, st>>>(w->M, w->B, mask_dev, obs_dev, seed, env_id0)));
+    CK(cudaGetLastError());
+    w->rollout_seed = seed; w->env_id0 = env_id0;
+    return 0;
+}
+
+static int launch_step(rs_world* w, const float* actions, float* obs, float* rew, uint8_t* done, int auto_reset, uint32_t seed,
+                       uint32_t env_id0, double* stats, cudaStream_t st) {
+    FAMILY_DISPATCH(w, (k_step<NL, MC><<<nblocks(w->n), 64, 0, st>>>(w->M, w->B, actions, obs, rew, done, auto_reset, seed, env_id0, stats)));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int rs_world_step(rs_world* w, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+                             int auto_reset, void* stream) {
+    if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail("rs_world_step: null buffer");
+    CK(cudaSetDevice(w->device));
+    return launch_step(w, actions_dev, obs_dev, reward_dev, done_dev, auto_reset, w->rollout_seed, w->env_id0, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int rs_world_step_stats(rs_world* w, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+                                   int auto_reset, double* stats_dev, void* stream) {
+    if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail("rs_world_step_stats: null buffer");
+    CK(cudaSetDevice(w->device));
+    return launch_step(w, actions_dev, obs_dev, reward_dev, done_dev, auto_reset, w->rollout_seed, w->env_id0, stats_dev, (cudaStream_t)stream);
+}
+
+extern "C" int rs_world_step_host(rs_world* w, const float* actions_host, float* obs_host, float* reward_host, uint8_t* done_host,
+                                  int auto_reset) {
+    CK(cudaSetDevice(w->device));
+    size_t N = (size_t)w->n, A = (size_t)w->desc.n_act, O = (size_t)w->desc.obs_dim;
+    memcpy(w->h_act, actions_host, sizeof(float) * N * A);
+    CK(cudaMemcpyAsync(w->d_act, w->h_act, sizeof(float) * N * A, cudaMemcpyHostToDevice, w->stream));
+    if (launch_step(w, w->d_act, w->d_obs, w->d_rew, w->d_done, auto_reset, w->rollout_seed, w->env_id0, nullptr, w->stream)) return 1;
+    CK(cudaMemcpyAsync(w->h_obs, w->d_obs, sizeof(float) * N * O, cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaMemcpyAsync(w->h_rew, w->d_rew, sizeof(float) * N, cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaMemcpyAsync(w->h_done, w->d_done, N, cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    memcpy(obs_host, w->h_obs, sizeof(float) * N * O);
+    memcpy(reward_host, w->h_rew, sizeof(float) * N);
+    memcpy(done_host, w->h_done, N);
+    return 0;
+}
+
+extern "C" int rs_world_substeps(rs_world* w, int n_substeps, const float* tau_host) {
+    CK(cudaSetDevice(w->device));
+    size_t N = (size_t)w->n; int nd = w->desc.n_dof;
+    if (tau_host && nd > 0) {
+        std::vector<float> t(N * nd);
+        for (size_t e = 0; e < N; e++) for (int d = 0; d < nd; d++) t[(size_t)d * N + e] = tau_host[e * nd + d];
+        CK(cudaMemcpy(w->B.tau, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice));
+    }
+    FAMILY_DISPATCH(w, (k_substeps<NL, MC><<<nblocks(w->n), 64, 0, w->stream>>>(w->M, w->B, n_substeps)));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(w->stream));
+    return 0;
+}
+
+extern "C" int rs_world_set_state(rs_world* w, const float* state_host, int clear_contacts) {
+    CK(cudaSetDevice(w->device));
+    size_t N = (size_t)w->n; int S = w->B.S;
+    std::vector<float> s(N * S);
+    for (size_t e = 0; e < N; e++) for (int f = 0; f < S; f++) s[(size_t)f * N + e] = state_host[e * S + f];
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(w->B.state, s.data(), sizeof(float) * s.size(), cudaMemcpyHostToDevice));
+    if (clear_contacts) CK(cudaMemset(w->B.ccount, 0, sizeof(int) * N));
+    return 0;
+}
+
+extern "C" int rs_world_get_state(rs_world* w, float* state_host) {
+    CK(cudaSetDevice(w->device));
+    size_t N = (size_t)w->n; int S = w->B.S;
+    std::vector<float> s(N * S);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(s.data(), w->B.state, sizeof(float) * s.size(), cudaMemcpyDeviceToHost));
+    for (size_t e = 0; e < N; e++) for (int f = 0; f < S; f++) state_host[e * S + f] = s[(size_t)f * N + e];
+    return 0;
+}
+
+extern "C" int rs_world_set_episode(rs_world* w, const double* potential, const float* initial_z, const float* feet_contact, const int* frame) {
+    CK(cudaSetDevice(w->device));
+    size_t N = (size_t)w->n; int F = w->desc.n_feet;
+    CK(cudaDeviceSynchronize());
+    if (potential) CK(cudaMemcpy(w->B.potential, potential, sizeof(double) * N, cudaMemcpyHostToDevice));
+    if (initial_z) CK(cudaMemcpy(w->B.initial_z, initial_z, sizeof(float) * N, cudaMemcpyHostToDevice));
+    if (frame) CK(cudaMemcpy(w->B.frame, frame, sizeof(int) * N, cudaMemcpyHostToDevice));
+    if (feet_contact && F > 0) {
+        std::vector<float> f(N * F);
+        for (size_t e = 0; e < N; e++) for (int k = 0; k < F; k++) f[(size_t)k * N + e] = feet_contact[e * F + k];
+        CK(cudaMemcpy(w->B.feet, f.data(), sizeof(float) * f.size(), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+extern "C" int rs_world_get_episode(rs_world* w, double* potential, float* initial_z, float* feet_contact, int* frame) {
+    CK(cudaSetDevice(w->device));
+    size_t N = (size_t)w->n; int F = w->desc.n_feet;
+    CK(cudaDeviceSynchronize());
+    if (potential) CK(cudaMemcpy(potential, w->B.potential, sizeof(double) * N, cudaMemcpyDeviceToHost));
+    if (initial_z) CK(cudaMemcpy(initial_z, w->B.initial_z, sizeof(float) * N, cudaMemcpyDeviceToHost));
+    if (frame) CK(cudaMemcpy(frame, w->B.frame, sizeof(int) * N, cudaMemcpyDeviceToHost));
+    if (feet_contact && F > 0) {
+        std::vector<float> f(N * F);
+        CK(cudaMemcpy(f.data(), w->B.feet, sizeof(float) * f.size(), cudaMemcpyDeviceToHost));
+        for (size_t e = 0; e < N; e++) for (int k = 0; k < F; k++) feet_contact[e * F + k] = f[(size_t)k * N + e];
+    }
+    return 0;
+}
+
+extern "C" int rs_world_link_poses(rs_world* w, float* out_host) {
+    CK(cudaSetDevice(w->device));
+    size_t cnt = (size_t)w->n * (w->desc.n_links + 1) * 10;
+    float* d = nullptr;
+    CK(cudaMalloc(&d, sizeof(float) * cnt));
+    FAMILY_DISPATCH(w, (k_link_poses<NL, MC><<<nblocks(w->n), 64, 0, w->stream>>>(w->M, w->B, d)));
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(out_host, d, sizeof(float) * cnt, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(std::string("rs_world_link_poses: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int rs_world_get_contacts(rs_world* w, int env, int* keys_host, float* data_host, int max_pts, int* count) {
+    CK(cudaSetDevice(w->device));
+    if (env < 0 || env >= w->n) return fail("rs_world_get_contacts: env out of range");
+    CK(cudaDeviceSynchronize());
+    int nc = 0;
+    CK(cudaMemcpy(&nc, w->B.ccount + env, sizeof(int), cudaMemcpyDeviceToHost));
+    if (nc > max_pts) nc = max_pts;
+    size_t N = (size_t)w->n;
+    for (int i = 0; i < nc; i++) {
+        CK(cudaMemcpy(keys_host + i, w->B.ckey + (size_t)i * N + env, sizeof(int), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < CDAT; k++)
+            CK(cudaMemcpy(data_host + i * CDAT + k, w->B.cdat + ((size_t)i * CDAT + k) * N + env, sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    *count = nc;
+    return 0;
+}
+
+extern "C" int rs_world_get_counts(rs_world* w, int* rows_host, int* contacts_host) {
+    CK(cudaSetDevice(w->device));
+    CK(cudaDeviceSynchronize());
+    if (rows_host) CK(cudaMemcpy(rows_host, w->B.nrows, sizeof(int) * w->n, cudaMemcpyDeviceToHost));
+    if (contacts_host) CK(cudaMemcpy(contacts_host, w->B.ncontacts, sizeof(int) * w->n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int rs_world_get_rewards5(rs_world* w, float* out_host) {
+    CK(cudaSetDevice(w->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out_host, w->B.rewards5, sizeof(float) * w->n * 5, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// implemented in rs_mlp.cu
+extern "C" int rs_policy_forward(rs_policy* p, const float* obs_dev, float* act_dev, int n, void* stream);
+
+extern "C" int rs_world_rollout(rs_world* w, rs_policy* p, int n_steps, uint32_t seed, uint32_t env_id0, double* stats_dev, void* stream) {
+    CK(cudaSetDevice(w->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int t = 0; t < n_steps; t++) {
+        const float* act = nullptr;
+        if (p) {
+            // obs of the previous step (or of reset) lives in d_obs
+            if (rs_policy_forward(p, w->d_obs, w->d_act, w->n, stream)) return 1;
+            act = w->d_act;
+        }
+        if (launch_step(w, act, w->d_obs, w->d_rew, w->d_done, 1, seed, env_id0, stats_dev, st)) return 1;
+    }
+    return 0;
+}
+
+// obs buffer owned by the world (the rollout's policy input); reset writes the first observation here
+extern "C" int rs_world_rollout_reset(rs_world* w, uint32_t seed, uint32_t env_id0, void* stream) {
+    return rs_world_reset(w, seed, env_id0, nullptr, w->d_obs, stream);
+}
+extern "C" int rs_world_rollout_buffers(rs_world* w, float** obs_dev, float** act_dev, float** rew_dev, uint8_t** done_dev) {
+    if (obs_dev) *obs_dev = w->d_obs;
+    if (act_dev) *act_dev = w->d_act;
+    if (rew_dev) *rew_dev = w->d_rew;
+    if (done_dev) *done_dev = w->d_done;
+    return 0;
+}

@@ -22,7 +22,7 @@ ENV_SPECS = {
     "RoboschoolHopper-v1": dict(
         xml="hopper.xml", robot="torso", A=3, O=15, power=0.75, feet=["foot"],
         alive_rule=RS_ALIVE_Z_AND_PITCH, alive_z=0.8, alive_bonus=1.0, cost_scale=1.0,
-        initial_z=None, coef={}, reward_threshold=2500.0),
+        initial_z=None, coef={}, max_contacts=8, reward_threshold=2500.0),
     "RoboschoolWalker2d-v1": dict(
         xml="walker2d.xml", robot="torso", A=6, O=22, power=0.40, feet=["foot", "foot_left"],
         alive_rule=RS_ALIVE_Z_AND_PITCH, alive_z=0.8, alive_bonus=1.0, cost_scale=1.0,
@@ -48,7 +48,7 @@ ENV_SPECS = {
         xml="inverted_pendulum.xml", robot="cart", A=1, O=5, power=1.0, feet=[],
         alive_rule=RS_ALIVE_ALWAYS, alive_z=0.0, alive_bonus=0.0, cost_scale=1.0,
         initial_z=None, coef={"slider": 100.0}, no_floor=True, timestep=0.0165, frame_skip=1,
-        act_joints=["slider"], reward_threshold=950.0),
+        act_joints=["slider"], max_contacts=4, reward_threshold=950.0),
 }
 
 
@@ -105,6 +105,7 @@ def apply_task(m: ModelDesc, spec: dict) -> ModelDesc:
         m.arr("reset_base_quat")[:] = [0, 0, 0, 1]
         m.reset_yaw_spread = rb["yaw_spread"]
     m.max_episode_steps = 1000
+    m.max_contacts = spec.get("max_contacts", 16)
     m.meta["env_id"] = spec.get("env_id", "")
     m.meta["reward_threshold"] = spec.get("reward_threshold")
     return m

@@ -1,0 +1,104 @@
+// emul.cpp -- runs the SAME fp32 per-env code as the CUDA kernels (rs_core.cuh) on the CPU, one env
+// at a time.  Test infrastructure for the GPU-less container: lets tests/ compare the kernel
+// arithmetic with the double-precision oracle before spending GPU time.  Never used by the product.
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../roboschool_b200/csrc/rs_devmodel.h"
+
+using namespace rs;
+constexpr int NL = RS_MAX_LINKS, MC = 16;
+typedef Work<NL, MC> W_t;
+
+struct Emul {
+    DevModel M;
+    int n;
+    std::vector<W_t> w;
+    std::vector<Episode> ep;
+    std::vector<float> ws, obs, rew;
+    std::vector<int> done;
+    std::vector<StepOut> out;
+    int rec, maxr;
+};
+
+extern "C" {
+void* emul_create(const rs_model_desc* m, int n) {
+    Emul* e = new Emul();
+    const char* err = nullptr;
+    if (build_dev_model(m, &e->M, &err)) { delete e; return nullptr; }
+    e->n = n; e->w.resize(n); e->ep.resize(n); e->out.resize(n);
+    for (int i = 0; i < n; i++) { memset(&e->w[i], 0, sizeof(W_t)); e->w[i].bquat[3] = 1; memset(&e->ep[i], 0, sizeof(Episode)); e->ep[i].initial_z = e->M.initial_z; }
+    e->rec = 2 * (6 + e->M.n_dof) + R_NSCALAR; e->maxr = NL + 3 * MC;
+    e->ws.resize((size_t)e->rec * e->maxr);
+    e->obs.resize((size_t)n * e->M.obs_dim); e->rew.resize(n); e->done.resize(n);
+    return e;
+}
+void emul_destroy(void* h) { delete (Emul*)h; }
+int emul_state_dim(void* h) { Emul* e = (Emul*)h; return (e->M.fixed_base ? 0 : 13) + 2 * e->M.n_dof; }
+void emul_set_state(void* h, int env, const double* s, int clear) {
+    Emul* e = (Emul*)h; W_t& W = e->w[env];
+    if (!e->M.fixed_base) { for (int k = 0; k < 3; k++) { W.bpos[k] = (float)s[k]; W.bw[k] = (float)s[7 + k]; W.bv[k] = (float)s[10 + k]; } for (int k = 0; k < 4; k++) W.bquat[k] = (float)s[3 + k]; s += 13; }
+    for (int d = 0; d < e->M.n_dof; d++) { W.q[d] = (float)s[d]; W.qd[d] = (float)s[e->M.n_dof + d]; }
+    if (clear) { W.ccount[0] = W.ccount[1] = 0; W.cur = 0; }
+}
+void emul_get_state(void* h, int env, double* s) {
+    Emul* e = (Emul*)h; W_t& W = e->w[env];
+    if (!e->M.fixed_base) { for (int k = 0; k < 3; k++) { s[k] = W.bpos[k]; s[7 + k] = W.bw[k]; s[10 + k] = W.bv[k]; } for (int k = 0; k < 4; k++) s[3 + k] = W.bquat[k]; s += 13; }
+    for (int d = 0; d < e->M.n_dof; d++) { s[d] = W.q[d]; s[e->M.n_dof + d] = W.qd[d]; }
+}
+void emul_set_tau(void* h, int env, const double* tau) { Emul* e = (Emul*)h; for (int d = 0; d < e->M.n_dof; d++) e->w[env].tau[d] = (float)tau[d]; }
+void emul_substeps(void* h, int env, int n) {
+    Emul* e = (Emul*)h; RowWS ws{e->ws.data(), 1};
+    for (int s = 0; s < n; s++) substep(e->M, e->w[env], ws);
+}
+void emul_reset_all(void* h, uint32_t seed, uint32_t env0) {
+    Emul* e = (Emul*)h;
+    for (int i = 0; i < e->n; i++) env_reset(e->M, e->w[i], e->ep[i], seed, env0 + i, &e->obs[(size_t)i * e->M.obs_dim], 1);
+}
+void emul_set_episode(void* h, int env, double potential, double initial_z, const double* fc, int frame) {
+    Emul* e = (Emul*)h; Episode& E = e->ep[env];
+    E.potential = potential; E.initial_z = (float)initial_z; E.frame = frame;
+    for (int k = 0; k < e->M.n_feet; k++) E.feet_contact[k] = (float)fc[k];
+}
+void emul_step(void* h, const double* actions, int auto_reset, uint32_t seed, uint32_t env0) {
+    Emul* e = (Emul*)h; RowWS ws{e->ws.data(), 1};
+    const DevModel& M = e->M;
+    for (int i = 0; i < e->n; i++) {
+        float a[RS_MAX_ACT];
+        for (int k = 0; k < M.n_act; k++) a[k] = (float)actions[(size_t)i * M.n_act + k];
+        W_t& W = e->w[i];
+        apply_action(M, W, a, 1);
+        for (int s = 0; s < M.frame_skip; s++) substep(M, W, ws);
+        float* obs = &e->obs[(size_t)i * M.obs_dim];
+        epilogue(M, W, e->ep[i], a, 1, obs, 1, e->out[i]);
+        int done = e->out[i].done;
+        if (auto_reset && (done || e->ep[i].frame >= M.max_episode_steps)) { env_reset(M, W, e->ep[i], seed, env0 + i, obs, 1); done = 1; }
+        e->rew[i] = e->out[i].reward; e->done[i] = done;
+    }
+}
+void emul_get_obs(void* h, double* obs, double* rew, int* done) {
+    Emul* e = (Emul*)h;
+    for (size_t k = 0; k < e->obs.size(); k++) obs[k] = e->obs[k];
+    for (int i = 0; i < e->n; i++) { rew[i] = e->rew[i]; done[i] = e->done[i]; }
+}
+void emul_get_rewards5(void* h, int env, double* r) { Emul* e = (Emul*)h; for (int k = 0; k < 5; k++) r[k] = e->out[env].rewards5[k]; }
+int emul_get_contacts(void* h, int env, double* out, int max_pts) {
+    Emul* e = (Emul*)h; W_t& W = e->w[env]; int c = 0, slot = 0, last = -1;
+    for (int i = 0; i < W.ccount[W.cur] && c < max_pts; i++) {
+        int key = W.ckey[W.cur][i];
+        slot = key == last ? slot + 1 : 0; last = key;
+        double* o = out + c * 12; const float* d = W.cdat[W.cur][i];
+        o[0] = key; o[1] = slot; o[2] = d[9]; o[3] = d[6]; o[4] = d[7]; o[5] = d[8];
+        float pA[3]; to_world(W, key < e->M.n_geoms ? e->M.g_link[key] + 1 : e->M.g_link[e->M.pair_a[key - e->M.n_geoms]] + 1, d, pA);
+        o[6] = pA[0]; o[7] = pA[1]; o[8] = pA[2]; o[9] = 0; o[10] = 0; o[11] = 0;
+        c++;
+    }
+    return c;
+}
+void emul_counts(void* h, int env, int* rows, int* contacts) { Emul* e = (Emul*)h; *rows = e->w[env].n_rows; *contacts = e->w[env].n_contacts; }
+void emul_link_poses(void* h, int env, double* out) {
+    Emul* e = (Emul*)h; W_t& W = e->w[env];
+    kinematics(e->M, W); velocities(e->M, W);
+    for (int b = 0; b <= e->M.n_links; b++) { float p[3], q[4], v[3]; body_pose(W, b, p, q, v); double* o = out + b * 10; for (int k = 0; k < 3; k++) { o[k] = p[k]; o[7 + k] = v[k]; } for (int k = 0; k < 4; k++) o[3 + k] = q[k]; }
+}
+}
