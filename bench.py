@@ -130,7 +130,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=300)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--envs-per-gpu", type=int, default=32768)
     ap.add_argument("--env", default=ENV_ID)

@@ -70,6 +70,11 @@ int rs_world_step(rs_world* w, const float* actions_dev, float* obs_dev, float* 
 int rs_world_step_stats(rs_world* w, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
                         int auto_reset, double* stats_dev, void* stream);
 
+/* Profiling twin of rs_world_step (auto_reset on): also returns clock64() warp-cycle totals per phase in
+ * cycles_host[8] = {kinematics, collide, aba, solve, integrate, epilogue+store, load+apply_action, total}. */
+int rs_world_step_profile(rs_world* w, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+                          unsigned long long* cycles_host, void* stream);
+
 /* Same call for callers holding HOST buffers (the reference's calling convention: numpy in, numpy
  * out): copies actions H2D, steps, copies obs/reward/done D2H on the world's stream and waits. */
 int rs_world_step_host(rs_world* w, const float* actions_host, float* obs_host, float* reward_host,

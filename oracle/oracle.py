@@ -55,6 +55,7 @@ def lib():
         L.oracle_counts.argtypes = [P, I, ip, ip]
         L.oracle_energy.argtypes = [P, I]
         L.oracle_energy.restype = D
+        L.oracle_foot_flags.argtypes = [P, I, ip, ip]
         L.oracle_hash.argtypes = [U, U, U, U]
         L.oracle_hash.restype = U
         _LIB = L
@@ -153,6 +154,12 @@ class OracleWorld:
         a, b = ctypes.c_int(), ctypes.c_int()
         self.L.oracle_counts(self.h, env, ctypes.byref(a), ctypes.byref(b))
         return a.value, b.value
+
+    def foot_flags(self, env):
+        g = np.zeros(8, dtype=np.int32)
+        o = np.zeros(8, dtype=np.int32)
+        self.L.oracle_foot_flags(self.h, env, _ip(g), _ip(o))
+        return g[:self.model.n_feet].copy(), o[:self.model.n_feet].copy()
 
     def energy(self, env):
         return self.L.oracle_energy(self.h, env)

@@ -892,12 +892,9 @@ static void epilogue(const rs_model_desc *m, oenv *e, const double *a) {
     }
     int A = m->n_act;
     double s1 = 0, s2 = 0;
-    for (int k = 0; k < A; k++) { double sp = e->obs[8 + 2 * k + 1]; /* joint_speeds are pre-clip in the reference */
-        s1 += fabs(a[k] * sp); s2 += a[k] * a[k]; }
-    (void)s1;
-    /* joint_speeds = j[1::2] BEFORE np.clip: recompute unclipped */
-    s1 = 0;
+    /* joint_speeds = j[1::2] is taken BEFORE np.clip (gym_forward_walker.py:49,76) */
     for (int k = 0; k < A; k++) {
+        s2 += a[k] * a[k];
         int d = m->act_dof[k], li = -1;
         for (int i = 0; i < m->n_links; i++) if (m->dof_idx[i] == d) li = i;
         float spd = (float)e->qd[d];
@@ -1080,5 +1077,8 @@ double oracle_energy(oracle_world *w, int env) {
         E += mass * m->gravity * e->pos[b][2];
     }
     return E;
+}
+void oracle_foot_flags(const oracle_world *w, int env, int *ground, int *other) {
+    for (int f = 0; f < w->m.n_feet; f++) foot_contacts(&w->m, &w->env[env], f, &ground[f], &other[f]);
 }
 uint32_t oracle_hash(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return rs_hash(a, b, c, d); }

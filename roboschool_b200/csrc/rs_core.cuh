@@ -879,14 +879,31 @@ RS_HD void integrate(const DevModel& M, Work<NL, MC>& W, float dt) {
     for (int d = 0; d < M.n_dof; d++) W.q[d] += dt * W.qd[d];
 }
 
+// optional per-phase cycle accounting (profiling build of the step kernel only)
+struct PhaseClock {
+    long long t[6];   // kinematics, collide, aba, solve, integrate, (epilogue)
+};
+#if defined(__CUDA_ARCH__)
+#define RS_CLOCK() clock64()
+#else
+#define RS_CLOCK() 0LL
+#endif
+
 template <int NL, int MC>
-RS_HD void substep(const DevModel& M, Work<NL, MC>& W, const RowWS& ws) {
+RS_HD void substep(const DevModel& M, Work<NL, MC>& W, const RowWS& ws, PhaseClock* pc = nullptr) {
     float dt = M.timestep;
+    long long c0 = 0, c1 = 0;
+    if (pc) c0 = RS_CLOCK();
     kinematics(M, W);
+    if (pc) { c1 = RS_CLOCK(); pc->t[0] += c1 - c0; c0 = c1; }
     collide(M, W);
+    if (pc) { c1 = RS_CLOCK(); pc->t[1] += c1 - c0; c0 = c1; }
     aba(M, W, dt);
+    if (pc) { c1 = RS_CLOCK(); pc->t[2] += c1 - c0; c0 = c1; }
     solve(M, W, dt, ws);
+    if (pc) { c1 = RS_CLOCK(); pc->t[3] += c1 - c0; c0 = c1; }
     integrate(M, W, dt);
+    if (pc) { c1 = RS_CLOCK(); pc->t[4] += c1 - c0; }
 }
 
 // ---------------------------------------------------------------------------------------------

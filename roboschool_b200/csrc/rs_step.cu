@@ -158,6 +158,42 @@ __global__ void __launch_bounds__(64) k_step(const __grid_constant__ DevModel M,
     }
 }
 
+// Profiling twin of k_step: same work, plus clock64() deltas per phase summed over threads into cyc[8].
+template <int NL, int MC>
+__global__ void __launch_bounds__(64) k_step_prof(const __grid_constant__ DevModel M, const DevBuf B, const float* __restrict__ actions,
+                                                  float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
+                                                  uint32_t seed, uint32_t env_id0, unsigned long long* __restrict__ cyc) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B.N) return;
+    Work<NL, MC> W;
+    Episode E;
+    long long t0 = clock64();
+    load_env(M, B, e, W, E);
+    float a[MA];
+    for (int k = 0; k < M.n_act; k++) a[k] = actions[(size_t)e * M.n_act + k];
+    apply_action(M, W, a, 1);
+    RowWS ws{B.rows + e, B.N};
+    PhaseClock pc;
+    for (int k = 0; k < 6; k++) pc.t[k] = 0;
+    long long t1 = clock64();
+    for (int s = 0; s < M.frame_skip; s++) substep(M, W, ws, &pc);
+    long long t2 = clock64();
+    float* o = obs + (size_t)e * M.obs_dim;
+    StepOut out;
+    epilogue(M, W, E, a, 1, o, 1, out);
+    int dn = out.done;
+    if (dn || E.frame >= M.max_episode_steps) { env_reset(M, W, E, seed, env_id0 + e, o, 1); dn = 1; }
+    rew[e] = out.reward; done[e] = (uint8_t)dn;
+    store_env(M, B, e, W, E);
+    long long t3 = clock64();
+    if ((threadIdx.x & 31) == 0) {   // one lane per warp: warp-level cycles
+        for (int k = 0; k < 5; k++) atomicAdd(cyc + k, (unsigned long long)pc.t[k]);
+        atomicAdd(cyc + 5, (unsigned long long)(t3 - t2));
+        atomicAdd(cyc + 6, (unsigned long long)(t1 - t0));
+        atomicAdd(cyc + 7, (unsigned long long)(t3 - t0));
+    }
+}
+
 template <int NL, int MC>
 __global__ void __launch_bounds__(64) k_reset(const __grid_constant__ DevModel M, const DevBuf B, const uint8_t* __restrict__ mask,
                                               float* __restrict__ obs, uint32_t seed, uint32_t env_id0) {
@@ -333,6 +369,24 @@ extern "C" int rs_world_step_stats(rs_world* w, const float* actions_dev, float*
     if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail("rs_world_step_stats: null buffer");
     CK(cudaSetDevice(w->device));
     return launch_step(w, actions_dev, obs_dev, reward_dev, done_dev, auto_reset, w->rollout_seed, w->env_id0, stats_dev, (cudaStream_t)stream);
+}
+
+// profiling: one step with per-phase warp-cycle totals -> cycles_host[8]
+// [kinematics, collide, aba, solve, integrate, epilogue+store, load+apply_action, total]
+extern "C" int rs_world_step_profile(rs_world* w, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+                                     unsigned long long* cycles_host, void* stream) {
+    CK(cudaSetDevice(w->device));
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc(&d, 8 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), (cudaStream_t)stream));
+    FAMILY_DISPATCH(w, (k_step_prof<NL, MC><<<nblocks(w->n), 64, 0, (cudaStream_t)stream>>>(w->M, w->B, actions_dev, obs_dev, reward_dev, done_dev,
+                                                                                          w->rollout_seed, w->env_id0, d)));
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaMemcpy(cycles_host, d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(std::string("rs_world_step_profile: ") + cudaGetErrorString(e));
+    return 0;
 }
 
 extern "C" int rs_world_step_host(rs_world* w, const float* actions_host, float* obs_host, float* reward_host, uint8_t* done_host,

@@ -1,0 +1,139 @@
+"""CPU tests of the oracle: closed-form physics, the reference-Python golden vectors for the
+epilogue, the MLP known answers, and the behavioural fixture (zoo policy walks)."""
+import os
+
+import numpy as np
+import pytest
+
+from roboschool_b200 import envspec
+from roboschool_b200.policy import load_zoo_weights
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_free_fall_closed_form(oracle_lib):
+    m = envspec.load_env_model("RoboschoolAnt-v1").clone()
+    m.lin_damping = 0; m.ang_damping = 0
+    w = oracle_lib.OracleWorld(m, 1)
+    w.reset(seed=1)
+    z0 = w.get_state(0)[2]
+    n = 20
+    w.substeps(0, n)
+    s = w.get_state(0)
+    t, h = n * m.timestep, m.timestep
+    # semi-implicit Euler: v_n = -g t ; z_n = z0 - g h^2 n(n+1)/2
+    assert abs(s[12] + m.gravity * t) < 1e-12
+    assert abs(s[2] - (z0 - m.gravity * h * h * n * (n + 1) / 2)) < 1e-12
+    assert np.abs(s[7:10]).max() < 1e-12   # no spurious rotation
+
+
+def test_pendulum_energy_first_order(oracle_lib):
+    """Energy error of the undamped cart-pole shrinks ~linearly with dt (semi-implicit Euler)."""
+    errs = []
+    for div in (1, 4, 16):
+        m = envspec.load_env_model("RoboschoolInvertedPendulum-v1").clone()
+        m.lin_damping = 0; m.ang_damping = 0; m.timestep = m.timestep / div
+        w = oracle_lib.OracleWorld(m, 1)
+        w.set_state(0, np.array([0.0, 1.0, 0.0, 0.0]))
+        e0 = w.energy(0)
+        w.substeps(0, 60 * div)
+        errs.append(abs(w.energy(0) - e0))
+    assert errs[1] < errs[0] / 2.5 and errs[2] < errs[1] / 2.5
+
+
+def test_momentum_and_energy_converge_in_free_flight(oracle_lib):
+    """Floating 19-link humanoid tumbling with internal joint motion, g=0, no damping/limits/contacts:
+    linear momentum and kinetic energy are invariants of the continuous dynamics, so their drift under
+    the semi-implicit integrator must shrink ~linearly with dt (checks ABA, Coriolis and bias terms)."""
+    dp, dE = [], []
+    for div in (1, 4, 16):
+        m = envspec.load_env_model("RoboschoolHumanoid-v1").clone()
+        m.lin_damping = 0; m.ang_damping = 0; m.gravity = 0.0; m.has_floor = 0; m.n_pairs = 0
+        m.timestep = m.timestep / div
+        for g in range(m.n_geoms):
+            m.g_floor[g] = 0
+        for i in range(m.n_links):
+            m.has_limit[i] = 0
+        w = oracle_lib.OracleWorld(m, 1)
+        w.reset(seed=2)
+        s = w.get_state(0)
+        rng = np.random.RandomState(0)
+        s[13 + 17:] = rng.uniform(-3, 3, 17)
+        s[7:13] = rng.uniform(-1, 1, 6)
+        w.set_state(0, s)
+        mass = np.array([m.base_mass] + [m.mass[i] for i in range(m.n_links)])
+        p0 = (mass[:, None] * w.link_poses(0)[:, 7:10]).sum(0)
+        e0 = w.energy(0)
+        w.substeps(0, 80 * div)
+        dp.append(np.abs((mass[:, None] * w.link_poses(0)[:, 7:10]).sum(0) - p0).max())
+        dE.append(abs(w.energy(0) - e0))
+    assert dp[1] < dp[0] / 3 and dp[2] < dp[1] / 3, dp
+    assert dE[1] < dE[0] / 3 and dE[2] < dE[1] / 3, dE
+
+
+def test_determinism_and_thread_independence(oracle_lib):
+    m = envspec.load_env_model("RoboschoolHopper-v1")
+    a = np.random.RandomState(0).uniform(-1, 1, (30, 8, 3))
+    outs = []
+    for threads in (1, 4):
+        w = oracle_lib.OracleWorld(m, 8)
+        w.reset(seed=5)
+        for t in range(30):
+            obs, rew, done = w.step(a[t], threads=threads)
+        outs.append((obs.copy(), w.get_state().copy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("env_id", ["RoboschoolHopper-v1", "RoboschoolAnt-v1", "RoboschoolHumanoid-v1"])
+def test_epilogue_matches_reference_python(env_id, oracle_lib):
+    """Golden vectors made by the reference's own gym_forward_walker.py (tools/gen_golden_epilogue.py)."""
+    g = np.load(os.path.join(GOLDEN, "epilogue_%s.npz" % env_id))
+    m = envspec.load_env_model(env_id)
+    w = oracle_lib.OracleWorld(m, 1)
+    w.reset(seed=int(g["seed"]))
+    assert np.abs(w.obs()[0][0] - g["ref_obs0"]).max() < 1e-6
+    nd = m.n_dof
+    for t in range(g["actions"].shape[0]):
+        obs, rew, done = w.step(g["actions"][t:t + 1])
+        s = w.get_state(0)
+        # the replayed trajectory must be the one the fixture was recorded from
+        assert np.abs(s[-2 * nd:-nd] - g["q"][t + 1]).max() < 1e-9, "fixture stale: rerun tools/gen_golden_epilogue.py"
+        assert np.abs(obs[0] - g["ref_obs"][t]).max() < 1e-6
+        assert abs(rew[0] - g["ref_rew"][t]) < 1e-6
+        assert bool(done[0]) == bool(g["ref_done"][t])
+        assert np.abs(w.rewards5(0) - g["ref_rewards5"][t]).max() < 1e-6
+
+
+def test_mlp_known_answers(oracle_lib):
+    """known answers computed from the shipped .weights files."""
+    f = oracle_lib.mlp_forward
+    w = load_zoo_weights("RoboschoolHopper-v1")
+    assert np.allclose(f(w, np.zeros(15)), [-0.1601551671, 0.2929517778, -0.7377750787], atol=1e-9)
+    X = np.random.RandomState(12345).uniform(-1, 1, (4, 15))
+    assert np.allclose(f(w, X)[0], [0.8471205376, -3.6975331127, 0.4903137045], atol=1e-9)
+    assert abs(f(w, X).sum() - 9.62946452367964) < 1e-9
+    w = load_zoo_weights("RoboschoolAnt-v1")
+    X = np.random.RandomState(12345).uniform(-1, 1, (4, 28))
+    assert abs(f(w, X).sum() + 29.475036116473614) < 1e-9
+    w = load_zoo_weights("RoboschoolHumanoid-v1")
+    assert np.allclose(f(w, np.zeros(44))[:6], [-0.296643717, 1.0570575815, -0.0424037259, 0.3779573418, 0.4688812382, 0.9736019632], atol=1e-9)
+    X = np.random.RandomState(12345).uniform(-1, 1, (4, 44))
+    assert abs(f(w, X).sum() - 16.448666567345803) < 1e-9
+
+
+def test_behavioural_fixture_humanoid_walks(oracle_lib):
+    """The reference's pretrained Humanoid policy (trained on the Bullet path) must keep walking on the
+    restated physics: reward_threshold 3500 per 1000 steps (roboschool/__init__.py:71-77)."""
+    m = envspec.load_env_model("RoboschoolHumanoid-v1")
+    wts = load_zoo_weights("RoboschoolHumanoid-v1")
+    n = 8
+    w = oracle_lib.OracleWorld(m, n)
+    w.reset(seed=1)
+    obs = w.obs()[0]
+    tot = np.zeros(n); alive = np.ones(n, bool)
+    for t in range(1000):
+        obs, rew, done = w.step(oracle_lib.mlp_forward(wts, obs), threads=4)
+        tot += rew * alive
+        alive &= ~done.astype(bool)
+    assert alive.all(), "humanoid fell"
+    assert tot.min() > 3500.0, tot
