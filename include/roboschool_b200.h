@@ -45,6 +45,8 @@ int rs_world_create(const rs_model_desc* model, int n_envs, int device, rs_world
 int rs_world_destroy(rs_world* w);
 
 int rs_world_n_envs(const rs_world* w);
+/* 0: runtime-topology step kernel; >0: step kernel specialised on a generated compile-time topology */
+int rs_world_kernel_variant(const rs_world* w);
 int rs_world_state_dim(const rs_world* w);
 int rs_world_obs_dim(const rs_world* w);
 int rs_world_act_dim(const rs_world* w);

@@ -240,18 +240,18 @@ RS_HD float rs_uniform(uint32_t seed, uint32_t env, uint32_t episode, uint32_t k
 // ---------------------------------------------------------------------------------------------
 // per-thread working set.  NL/MC are capacities chosen per model family at launch.
 // ---------------------------------------------------------------------------------------------
-template <int NL, int MC>
+template <int NL, int MC, bool SL = false>   // SL ("slim"): the static-topology path keeps the link cache in shared memory
 struct Work {
     // generalized state
     float bpos[3], bquat[4], bw[3], bv[3];
     float q[NL], qd[NL], tau[NL];
     // kinematics (valid after kinematics())
-    float Rpl[NL][9], rvec[NL][3];
+    float Rpl[SL ? 1 : NL][9], rvec[SL ? 1 : NL][3];
     float Rwl[NL + 1][9], pos[NL + 1][3];
     // ABA cache for the unit-impulse response passes
-    float h[NL][6], invD[NL];
+    float h[SL ? 1 : NL][6], invD[SL ? 1 : NL];
     float Lb[21];
-    float vel[NL + 1][6];
+    float vel[SL ? 1 : NL + 1][6];
     // live contact points, double buffered (old list -> new list every sub-step)
     int ckey[2][MC];             // manifold id (floor: geom index ; self pair: n_geoms + pair index)
     float cdat[2][MC][CDAT];
@@ -266,14 +266,14 @@ struct RowWS {
     int stride;    // distance (floats) between consecutive elements of one thread's record
     RS_HD float& at(int row, int rec, int k) const { return p[(size_t)(row * rec + k) * stride]; }
 };
-// record layout: [0,nd) J ; [nd,2nd) unit response ; then the scalars below
-enum { R_RHS = 0, R_INVD, R_LO, R_HI, R_APPLIED, R_FRIC, R_FIDX, R_NSCALAR };
+// record layout: [0,nd) J ; [nd,2nd) unit response M^-1 J^T   (row scalars stay thread-private)
+enum { R_NSCALAR = 0 };
 
 // ---------------------------------------------------------------------------------------------
 // kinematics: rot_from_parent / cachedRVector / world transforms     (btMultiBody, forwardKinematics)
 // ---------------------------------------------------------------------------------------------
-template <int NL, int MC>
-RS_HD void kinematics(const DevModel& M, Work<NL, MC>& W) {
+template <int NL, int MC, bool SL>
+RS_HD void kinematics(const DevModel& M, Work<NL, MC, SL>& W) {
     float Rbw[9];
     quat_to_mat(Rbw, W.bquat[0], W.bquat[1], W.bquat[2], W.bquat[3]);
 #pragma unroll
@@ -311,8 +311,8 @@ RS_HD void kinematics(const DevModel& M, Work<NL, MC>& W) {
     }
 }
 
-template <int NL, int MC>
-RS_HD void velocities(const DevModel& M, Work<NL, MC>& W) {
+template <int NL, int MC, bool SL>
+RS_HD void velocities(const DevModel& M, Work<NL, MC, SL>& W) {
     if (M.fixed_base) {
 #pragma unroll
         for (int k = 0; k < 6; k++) W.vel[0][k] = 0;
@@ -329,8 +329,8 @@ RS_HD void velocities(const DevModel& M, Work<NL, MC>& W) {
     }
 }
 
-template <int NL, int MC>
-RS_HD void clamp_vel(const DevModel& M, Work<NL, MC>& W) {
+template <int NL, int MC, bool SL>
+RS_HD void clamp_vel(const DevModel& M, Work<NL, MC, SL>& W) {
     float c = M.max_coord_vel;
     if (!M.fixed_base) {
 #pragma unroll
@@ -342,8 +342,8 @@ RS_HD void clamp_vel(const DevModel& M, Work<NL, MC>& W) {
 // ---------------------------------------------------------------------------------------------
 // btMultiBody::computeAccelerationsArticulatedBodyAlgorithmMultiDof + applyDeltaVeeMultiDof(dt)
 // ---------------------------------------------------------------------------------------------
-template <int NL, int MC>
-RS_HD void aba(const DevModel& M, Work<NL, MC>& W, float dt) {
+template <int NL, int MC, bool SL>
+RS_HD void aba(const DevModel& M, Work<NL, MC, SL>& W, float dt) {
     const int n = M.n_links;
     float IA[NL + 1][21];
     float Z[NL + 1][6], c[NL][6], Y[NL];
@@ -465,9 +465,9 @@ RS_HD void aba(const DevModel& M, Work<NL, MC>& W, float dt) {
 // articulated-body corrections; the second sweep distributes accelerations.  jtau: optional
 // generalized joint force (limit rows).  J and u are ACCUMULATED into the row record.
 // ---------------------------------------------------------------------------------------------
-template <int NL, int MC>
-RS_HD float row_response(const DevModel& M, const Work<NL, MC>& W, int body, const float* wrench, int jdof, float jdir,
-                         const RowWS& ws, int row, int rec, bool first) {
+template <int NL, int MC, bool SL>
+RS_HD float row_response(const DevModel& M, const Work<NL, MC, SL>& W, int body, const float* wrench, int jdof, float jdir,
+                         const RowWS& ws, int row, int rec, bool first, const float* vel, float* relvel) {
     const int n = M.n_links, nd = 6 + M.n_dof;
     float F[NL + 1][6], Z[NL + 1][6], Y[NL];
     for (int b = 0; b <= n; b++) {
@@ -494,6 +494,7 @@ RS_HD float row_response(const DevModel& M, const Work<NL, MC>& W, int body, con
             for (int k = 0; k < 6; k++) Zt[k] += W.h[i][k] * kk;
             float& J = ws.at(row, rec, 6 + d);
             J = first ? j : J + j;
+            *relvel += j * vel[6 + d];
         } else Y[i] = 0;
         xf_force_inv_add(Z[p + 1], W.Rpl[i], W.rvec[i], Zt);
         xf_force_inv_add(F[p + 1], W.Rpl[i], W.rvec[i], F[i + 1]);
@@ -517,6 +518,7 @@ RS_HD float row_response(const DevModel& M, const Work<NL, MC>& W, int body, con
             if (first) { J0 = jw[k]; J1 = jv[k]; U0 = uw[k]; U1 = uv[k]; }
             else { J0 += jw[k]; J1 += jv[k]; U0 += uw[k]; U1 += uv[k]; }
             denom += jw[k] * uw[k] + jv[k] * uv[k];
+            *relvel += jw[k] * vel[k] + jv[k] * vel[3 + k];
         }
     }
     for (int i = 0; i < n; i++) {
@@ -537,8 +539,8 @@ RS_HD float row_response(const DevModel& M, const Work<NL, MC>& W, int body, con
 }
 
 // wrench of a unit force along `dir` applied at world point `p`, in body b's coordinates about its COM
-template <int NL, int MC>
-RS_HD void unit_wrench(const Work<NL, MC>& W, int b, const float* p, const float* dir, float* out) {
+template <int NL, int MC, bool SL>
+RS_HD void unit_wrench(const Work<NL, MC, SL>& W, int b, const float* p, const float* dir, float* out) {
     float rw[3] = {p[0] - W.pos[b][0], p[1] - W.pos[b][1], p[2] - W.pos[b][2]}, rl[3], nl[3];
     mulv(rl, W.Rwl[b], rw); mulv(nl, W.Rwl[b], dir);
     cross3(out, rl, nl);
@@ -549,13 +551,13 @@ RS_HD void unit_wrench(const Work<NL, MC>& W, int b, const float* p, const float
 // narrowphase + persistent manifolds (btConvexPlaneCollisionAlgorithm, GJK-equivalent closest
 // points for sphere/capsule pairs, btPersistentManifold add/replace/refresh)
 // ---------------------------------------------------------------------------------------------
-template <int NL, int MC>
-RS_HD void to_world(const Work<NL, MC>& W, int b, const float* l, float* w) {
+template <int NL, int MC, bool SL>
+RS_HD void to_world(const Work<NL, MC, SL>& W, int b, const float* l, float* w) {
     float t[3]; tmulv(t, W.Rwl[b], l);
     w[0] = W.pos[b][0] + t[0]; w[1] = W.pos[b][1] + t[1]; w[2] = W.pos[b][2] + t[2];
 }
-template <int NL, int MC>
-RS_HD void to_local(const Work<NL, MC>& W, int b, const float* w, float* l) {
+template <int NL, int MC, bool SL>
+RS_HD void to_local(const Work<NL, MC, SL>& W, int b, const float* w, float* l) {
     float t[3] = {w[0] - W.pos[b][0], w[1] - W.pos[b][1], w[2] - W.pos[b][2]};
     mulv(l, W.Rwl[b], t);
 }
@@ -611,8 +613,8 @@ RS_HD int sort_cached_points(const Manifold4& mf, const float* np) {
     return best;
 }
 
-template <int NL, int MC>
-RS_HD void manifold_add(Manifold4& mf, const Work<NL, MC>& W, int bA, int bB, const float* n, const float* pOnB, float depth, float thresh) {
+template <int NL, int MC, bool SL>
+RS_HD void manifold_add(Manifold4& mf, const Work<NL, MC, SL>& W, int bA, int bB, const float* n, const float* pOnB, float depth, float thresh) {
     if (depth > thresh) return;
     float np[CDAT];
     float pA[3] = {pOnB[0] + n[0] * depth, pOnB[1] + n[1] * depth, pOnB[2] + n[2] * depth};
@@ -635,8 +637,8 @@ RS_HD void manifold_add(Manifold4& mf, const Work<NL, MC>& W, int bA, int bB, co
     }
 }
 
-template <int NL, int MC>
-RS_HD void manifold_refresh(Manifold4& mf, const Work<NL, MC>& W, int bA, int bB, float thresh) {
+template <int NL, int MC, bool SL>
+RS_HD void manifold_refresh(Manifold4& mf, const Work<NL, MC, SL>& W, int bA, int bB, float thresh) {
     bool rem[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -671,8 +673,8 @@ RS_HD void manifold_refresh(Manifold4& mf, const Work<NL, MC>& W, int bA, int bB
     }
 }
 
-template <int NL, int MC>
-RS_HD void collide(const DevModel& M, Work<NL, MC>& W) {
+template <int NL, int MC, bool SL>
+RS_HD void collide(const DevModel& M, Work<NL, MC, SL>& W) {
     const int old = W.cur, nw = 1 - W.cur;
     int oi = 0, no = 0;
     const int nold = W.ccount[old];
@@ -741,49 +743,61 @@ RS_HD void collide(const DevModel& M, Work<NL, MC>& W) {
 // constraint rows + projected Gauss-Seidel (btMultiBodyConstraintSolver), Bullet's row order:
 // per iteration: non-contact rows (alternating direction), normal rows, friction rows.
 // ---------------------------------------------------------------------------------------------
-template <int NL, int MC>
-RS_HD void resolve_row(const RowWS& ws, int row, int rec, int nd, float* dv) {
+// resolveSingleConstraintRowGeneric.  All 2*nd loads of the row are issued back to back (independent
+// addresses) before the first use, so the workspace latency is paid once per row, not once per element.
+template <int NDMAX>
+RS_HD void resolve_row(const RowWS& ws, int row, int rec, int nd, float* dv, float rhs, float invd, float lo, float hi, float& applied) {
+    float j[NDMAX], u[NDMAX];
+#pragma unroll
+    for (int k = 0; k < NDMAX; k++) { j[k] = 0.f; u[k] = 0.f; if (k < nd) { j[k] = ws.at(row, rec, k); u[k] = ws.at(row, rec, nd + k); } }
     float dot = 0.f;
-    for (int k = 0; k < nd; k++) dot += ws.at(row, rec, k) * dv[k];
-    float invd = ws.at(row, rec, 2 * nd + R_INVD);
-    float dimp = ws.at(row, rec, 2 * nd + R_RHS) - dot * invd;
-    float& applied = ws.at(row, rec, 2 * nd + R_APPLIED);
-    float lo = ws.at(row, rec, 2 * nd + R_LO), hi = ws.at(row, rec, 2 * nd + R_HI);
+#pragma unroll
+    for (int k = 0; k < NDMAX; k++) dot += j[k] * dv[k];
+    float dimp = rhs - dot * invd;
     float sum = applied + dimp;
     if (sum < lo) { dimp = lo - applied; applied = lo; }
     else if (sum > hi) { dimp = hi - applied; applied = hi; }
     else applied = sum;
-    for (int k = 0; k < nd; k++) dv[k] += ws.at(row, rec, nd + k) * dimp;
+#pragma unroll
+    for (int k = 0; k < NDMAX; k++) dv[k] += u[k] * dimp;
 }
 
-template <int NL, int MC>
-RS_HD void solve(const DevModel& M, Work<NL, MC>& W, float dt, const RowWS& ws) {
-    const int nd = 6 + M.n_dof, rec = 2 * nd + R_NSCALAR;
+// `resp(body, wrench, jdof, jdir, row, rec, first) -> denom` fills J / M^-1 J^T of a row (generic or static sweeps)
+template <int NL, int MC, bool SL, class Resp>
+RS_HD void solve_with(const DevModel& M, Work<NL, MC, SL>& W, float dt, const RowWS& ws, Resp&& resp) {
+    constexpr int NDMAX = 6 + NL;
+    const int nd = 6 + M.n_dof, rec = 2 * nd;
     const int NC0 = 0, CN0 = NL, CF0 = NL + MC;    // row-index bases of the three groups
     int n_nc = 0, n_cn = 0, n_cf = 0;
-    float vel[6 + NL];
+    // row scalars stay thread-private; only J and M^-1 J^T (2*nd floats per row) go to the workspace
+    float r_rhs[NL + 3 * MC], r_invd[NL + 3 * MC], r_applied[NL + 3 * MC], r_hi[NL];
+    float vel[NDMAX];
 #pragma unroll
-    for (int k = 0; k < 3; k++) { vel[k] = M.fixed_base ? 0.f : W.bw[k]; vel[3 + k] = M.fixed_base ? 0.f : W.bv[k]; }
-    for (int d = 0; d < M.n_dof; d++) vel[6 + d] = W.qd[d];
+    for (int k = 0; k < NDMAX; k++) vel[k] = 0.f;
+    if (!M.fixed_base) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { vel[k] = W.bw[k]; vel[3 + k] = W.bv[k]; }
+    }
+#pragma unroll
+    for (int d = 0; d < NL; d++) if (d < M.n_dof) vel[6 + d] = W.qd[d];
     const float inv_dt = 1.0f / dt;
     // joint limits: rows only when violated (btMultiBodyJointLimitConstraint::createConstraintRows)
     for (int i = 0; i < M.n_links; i++) {
         int d = M.dof_idx[i];
         if (!M.has_limit[i] || d < 0) continue;
+        float q = W.q[d];
 #pragma unroll
         for (int side = 0; side < 2; side++) {
-            float pen = side == 0 ? W.q[d] - M.lim_lo[i] : M.lim_hi[i] - W.q[d];
+            float pen = side == 0 ? q - M.lim_lo[i] : M.lim_hi[i] - q;
             if (pen > 0.f) continue;
             float dir = side == 0 ? 1.f : -1.f;
             int row = NC0 + n_nc++;
-            float denom = row_response(M, W, -1, nullptr, d, dir, ws, row, rec, true);
+            float relvel = 0.f;
+            float denom = resp(-1, (const float*)nullptr, d, dir, row, rec, true, (const float*)vel, &relvel);
             float invd = denom > RS_FLT_EPS ? 1.0f / denom : 0.f;
-            float relvel = dir * vel[6 + d];
             float erp = pen > M.split_thresh ? M.erp : M.erp2;
-            float rhs = pen > M.split_thresh ? (-pen * erp * inv_dt - relvel) * invd : (-relvel) * invd;
-            ws.at(row, rec, 2 * nd + R_RHS) = rhs; ws.at(row, rec, 2 * nd + R_INVD) = invd;
-            ws.at(row, rec, 2 * nd + R_LO) = 0.f; ws.at(row, rec, 2 * nd + R_HI) = M.max_limit_impulse;
-            ws.at(row, rec, 2 * nd + R_APPLIED) = 0.f;
+            r_rhs[row] = pen > M.split_thresh ? (-pen * erp * inv_dt - relvel) * invd : (-relvel) * invd;
+            r_invd[row] = invd; r_applied[row] = 0.f; r_hi[row] = M.max_limit_impulse;
         }
     }
     // contacts in pool order (manifold id, slot)
@@ -791,58 +805,61 @@ RS_HD void solve(const DevModel& M, Work<NL, MC>& W, float dt, const RowWS& ws) 
     for (int ci = 0; ci < nc; ci++) {
         int key = W.ckey[cur][ci];
         const float* cd = W.cdat[cur][ci];
-        int bA, bB; float fric;
-        if (key < M.n_geoms) { bA = M.g_link[key] + 1; bB = -1; fric = M.g_fric_floor[key]; }
-        else { int pk = key - M.n_geoms; bA = M.g_link[M.pair_a[pk]] + 1; bB = M.g_link[M.pair_b[pk]] + 1; fric = M.pair_friction[pk]; }
+        int bA, bB;
+        if (key < M.n_geoms) { bA = M.g_link[key] + 1; bB = -1; }
+        else { int pk = key - M.n_geoms; bA = M.g_link[M.pair_a[pk]] + 1; bB = M.g_link[M.pair_b[pk]] + 1; }
         float pA[3], pB[3];
         to_world(W, bA, cd, pA);
         if (bB >= 0) to_world(W, bB, cd + 3, pB);
         float dirs[3][3];
         dirs[0][0] = cd[6]; dirs[0][1] = cd[7]; dirs[0][2] = cd[8];
         plane_space(dirs[0], dirs[1], dirs[2]);
-        int nrow = CN0 + n_cn;
+#pragma unroll
         for (int w = 0; w < 3; w++) {
-            int row = (w == 0) ? CN0 + n_cn++ : CF0 + n_cf++;
-            float wr[6];
+            int row = (w == 0) ? CN0 + n_cn : CF0 + 2 * n_cn + (w - 1);
+            float wr[6], relvel = 0.f;
             unit_wrench(W, bA, pA, dirs[w], wr);
-            float denom = row_response(M, W, bA, wr, -1, 0.f, ws, row, rec, true);
+            float denom = resp(bA, (const float*)wr, -1, 0.f, row, rec, true, (const float*)vel, &relvel);
             if (bB >= 0) {
                 float nneg[3] = {-dirs[w][0], -dirs[w][1], -dirs[w][2]};
                 unit_wrench(W, bB, pB, nneg, wr);
-                denom += row_response(M, W, bB, wr, -1, 0.f, ws, row, rec, false);
+                denom += resp(bB, (const float*)wr, -1, 0.f, row, rec, false, (const float*)vel, &relvel);
             }
             float invd = denom > RS_FLT_EPS ? 1.0f / denom : 0.f;
-            float relvel = 0.f;
-            for (int k = 0; k < nd; k++) relvel += ws.at(row, rec, k) * vel[k];
-            float rhs, lo, hi;
+            float rhs;
             if (w == 0) {
                 float pen = cd[9];
                 float erp = pen > M.split_thresh ? M.erp : M.erp2;
                 float posErr = 0.f, velErr = -relvel;
                 if (pen > 0.f) velErr -= pen * inv_dt; else posErr = -pen * erp * inv_dt;
                 rhs = pen > M.split_thresh ? (posErr + velErr) * invd : velErr * invd;
-                lo = 0.f; hi = 1e10f;
-            } else { rhs = -relvel * invd; lo = -fric; hi = fric; }
-            ws.at(row, rec, 2 * nd + R_RHS) = rhs; ws.at(row, rec, 2 * nd + R_INVD) = invd;
-            ws.at(row, rec, 2 * nd + R_LO) = lo; ws.at(row, rec, 2 * nd + R_HI) = hi;
-            ws.at(row, rec, 2 * nd + R_APPLIED) = 0.f; ws.at(row, rec, 2 * nd + R_FRIC) = fric;
-            ws.at(row, rec, 2 * nd + R_FIDX) = (float)nrow;
+            } else rhs = -relvel * invd;
+            r_rhs[row] = rhs; r_invd[row] = invd; r_applied[row] = 0.f;
         }
+        n_cn++;
     }
+    n_cf = 2 * n_cn;
     W.n_rows = n_nc + n_cn + n_cf; W.n_contacts = n_cn;
     if (W.n_rows == 0) return;
-    float dv[6 + NL];
-    for (int k = 0; k < nd; k++) dv[k] = 0.f;
+    float dv[NDMAX];
+#pragma unroll
+    for (int k = 0; k < NDMAX; k++) dv[k] = 0.f;
     for (int it = 0; it < M.n_iter; it++) {
-        for (int j = 0; j < n_nc; j++) { int idx = (it & 1) ? j : n_nc - 1 - j; resolve_row<NL, MC>(ws, NC0 + idx, rec, nd, dv); }
-        for (int j = 0; j < n_cn; j++) resolve_row<NL, MC>(ws, CN0 + j, rec, nd, dv);
+        for (int j = 0; j < n_nc; j++) {
+            int row = NC0 + ((it & 1) ? j : n_nc - 1 - j);
+            resolve_row<NDMAX>(ws, row, rec, nd, dv, r_rhs[row], r_invd[row], 0.f, r_hi[row], r_applied[row]);
+        }
+        for (int j = 0; j < n_cn; j++) {
+            int row = CN0 + j;
+            resolve_row<NDMAX>(ws, row, rec, nd, dv, r_rhs[row], r_invd[row], 0.f, 1e10f, r_applied[row]);
+        }
         for (int j = 0; j < n_cf; j++) {
-            int row = CF0 + j;
-            float tot = ws.at((int)ws.at(row, rec, 2 * nd + R_FIDX), rec, 2 * nd + R_APPLIED);
+            int row = CF0 + j, ci = j >> 1;
+            float tot = r_applied[CN0 + ci];
             if (tot > 0.f) {
-                float fr = ws.at(row, rec, 2 * nd + R_FRIC);
-                ws.at(row, rec, 2 * nd + R_LO) = -fr * tot; ws.at(row, rec, 2 * nd + R_HI) = fr * tot;
-                resolve_row<NL, MC>(ws, row, rec, nd, dv);
+                int key = W.ckey[cur][ci];
+                float fr = key < M.n_geoms ? M.g_fric_floor[key] : M.pair_friction[key - M.n_geoms];
+                resolve_row<NDMAX>(ws, row, rec, nd, dv, r_rhs[row], r_invd[row], -fr * tot, fr * tot, r_applied[row]);
             }
         }
     }
@@ -850,15 +867,23 @@ RS_HD void solve(const DevModel& M, Work<NL, MC>& W, float dt, const RowWS& ws) 
 #pragma unroll
         for (int k = 0; k < 3; k++) { W.bw[k] += dv[k]; W.bv[k] += dv[3 + k]; }
     }
-    for (int d = 0; d < M.n_dof; d++) W.qd[d] += dv[6 + d];
+#pragma unroll
+    for (int d = 0; d < NL; d++) if (d < M.n_dof) W.qd[d] += dv[6 + d];
     clamp_vel(M, W);
+}
+
+template <int NL, int MC, bool SL>
+RS_HD void solve(const DevModel& M, Work<NL, MC, SL>& W, float dt, const RowWS& ws) {
+    solve_with(M, W, dt, ws, [&](int body, const float* wr, int jdof, float jdir, int row, int rec, bool first, const float* vel, float* relvel) {
+        return row_response(M, W, body, wr, jdof, jdir, ws, row, rec, first, vel, relvel);
+    });
 }
 
 // ---------------------------------------------------------------------------------------------
 // btMultiBody::stepPositionsMultiDof
 // ---------------------------------------------------------------------------------------------
-template <int NL, int MC>
-RS_HD void integrate(const DevModel& M, Work<NL, MC>& W, float dt) {
+template <int NL, int MC, bool SL>
+RS_HD void integrate(const DevModel& M, Work<NL, MC, SL>& W, float dt) {
     if (!M.fixed_base) {
 #pragma unroll
         for (int k = 0; k < 3; k++) W.bpos[k] += dt * W.bv[k];
@@ -889,8 +914,8 @@ struct PhaseClock {
 #define RS_CLOCK() 0LL
 #endif
 
-template <int NL, int MC>
-RS_HD void substep(const DevModel& M, Work<NL, MC>& W, const RowWS& ws, PhaseClock* pc = nullptr) {
+template <int NL, int MC, bool SL>
+RS_HD void substep(const DevModel& M, Work<NL, MC, SL>& W, const RowWS& ws, PhaseClock* pc = nullptr) {
     float dt = M.timestep;
     long long c0 = 0, c1 = 0;
     if (pc) c0 = RS_CLOCK();
@@ -916,8 +941,8 @@ RS_HD void mat_to_quat(const float* R, float* q) {  // R: local->world
     else if (R[4] > R[8]) { float s = sqrtf(1.0f + R[4] - R[0] - R[8]) * 2; q[3] = (R[2] - R[6]) / s; q[0] = (R[1] + R[3]) / s; q[1] = 0.25f * s; q[2] = (R[5] + R[7]) / s; }
     else { float s = sqrtf(1.0f + R[8] - R[0] - R[4]) * 2; q[3] = (R[3] - R[1]) / s; q[0] = (R[2] + R[6]) / s; q[1] = (R[5] + R[7]) / s; q[2] = 0.25f * s; }
 }
-template <int NL, int MC>
-RS_HD void body_pose(const Work<NL, MC>& W, int b, float* pos, float* quat, float* linvel) {
+template <int NL, int MC, bool SL>
+RS_HD void body_pose(const Work<NL, MC, SL>& W, int b, float* pos, float* quat, float* linvel) {
     pos[0] = W.pos[b][0]; pos[1] = W.pos[b][1]; pos[2] = W.pos[b][2];
     if (b == 0) { quat[0] = W.bquat[0]; quat[1] = W.bquat[1]; quat[2] = W.bquat[2]; quat[3] = W.bquat[3]; }
     else {
@@ -955,9 +980,9 @@ RS_HD void rel_joint(const DevModel& M, int li, float q, float qd, float* pos, f
 }
 
 // writes obs[k*ostride]; returns walk_target_dist (double) and pitch
-template <int NL, int MC>
-RS_HD void calc_state(const DevModel& M, Work<NL, MC>& W, Episode& E, float* obs, int ostride, double* dist, float* pitch, int* at_limit) {
-    kinematics(M, W); velocities(M, W);
+template <int NL, int MC, bool SL>
+RS_HD void calc_state_core(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, const float* bp, const float* bq, const float* bv,
+                           float* obs, int ostride, double* dist, float* pitch, int* at_limit) {
     const int A = M.n_act;
     int nlim = 0;
     for (int k = 0; k < A; k++) {
@@ -969,8 +994,6 @@ RS_HD void calc_state(const DevModel& M, Work<NL, MC>& W, Episode& E, float* obs
         obs[(8 + 2 * k + 1) * ostride] = fminf(fmaxf(s, -5.f), 5.f);
     }
     *at_limit = nlim;
-    float bp[3], bq[4], bv[3];
-    body_pose(W, M.body_link + 1, bp, bq, bv);
     float mx = 0.f, my = 0.f;
     for (int k = 0; k < M.n_parts; k++) { mx += W.pos[M.part_link[k] + 1][0]; my += W.pos[M.part_link[k] + 1][1]; }
     mx /= (float)M.n_parts; my /= (float)M.n_parts;
@@ -997,10 +1020,20 @@ RS_HD void calc_state(const DevModel& M, Work<NL, MC>& W, Episode& E, float* obs
     *pitch = p;
 }
 
-template <int NL, int MC>
-RS_HD void epilogue(const DevModel& M, Work<NL, MC>& W, Episode& E, const float* act, int astride, float* obs, int ostride, StepOut& out) {
+// generic wrapper: world transforms + link velocities by the runtime-topology sweeps
+template <int NL, int MC, bool SL>
+RS_HD void calc_state(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, float* obs, int ostride, double* dist, float* pitch, int* at_limit) {
+    kinematics(M, W); velocities(M, W);
+    float bp[3], bq[4], bv[3];
+    body_pose(W, M.body_link + 1, bp, bq, bv);
+    calc_state_core(M, W, E, bp, bq, bv, obs, ostride, dist, pitch, at_limit);
+}
+
+// `cs(obs, ostride, &dist, &pitch, &at_limit)` computes the observation (generic or static kinematics)
+template <int NL, int MC, bool SL, class CS>
+RS_HD void epilogue_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, const float* act, int astride, float* obs, int ostride, StepOut& out, CS&& cs) {
     double dist; float pitch; int at_limit;
-    calc_state(M, W, E, obs, ostride, &dist, &pitch, &at_limit);
+    cs(obs, ostride, &dist, &pitch, &at_limit);
     float z = obs[0] + E.initial_z;
     float alive;
     if (M.alive_rule == RS_ALIVE_Z_AND_PITCH) alive = (z > M.alive_z && fabsf(pitch) < 1.0f) ? M.alive_bonus : -1.f;
@@ -1040,9 +1073,16 @@ RS_HD void epilogue(const DevModel& M, Work<NL, MC>& W, Episode& E, const float*
     E.frame++;
 }
 
+template <int NL, int MC, bool SL>
+RS_HD void epilogue(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, const float* act, int astride, float* obs, int ostride, StepOut& out) {
+    epilogue_with(M, W, E, act, astride, obs, ostride, out, [&](float* o, int os, double* dist, float* pitch, int* al) {
+        calc_state(M, W, E, o, os, dist, pitch, al);
+    });
+}
+
 // reset to the reference's reset distribution (gym_forward_walker.py:24-30, gym_mujoco_walkers.py:106-128)
-template <int NL, int MC>
-RS_HD void env_reset(const DevModel& M, Work<NL, MC>& W, Episode& E, uint32_t seed, uint32_t env_id, float* obs, int ostride) {
+template <int NL, int MC, bool SL, class CS>
+RS_HD void env_reset_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, uint32_t seed, uint32_t env_id, float* obs, int ostride, CS&& cs) {
     E.episode++;
     for (int d = 0; d < M.n_dof; d++) { W.q[d] = 0.f; W.qd[d] = 0.f; W.tau[d] = 0.f; }
     for (int k = 0; k < M.n_act; k++) {
@@ -1063,13 +1103,19 @@ RS_HD void env_reset(const DevModel& M, Work<NL, MC>& W, Episode& E, uint32_t se
     E.initial_z = M.initial_z;
     E.frame = 0;
     double dist; float pitch; int al;
-    calc_state(M, W, E, obs, ostride, &dist, &pitch, &al);
+    cs(obs, ostride, &dist, &pitch, &al);
     E.potential = -dist / M.dt_env;
+}
+template <int NL, int MC, bool SL>
+RS_HD void env_reset(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, uint32_t seed, uint32_t env_id, float* obs, int ostride) {
+    env_reset_with(M, W, E, seed, env_id, obs, ostride, [&](float* o, int os, double* dist, float* pitch, int* al) {
+        calc_state(M, W, E, o, os, dist, pitch, al);
+    });
 }
 
 // apply_action: torque = float(power*coef*clip(a,-1,1))  (gym_forward_walker.py:40-43; set_motor_torque(float))
-template <int NL, int MC>
-RS_HD void apply_action(const DevModel& M, Work<NL, MC>& W, const float* act, int astride) {
+template <int NL, int MC, bool SL>
+RS_HD void apply_action(const DevModel& M, Work<NL, MC, SL>& W, const float* act, int astride) {
     for (int d = 0; d < M.n_dof; d++) W.tau[d] = 0.f;
     for (int k = 0; k < M.n_act; k++) {
         float a = fminf(fmaxf(act[k * astride], -1.f), 1.f);

@@ -1,0 +1,446 @@
+// rs_static.cuh -- tree sweeps specialised on a compile-time topology (rs_topo_gen.h).
+//
+// Same arithmetic as the generic sweeps in rs_core.cuh (kinematics / ABA / unit-impulse response), but
+// every loop over links is unrolled against constexpr parent/dof tables: accumulators of the
+// leaves->root and root->leaves sweeps live in registers, joint-subspace dot products collapse to the
+// non-zero terms, and the per-link cache that the response passes re-read for every constraint row
+// (cos q, sin q, h = I^A S, 1/D, Cholesky factor of the base inertia: 9*NL+21 floats per env) is staged
+// in SHARED memory, laid out [slot][lane] so a warp's accesses are conflict-free.
+#pragma once
+#include <utility>
+#include "rs_core.cuh"
+#include "rs_topo_gen.h"
+
+namespace rs {
+
+template <class F, int... Is>
+RS_HD void static_for_impl(F&& f, std::integer_sequence<int, Is...>) { (f(std::integral_constant<int, Is>{}), ...); }
+template <int N, class F>
+RS_HD void static_for(F&& f) { static_for_impl(f, std::make_integer_sequence<int, N>{}); }
+template <int N, class F, int... Is>
+RS_HD void static_rfor_impl(F&& f, std::integer_sequence<int, Is...>) { (f(std::integral_constant<int, N - 1 - Is>{}), ...); }
+template <int N, class F>
+RS_HD void static_rfor(F&& f) { static_rfor_impl<N>(f, std::make_integer_sequence<int, N>{}); }
+
+// multiply by a compile-time constant, folding 0 / +-1 (IEEE forbids the compiler to do it on its own)
+#define RS_CM(cst, x) ((cst) == 0.0f ? 0.0f : ((cst) == 1.0f ? (x) : ((cst) == -1.0f ? -(x) : (cst) * (x))))
+
+// per-env link cache in shared memory: element k of this lane lives at p[k * STRIDE]
+template <int STRIDE>
+struct LinkCache {
+    float* p;
+    RS_HD float& at(int k) const { return p[k * STRIDE]; }
+};
+template <class T> constexpr int lc_cs() { return 0; }
+template <class T> constexpr int lc_h() { return 2 * T::NL; }
+template <class T> constexpr int lc_invd() { return 8 * T::NL; }
+template <class T> constexpr int lc_lb() { return 9 * T::NL; }
+template <class T> constexpr int lc_size() { return 9 * T::NL + 21; }
+
+// S . x for link I with the constant joint subspace
+template <class T, int I>
+RS_HD float sdot(const float* x) {
+    constexpr float s0 = T::Sw[3 * I], s1 = T::Sw[3 * I + 1], s2 = T::Sw[3 * I + 2], s3 = T::Sv[3 * I], s4 = T::Sv[3 * I + 1], s5 = T::Sv[3 * I + 2];
+    return RS_CM(s0, x[0]) + RS_CM(s1, x[1]) + RS_CM(s2, x[2]) + RS_CM(s3, x[3]) + RS_CM(s4, x[4]) + RS_CM(s5, x[5]);
+}
+// x += a * S
+template <class T, int I>
+RS_HD void saxpy(float* x, float a) {
+    constexpr float s0 = T::Sw[3 * I], s1 = T::Sw[3 * I + 1], s2 = T::Sw[3 * I + 2], s3 = T::Sv[3 * I], s4 = T::Sv[3 * I + 1], s5 = T::Sv[3 * I + 2];
+    x[0] += RS_CM(s0, a); x[1] += RS_CM(s1, a); x[2] += RS_CM(s2, a);
+    x[3] += RS_CM(s3, a); x[4] += RS_CM(s4, a); x[5] += RS_CM(s5, a);
+}
+
+// rotation parent->link coords and COM offset of link I from (cos q, sin q, q)
+template <class T, int I>
+RS_HD void link_xform(float c, float s, float q, float* R, float* r) {
+    constexpr float R0_0 = T::R0[9 * I], R0_1 = T::R0[9 * I + 1], R0_2 = T::R0[9 * I + 2], R0_3 = T::R0[9 * I + 3], R0_4 = T::R0[9 * I + 4],
+                    R0_5 = T::R0[9 * I + 5], R0_6 = T::R0[9 * I + 6], R0_7 = T::R0[9 * I + 7], R0_8 = T::R0[9 * I + 8];
+    constexpr float ax = T::axis[3 * I], ay = T::axis[3 * I + 1], az = T::axis[3 * I + 2];
+    constexpr bool r0_identity = R0_0 == 1.0f && R0_4 == 1.0f && R0_8 == 1.0f && R0_1 == 0.0f && R0_2 == 0.0f && R0_3 == 0.0f &&
+                                 R0_5 == 0.0f && R0_6 == 0.0f && R0_7 == 0.0f;
+    constexpr int jt = T::jtype[I];
+    if constexpr (jt == RS_JOINT_REVOLUTE) {
+        // rotation by -q about the axis:  c I + (1-c) a a^T - s [a]x
+        const float k = 1.0f - c;
+        float Ra[9];
+        Ra[0] = c + RS_CM(ax * ax, k);          Ra[1] = RS_CM(ax * ay, k) + RS_CM(az, s); Ra[2] = RS_CM(ax * az, k) - RS_CM(ay, s);
+        Ra[3] = RS_CM(ay * ax, k) - RS_CM(az, s); Ra[4] = c + RS_CM(ay * ay, k);          Ra[5] = RS_CM(ay * az, k) + RS_CM(ax, s);
+        Ra[6] = RS_CM(az * ax, k) + RS_CM(ay, s); Ra[7] = RS_CM(az * ay, k) - RS_CM(ax, s); Ra[8] = c + RS_CM(az * az, k);
+        if constexpr (r0_identity) {
+#pragma unroll
+            for (int j = 0; j < 9; j++) R[j] = Ra[j];
+        } else {
+            const float R0v[9] = {R0_0, R0_1, R0_2, R0_3, R0_4, R0_5, R0_6, R0_7, R0_8};
+            mul33(R, Ra, R0v);
+        }
+    } else {
+        R[0] = R0_0; R[1] = R0_1; R[2] = R0_2; R[3] = R0_3; R[4] = R0_4; R[5] = R0_5; R[6] = R0_6; R[7] = R0_7; R[8] = R0_8;
+    }
+    constexpr float ex = T::e[3 * I], ey = T::e[3 * I + 1], ez = T::e[3 * I + 2];
+    constexpr float dx = T::d[3 * I], dy = T::d[3 * I + 1], dz = T::d[3 * I + 2];
+    r[0] = RS_CM(ex, R[0]) + RS_CM(ey, R[1]) + RS_CM(ez, R[2]) + dx;
+    r[1] = RS_CM(ex, R[3]) + RS_CM(ey, R[4]) + RS_CM(ez, R[5]) + dy;
+    r[2] = RS_CM(ex, R[6]) + RS_CM(ey, R[7]) + RS_CM(ez, R[8]) + dz;
+    if constexpr (jt == RS_JOINT_PRISMATIC) { r[0] += RS_CM(ax, q); r[1] += RS_CM(ay, q); r[2] += RS_CM(az, q); }
+}
+
+template <class T, int I, int STRIDE>
+RS_HD void cached_xform(const LinkCache<STRIDE>& lc, const float* qv, float* R, float* r) {
+    float c = 1.0f, s = 0.0f, q = 0.0f;
+    constexpr int jt = T::jtype[I], dI = T::dof[I];
+    if constexpr (jt == RS_JOINT_REVOLUTE) { c = lc.at(lc_cs<T>() + 2 * I); s = lc.at(lc_cs<T>() + 2 * I + 1); }
+    if constexpr (jt == RS_JOINT_PRISMATIC) q = qv[dI];
+    link_xform<T, I>(c, s, q, R, r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kinematics: fills the (cos, sin) cache and the world transforms W.Rwl / W.pos (thread-private,
+// read by the narrowphase / contact rows / epilogue by dynamic body index)
+// ---------------------------------------------------------------------------------------------
+template <class T, int NL, int MC, bool SL, int STRIDE>
+RS_HD void static_kinematics(Work<NL, MC, SL>& W, const LinkCache<STRIDE>& lc) {
+    float Rbw[9];
+    quat_to_mat(Rbw, W.bquat[0], W.bquat[1], W.bquat[2], W.bquat[3]);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) W.Rwl[0][i * 3 + j] = Rbw[j * 3 + i];
+    W.pos[0][0] = W.bpos[0]; W.pos[0][1] = W.bpos[1]; W.pos[0][2] = W.bpos[2];
+    static_for<T::NL>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int p = T::parent[i], jt = T::jtype[i], dI = T::dof[i];
+        float c = 1.0f, s = 0.0f, q = 0.0f;
+        if constexpr (jt == RS_JOINT_REVOLUTE) {
+            sincosf(W.q[dI], &s, &c);
+            lc.at(lc_cs<T>() + 2 * i) = c; lc.at(lc_cs<T>() + 2 * i + 1) = s;
+        }
+        if constexpr (jt == RS_JOINT_PRISMATIC) q = W.q[dI];
+        float R[9], r[3];
+        link_xform<T, i>(c, s, q, R, r);
+        mul33(W.Rwl[i + 1], R, W.Rwl[p + 1]);
+        float rw[3];
+        tmulv(rw, W.Rwl[i + 1], r);
+        W.pos[i + 1][0] = W.pos[p + 1][0] + rw[0]; W.pos[i + 1][1] = W.pos[p + 1][1] + rw[1]; W.pos[i + 1][2] = W.pos[p + 1][2] + rw[2];
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+// ABA (computeAccelerationsArticulatedBodyAlgorithmMultiDof + applyDeltaVeeMultiDof)
+// ---------------------------------------------------------------------------------------------
+template <class T, int NL, int MC, bool SL, int STRIDE>
+RS_HD void static_aba(const DevModel& M, Work<NL, MC, SL>& W, const LinkCache<STRIDE>& lc, float dt) {
+    constexpr int n = T::NL;
+    float vel[n + 1][6], Z[n + 1][6], c[n][6], Y[n];
+    // ---- root -> leaves: velocities, bias forces, Coriolis ----
+    if constexpr (T::FIXED_BASE) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) { vel[0][k] = 0.f; Z[0][k] = 0.f; }
+    } else {
+        mulv(vel[0], W.Rwl[0], W.bw); mulv(vel[0] + 3, W.Rwl[0], W.bv);
+    }
+    auto bias = [&](const float* v, float mass, const float* I3, const float* Rwl, float* Zb) {
+        // gravity as an applied force rotated into link coords: only the z column of Rwl is needed
+        float g = -M.gravity * mass;
+        float fl[3] = {Rwl[2] * g, Rwl[5] * g, Rwl[8] * g};
+        float wn = sqrtf(dot3(v, v)), vn = sqrtf(dot3(v + 3, v + 3));
+        float Iw[3] = {I3[0] * v[0], I3[1] * v[1], I3[2] * v[2]};
+        float ka = M.ang_damping * (1.0f + wn), kl = M.lin_damping * (1.0f + vn);
+        float g1[3], g2[3];
+        cross3(g1, v, Iw); cross3(g2, v, v + 3);
+        float gy = M.use_gyro;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { Zb[k] = Iw[k] * ka + gy * g1[k]; Zb[3 + k] = -fl[k] + mass * v[3 + k] * kl + mass * g2[k]; }
+    };
+    constexpr float bI0 = T::base_inertia[0], bI1 = T::base_inertia[1], bI2 = T::base_inertia[2], bM = T::base_mass;
+    if constexpr (!T::FIXED_BASE) {
+        const float I3[3] = {bI0, bI1, bI2};
+        bias(vel[0], bM, I3, W.Rwl[0], Z[0]);
+    }
+    static_for<n>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int p = T::parent[i];
+        constexpr int dI = T::dof[i];
+        constexpr float mI = T::mass[i], i0 = T::inertia[3 * i], i1 = T::inertia[3 * i + 1], i2 = T::inertia[3 * i + 2];
+        float R[9], r[3];
+        cached_xform<T, i>(lc, W.q, R, r);
+        xf_motion(vel[i + 1], R, r, vel[p + 1]);
+        if constexpr (dI >= 0) {
+            float qd = W.qd[dI];
+            saxpy<T, i>(vel[i + 1], qd);
+            // c = v x (S qd)
+            float jv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            saxpy<T, i>(jv, qd);
+            const float* v = vel[i + 1];
+            float t1[3], t2[3];
+            cross3(c[i], v, jv);
+            cross3(t1, v, jv + 3); cross3(t2, v + 3, jv);
+            c[i][3] = t1[0] + t2[0]; c[i][4] = t1[1] + t2[1]; c[i][5] = t1[2] + t2[2];
+        }
+        const float I3[3] = {i0, i1, i2};
+        bias(vel[i + 1], mI, I3, W.Rwl[i + 1], Z[i + 1]);
+    });
+    // ---- leaves -> root: articulated inertias, h, D, Y ----
+    float IA[n + 1][21];
+    auto init_rigid = [&](float* I, float mass, float ix, float iy, float iz) {
+#pragma unroll
+        for (int k = 0; k < 21; k++) I[k] = 0.f;
+        I[0] = ix; I[3] = iy; I[5] = iz; I[15] = mass; I[18] = mass; I[20] = mass;
+    };
+    static_rfor<n>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int p = T::parent[i], dI = T::dof[i], pp = p >= 0 ? p : 0;
+        constexpr bool is_leaf = T::leaf[i] != 0, is_first = T::first_fold[i] != 0;
+        constexpr float mI = T::mass[i], i0 = T::inertia[3 * i], i1 = T::inertia[3 * i + 1], i2 = T::inertia[3 * i + 2];
+        constexpr float mP = T::mass[pp], p0 = T::inertia[3 * pp], p1 = T::inertia[3 * pp + 1], p2 = T::inertia[3 * pp + 2];
+        constexpr float s0 = T::Sw[3 * i], s1 = T::Sw[3 * i + 1], s2 = T::Sw[3 * i + 2], s3 = T::Sv[3 * i], s4 = T::Sv[3 * i + 1], s5 = T::Sv[3 * i + 2];
+        if constexpr (is_leaf) init_rigid(IA[i + 1], mI, i0, i1, i2);
+        float R[9], r[3];
+        cached_xform<T, i>(lc, W.q, R, r);
+        float Zt[6];
+        if constexpr (dI >= 0) {
+            float S[6] = {s0, s1, s2, s3, s4, s5};
+            float h[6];
+            inertia_mul(h, IA[i + 1], S);
+            float D = sdot<T, i>(h);
+            float y = W.tau[dI] - sdot<T, i>(Z[i + 1]) - dot6(c[i], h);
+            float invD = 1.0f / D;
+            Y[i] = y;
+            lc.at(lc_invd<T>() + i) = invD;
+#pragma unroll
+            for (int k = 0; k < 6; k++) lc.at(lc_h<T>() + 6 * i + k) = h[k];
+            float Ic[6];
+            inertia_mul(Ic, IA[i + 1], c[i]);
+            float kk = invD * y;
+#pragma unroll
+            for (int k = 0; k < 6; k++) Zt[k] = Z[i + 1][k] + Ic[k] + h[k] * kk;
+            float* I = IA[i + 1];
+            I[0] -= h[0] * h[0] * invD; I[1] -= h[0] * h[1] * invD; I[2] -= h[0] * h[2] * invD;
+            I[3] -= h[1] * h[1] * invD; I[4] -= h[1] * h[2] * invD; I[5] -= h[2] * h[2] * invD;
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int b2 = 0; b2 < 3; b2++) I[6 + a * 3 + b2] -= h[a] * h[3 + b2] * invD;
+            I[15] -= h[3] * h[3] * invD; I[16] -= h[3] * h[4] * invD; I[17] -= h[3] * h[5] * invD;
+            I[18] -= h[4] * h[4] * invD; I[19] -= h[4] * h[5] * invD; I[20] -= h[5] * h[5] * invD;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 6; k++) Zt[k] = Z[i + 1][k];
+        }
+        // first child to fold initialises the parent's accumulator with the parent's rigid-body inertia
+        if constexpr (is_first) {
+            if constexpr (p >= 0) init_rigid(IA[p + 1], mP, p0, p1, p2);
+            else init_rigid(IA[0], bM, bI0, bI1, bI2);
+        }
+        inertia_to_parent_add(IA[p + 1], IA[i + 1], R, r);
+        xf_force_inv_add(Z[p + 1], R, r, Zt);
+    });
+    // ---- base acceleration + root -> leaves joint accelerations ----
+    float acc[n + 1][6];
+    if constexpr (T::FIXED_BASE) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) acc[0][k] = 0.f;
+    } else {
+        if constexpr (T::base_leaf != 0) init_rigid(IA[0], bM, bI0, bI1, bI2);
+        float Lb[21], rr[6];
+        chol6(Lb, IA[0]);
+#pragma unroll
+        for (int k = 0; k < 21; k++) lc.at(lc_lb<T>() + k) = Lb[k];
+        chol6_solve(rr, Lb, Z[0]);
+#pragma unroll
+        for (int k = 0; k < 6; k++) acc[0][k] = -rr[k];
+    }
+    static_for<n>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int p = T::parent[i];
+        float R[9], r[3];
+        cached_xform<T, i>(lc, W.q, R, r);
+        xf_motion(acc[i + 1], R, r, acc[p + 1]);
+        constexpr int dI = T::dof[i];
+        if constexpr (dI >= 0) {
+            float h[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) h[k] = lc.at(lc_h<T>() + 6 * i + k);
+            float a = lc.at(lc_invd<T>() + i) * (Y[i] - dot6(acc[i + 1], h));
+#pragma unroll
+            for (int k = 0; k < 6; k++) acc[i + 1][k] += c[i][k];
+            saxpy<T, i>(acc[i + 1], a);
+            W.qd[dI] += dt * a;
+        }
+    });
+    if constexpr (!T::FIXED_BASE) {
+        float wd[3], vd[3], t[3], wxv[3];
+        tmulv(wd, W.Rwl[0], acc[0]);
+        cross3(wxv, vel[0], vel[0] + 3);
+        t[0] = acc[0][3] + wxv[0]; t[1] = acc[0][4] + wxv[1]; t[2] = acc[0][5] + wxv[2];
+        tmulv(vd, W.Rwl[0], t);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { W.bw[k] += dt * wd[k]; W.bv[k] += dt * vd[k]; }
+    }
+    clamp_vel(M, W);
+}
+
+// ---------------------------------------------------------------------------------------------
+// unit-impulse response (fillContactJacobianMultiDof + calcAccelerationDeltasMultiDof), static sweeps.
+// Same contract as the generic row_response().
+// ---------------------------------------------------------------------------------------------
+template <class T, int NL, int MC, bool SL, int STRIDE>
+RS_HD float static_row_response(const Work<NL, MC, SL>& W, const LinkCache<STRIDE>& lc, int body, const float* wrench, int jdof, float jdir,
+                                const RowWS& ws, int row, int rec, bool first, const float* vel, float* relvel) {
+    constexpr int n = T::NL, nd = 6 + T::ND;
+    float F[n + 1][6], Z[n + 1][6], Y[n], jd[n];
+    static_for<n + 1>([&](auto bc) {
+        constexpr int b = decltype(bc)::value;
+        const bool hit = (b == body);
+#pragma unroll
+        for (int k = 0; k < 6; k++) { float w = hit ? wrench[k] : 0.f; F[b][k] = w; Z[b][k] = -w; }
+    });
+    float denom = 0.f;
+    static_rfor<n>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int p = T::parent[i];
+        float R[9], r[3];
+        cached_xform<T, i>(lc, W.q, R, r);
+        float Zt[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) Zt[k] = Z[i + 1][k];
+        constexpr int d = T::dof[i];
+        if constexpr (d >= 0) {
+            const float jj = (d == jdof) ? jdir : 0.f;
+            float j = sdot<T, i>(F[i + 1]) + jj;
+            float y = jj - sdot<T, i>(Z[i + 1]);
+            Y[i] = y; jd[i] = j;
+            float kk = lc.at(lc_invd<T>() + i) * y;
+#pragma unroll
+            for (int k = 0; k < 6; k++) Zt[k] += lc.at(lc_h<T>() + 6 * i + k) * kk;
+            float& J = ws.at(row, rec, 6 + d);
+            J = first ? j : J + j;
+            *relvel += j * vel[6 + d];
+        }
+        xf_force_inv_add(Z[p + 1], R, r, Zt);
+        xf_force_inv_add(F[p + 1], R, r, F[i + 1]);
+    });
+    float acc[n + 1][6];
+    if constexpr (T::FIXED_BASE) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) { acc[0][k] = 0.f; if (first) { ws.at(row, rec, k) = 0.f; ws.at(row, rec, nd + k) = 0.f; } }
+    } else {
+        float jw[3], jv[3], rr[6], uw[3], uv[3], Lb[21];
+#pragma unroll
+        for (int k = 0; k < 21; k++) Lb[k] = lc.at(lc_lb<T>() + k);
+        tmulv(jw, W.Rwl[0], F[0]); tmulv(jv, W.Rwl[0], F[0] + 3);
+        chol6_solve(rr, Lb, Z[0]);
+#pragma unroll
+        for (int k = 0; k < 6; k++) acc[0][k] = -rr[k];
+        tmulv(uw, W.Rwl[0], acc[0]); tmulv(uv, W.Rwl[0], acc[0] + 3);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            float& J0 = ws.at(row, rec, k); float& J1 = ws.at(row, rec, 3 + k);
+            float& U0 = ws.at(row, rec, nd + k); float& U1 = ws.at(row, rec, nd + 3 + k);
+            if (first) { J0 = jw[k]; J1 = jv[k]; U0 = uw[k]; U1 = uv[k]; }
+            else { J0 += jw[k]; J1 += jv[k]; U0 += uw[k]; U1 += uv[k]; }
+            denom += jw[k] * uw[k] + jv[k] * uv[k];
+            *relvel += jw[k] * vel[k] + jv[k] * vel[3 + k];
+        }
+    }
+    static_for<n>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int p = T::parent[i];
+        float R[9], r[3];
+        cached_xform<T, i>(lc, W.q, R, r);
+        xf_motion(acc[i + 1], R, r, acc[p + 1]);
+        constexpr int d = T::dof[i];
+        if constexpr (d >= 0) {
+            float h[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) h[k] = lc.at(lc_h<T>() + 6 * i + k);
+            float a = lc.at(lc_invd<T>() + i) * (Y[i] - dot6(acc[i + 1], h));
+            saxpy<T, i>(acc[i + 1], a);
+            float& U = ws.at(row, rec, nd + 6 + d);
+            U = first ? a : U + a;
+            denom += jd[i] * a;
+        }
+    });
+    return denom;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sub-step / observation with the static sweeps
+// ---------------------------------------------------------------------------------------------
+template <class T, int NL, int MC, bool SL, int STRIDE>
+RS_HD void substep_static(const DevModel& M, Work<NL, MC, SL>& W, const RowWS& ws, const LinkCache<STRIDE>& lc, PhaseClock* pc = nullptr) {
+    float dt = M.timestep;
+    long long c0 = 0, c1 = 0;
+    if (pc) c0 = RS_CLOCK();
+    static_kinematics<T>(W, lc);
+    if (pc) { c1 = RS_CLOCK(); pc->t[0] += c1 - c0; c0 = c1; }
+    collide(M, W);
+    if (pc) { c1 = RS_CLOCK(); pc->t[1] += c1 - c0; c0 = c1; }
+    static_aba<T>(M, W, lc, dt);
+    if (pc) { c1 = RS_CLOCK(); pc->t[2] += c1 - c0; c0 = c1; }
+    solve_with(M, W, dt, ws, [&](int body, const float* wr, int jdof, float jdir, int row, int rec, bool first, const float* vel, float* relvel) {
+        return static_row_response<T>(W, lc, body, wr, jdof, jdir, ws, row, rec, first, vel, relvel);
+    });
+    if (pc) { c1 = RS_CLOCK(); pc->t[3] += c1 - c0; c0 = c1; }
+    integrate(M, W, dt);
+    if (pc) { c1 = RS_CLOCK(); pc->t[4] += c1 - c0; }
+}
+
+template <class T, int NL, int MC, bool SL, int STRIDE>
+RS_HD void static_calc_state(const DevModel& M, Work<NL, MC, SL>& W, const LinkCache<STRIDE>& lc, Episode& E, float* obs, int ostride,
+                             double* dist, float* pitch, int* at_limit) {
+    constexpr int n = T::NL;
+    static_kinematics<T>(W, lc);
+    float vel[n + 1][6];
+    if constexpr (T::FIXED_BASE) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) vel[0][k] = 0.f;
+    } else { mulv(vel[0], W.Rwl[0], W.bw); mulv(vel[0] + 3, W.Rwl[0], W.bv); }
+    const int body = M.body_link + 1;
+    float vl[3] = {vel[0][3], vel[0][4], vel[0][5]};
+    static_for<n>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int p = T::parent[i];
+        float R[9], r[3];
+        cached_xform<T, i>(lc, W.q, R, r);
+        xf_motion(vel[i + 1], R, r, vel[p + 1]);
+        constexpr int dI = T::dof[i];
+        if constexpr (dI >= 0) saxpy<T, i>(vel[i + 1], W.qd[dI]);
+        if (body == i + 1) { vl[0] = vel[i + 1][3]; vl[1] = vel[i + 1][4]; vl[2] = vel[i + 1][5]; }
+    });
+    float bp[3] = {W.pos[body][0], W.pos[body][1], W.pos[body][2]}, bq[4], bv[3];
+    if (body == 0) { bq[0] = W.bquat[0]; bq[1] = W.bquat[1]; bq[2] = W.bquat[2]; bq[3] = W.bquat[3]; }
+    else {
+        float Rlw[9];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) Rlw[i * 3 + j] = W.Rwl[body][j * 3 + i];
+        mat_to_quat(Rlw, bq);
+    }
+    tmulv(bv, W.Rwl[body], vl);
+    calc_state_core(M, W, E, bp, bq, bv, obs, ostride, dist, pitch, at_limit);
+}
+
+// true iff the run-time descriptor is exactly the model this topology was generated from
+template <class T>
+inline bool topo_matches(const DevModel& D) {
+    if (D.n_links != T::NL || D.n_dof != T::ND || D.fixed_base != T::FIXED_BASE) return false;
+    auto eq = [](float a, float b) { return fabsf(a - b) <= 1e-6f * fmaxf(1.0f, fabsf(b)); };
+    for (int i = 0; i < T::NL; i++) {
+        if (D.parent[i] != T::parent[i] || D.jtype[i] != T::jtype[i] || D.dof_idx[i] != T::dof[i]) return false;
+        if (!eq(D.mass[i], T::mass[i])) return false;
+        for (int k = 0; k < 3; k++) {
+            if (!eq(D.axis[i][k], T::axis[3 * i + k]) || !eq(D.e_vec[i][k], T::e[3 * i + k]) || !eq(D.d_vec[i][k], T::d[3 * i + k]) ||
+                !eq(D.Sw[i][k], T::Sw[3 * i + k]) || !eq(D.Sv[i][k], T::Sv[3 * i + k]) || !eq(D.inertia[i][k], T::inertia[3 * i + k])) return false;
+        }
+        for (int k = 0; k < 9; k++) if (!eq(D.R0[i][k], T::R0[9 * i + k])) return false;
+    }
+    if (!T::FIXED_BASE) {
+        if (!eq(D.base_mass, T::base_mass)) return false;
+        for (int k = 0; k < 3; k++) if (!eq(D.base_inertia[k], T::base_inertia[k])) return false;
+    }
+    return true;
+}
+
+}  // namespace rs

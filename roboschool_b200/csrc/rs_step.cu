@@ -9,11 +9,13 @@
 // actions/obs are the caller's row-major [N][A] / [N][O] tensors.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
 #include "../../include/roboschool_b200.h"
 #include "rs_devmodel.h"
+#include "rs_static.cuh"
 
 using namespace rs;
 
@@ -37,6 +39,7 @@ struct rs_world {
     DevModel M;
     DevBuf B;
     int device, n, family;   // family: 0 (NL<=6), 1 (NL<=12), 2 (NL<=24)
+    int topo;                // 0: runtime-topology kernel; 1..4: kernel specialised on a generated topology (rs_topo_gen.h)
     cudaStream_t stream;
     // pinned staging + device staging for the host-buffer entry point
     float *h_act, *h_obs, *h_rew; uint8_t* h_done;
@@ -46,8 +49,8 @@ struct rs_world {
 };
 
 // ----------------------------------------------------------------------------------------------
-template <int NL, int MC>
-__device__ __forceinline__ void load_env(const DevModel& M, const DevBuf& B, int e, Work<NL, MC>& W, Episode& E) {
+template <int NL, int MC, bool SL>
+__device__ __forceinline__ void load_env(const DevModel& M, const DevBuf& B, int e, Work<NL, MC, SL>& W, Episode& E) {
     const int N = B.N;
     const float* s = B.state + e;
     int f = 0;
@@ -79,8 +82,8 @@ __device__ __forceinline__ void load_env(const DevModel& M, const DevBuf& B, int
     W.n_rows = 0; W.n_contacts = 0;
 }
 
-template <int NL, int MC>
-__device__ __forceinline__ void store_env(const DevModel& M, const DevBuf& B, int e, const Work<NL, MC>& W, const Episode& E) {
+template <int NL, int MC, bool SL>
+__device__ __forceinline__ void store_env(const DevModel& M, const DevBuf& B, int e, const Work<NL, MC, SL>& W, const Episode& E) {
     const int N = B.N;
     float* s = B.state + e;
     int f = 0;
@@ -156,6 +159,77 @@ __global__ void __launch_bounds__(64) k_step(const __grid_constant__ DevModel M,
             atomicAdd(stats + 4, st_rows); atomicAdd(stats + 5, st_con); atomicAdd(stats + 6, st_steps);
         }
     }
+}
+
+// Step kernel specialised on a compile-time topology: one warp per CTA (32 envs), link cache in shared memory.
+// PROF: also accumulate clock64() deltas per phase into cyc[8] (profiling twin).
+template <class T, int MC, bool PROF>
+__global__ void __launch_bounds__(32) k_step_static(const __grid_constant__ DevModel M, const DevBuf B, const float* __restrict__ actions,
+                                                    float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
+                                                    int auto_reset, uint32_t seed, uint32_t env_id0, double* __restrict__ stats,
+                                                    unsigned long long* __restrict__ cyc) {
+    extern __shared__ float s_lc[];
+    const int e = blockIdx.x * 32 + threadIdx.x;
+    double st_rew = 0, st_ep = 0, st_len = 0, st_nf = 0, st_rows = 0, st_con = 0, st_steps = 0;
+    if (e < B.N) {
+        long long t0 = 0, t1 = 0, t2 = 0;
+        if (PROF) t0 = clock64();
+        Work<T::NL, MC, true> W;
+        Episode E;
+        LinkCache<32> lc{s_lc + threadIdx.x};
+        load_env(M, B, e, W, E);
+        float a[MA];
+        if (actions) { for (int k = 0; k < M.n_act; k++) a[k] = actions[(size_t)e * M.n_act + k]; }
+        else { for (int k = 0; k < M.n_act; k++) a[k] = 2.f * rs_uniform(seed ^ 0xA5A5A5A5u, env_id0 + e, E.episode * 1024u + (uint32_t)E.frame, (uint32_t)k) - 1.f; }
+        apply_action(M, W, a, 1);
+        RowWS ws{B.rows + e, B.N};
+        PhaseClock pc;
+        if (PROF) { for (int k = 0; k < 6; k++) pc.t[k] = 0; t1 = clock64(); }
+        for (int s = 0; s < M.frame_skip; s++) substep_static<T>(M, W, ws, lc, PROF ? &pc : nullptr);
+        if (PROF) t2 = clock64();
+        float* o = obs + (size_t)e * M.obs_dim;
+        StepOut out;
+        auto cs = [&](float* oo, int os, double* dist, float* pitch, int* al) { static_calc_state<T>(M, W, lc, E, oo, os, dist, pitch, al); };
+        epilogue_with(M, W, E, a, 1, o, 1, out, cs);
+        int dn = out.done;
+        bool finite = true;
+        for (int k = 0; k < M.obs_dim; k++) finite = finite && isfinite(o[k]);
+        int finished = dn || E.frame >= M.max_episode_steps;
+        st_rew = out.reward; st_rows = W.n_rows; st_con = W.n_contacts; st_steps = 1; st_nf = finite ? 0 : 1;
+        if (finished) { st_ep = 1; st_len = E.frame; }
+        if (auto_reset && finished) { env_reset_with(M, W, E, seed, env_id0 + e, o, 1, cs); dn = 1; }
+        rew[e] = out.reward; done[e] = (uint8_t)dn;
+        if (B.rewards5) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) B.rewards5[(size_t)e * 5 + k] = out.rewards5[k];
+        }
+        store_env(M, B, e, W, E);
+        if (PROF && (threadIdx.x & 31) == 0) {
+            long long t3 = clock64();
+            for (int k = 0; k < 5; k++) atomicAdd(cyc + k, (unsigned long long)pc.t[k]);
+            atomicAdd(cyc + 5, (unsigned long long)(t3 - t2));
+            atomicAdd(cyc + 6, (unsigned long long)(t1 - t0));
+            atomicAdd(cyc + 7, (unsigned long long)(t3 - t0));
+        }
+    }
+    if (stats) {
+        st_rew = warp_sum(st_rew); st_ep = warp_sum(st_ep); st_len = warp_sum(st_len); st_nf = warp_sum(st_nf);
+        st_rows = warp_sum(st_rows); st_con = warp_sum(st_con); st_steps = warp_sum(st_steps);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(stats + 0, st_rew); atomicAdd(stats + 1, st_ep); atomicAdd(stats + 2, st_len); atomicAdd(stats + 3, st_nf);
+            atomicAdd(stats + 4, st_rows); atomicAdd(stats + 5, st_con); atomicAdd(stats + 6, st_steps);
+        }
+    }
+}
+
+template <class T, int MC, bool PROF>
+static int launch_static(rs_world* w, const float* actions, float* obs, float* rew, uint8_t* done, int auto_reset, uint32_t seed,
+                         uint32_t env_id0, double* stats, unsigned long long* cyc, cudaStream_t st) {
+    const size_t smem = sizeof(float) * 32 * lc_size<T>();
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_step_static<T, MC, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    k_step_static<T, MC, PROF><<<(w->n + 31) / 32, 32, smem, st>>>(w->M, w->B, actions, obs, rew, done, auto_reset, seed, env_id0, stats, cyc);
+    return 0;
 }
 
 // Profiling twin of k_step: same work, plus clock64() deltas per phase summed over threads into cyc[8].
@@ -269,6 +343,13 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
     int NL, MC;
     w->family = family_of(model, &NL, &MC);
     if (w->family < 0) { delete w; return fail("rs_world_create: model exceeds kernel capacity (links<=20, contacts<=16)"); }
+    w->topo = 0;
+    if (!getenv("RS_FORCE_GENERIC")) {
+        if (topo_matches<TopoHumanoid>(w->M) && model->max_contacts <= 16) w->topo = 1;
+        else if (topo_matches<TopoAnt>(w->M) && model->max_contacts <= 16) w->topo = 2;
+        else if (topo_matches<TopoHopper>(w->M) && model->max_contacts <= 8) w->topo = 3;
+        else if (topo_matches<TopoWalker2d>(w->M) && model->max_contacts <= 16) w->topo = 4;
+    }
     w->device = device; w->n = n_envs;
     DevBuf& B = w->B;
     B.N = n_envs; B.S = (model->fixed_base ? 0 : 13) + 2 * model->n_dof; B.MCcap = MC;
@@ -334,6 +415,7 @@ extern "C" int rs_world_destroy(rs_world* w) {
 }
 
 extern "C" int rs_world_n_envs(const rs_world* w) { return w->n; }
+extern "C" int rs_world_kernel_variant(const rs_world* w) { return w->topo; }
 extern "C" int rs_world_state_dim(const rs_world* w) { return w->B.S; }
 extern "C" int rs_world_obs_dim(const rs_world* w) { return w->desc.obs_dim; }
 extern "C" int rs_world_act_dim(const rs_world* w) { return w->desc.n_act; }
@@ -352,6 +434,13 @@ extern "C" int rs_world_reset(rs_world* w, uint32_t seed, uint32_t env_id0, cons
 
 static int launch_step(rs_world* w, const float* actions, float* obs, float* rew, uint8_t* done, int auto_reset, uint32_t seed,
                        uint32_t env_id0, double* stats, cudaStream_t st) {
+    switch (w->topo) {
+        case 1: launch_static<TopoHumanoid, 16, false>(w, actions, obs, rew, done, auto_reset, seed, env_id0, stats, nullptr, st); CK(cudaGetLastError()); return 0;
+        case 2: launch_static<TopoAnt, 16, false>(w, actions, obs, rew, done, auto_reset, seed, env_id0, stats, nullptr, st); CK(cudaGetLastError()); return 0;
+        case 3: launch_static<TopoHopper, 8, false>(w, actions, obs, rew, done, auto_reset, seed, env_id0, stats, nullptr, st); CK(cudaGetLastError()); return 0;
+        case 4: launch_static<TopoWalker2d, 16, false>(w, actions, obs, rew, done, auto_reset, seed, env_id0, stats, nullptr, st); CK(cudaGetLastError()); return 0;
+        default: break;
+    }
     FAMILY_DISPATCH(w, (k_step<NL, MC><<<nblocks(w->n), 64, 0, st>>>(w->M, w->B, actions, obs, rew, done, auto_reset, seed, env_id0, stats)));
     CK(cudaGetLastError());
     return 0;
@@ -379,8 +468,16 @@ extern "C" int rs_world_step_profile(rs_world* w, const float* actions_dev, floa
     unsigned long long* d = nullptr;
     CK(cudaMalloc(&d, 8 * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), (cudaStream_t)stream));
-    FAMILY_DISPATCH(w, (k_step_prof<NL, MC><<<nblocks(w->n), 64, 0, (cudaStream_t)stream>>>(w->M, w->B, actions_dev, obs_dev, reward_dev, done_dev,
-                                                                                          w->rollout_seed, w->env_id0, d)));
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (w->topo) {
+        case 1: launch_static<TopoHumanoid, 16, true>(w, actions_dev, obs_dev, reward_dev, done_dev, 1, w->rollout_seed, w->env_id0, nullptr, d, st); break;
+        case 2: launch_static<TopoAnt, 16, true>(w, actions_dev, obs_dev, reward_dev, done_dev, 1, w->rollout_seed, w->env_id0, nullptr, d, st); break;
+        case 3: launch_static<TopoHopper, 8, true>(w, actions_dev, obs_dev, reward_dev, done_dev, 1, w->rollout_seed, w->env_id0, nullptr, d, st); break;
+        case 4: launch_static<TopoWalker2d, 16, true>(w, actions_dev, obs_dev, reward_dev, done_dev, 1, w->rollout_seed, w->env_id0, nullptr, d, st); break;
+        default:
+            FAMILY_DISPATCH(w, (k_step_prof<NL, MC><<<nblocks(w->n), 64, 0, st>>>(w->M, w->B, actions_dev, obs_dev, reward_dev, done_dev,
+                                                                                  w->rollout_seed, w->env_id0, d)));
+    }
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
     if (e == cudaSuccess) e = cudaMemcpy(cycles_host, d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);

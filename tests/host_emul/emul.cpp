@@ -5,6 +5,7 @@
 #include <string.h>
 #include <vector>
 #include "../../roboschool_b200/csrc/rs_devmodel.h"
+#include "../../roboschool_b200/csrc/rs_static.cuh"
 
 using namespace rs;
 constexpr int NL = RS_MAX_LINKS, MC = 16;
@@ -19,7 +20,30 @@ struct Emul {
     std::vector<int> done;
     std::vector<StepOut> out;
     int rec, maxr;
+    int topo;                 // 0 generic, 1 humanoid, 2 ant, 3 hopper, 4 walker2d (static-topology sweeps)
+    std::vector<float> lcbuf; // per-env link cache (shared memory on the GPU)
+    int lcsize;
 };
+
+template <class T>
+static void step_env_static(Emul* e, int i, const float* a, int auto_reset, uint32_t seed, uint32_t env0) {
+    const DevModel& M = e->M; W_t& W = e->w[i]; RowWS ws{e->ws.data(), 1};
+    LinkCache<1> lc{e->lcbuf.data() + (size_t)i * e->lcsize};
+    apply_action(M, W, a, 1);
+    for (int s = 0; s < M.frame_skip; s++) substep_static<T>(M, W, ws, lc);
+    float* obs = &e->obs[(size_t)i * M.obs_dim];
+    auto cs = [&](float* o, int os, double* dist, float* pitch, int* al) { static_calc_state<T>(M, W, lc, e->ep[i], o, os, dist, pitch, al); };
+    epilogue_with(M, W, e->ep[i], a, 1, obs, 1, e->out[i], cs);
+    int done = e->out[i].done;
+    if (auto_reset && (done || e->ep[i].frame >= M.max_episode_steps)) { env_reset_with(M, W, e->ep[i], seed, env0 + i, obs, 1, cs); done = 1; }
+    e->rew[i] = e->out[i].reward; e->done[i] = done;
+}
+template <class T>
+static void substeps_static(Emul* e, int env, int n) {
+    RowWS ws{e->ws.data(), 1};
+    LinkCache<1> lc{e->lcbuf.data() + (size_t)env * e->lcsize};
+    for (int s = 0; s < n; s++) substep_static<T>(e->M, e->w[env], ws, lc);
+}
 
 extern "C" {
 void* emul_create(const rs_model_desc* m, int n) {
@@ -31,7 +55,20 @@ void* emul_create(const rs_model_desc* m, int n) {
     e->rec = 2 * (6 + e->M.n_dof) + R_NSCALAR; e->maxr = NL + 3 * MC;
     e->ws.resize((size_t)e->rec * e->maxr);
     e->obs.resize((size_t)n * e->M.obs_dim); e->rew.resize(n); e->done.resize(n);
+    e->topo = 0; e->lcsize = 9 * RS_MAX_LINKS + 21; e->lcbuf.assign((size_t)n * e->lcsize, 0.f);
     return e;
+}
+// select the static-topology sweeps if the descriptor matches a generated topology; returns the topology id
+int emul_use_static(void* h, int on) {
+    Emul* e = (Emul*)h;
+    e->topo = 0;
+    if (on) {
+        if (topo_matches<TopoHumanoid>(e->M)) e->topo = 1;
+        else if (topo_matches<TopoAnt>(e->M)) e->topo = 2;
+        else if (topo_matches<TopoHopper>(e->M)) e->topo = 3;
+        else if (topo_matches<TopoWalker2d>(e->M)) e->topo = 4;
+    }
+    return e->topo;
 }
 void emul_destroy(void* h) { delete (Emul*)h; }
 int emul_state_dim(void* h) { Emul* e = (Emul*)h; return (e->M.fixed_base ? 0 : 13) + 2 * e->M.n_dof; }
@@ -49,6 +86,12 @@ void emul_get_state(void* h, int env, double* s) {
 void emul_set_tau(void* h, int env, const double* tau) { Emul* e = (Emul*)h; for (int d = 0; d < e->M.n_dof; d++) e->w[env].tau[d] = (float)tau[d]; }
 void emul_substeps(void* h, int env, int n) {
     Emul* e = (Emul*)h; RowWS ws{e->ws.data(), 1};
+    switch (e->topo) {
+        case 1: substeps_static<TopoHumanoid>(e, env, n); return;
+        case 2: substeps_static<TopoAnt>(e, env, n); return;
+        case 3: substeps_static<TopoHopper>(e, env, n); return;
+        case 4: substeps_static<TopoWalker2d>(e, env, n); return;
+    }
     for (int s = 0; s < n; s++) substep(e->M, e->w[env], ws);
 }
 void emul_reset_all(void* h, uint32_t seed, uint32_t env0) {
@@ -67,6 +110,15 @@ void emul_step(void* h, const double* actions, int auto_reset, uint32_t seed, ui
         float a[RS_MAX_ACT];
         for (int k = 0; k < M.n_act; k++) a[k] = (float)actions[(size_t)i * M.n_act + k];
         W_t& W = e->w[i];
+        if (e->topo) {
+            switch (e->topo) {
+                case 1: step_env_static<TopoHumanoid>(e, i, a, auto_reset, seed, env0); break;
+                case 2: step_env_static<TopoAnt>(e, i, a, auto_reset, seed, env0); break;
+                case 3: step_env_static<TopoHopper>(e, i, a, auto_reset, seed, env0); break;
+                default: step_env_static<TopoWalker2d>(e, i, a, auto_reset, seed, env0); break;
+            }
+            continue;
+        }
         apply_action(M, W, a, 1);
         for (int s = 0; s < M.frame_skip; s++) substep(M, W, ws);
         float* obs = &e->obs[(size_t)i * M.obs_dim];

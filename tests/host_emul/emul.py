@@ -12,6 +12,8 @@ def build(force=False):
     srcs = [os.path.join(_HERE, "emul.cpp"),
             os.path.join(_HERE, "..", "..", "roboschool_b200", "csrc", "rs_core.cuh"),
             os.path.join(_HERE, "..", "..", "roboschool_b200", "csrc", "rs_devmodel.h"),
+            os.path.join(_HERE, "..", "..", "roboschool_b200", "csrc", "rs_static.cuh"),
+            os.path.join(_HERE, "..", "..", "roboschool_b200", "csrc", "rs_topo_gen.h"),
             os.path.join(_HERE, "..", "..", "include", "rs_model.h")]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++",
@@ -27,6 +29,7 @@ def lib():
         dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
         L.emul_create.restype = P; L.emul_create.argtypes = [P, I]
         L.emul_destroy.argtypes = [P]
+        L.emul_use_static.argtypes = [P, I]
         L.emul_state_dim.argtypes = [P]
         L.emul_set_state.argtypes = [P, I, dp, I]
         L.emul_get_state.argtypes = [P, I, dp]
@@ -54,6 +57,12 @@ class EmulWorld:
         self.h = self.L.emul_create(ctypes.addressof(model), n_envs)
         assert self.h
         self.sdim = self.L.emul_state_dim(self.h)
+        self.topo = 0
+
+    def use_static(self, on=True):
+        """Switch to the static-topology sweeps (rs_static.cuh); returns the matched topology id (0 = none)."""
+        self.topo = self.L.emul_use_static(self.h, int(on))
+        return self.topo
 
     def __del__(self):
         try: self.L.emul_destroy(self.h)

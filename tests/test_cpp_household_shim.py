@@ -1,0 +1,90 @@
+"""The drop-in boundary: the reference's UNMODIFIED Python env classes (from /root/reference) run on top
+of roboschool_b200.cpp_household.  On this GPU-less box the shim's backend is swapped for the oracle
+(tests/oracle_backend.py); the shim logic under test -- load_mjcf, joints/parts ordering, torque
+caching, step(frame_skip), pose/speed readback, contact_list, reset_current_position,
+set_pose_and_speed -- is identical for the CUDA backend."""
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+from tests.conftest import HAVE_REF
+
+pytestmark = pytest.mark.skipif(not HAVE_REF, reason="reference Python sources not present")
+
+
+@pytest.fixture()
+def ref_roboschool(monkeypatch, oracle_lib):
+    from tools.gen_golden_epilogue import install_stub_gym
+    import roboschool_b200.cpp_household as shim
+    from tests.oracle_backend import OracleBackend
+    monkeypatch.setattr(shim, "_make_backend", lambda model, n_envs=1, device=0: OracleBackend(model, n_envs))
+    shim.World._model_cache.clear()
+    install_stub_gym()
+    for k in [k for k in sys.modules if k == "roboschool" or k.startswith("roboschool.")]:
+        del sys.modules[k]
+    monkeypatch.syspath_prepend("/root/reference")
+    sys.modules["roboschool.cpp_household"] = shim
+    warnings.simplefilter("ignore")
+    import roboschool
+    yield roboschool
+    for k in [k for k in sys.modules if k == "roboschool" or k.startswith("roboschool.")]:
+        del sys.modules[k]
+
+
+class _Spec:
+    max_episode_steps = 1000
+
+
+@pytest.mark.parametrize("cls,env_id", [("RoboschoolHopper", "RoboschoolHopper-v1"), ("RoboschoolAnt", "RoboschoolAnt-v1"),
+                                        ("RoboschoolHumanoid", "RoboschoolHumanoid-v1")])
+def test_reference_env_runs_on_shim_and_matches_fused_path(cls, env_id, ref_roboschool, oracle_lib):
+    from roboschool_b200 import envspec
+    env = getattr(ref_roboschool, cls)()
+    env.spec = _Spec()
+    env.seed(3)
+    obs0 = env.reset()
+    m = envspec.load_env_model(env_id)
+    assert obs0.shape == (m.obs_dim,) and obs0.dtype == np.float32
+    assert [j.name for j in env.ordered_joints] == m.meta["ordered_joints"]
+    # take the shim's post-reset state as the start of a fused (batched-path) oracle rollout
+    robot = env.cpp_robot
+    s0 = robot._backend.get_state()[0]
+    o = oracle_lib.OracleWorld(m, 1)
+    o.set_state(0, s0)
+    o.set_episode(0, env.potential, env.initial_z if env.initial_z is not None else -1.0, np.zeros(m.n_feet), 0)
+    rng = np.random.RandomState(0)
+    for t in range(30):
+        a = rng.uniform(-1, 1, m.n_act).astype(np.float32)
+        ob, rew, done, _ = env.step(a)
+        oo, orw, od = o.step(a[None].astype(np.float64))
+        assert np.abs(ob - oo[0]).max() < 1e-5, (t, np.abs(ob - oo[0]).max())
+        assert abs(rew - orw[0]) < 1e-4
+        assert bool(done) == bool(od[0])
+
+
+def test_pose_math_roundtrip():
+    import roboschool_b200.cpp_household as shim
+    p = shim.Pose()
+    p.set_rpy(0.3, -0.2, 1.1)
+    r, pi, y = p.rpy()
+    assert abs(r - 0.3) < 1e-12 and abs(pi + 0.2) < 1e-12 and abs(y - 1.1) < 1e-12
+    p.set_xyz(1, 2, 3); p.move_xyz(1, 0, -1)
+    assert p.xyz() == (2, 2, 2)
+    q = shim.Pose(); q.set_rpy(0, 0, 0.5)
+    q.rotate_z(0.25)
+    assert abs(q.rpy()[2] - 0.75) < 1e-12
+    a = shim.Pose(); a.set_rpy(0, 0, np.pi / 2); a.set_xyz(1, 0, 0)
+    b = shim.Pose(); b.set_xyz(1, 0, 0)
+    c = a.dot(b)
+    assert np.allclose(c.xyz(), (1, 1, 0), atol=1e-12)
+
+
+def test_load_failure_is_silent_like_reference(capsys):
+    import roboschool_b200.cpp_household as shim
+    w = shim.World(9.8, 0.0165 / 4)
+    assert w.load_mjcf("/nonexistent/robot.xml") == []
+    assert "cannot load MJCF" in capsys.readouterr().err
+    assert w.step(4) is False
