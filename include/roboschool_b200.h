@@ -82,6 +82,12 @@ int rs_world_step_profile(rs_world* w, const float* actions_dev, float* obs_dev,
 int rs_world_step_host(rs_world* w, const float* actions_host, float* obs_host, float* reward_host,
                        uint8_t* done_host, int auto_reset);
 
+/* policy + step for callers whose observations live in HOST memory (numpy): H2D obs_in -> policy forward on the
+ * tensor cores -> env step with auto-reset -> D2H obs_out/reward/done; one stream synchronisation.
+ * obs_in_host == NULL continues from the observations already on the device. */
+int rs_world_policy_step_host(rs_world* w, rs_policy* p, const float* obs_in_host, float* obs_out_host, float* reward_host,
+                              uint8_t* done_host);
+
 /* Physics only: n sub-steps with explicit joint torques tau_host[n_envs][ndof] (NULL = keep the
  * torques of the last call); no task logic.  Joint::set_motor_torque + World::bullet_step
  * (physics-bullet.cpp:497-508, 358-412). */

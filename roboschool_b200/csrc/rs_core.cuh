@@ -50,6 +50,7 @@ struct DevModel {
     float break_thresh[ML + 1];
     int g_link[MG], g_type[MG], g_floor[MG];
     float g_p0[MG][3], g_p1[MG][3], g_radius[MG], g_fric_floor[MG];
+    float g_bound[MG];                // bounding-sphere radius about the segment midpoint (half length + radius)
     unsigned char pair_a[MP], pair_b[MP], pair_ss[MP];
     float pair_thresh[MP], pair_friction[MP];
     float gravity, timestep, lin_damping, ang_damping, max_coord_vel, erp, erp2, split_thresh, max_limit_impulse, use_gyro;
@@ -679,7 +680,31 @@ RS_HD void collide(const DevModel& M, Work<NL, MC, SL>& W) {
     int oi = 0, no = 0;
     const int nold = W.ccount[old];
     const int nman = M.n_geoms + M.n_pairs;
+    // world end points of every geom, once per sub-step (each geom takes part in many pairs)
+    float gw[MG][6];
+    for (int g = 0; g < M.n_geoms; g++) {
+        int b = M.g_link[g] + 1;
+        to_world(W, b, M.g_p0[g], gw[g]);
+        if (M.g_type[g] == RS_GEOM_CAPSULE) to_world(W, b, M.g_p1[g], gw[g] + 3);
+        else { gw[g][3] = gw[g][0]; gw[g][4] = gw[g][1]; gw[g][5] = gw[g][2]; }
+    }
     for (int k = 0; k < nman; k++) {
+        const bool has_old = (oi < nold && W.ckey[old][oi] == k);
+        // cheap rejects first: nothing cached for this manifold and the shapes are out of reach
+        if (!has_old) {
+            if (k < M.n_geoms) {
+                if (!M.g_floor[k]) continue;
+                float zmin = fminf(gw[k][2], gw[k][5]) - M.g_radius[k];
+                if (!(zmin < M.break_thresh[M.g_link[k] + 1])) continue;
+            } else {
+                int pk = k - M.n_geoms, ga = M.pair_a[pk], gb = M.pair_b[pk];
+                float dx = 0.5f * (gw[ga][0] + gw[ga][3] - gw[gb][0] - gw[gb][3]);
+                float dy = 0.5f * (gw[ga][1] + gw[ga][4] - gw[gb][1] - gw[gb][4]);
+                float dz = 0.5f * (gw[ga][2] + gw[ga][5] - gw[gb][2] - gw[gb][5]);
+                float reach = M.g_bound[ga] + M.g_bound[gb] + M.pair_thresh[pk];
+                if (dx * dx + dy * dy + dz * dz > reach * reach) continue;
+            }
+        }
         Manifold4 mf; mf.n = 0;
         while (oi < nold && W.ckey[old][oi] == k) {
 #pragma unroll
@@ -693,16 +718,12 @@ RS_HD void collide(const DevModel& M, Work<NL, MC, SL>& W) {
             if (!M.g_floor[k]) continue;
             int b = M.g_link[k] + 1;
             float thr = M.break_thresh[b];
-            float c0[3], c1[3];
-            to_world(W, b, M.g_p0[k], c0);
-            if (M.g_type[k] == RS_GEOM_CAPSULE) {
-                to_world(W, b, M.g_p1[k], c1);
-                if (c1[2] < c0[2]) { c0[0] = c1[0]; c0[1] = c1[1]; c0[2] = c1[2]; }
-            }
-            float dist = c0[2] - M.g_radius[k];
+            // support vertex in -z: lower end sphere, first end wins ties
+            const float* c = (M.g_type[k] == RS_GEOM_CAPSULE && gw[k][5] < gw[k][2]) ? gw[k] + 3 : gw[k];
+            float dist = c[2] - M.g_radius[k];
             if (dist < thr) {
                 const float nz[3] = {0.f, 0.f, 1.f};
-                float pOnB[3] = {c0[0], c0[1], 0.f};
+                float pOnB[3] = {c[0], c[1], 0.f};
                 manifold_add(mf, W, b, -1, nz, pOnB, dist, thr);
             }
             if (mf.n) manifold_refresh(mf, W, b, -1, thr);
@@ -711,10 +732,8 @@ RS_HD void collide(const DevModel& M, Work<NL, MC, SL>& W) {
             int ga = M.pair_a[pk], gb = M.pair_b[pk];
             int bA = M.g_link[ga] + 1, bB = M.g_link[gb] + 1;
             float thr = M.pair_thresh[pk];
-            float a0[3], a1[3], b0[3], b1[3], cA[3], cB[3];
-            to_world(W, bA, M.g_p0[ga], a0); to_world(W, bA, M.g_p1[ga], a1);
-            to_world(W, bB, M.g_p0[gb], b0); to_world(W, bB, M.g_p1[gb], b1);
-            seg_seg_closest(a0, a1, b0, b1, cA, cB);
+            float cA[3], cB[3];
+            seg_seg_closest(gw[ga], gw[ga] + 3, gw[gb], gw[gb] + 3, cA, cB);
             float d[3] = {cA[0] - cB[0], cA[1] - cB[1], cA[2] - cB[2]};
             float len = sqrtf(dot3(d, d)), rB = M.g_radius[gb];
             float dist = len - M.g_radius[ga] - rB;

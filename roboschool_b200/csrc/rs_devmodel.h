@@ -1,5 +1,6 @@
 // rs_devmodel.h -- host-side conversion rs_model_desc (doubles) -> rs::DevModel (floats + derived tables).
 #pragma once
+#include <math.h>
 #include <string.h>
 #include "rs_core.cuh"
 
@@ -51,6 +52,10 @@ inline int build_dev_model(const rs_model_desc* m, DevModel* D, const char** err
         D->g_link[g] = m->g_link[g]; D->g_type[g] = m->g_type[g]; D->g_floor[g] = m->g_floor[g];
         for (int k = 0; k < 3; k++) { D->g_p0[g][k] = (float)m->g_p0[g][k]; D->g_p1[g][k] = (float)m->g_p1[g][k]; }
         D->g_radius[g] = (float)m->g_radius[g];
+        {
+            double dx = m->g_p1[g][0] - m->g_p0[g][0], dy = m->g_p1[g][1] - m->g_p0[g][1], dz = m->g_p1[g][2] - m->g_p0[g][2];
+            D->g_bound[g] = (float)(0.5 * sqrt(dx * dx + dy * dy + dz * dz) + m->g_radius[g]) * 1.0001f + 1e-6f;
+        }
         D->g_fric_floor[g] = (float)(m->g_friction[g] * m->floor_friction);
     }
     for (int k = 0; k < m->n_pairs; k++) {

@@ -284,16 +284,22 @@ RS_HD void static_aba(const DevModel& M, Work<NL, MC, SL>& W, const LinkCache<ST
 // unit-impulse response (fillContactJacobianMultiDof + calcAccelerationDeltasMultiDof), static sweeps.
 // Same contract as the generic row_response().
 // ---------------------------------------------------------------------------------------------
-template <class T, int NL, int MC, bool SL, int STRIDE>
+// HASW=false: pure joint-space row (joint limit): no wrench to walk up the tree, J is the unit vector e_jdof
+template <class T, bool HASW, int NL, int MC, bool SL, int STRIDE>
 RS_HD float static_row_response(const Work<NL, MC, SL>& W, const LinkCache<STRIDE>& lc, int body, const float* wrench, int jdof, float jdir,
                                 const RowWS& ws, int row, int rec, bool first, const float* vel, float* relvel) {
     constexpr int n = T::NL, nd = 6 + T::ND;
-    float F[n + 1][6], Z[n + 1][6], Y[n], jd[n];
+    float F[HASW ? n + 1 : 1][6], Z[n + 1][6], Y[n], jd[n];
     static_for<n + 1>([&](auto bc) {
         constexpr int b = decltype(bc)::value;
-        const bool hit = (b == body);
+        if constexpr (HASW) {
+            const bool hit = (b == body);
 #pragma unroll
-        for (int k = 0; k < 6; k++) { float w = hit ? wrench[k] : 0.f; F[b][k] = w; Z[b][k] = -w; }
+            for (int k = 0; k < 6; k++) { float w = hit ? wrench[k] : 0.f; F[b][k] = w; Z[b][k] = -w; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 6; k++) Z[b][k] = 0.f;
+        }
     });
     float denom = 0.f;
     static_rfor<n>([&](auto ic) {
@@ -307,7 +313,8 @@ RS_HD float static_row_response(const Work<NL, MC, SL>& W, const LinkCache<STRID
         constexpr int d = T::dof[i];
         if constexpr (d >= 0) {
             const float jj = (d == jdof) ? jdir : 0.f;
-            float j = sdot<T, i>(F[i + 1]) + jj;
+            float j = jj;
+            if constexpr (HASW) j += sdot<T, i>(F[i + 1]);
             float y = jj - sdot<T, i>(Z[i + 1]);
             Y[i] = y; jd[i] = j;
             float kk = lc.at(lc_invd<T>() + i) * y;
@@ -318,17 +325,17 @@ RS_HD float static_row_response(const Work<NL, MC, SL>& W, const LinkCache<STRID
             *relvel += j * vel[6 + d];
         }
         xf_force_inv_add(Z[p + 1], R, r, Zt);
-        xf_force_inv_add(F[p + 1], R, r, F[i + 1]);
+        if constexpr (HASW) xf_force_inv_add(F[p + 1], R, r, F[i + 1]);
     });
     float acc[n + 1][6];
     if constexpr (T::FIXED_BASE) {
 #pragma unroll
         for (int k = 0; k < 6; k++) { acc[0][k] = 0.f; if (first) { ws.at(row, rec, k) = 0.f; ws.at(row, rec, nd + k) = 0.f; } }
     } else {
-        float jw[3], jv[3], rr[6], uw[3], uv[3], Lb[21];
+        float jw[3] = {0.f, 0.f, 0.f}, jv[3] = {0.f, 0.f, 0.f}, rr[6], uw[3], uv[3], Lb[21];
 #pragma unroll
         for (int k = 0; k < 21; k++) Lb[k] = lc.at(lc_lb<T>() + k);
-        tmulv(jw, W.Rwl[0], F[0]); tmulv(jv, W.Rwl[0], F[0] + 3);
+        if constexpr (HASW) { tmulv(jw, W.Rwl[0], F[0]); tmulv(jv, W.Rwl[0], F[0] + 3); }
         chol6_solve(rr, Lb, Z[0]);
 #pragma unroll
         for (int k = 0; k < 6; k++) acc[0][k] = -rr[k];
@@ -379,7 +386,8 @@ RS_HD void substep_static(const DevModel& M, Work<NL, MC, SL>& W, const RowWS& w
     static_aba<T>(M, W, lc, dt);
     if (pc) { c1 = RS_CLOCK(); pc->t[2] += c1 - c0; c0 = c1; }
     solve_with(M, W, dt, ws, [&](int body, const float* wr, int jdof, float jdir, int row, int rec, bool first, const float* vel, float* relvel) {
-        return static_row_response<T>(W, lc, body, wr, jdof, jdir, ws, row, rec, first, vel, relvel);
+        if (body < 0) return static_row_response<T, false>(W, lc, body, wr, jdof, jdir, ws, row, rec, first, vel, relvel);
+        return static_row_response<T, true>(W, lc, body, wr, jdof, jdir, ws, row, rec, first, vel, relvel);
     });
     if (pc) { c1 = RS_CLOCK(); pc->t[3] += c1 - c0; c0 = c1; }
     integrate(M, W, dt);

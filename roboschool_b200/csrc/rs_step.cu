@@ -632,6 +632,29 @@ extern "C" int rs_world_rollout(rs_world* w, rs_policy* p, int n_steps, uint32_t
     return 0;
 }
 
+// End-to-end call for callers whose observations live in HOST memory: H2D obs -> policy on the tensor cores ->
+// env step (auto-reset) -> D2H obs/reward/done, all on the world's stream, one synchronisation at the end.
+extern "C" int rs_world_policy_step_host(rs_world* w, rs_policy* p, const float* obs_in_host, float* obs_out_host, float* reward_host,
+                                         uint8_t* done_host) {
+    if (!p || !obs_out_host || !reward_host || !done_host) return fail("rs_world_policy_step_host: null argument");
+    CK(cudaSetDevice(w->device));
+    size_t N = (size_t)w->n, O = (size_t)w->desc.obs_dim;
+    if (obs_in_host) {   // NULL: continue from the observations already on the device (after rs_world_rollout_reset / rollout)
+        memcpy(w->h_obs, obs_in_host, sizeof(float) * N * O);
+        CK(cudaMemcpyAsync(w->d_obs, w->h_obs, sizeof(float) * N * O, cudaMemcpyHostToDevice, w->stream));
+    }
+    if (rs_policy_forward(p, w->d_obs, w->d_act, w->n, (void*)w->stream)) return 1;
+    if (launch_step(w, w->d_act, w->d_obs, w->d_rew, w->d_done, 1, w->rollout_seed, w->env_id0, nullptr, w->stream)) return 1;
+    CK(cudaMemcpyAsync(w->h_obs, w->d_obs, sizeof(float) * N * O, cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaMemcpyAsync(w->h_rew, w->d_rew, sizeof(float) * N, cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaMemcpyAsync(w->h_done, w->d_done, N, cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    memcpy(obs_out_host, w->h_obs, sizeof(float) * N * O);
+    memcpy(reward_host, w->h_rew, sizeof(float) * N);
+    memcpy(done_host, w->h_done, N);
+    return 0;
+}
+
 // obs buffer owned by the world (the rollout's policy input); reset writes the first observation here
 extern "C" int rs_world_rollout_reset(rs_world* w, uint32_t seed, uint32_t env_id0, void* stream) {
     return rs_world_reset(w, seed, env_id0, nullptr, w->d_obs, stream);

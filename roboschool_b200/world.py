@@ -60,6 +60,15 @@ class BatchedWorld:
         _lib.check(self.L.rs_world_step_host(self.h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data, int(auto_reset)))
         return obs, rew, done
 
+    def policy_step_host(self, policy, obs_in):
+        """obs (host) -> policy (tensor cores) -> step (auto-reset) -> obs, reward, done (host)."""
+        o = None if obs_in is None else np.ascontiguousarray(obs_in, dtype=np.float32).reshape(self.n, self.O)
+        obs = np.empty((self.n, self.O), dtype=np.float32)
+        rew = np.empty(self.n, dtype=np.float32)
+        done = np.empty(self.n, dtype=np.uint8)
+        _lib.check(self.L.rs_world_policy_step_host(self.h, policy.h, _ptr(o), obs.ctypes.data, rew.ctypes.data, done.ctypes.data))
+        return obs, rew, done
+
     def substeps(self, n, tau=None):
         t = None
         if tau is not None:
