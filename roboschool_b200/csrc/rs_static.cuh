@@ -286,7 +286,7 @@ RS_HD void static_aba(const DevModel& M, Work<NL, MC, SL>& W, const LinkCache<ST
 // ---------------------------------------------------------------------------------------------
 // HASW=false: pure joint-space row (joint limit): no wrench to walk up the tree, J is the unit vector e_jdof
 template <class T, bool HASW, int NL, int MC, bool SL, int STRIDE>
-RS_HD float static_row_response(const Work<NL, MC, SL>& W, const LinkCache<STRIDE>& lc, int body, const float* wrench, int jdof, float jdir,
+RS_HDN float static_row_response(const Work<NL, MC, SL>& W, const LinkCache<STRIDE>& lc, int body, const float* wrench, int jdof, float jdir,
                                 const RowWS& ws, int row, int rec, bool first, const float* vel, float* relvel) {
     constexpr int n = T::NL, nd = 6 + T::ND;
     float F[HASW ? n + 1 : 1][6], Z[n + 1][6], Y[n], jd[n];
