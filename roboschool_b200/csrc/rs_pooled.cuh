@@ -1,0 +1,454 @@
+// rs_pooled.cuh -- constraint-row setup balanced across the lanes of a warp ("row pooling").
+//
+// The step kernel maps one env to one lane.  Envs differ in how many constraint rows they have in a
+// sub-step (Humanoid: mean 3-4, max 8-12 inside one warp), and building a row -- its Jacobian and its
+// unit-impulse response M^-1 J^T, i.e. btMultiBody::fillContactJacobianMultiDof +
+// calcAccelerationDeltasMultiDof -- is the most expensive part of the sub-step.  Here the warp pools the
+// row-building TASKS of its 32 envs and deals them out evenly:
+//
+//   owner lanes   enumerate their limit rows / contact points, write one task descriptor each into the
+//                 warp's pool (slots assigned by a warp prefix sum = ballot-style compaction);
+//   all lanes     take tasks t = lane, lane+32, ...: one task = one limit row (1 right-hand side) or one
+//                 contact point (normal + 2 friction rows = 3 right-hand sides through ONE pair of tree
+//                 sweeps).  The lane reads the OWNER env's link cache (cos/sin, h, 1/D, base Cholesky,
+//                 base rotation) from shared memory -- laid out [slot][lane], so any lane can read any
+//                 env of the warp without bank conflicts -- and writes J, M^-1 J^T and the row's
+//                 denominator into the pool, [word][slot], slot-contiguous => coalesced;
+//   owner lanes   run Bullet's projected Gauss-Seidel over their own rows exactly as before.
+//
+// The leaves->root sweep only visits the links between the loaded body and the root (the wrench is zero
+// elsewhere); the root->leaves sweep visits every link.  Arithmetic per row is the same as in
+// static_row_response(); the denominator J.M^-1 J^T is taken as wrench . (spatial response of the body),
+// which is the same sum in a different association.
+//
+// The functions are __host__ __device__: tests/host_emul runs them with a 1-lane "warp" (WarpHost).
+#pragma once
+#include "rs_static.cuh"
+
+namespace rs {
+
+// pool of row records shared by the lanes of a warp: word k of slot s at p[k * cap + s]
+struct RowPool {
+    float* p;
+    int cap;
+    RS_HD float& at(int slot, int k) const { return p[(size_t)k * cap + slot]; }
+};
+// words of a row record: [0,nd) J ; [nd,2nd) M^-1 J^T ; [2nd] denominator.  A task descriptor lives in
+// words [0,25) of the task's first row slot until the task is executed (needs 2*nd+1 >= 25).
+constexpr int POOL_DESC_WORDS = 25;
+template <class T> constexpr int pool_rec() { return 2 * (6 + T::ND) + 1; }
+
+struct WarpHost {
+    static constexpr int WIDTH = 1;
+    RS_HD int lane() const { return 0; }
+    RS_HD int excl_scan(int v, int& total) const { total = v; return 0; }
+    RS_HD void sync() const {}
+};
+#ifdef __CUDACC__
+struct WarpDev {
+    static constexpr int WIDTH = 32;
+    RS_HD int lane() const {
+#ifdef __CUDA_ARCH__
+        return threadIdx.x & 31;
+#else
+        return 0;
+#endif
+    }
+    RS_HD int excl_scan(int v, int& total) const {
+#ifdef __CUDA_ARCH__
+        int x = v;
+        const int l = threadIdx.x & 31;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (l >= o) x += y; }
+        total = __shfl_sync(0xffffffffu, x, 31);
+        return x - v;
+#else
+        total = v; return 0;
+#endif
+    }
+    RS_HD void sync() const {
+#ifdef __CUDA_ARCH__
+        __syncwarp();
+#endif
+    }
+};
+#endif
+
+RS_HD float i2f(int v) { union { int i; float f; } u; u.i = v; return u.f; }
+RS_HD int f2i(float v) { union { int i; float f; } u; u.f = v; return u.i; }
+
+// spatial force child->parent (assign): f' = R^T f ; t' = R^T (t + r x f)
+RS_HD void xf_force_inv(float* out, const float* R, const float* r, const float* in) {
+    float c[3], t[3];
+    cross3(c, r, in + 3);
+    t[0] = in[0] + c[0]; t[1] = in[1] + c[1]; t[2] = in[2] + c[2];
+    tmulv(out, R, t);
+    tmulv(out + 3, R, in + 3);
+}
+
+// ---------------------------------------------------------------------------------------------
+// NR simultaneous unit-impulse responses that share the loaded body.
+//   HASW: the right-hand sides are wrenches wr[rr] (torque;force) on body `body` (0 = base, i+1 = link i), in that
+//         body's coordinates about its COM.  !HASW: one unit generalized force jdir on the joint of link `body-1`.
+//   Rows go to pool slots slot0 .. slot0+NR-1.  first: overwrite; else accumulate (second body of a pair).
+//   denom[rr] = J . M^-1 J^T of THIS side.
+// ---------------------------------------------------------------------------------------------
+template <class T, int NR, bool HASW, int STRIDE>
+RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*wr)[6], float jdir,
+                           const RowPool& pool, int slot0, bool first, float* denom) {
+    constexpr int n = T::NL, nd = 6 + T::ND;
+    float F[HASW ? NR : 1][6], Z[NR][6], Y[NR][n];
+#pragma unroll
+    for (int rr = 0; rr < NR; rr++) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            if constexpr (HASW) { F[rr][k] = wr[rr][k]; Z[rr][k] = -wr[rr][k]; }
+            else Z[rr][k] = 0.f;
+        }
+        denom[rr] = 0.f;
+    }
+    int cur = body;   // body whose frame F/Z are expressed in; walks to the root
+    static_rfor<n>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int p = T::parent[i], d = T::dof[i];
+        const bool on = (cur == i + 1);
+        if (on) {
+            float R[9], r[3];
+            cached_xform<T, i>(lc, R, r);
+            if constexpr (d >= 0) {
+                float h[6];
+#pragma unroll
+                for (int k = 0; k < 6; k++) h[k] = lc.at(lc_h<T>() + 6 * i + k);
+                const float invD = lc.at(lc_invd<T>() + i);
+                const float jj = (!HASW && body == i + 1) ? jdir : 0.f;
+#pragma unroll
+                for (int rr = 0; rr < NR; rr++) {
+                    float j = jj;
+                    if constexpr (HASW) j += sdot<T, i>(F[rr]);
+                    const float y = jj - sdot<T, i>(Z[rr]);
+                    Y[rr][i] = y;
+                    const float kk = invD * y;
+#pragma unroll
+                    for (int k = 0; k < 6; k++) Z[rr][k] += h[k] * kk;
+                    float& J = pool.at(slot0 + rr, 6 + d);
+                    J = first ? j : J + j;
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < NR; rr++) {
+                float t[6];
+                xf_force_inv(t, R, r, Z[rr]);
+#pragma unroll
+                for (int k = 0; k < 6; k++) Z[rr][k] = t[k];
+                if constexpr (HASW) {
+                    xf_force_inv(t, R, r, F[rr]);
+#pragma unroll
+                    for (int k = 0; k < 6; k++) F[rr][k] = t[k];
+                }
+            }
+            cur = p + 1;
+        } else {
+            if constexpr (d >= 0) {
+#pragma unroll
+                for (int rr = 0; rr < NR; rr++) { Y[rr][i] = 0.f; if (first) pool.at(slot0 + rr, 6 + d) = 0.f; }
+            }
+        }
+    });
+    float acc[NR][n + 1][6];
+    if constexpr (T::FIXED_BASE) {
+#pragma unroll
+        for (int rr = 0; rr < NR; rr++) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                acc[rr][0][k] = 0.f;
+                if (first) { pool.at(slot0 + rr, k) = 0.f; pool.at(slot0 + rr, nd + k) = 0.f; }
+            }
+        }
+    } else {
+        float Lb[21], Rb[9];
+#pragma unroll
+        for (int k = 0; k < 21; k++) Lb[k] = lc.at(lc_lb<T>() + k);
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rb[k] = lc.at(lc_rb<T>() + k);
+#pragma unroll
+        for (int rr = 0; rr < NR; rr++) {
+            float jw[3] = {0.f, 0.f, 0.f}, jv[3] = {0.f, 0.f, 0.f}, sol[6], uw[3], uv[3];
+            if constexpr (HASW) { tmulv(jw, Rb, F[rr]); tmulv(jv, Rb, F[rr] + 3); }
+            chol6_solve(sol, Lb, Z[rr]);
+#pragma unroll
+            for (int k = 0; k < 6; k++) acc[rr][0][k] = -sol[k];
+            tmulv(uw, Rb, acc[rr][0]); tmulv(uv, Rb, acc[rr][0] + 3);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                float& J0 = pool.at(slot0 + rr, k); float& J1 = pool.at(slot0 + rr, 3 + k);
+                float& U0 = pool.at(slot0 + rr, nd + k); float& U1 = pool.at(slot0 + rr, nd + 3 + k);
+                if (first) { J0 = jw[k]; J1 = jv[k]; U0 = uw[k]; U1 = uv[k]; }
+                else { J0 += jw[k]; J1 += jv[k]; U0 += uw[k]; U1 += uv[k]; }
+            }
+            if constexpr (HASW) { if (body == 0) denom[rr] = dot6(wr[rr], acc[rr][0]); }
+        }
+    }
+    static_for<n>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr int p = T::parent[i], d = T::dof[i];
+        float R[9], r[3];
+        cached_xform<T, i>(lc, R, r);
+        float h[6], invD = 0.f;
+        if constexpr (d >= 0) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) h[k] = lc.at(lc_h<T>() + 6 * i + k);
+            invD = lc.at(lc_invd<T>() + i);
+        }
+#pragma unroll
+        for (int rr = 0; rr < NR; rr++) {
+            xf_motion(acc[rr][i + 1], R, r, acc[rr][p + 1]);
+            if constexpr (d >= 0) {
+                const float a = invD * (Y[rr][i] - dot6(acc[rr][i + 1], h));
+                saxpy<T, i>(acc[rr][i + 1], a);
+                float& U = pool.at(slot0 + rr, nd + 6 + d);
+                U = first ? a : U + a;
+                if constexpr (!HASW) { if (body == i + 1) denom[rr] = a * jdir; }
+            }
+            if constexpr (HASW) { if (body == i + 1) denom[rr] = dot6(wr[rr], acc[rr][i + 1]); }
+        }
+    });
+}
+
+// resolveSingleConstraintRowGeneric on a pooled row record
+template <int ND>
+RS_HD void resolve_pooled(const RowPool& pool, int slot, float* dv, float rhs, float invd, float lo, float hi, float& applied) {
+    float j[ND], u[ND];
+#pragma unroll
+    for (int k = 0; k < ND; k++) { j[k] = pool.at(slot, k); u[k] = pool.at(slot, ND + k); }
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < ND; k++) dot += j[k] * dv[k];
+    float dimp = rhs - dot * invd;
+    float sum = applied + dimp;
+    if (sum < lo) { dimp = lo - applied; applied = lo; }
+    else if (sum > hi) { dimp = hi - applied; applied = hi; }
+    else applied = sum;
+#pragma unroll
+    for (int k = 0; k < ND; k++) dv[k] += u[k] * dimp;
+}
+
+// ---------------------------------------------------------------------------------------------
+// btMultiBodyConstraintSolver for one sub-step, rows built by the whole warp.
+//   valid   : this lane owns a live env (the tail warp's spare lanes only help)
+//   lc_lane0: link cache of lane 0 of this warp; the cache of lane o is lc_lane0 + o (host: o == 0)
+// ---------------------------------------------------------------------------------------------
+template <class T, class Warp, int NL, int MC, bool SL, int STRIDE>
+RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL, MC, SL>& W, float dt, const RowPool& pool, float* lc_lane0) {
+    static_assert(pool_rec<T>() >= POOL_DESC_WORDS, "row record too small to hold a task descriptor");
+    constexpr int nd = 6 + T::ND, n = T::NL;
+    const int lane = warp.lane();
+    // ---- owner: enumerate rows ----
+    int n_nc = 0, nc = 0;
+    int lim_code[n > 0 ? n : 1];
+    float lim_pen[n > 0 ? n : 1];
+    if (valid) {
+        static_for<n>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr int d = T::dof[i];
+            if constexpr (d >= 0) {
+                if (M.has_limit[i]) {
+                    const float q = W.q[d];
+                    const float plo = q - M.lim_lo[i], phi = M.lim_hi[i] - q;
+                    // btMultiBodyJointLimitConstraint: a row per violated side (lower first)
+                    if (!(plo > 0.f)) { lim_code[n_nc] = lane | ((i + 1) << 8); lim_pen[n_nc] = plo; n_nc++; }
+                    else if (!(phi > 0.f)) { lim_code[n_nc] = lane | ((i + 1) << 8) | (1 << 16); lim_pen[n_nc] = phi; n_nc++; }
+                }
+            }
+        });
+        nc = W.ccount[W.cur];
+    }
+    int LT, CT;
+    const int lbase = warp.excl_scan(n_nc, LT);
+    const int cbase = warp.excl_scan(nc, CT);
+    W.n_rows = n_nc + 3 * nc; W.n_contacts = nc;
+    if (LT + CT == 0) return;   // warp-uniform
+    const int cur = W.cur;
+    for (int j = 0; j < n_nc; j++) pool.at(lbase + j, 0) = i2f(lim_code[j]);
+    for (int ci = 0; ci < nc; ci++) {
+        const int key = W.ckey[cur][ci];
+        const float* cd = W.cdat[cur][ci];
+        int bA, bB;
+        if (key < M.n_geoms) { bA = M.g_link[key] + 1; bB = -1; }
+        else { int pk = key - M.n_geoms; bA = M.g_link[M.pair_a[pk]] + 1; bB = M.g_link[M.pair_b[pk]] + 1; }
+        float dirs[3][3];
+        dirs[0][0] = cd[6]; dirs[0][1] = cd[7]; dirs[0][2] = cd[8];
+        plane_space(dirs[0], dirs[1], dirs[2]);
+        const int slot = LT + 3 * (cbase + ci);
+        pool.at(slot, 0) = i2f(lane | (bA << 8) | ((bB + 1) << 16));
+#pragma unroll
+        for (int k = 0; k < 3; k++) pool.at(slot, 1 + k) = cd[k];
+#pragma unroll
+        for (int w = 0; w < 3; w++) {
+            float dl[3];
+            mulv(dl, W.Rwl[bA], dirs[w]);
+#pragma unroll
+            for (int k = 0; k < 3; k++) pool.at(slot, 4 + 3 * w + k) = dl[k];
+        }
+        if (bB >= 0) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) pool.at(slot, 13 + k) = cd[3 + k];
+#pragma unroll
+            for (int w = 0; w < 3; w++) {
+                float dl[3];
+                mulv(dl, W.Rwl[bB], dirs[w]);
+#pragma unroll
+                for (int k = 0; k < 3; k++) pool.at(slot, 16 + 3 * w + k) = -dl[k];
+            }
+        }
+    }
+    warp.sync();
+    // ---- all lanes: limit-row tasks ----
+    for (int t0 = 0; t0 < LT; t0 += Warp::WIDTH) {
+        const int t = t0 + lane;
+        if (t < LT) {
+            const int code = f2i(pool.at(t, 0));
+            const int o = code & 255, body = (code >> 8) & 255;
+            const float dir = (code >> 16) ? -1.f : 1.f;
+            LinkCache<STRIDE> lco{lc_lane0 + o};
+            float dn[1];
+            pooled_response<T, 1, false>(lco, body, (const float (*)[6]) nullptr, dir, pool, t, true, dn);
+            pool.at(t, 2 * nd) = dn[0];
+        }
+    }
+    // ---- all lanes: contact-point tasks (normal + 2 friction rows each) ----
+    for (int t0 = 0; t0 < CT; t0 += Warp::WIDTH) {
+        const int t = t0 + lane;
+        if (t < CT) {
+            const int slot = LT + 3 * t;
+            float desc[POOL_DESC_WORDS];
+            const int code = f2i(pool.at(slot, 0));
+            const int o = code & 255, bA = (code >> 8) & 255, bB = ((code >> 16) & 255) - 1;
+#pragma unroll
+            for (int k = 1; k < 13; k++) desc[k] = pool.at(slot, k);
+            if (bB >= 0) {
+#pragma unroll
+                for (int k = 13; k < POOL_DESC_WORDS; k++) desc[k] = pool.at(slot, k);
+            }
+            LinkCache<STRIDE> lco{lc_lane0 + o};
+            float dsum[3] = {0.f, 0.f, 0.f};
+            const int nside = bB >= 0 ? 2 : 1;
+            for (int side = 0; side < nside; side++) {
+                const float* ds = desc + 1 + 12 * side;
+                float wr[3][6], dn[3];
+#pragma unroll
+                for (int w = 0; w < 3; w++) {
+                    cross3(wr[w], ds, ds + 3 + 3 * w);
+                    wr[w][3] = ds[3 + 3 * w]; wr[w][4] = ds[4 + 3 * w]; wr[w][5] = ds[5 + 3 * w];
+                }
+                pooled_response<T, 3, true>(lco, side == 0 ? bA : bB, (const float (*)[6]) wr, 0.f, pool, slot, side == 0, dn);
+                dsum[0] += dn[0]; dsum[1] += dn[1]; dsum[2] += dn[2];
+            }
+#pragma unroll
+            for (int w = 0; w < 3; w++) pool.at(slot + w, 2 * nd) = dsum[w];
+        }
+    }
+    warp.sync();
+    if (!valid || W.n_rows == 0) return;
+    // ---- owner: right-hand sides, then PGS in Bullet's order ----
+    float vel[nd];
+#pragma unroll
+    for (int k = 0; k < nd; k++) vel[k] = 0.f;
+    if constexpr (!T::FIXED_BASE) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { vel[k] = W.bw[k]; vel[3 + k] = W.bv[k]; }
+    }
+#pragma unroll
+    for (int d = 0; d < T::ND; d++) vel[6 + d] = W.qd[d];
+    const float inv_dt = 1.0f / dt;
+    float r_rhs[n + 3 * MC], r_invd[n + 3 * MC], r_applied[n + 3 * MC];
+    auto row_relvel = [&](int slot) {
+        float j[nd], s = 0.f;
+#pragma unroll
+        for (int k = 0; k < nd; k++) j[k] = pool.at(slot, k);
+#pragma unroll
+        for (int k = 0; k < nd; k++) s += j[k] * vel[k];
+        return s;
+    };
+    // local row index: [0,n_nc) limits ; n_nc + 3*ci + w  contact ci, direction w
+    for (int j = 0; j < n_nc; j++) {
+        const int slot = lbase + j;
+        const float relvel = row_relvel(slot), denom = pool.at(slot, 2 * nd), pen = lim_pen[j];
+        const float invd = denom > RS_FLT_EPS ? 1.0f / denom : 0.f;
+        const float erp = pen > M.split_thresh ? M.erp : M.erp2;
+        r_rhs[j] = pen > M.split_thresh ? (-pen * erp * inv_dt - relvel) * invd : (-relvel) * invd;
+        r_invd[j] = invd; r_applied[j] = 0.f;
+    }
+    for (int ci = 0; ci < nc; ci++) {
+        const float pen = W.cdat[cur][ci][9];
+#pragma unroll
+        for (int w = 0; w < 3; w++) {
+            const int slot = LT + 3 * (cbase + ci) + w, row = n_nc + 3 * ci + w;
+            const float relvel = row_relvel(slot), denom = pool.at(slot, 2 * nd);
+            const float invd = denom > RS_FLT_EPS ? 1.0f / denom : 0.f;
+            float rhs;
+            if (w == 0) {
+                const float erp = pen > M.split_thresh ? M.erp : M.erp2;
+                float posErr = 0.f, velErr = -relvel;
+                if (pen > 0.f) velErr -= pen * inv_dt; else posErr = -pen * erp * inv_dt;
+                rhs = pen > M.split_thresh ? (posErr + velErr) * invd : velErr * invd;
+            } else rhs = -relvel * invd;
+            r_rhs[row] = rhs; r_invd[row] = invd; r_applied[row] = 0.f;
+        }
+    }
+    float dv[nd];
+#pragma unroll
+    for (int k = 0; k < nd; k++) dv[k] = 0.f;
+    const float lim_hi_imp = M.max_limit_impulse;
+    for (int it = 0; it < M.n_iter; it++) {
+        for (int j = 0; j < n_nc; j++) {
+            const int row = (it & 1) ? j : n_nc - 1 - j;
+            resolve_pooled<nd>(pool, lbase + row, dv, r_rhs[row], r_invd[row], 0.f, lim_hi_imp, r_applied[row]);
+        }
+        for (int ci = 0; ci < nc; ci++) {
+            const int row = n_nc + 3 * ci;
+            resolve_pooled<nd>(pool, LT + 3 * (cbase + ci), dv, r_rhs[row], r_invd[row], 0.f, 1e10f, r_applied[row]);
+        }
+        for (int ci = 0; ci < nc; ci++) {
+            const float tot = r_applied[n_nc + 3 * ci];
+            if (tot > 0.f) {
+                const int key = W.ckey[cur][ci];
+                const float fr = key < M.n_geoms ? M.g_fric_floor[key] : M.pair_friction[key - M.n_geoms];
+#pragma unroll
+                for (int w = 1; w < 3; w++) {
+                    const int row = n_nc + 3 * ci + w;
+                    resolve_pooled<nd>(pool, LT + 3 * (cbase + ci) + w, dv, r_rhs[row], r_invd[row], -fr * tot, fr * tot, r_applied[row]);
+                }
+            }
+        }
+    }
+    if constexpr (!T::FIXED_BASE) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { W.bw[k] += dv[k]; W.bv[k] += dv[3 + k]; }
+    }
+#pragma unroll
+    for (int d = 0; d < T::ND; d++) W.qd[d] += dv[6 + d];
+    clamp_vel(M, W);
+}
+
+// one sub-step with the pooled solver; every lane of the warp must call it (valid == false: helper only)
+template <class T, class Warp, int NL, int MC, bool SL, int STRIDE>
+RS_HD void substep_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL, MC, SL>& W, const RowPool& pool,
+                          const LinkCache<STRIDE>& lc, float* lc_lane0, PhaseClock* pc = nullptr) {
+    const float dt = M.timestep;
+    long long c0 = 0, c1 = 0;
+    if (pc) c0 = RS_CLOCK();
+    if (valid) static_kinematics<T>(W, lc);
+    if (pc) { c1 = RS_CLOCK(); pc->t[0] += c1 - c0; c0 = c1; }
+    if (valid) collide(M, W);
+    if (pc) { c1 = RS_CLOCK(); pc->t[1] += c1 - c0; c0 = c1; }
+    if (valid) static_aba<T>(M, W, lc, dt);
+    if (pc) { c1 = RS_CLOCK(); pc->t[2] += c1 - c0; c0 = c1; }
+    warp.sync();   // link caches complete before other lanes read them
+    solve_pooled<T, Warp, NL, MC, SL, STRIDE>(warp, valid, M, W, dt, pool, lc_lane0);
+    warp.sync();   // all helpers done with this sub-step's caches before kinematics overwrites them
+    if (pc) { c1 = RS_CLOCK(); pc->t[3] += c1 - c0; c0 = c1; }
+    if (valid) integrate(M, W, dt);
+    if (pc) { c1 = RS_CLOCK(); pc->t[4] += c1 - c0; }
+}
+
+}  // namespace rs

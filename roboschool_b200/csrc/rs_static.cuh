@@ -35,7 +35,8 @@ template <class T> constexpr int lc_cs() { return 0; }
 template <class T> constexpr int lc_h() { return 2 * T::NL; }
 template <class T> constexpr int lc_invd() { return 8 * T::NL; }
 template <class T> constexpr int lc_lb() { return 9 * T::NL; }
-template <class T> constexpr int lc_size() { return 9 * T::NL + 21; }
+template <class T> constexpr int lc_rb() { return 9 * T::NL + 21; }     // base rotation (world -> base coords), 9 floats
+template <class T> constexpr int lc_size() { return 9 * T::NL + 30; }
 
 // S . x for link I with the constant joint subspace
 template <class T, int I>
@@ -85,12 +86,13 @@ RS_HD void link_xform(float c, float s, float q, float* R, float* r) {
     if constexpr (jt == RS_JOINT_PRISMATIC) { r[0] += RS_CM(ax, q); r[1] += RS_CM(ay, q); r[2] += RS_CM(az, q); }
 }
 
+// (prismatic joints keep q in the cos slot, so that any lane of the warp can rebuild any env's transforms)
 template <class T, int I, int STRIDE>
-RS_HD void cached_xform(const LinkCache<STRIDE>& lc, const float* qv, float* R, float* r) {
+RS_HD void cached_xform(const LinkCache<STRIDE>& lc, float* R, float* r) {
     float c = 1.0f, s = 0.0f, q = 0.0f;
-    constexpr int jt = T::jtype[I], dI = T::dof[I];
+    constexpr int jt = T::jtype[I];
     if constexpr (jt == RS_JOINT_REVOLUTE) { c = lc.at(lc_cs<T>() + 2 * I); s = lc.at(lc_cs<T>() + 2 * I + 1); }
-    if constexpr (jt == RS_JOINT_PRISMATIC) q = qv[dI];
+    if constexpr (jt == RS_JOINT_PRISMATIC) q = lc.at(lc_cs<T>() + 2 * I);
     link_xform<T, I>(c, s, q, R, r);
 }
 
@@ -107,6 +109,8 @@ RS_HD void static_kinematics(Work<NL, MC, SL>& W, const LinkCache<STRIDE>& lc) {
 #pragma unroll
         for (int j = 0; j < 3; j++) W.Rwl[0][i * 3 + j] = Rbw[j * 3 + i];
     W.pos[0][0] = W.bpos[0]; W.pos[0][1] = W.bpos[1]; W.pos[0][2] = W.bpos[2];
+#pragma unroll
+    for (int k = 0; k < 9; k++) lc.at(lc_rb<T>() + k) = W.Rwl[0][k];
     static_for<T::NL>([&](auto ic) {
         constexpr int i = decltype(ic)::value;
         constexpr int p = T::parent[i], jt = T::jtype[i], dI = T::dof[i];
@@ -115,7 +119,7 @@ RS_HD void static_kinematics(Work<NL, MC, SL>& W, const LinkCache<STRIDE>& lc) {
             sincosf(W.q[dI], &s, &c);
             lc.at(lc_cs<T>() + 2 * i) = c; lc.at(lc_cs<T>() + 2 * i + 1) = s;
         }
-        if constexpr (jt == RS_JOINT_PRISMATIC) q = W.q[dI];
+        if constexpr (jt == RS_JOINT_PRISMATIC) { q = W.q[dI]; lc.at(lc_cs<T>() + 2 * i) = q; }
         float R[9], r[3];
         link_xform<T, i>(c, s, q, R, r);
         mul33(W.Rwl[i + 1], R, W.Rwl[p + 1]);
@@ -163,7 +167,7 @@ RS_HD void static_aba(const DevModel& M, Work<NL, MC, SL>& W, const LinkCache<ST
         constexpr int dI = T::dof[i];
         constexpr float mI = T::mass[i], i0 = T::inertia[3 * i], i1 = T::inertia[3 * i + 1], i2 = T::inertia[3 * i + 2];
         float R[9], r[3];
-        cached_xform<T, i>(lc, W.q, R, r);
+        cached_xform<T, i>(lc, R, r);
         xf_motion(vel[i + 1], R, r, vel[p + 1]);
         if constexpr (dI >= 0) {
             float qd = W.qd[dI];
@@ -196,7 +200,7 @@ RS_HD void static_aba(const DevModel& M, Work<NL, MC, SL>& W, const LinkCache<ST
         constexpr float s0 = T::Sw[3 * i], s1 = T::Sw[3 * i + 1], s2 = T::Sw[3 * i + 2], s3 = T::Sv[3 * i], s4 = T::Sv[3 * i + 1], s5 = T::Sv[3 * i + 2];
         if constexpr (is_leaf) init_rigid(IA[i + 1], mI, i0, i1, i2);
         float R[9], r[3];
-        cached_xform<T, i>(lc, W.q, R, r);
+        cached_xform<T, i>(lc, R, r);
         float Zt[6];
         if constexpr (dI >= 0) {
             float S[6] = {s0, s1, s2, s3, s4, s5};
@@ -254,7 +258,7 @@ RS_HD void static_aba(const DevModel& M, Work<NL, MC, SL>& W, const LinkCache<ST
         constexpr int i = decltype(ic)::value;
         constexpr int p = T::parent[i];
         float R[9], r[3];
-        cached_xform<T, i>(lc, W.q, R, r);
+        cached_xform<T, i>(lc, R, r);
         xf_motion(acc[i + 1], R, r, acc[p + 1]);
         constexpr int dI = T::dof[i];
         if constexpr (dI >= 0) {
@@ -306,7 +310,7 @@ RS_HDN float static_row_response(const Work<NL, MC, SL>& W, const LinkCache<STRI
         constexpr int i = decltype(ic)::value;
         constexpr int p = T::parent[i];
         float R[9], r[3];
-        cached_xform<T, i>(lc, W.q, R, r);
+        cached_xform<T, i>(lc, R, r);
         float Zt[6];
 #pragma unroll
         for (int k = 0; k < 6; k++) Zt[k] = Z[i + 1][k];
@@ -354,7 +358,7 @@ RS_HDN float static_row_response(const Work<NL, MC, SL>& W, const LinkCache<STRI
         constexpr int i = decltype(ic)::value;
         constexpr int p = T::parent[i];
         float R[9], r[3];
-        cached_xform<T, i>(lc, W.q, R, r);
+        cached_xform<T, i>(lc, R, r);
         xf_motion(acc[i + 1], R, r, acc[p + 1]);
         constexpr int d = T::dof[i];
         if constexpr (d >= 0) {
@@ -410,7 +414,7 @@ RS_HD void static_calc_state(const DevModel& M, Work<NL, MC, SL>& W, const LinkC
         constexpr int i = decltype(ic)::value;
         constexpr int p = T::parent[i];
         float R[9], r[3];
-        cached_xform<T, i>(lc, W.q, R, r);
+        cached_xform<T, i>(lc, R, r);
         xf_motion(vel[i + 1], R, r, vel[p + 1]);
         constexpr int dI = T::dof[i];
         if constexpr (dI >= 0) saxpy<T, i>(vel[i + 1], W.qd[dI]);

@@ -15,7 +15,7 @@
 #include <vector>
 #include "../../include/roboschool_b200.h"
 #include "rs_devmodel.h"
-#include "rs_static.cuh"
+#include "rs_pooled.cuh"
 
 using namespace rs;
 
@@ -161,7 +161,9 @@ __global__ void __launch_bounds__(64) k_step(const __grid_constant__ DevModel M,
     }
 }
 
-// Step kernel specialised on a compile-time topology: one warp per CTA (32 envs), link cache in shared memory.
+// Step kernel specialised on a compile-time topology: one warp per CTA (32 envs), link cache in shared memory,
+// constraint rows built by the whole warp (rs_pooled.cuh).  Every lane runs the kernel to the end: the spare lanes of
+// the tail warp own no env (valid == false) but still help with the warp's row tasks.
 // PROF: also accumulate clock64() deltas per phase into cyc[8] (profiling twin).
 template <class T, int MC, bool PROF>
 __global__ void __launch_bounds__(32) k_step_static(const __grid_constant__ DevModel M, const DevBuf B, const float* __restrict__ actions,
@@ -170,23 +172,27 @@ __global__ void __launch_bounds__(32) k_step_static(const __grid_constant__ DevM
                                                     unsigned long long* __restrict__ cyc) {
     extern __shared__ float s_lc[];
     const int e = blockIdx.x * 32 + threadIdx.x;
+    const bool valid = e < B.N;
     double st_rew = 0, st_ep = 0, st_len = 0, st_nf = 0, st_rows = 0, st_con = 0, st_steps = 0;
-    if (e < B.N) {
-        long long t0 = 0, t1 = 0, t2 = 0;
-        if (PROF) t0 = clock64();
-        Work<T::NL, MC, true> W;
-        Episode E;
-        LinkCache<32> lc{s_lc + threadIdx.x};
+    long long t0 = 0, t1 = 0, t2 = 0;
+    if (PROF) t0 = clock64();
+    Work<T::NL, MC, true> W;
+    Episode E;
+    LinkCache<32> lc{s_lc + threadIdx.x};
+    float a[MA];
+    if (valid) {
         load_env(M, B, e, W, E);
-        float a[MA];
         if (actions) { for (int k = 0; k < M.n_act; k++) a[k] = actions[(size_t)e * M.n_act + k]; }
         else { for (int k = 0; k < M.n_act; k++) a[k] = 2.f * rs_uniform(seed ^ 0xA5A5A5A5u, env_id0 + e, E.episode * 1024u + (uint32_t)E.frame, (uint32_t)k) - 1.f; }
         apply_action(M, W, a, 1);
-        RowWS ws{B.rows + e, B.N};
-        PhaseClock pc;
-        if (PROF) { for (int k = 0; k < 6; k++) pc.t[k] = 0; t1 = clock64(); }
-        for (int s = 0; s < M.frame_skip; s++) substep_static<T>(M, W, ws, lc, PROF ? &pc : nullptr);
-        if (PROF) t2 = clock64();
+    }
+    const RowPool pool{B.rows + (size_t)blockIdx.x * ((size_t)32 * B.maxr * B.rec), 32 * B.maxr};
+    const WarpDev warp;
+    PhaseClock pc;
+    if (PROF) { for (int k = 0; k < 6; k++) pc.t[k] = 0; t1 = clock64(); }
+    for (int s = 0; s < M.frame_skip; s++) substep_pooled<T>(warp, valid, M, W, pool, lc, s_lc, PROF ? &pc : nullptr);
+    if (PROF) t2 = clock64();
+    if (valid) {
         float* o = obs + (size_t)e * M.obs_dim;
         StepOut out;
         auto cs = [&](float* oo, int os, double* dist, float* pitch, int* al) { static_calc_state<T>(M, W, lc, E, oo, os, dist, pitch, al); };
@@ -204,13 +210,13 @@ __global__ void __launch_bounds__(32) k_step_static(const __grid_constant__ DevM
             for (int k = 0; k < 5; k++) B.rewards5[(size_t)e * 5 + k] = out.rewards5[k];
         }
         store_env(M, B, e, W, E);
-        if (PROF && (threadIdx.x & 31) == 0) {
-            long long t3 = clock64();
-            for (int k = 0; k < 5; k++) atomicAdd(cyc + k, (unsigned long long)pc.t[k]);
-            atomicAdd(cyc + 5, (unsigned long long)(t3 - t2));
-            atomicAdd(cyc + 6, (unsigned long long)(t1 - t0));
-            atomicAdd(cyc + 7, (unsigned long long)(t3 - t0));
-        }
+    }
+    if (PROF && threadIdx.x == 0) {
+        long long t3 = clock64();
+        for (int k = 0; k < 5; k++) atomicAdd(cyc + k, (unsigned long long)pc.t[k]);
+        atomicAdd(cyc + 5, (unsigned long long)(t3 - t2));
+        atomicAdd(cyc + 6, (unsigned long long)(t1 - t0));
+        atomicAdd(cyc + 7, (unsigned long long)(t3 - t0));
     }
     if (stats) {
         st_rew = warp_sum(st_rew); st_ep = warp_sum(st_ep); st_len = warp_sum(st_len); st_nf = warp_sum(st_nf);
@@ -353,7 +359,7 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
     w->device = device; w->n = n_envs;
     DevBuf& B = w->B;
     B.N = n_envs; B.S = (model->fixed_base ? 0 : 13) + 2 * model->n_dof; B.MCcap = MC;
-    B.rec = 2 * (6 + model->n_dof) + R_NSCALAR; B.maxr = NL + 3 * MC;
+    B.rec = 2 * (6 + model->n_dof) + 1; B.maxr = NL + 3 * MC;   // +1: pooled rows keep their denominator in the record
     size_t N = (size_t)n_envs;
     CK(cudaMalloc(&B.state, sizeof(float) * N * (B.S > 0 ? B.S : 1)));
     CK(cudaMalloc(&B.ccount, sizeof(int) * N));
@@ -364,7 +370,7 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
     CK(cudaMalloc(&B.feet, sizeof(float) * N * MF));
     CK(cudaMalloc(&B.frame, sizeof(int) * N));
     CK(cudaMalloc(&B.episode, sizeof(uint32_t) * N));
-    CK(cudaMalloc(&B.rows, sizeof(float) * N * B.rec * B.maxr));
+    CK(cudaMalloc(&B.rows, sizeof(float) * (size_t)((n_envs + 31) / 32 * 32) * B.rec * B.maxr));   // one pool per warp of 32 envs
     CK(cudaMalloc(&B.tau, sizeof(float) * N * (model->n_dof > 0 ? model->n_dof : 1)));
     CK(cudaMalloc(&B.rewards5, sizeof(float) * N * 5));
     CK(cudaMalloc(&B.nrows, sizeof(int) * N));

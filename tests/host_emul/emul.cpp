@@ -5,7 +5,7 @@
 #include <string.h>
 #include <vector>
 #include "../../roboschool_b200/csrc/rs_devmodel.h"
-#include "../../roboschool_b200/csrc/rs_static.cuh"
+#include "../../roboschool_b200/csrc/rs_pooled.cuh"
 
 using namespace rs;
 constexpr int NL = RS_MAX_LINKS, MC = 16;
@@ -27,10 +27,10 @@ struct Emul {
 
 template <class T>
 static void step_env_static(Emul* e, int i, const float* a, int auto_reset, uint32_t seed, uint32_t env0) {
-    const DevModel& M = e->M; W_t& W = e->w[i]; RowWS ws{e->ws.data(), 1};
+    const DevModel& M = e->M; W_t& W = e->w[i]; RowPool pool{e->ws.data(), e->maxr};
     LinkCache<1> lc{e->lcbuf.data() + (size_t)i * e->lcsize};
     apply_action(M, W, a, 1);
-    for (int s = 0; s < M.frame_skip; s++) substep_static<T>(M, W, ws, lc);
+    for (int s = 0; s < M.frame_skip; s++) substep_pooled<T>(WarpHost(), true, M, W, pool, lc, lc.p);
     float* obs = &e->obs[(size_t)i * M.obs_dim];
     auto cs = [&](float* o, int os, double* dist, float* pitch, int* al) { static_calc_state<T>(M, W, lc, e->ep[i], o, os, dist, pitch, al); };
     epilogue_with(M, W, e->ep[i], a, 1, obs, 1, e->out[i], cs);
@@ -40,9 +40,9 @@ static void step_env_static(Emul* e, int i, const float* a, int auto_reset, uint
 }
 template <class T>
 static void substeps_static(Emul* e, int env, int n) {
-    RowWS ws{e->ws.data(), 1};
+    RowPool pool{e->ws.data(), e->maxr};
     LinkCache<1> lc{e->lcbuf.data() + (size_t)env * e->lcsize};
-    for (int s = 0; s < n; s++) substep_static<T>(e->M, e->w[env], ws, lc);
+    for (int s = 0; s < n; s++) substep_pooled<T>(WarpHost(), true, e->M, e->w[env], pool, lc, lc.p);
 }
 
 extern "C" {
@@ -52,10 +52,10 @@ void* emul_create(const rs_model_desc* m, int n) {
     if (build_dev_model(m, &e->M, &err)) { delete e; return nullptr; }
     e->n = n; e->w.resize(n); e->ep.resize(n); e->out.resize(n);
     for (int i = 0; i < n; i++) { memset(&e->w[i], 0, sizeof(W_t)); e->w[i].bquat[3] = 1; memset(&e->ep[i], 0, sizeof(Episode)); e->ep[i].initial_z = e->M.initial_z; }
-    e->rec = 2 * (6 + e->M.n_dof) + R_NSCALAR; e->maxr = NL + 3 * MC;
+    e->rec = 2 * (6 + e->M.n_dof) + 1; e->maxr = NL + 3 * MC;
     e->ws.resize((size_t)e->rec * e->maxr);
     e->obs.resize((size_t)n * e->M.obs_dim); e->rew.resize(n); e->done.resize(n);
-    e->topo = 0; e->lcsize = 9 * RS_MAX_LINKS + 21; e->lcbuf.assign((size_t)n * e->lcsize, 0.f);
+    e->topo = 0; e->lcsize = 9 * RS_MAX_LINKS + 30; e->lcbuf.assign((size_t)n * e->lcsize, 0.f);
     return e;
 }
 // select the static-topology sweeps if the descriptor matches a generated topology; returns the topology id

@@ -13,6 +13,7 @@ def build(force=False):
             os.path.join(_HERE, "..", "..", "roboschool_b200", "csrc", "rs_core.cuh"),
             os.path.join(_HERE, "..", "..", "roboschool_b200", "csrc", "rs_devmodel.h"),
             os.path.join(_HERE, "..", "..", "roboschool_b200", "csrc", "rs_static.cuh"),
+            os.path.join(_HERE, "..", "..", "roboschool_b200", "csrc", "rs_pooled.cuh"),
             os.path.join(_HERE, "..", "..", "roboschool_b200", "csrc", "rs_topo_gen.h"),
             os.path.join(_HERE, "..", "..", "include", "rs_model.h")]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):

@@ -14,12 +14,17 @@ def emul():
     return e
 
 
+@pytest.mark.parametrize("static", [False, True], ids=["generic", "static-pooled"])
 @pytest.mark.parametrize("env_id", ["RoboschoolHopper-v1", "RoboschoolAnt-v1", "RoboschoolHumanoid-v1"])
-def test_emul_teacher_forced(env_id, emul, oracle_lib):
+def test_emul_teacher_forced(env_id, static, emul, oracle_lib):
+    """static=True runs the compile-time-topology sweeps with the pooled row builder (rs_static.cuh,
+    rs_pooled.cuh) -- the code the shipped models run on the GPU; False the runtime-topology twin."""
     m = envspec.load_env_model(env_id)
     n = 32
     o = oracle_lib.OracleWorld(m, n)
     e = emul.EmulWorld(m, n)
+    if static:
+        assert e.use_static(True) > 0
     o.reset(seed=5); e.reset(seed=5)
     assert np.abs(np.stack([e.get_state(i) for i in range(n)]) - o.get_state()).max() < 1e-6
     rng = np.random.RandomState(1)
