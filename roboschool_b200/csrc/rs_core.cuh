@@ -234,6 +234,13 @@ RS_HD uint32_t rs_hash(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     h = (h ^ (h >> 13)) * 0xC2B2AE35u; h ^= h >> 16;
     return h;
 }
+RS_HD int rs_ctz(uint32_t x) {   // index of the lowest set bit (x != 0)
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
 RS_HD float rs_uniform(uint32_t seed, uint32_t env, uint32_t episode, uint32_t k) {
     return (float)(rs_hash(seed, env, episode, k) >> 8) * (1.0f / 16777216.0f);
 }
@@ -258,6 +265,7 @@ struct Work {
     float cdat[2][MC][CDAT];
     int ccount[2];
     int cur;
+    float gw[MG][6];             // world end points of the collision geoms (this sub-step)
     int n_rows, n_contacts;      // of the last solve (reported)
 };
 
@@ -674,6 +682,60 @@ RS_HD void manifold_refresh(Manifold4& mf, const Work<NL, MC, SL>& W, int bA, in
     }
 }
 
+// one manifold (floor geom k < n_geoms, or self pair k - n_geoms): cached points of the old list, narrowphase,
+// refresh, append to the new list.  gw: world end points of every geom.  oi / no: cursors into the old / new list.
+template <int NL, int MC, bool SL>
+RS_HD void collide_manifold(const DevModel& M, Work<NL, MC, SL>& W, const float (*gw)[6], int k, int old, int nw, int nold, int& oi, int& no) {
+    Manifold4 mf; mf.n = 0;
+    while (oi < nold && W.ckey[old][oi] == k) {
+#pragma unroll
+        for (int s = 0; s < 4; s++) if (s == mf.n) {
+#pragma unroll
+            for (int j = 0; j < CDAT; j++) mf.d[s][j] = W.cdat[old][oi][j];
+        }
+        mf.n++; oi++;
+    }
+    if (k < M.n_geoms) {
+        if (!M.g_floor[k]) return;
+        int b = M.g_link[k] + 1;
+        float thr = M.break_thresh[b];
+        // support vertex in -z: lower end sphere, first end wins ties
+        const float* c = (M.g_type[k] == RS_GEOM_CAPSULE && gw[k][5] < gw[k][2]) ? gw[k] + 3 : gw[k];
+        float dist = c[2] - M.g_radius[k];
+        if (dist < thr) {
+            const float nz[3] = {0.f, 0.f, 1.f};
+            float pOnB[3] = {c[0], c[1], 0.f};
+            manifold_add(mf, W, b, -1, nz, pOnB, dist, thr);
+        }
+        if (mf.n) manifold_refresh(mf, W, b, -1, thr);
+    } else {
+        int pk = k - M.n_geoms;
+        int ga = M.pair_a[pk], gb = M.pair_b[pk];
+        int bA = M.g_link[ga] + 1, bB = M.g_link[gb] + 1;
+        float thr = M.pair_thresh[pk];
+        float cA[3], cB[3];
+        seg_seg_closest(gw[ga], gw[ga] + 3, gw[gb], gw[gb] + 3, cA, cB);
+        float d[3] = {cA[0] - cB[0], cA[1] - cB[1], cA[2] - cB[2]};
+        float len = sqrtf(dot3(d, d)), rB = M.g_radius[gb];
+        float dist = len - M.g_radius[ga] - rB;
+        bool hit = M.pair_ss[pk] ? (dist <= 0.f) : (dist < thr);
+        if (hit) {
+            float nn[3] = {1.f, 0.f, 0.f};
+            if (len > 1e-12f) { float il = 1.0f / len; nn[0] = d[0] * il; nn[1] = d[1] * il; nn[2] = d[2] * il; }
+            float pOnB[3] = {cB[0] + nn[0] * rB, cB[1] + nn[1] * rB, cB[2] + nn[2] * rB};
+            manifold_add(mf, W, bA, bB, nn, pOnB, dist, thr);
+        }
+        if (mf.n) manifold_refresh(mf, W, bA, bB, thr);
+    }
+#pragma unroll
+    for (int s = 0; s < 4; s++) if (s < mf.n && no < MC && no < M.max_contacts) {
+        W.ckey[nw][no] = k;
+#pragma unroll
+        for (int j = 0; j < CDAT; j++) W.cdat[nw][no][j] = mf.d[s][j];
+        no++;
+    }
+}
+
 template <int NL, int MC, bool SL>
 RS_HD void collide(const DevModel& M, Work<NL, MC, SL>& W) {
     const int old = W.cur, nw = 1 - W.cur;
@@ -681,7 +743,7 @@ RS_HD void collide(const DevModel& M, Work<NL, MC, SL>& W) {
     const int nold = W.ccount[old];
     const int nman = M.n_geoms + M.n_pairs;
     // world end points of every geom, once per sub-step (each geom takes part in many pairs)
-    float gw[MG][6];
+    float (*gw)[6] = W.gw;
     for (int g = 0; g < M.n_geoms; g++) {
         int b = M.g_link[g] + 1;
         to_world(W, b, M.g_p0[g], gw[g]);
@@ -705,54 +767,7 @@ RS_HD void collide(const DevModel& M, Work<NL, MC, SL>& W) {
                 if (dx * dx + dy * dy + dz * dz > reach * reach) continue;
             }
         }
-        Manifold4 mf; mf.n = 0;
-        while (oi < nold && W.ckey[old][oi] == k) {
-#pragma unroll
-            for (int s = 0; s < 4; s++) if (s == mf.n) {
-#pragma unroll
-                for (int j = 0; j < CDAT; j++) mf.d[s][j] = W.cdat[old][oi][j];
-            }
-            mf.n++; oi++;
-        }
-        if (k < M.n_geoms) {
-            if (!M.g_floor[k]) continue;
-            int b = M.g_link[k] + 1;
-            float thr = M.break_thresh[b];
-            // support vertex in -z: lower end sphere, first end wins ties
-            const float* c = (M.g_type[k] == RS_GEOM_CAPSULE && gw[k][5] < gw[k][2]) ? gw[k] + 3 : gw[k];
-            float dist = c[2] - M.g_radius[k];
-            if (dist < thr) {
-                const float nz[3] = {0.f, 0.f, 1.f};
-                float pOnB[3] = {c[0], c[1], 0.f};
-                manifold_add(mf, W, b, -1, nz, pOnB, dist, thr);
-            }
-            if (mf.n) manifold_refresh(mf, W, b, -1, thr);
-        } else {
-            int pk = k - M.n_geoms;
-            int ga = M.pair_a[pk], gb = M.pair_b[pk];
-            int bA = M.g_link[ga] + 1, bB = M.g_link[gb] + 1;
-            float thr = M.pair_thresh[pk];
-            float cA[3], cB[3];
-            seg_seg_closest(gw[ga], gw[ga] + 3, gw[gb], gw[gb] + 3, cA, cB);
-            float d[3] = {cA[0] - cB[0], cA[1] - cB[1], cA[2] - cB[2]};
-            float len = sqrtf(dot3(d, d)), rB = M.g_radius[gb];
-            float dist = len - M.g_radius[ga] - rB;
-            bool hit = M.pair_ss[pk] ? (dist <= 0.f) : (dist < thr);
-            if (hit) {
-                float nn[3] = {1.f, 0.f, 0.f};
-                if (len > 1e-12f) { float il = 1.0f / len; nn[0] = d[0] * il; nn[1] = d[1] * il; nn[2] = d[2] * il; }
-                float pOnB[3] = {cB[0] + nn[0] * rB, cB[1] + nn[1] * rB, cB[2] + nn[2] * rB};
-                manifold_add(mf, W, bA, bB, nn, pOnB, dist, thr);
-            }
-            if (mf.n) manifold_refresh(mf, W, bA, bB, thr);
-        }
-#pragma unroll
-        for (int s = 0; s < 4; s++) if (s < mf.n && no < MC && no < M.max_contacts) {
-            W.ckey[nw][no] = k;
-#pragma unroll
-            for (int j = 0; j < CDAT; j++) W.cdat[nw][no][j] = mf.d[s][j];
-            no++;
-        }
+        collide_manifold(M, W, gw, k, old, nw, nold, oi, no);
     }
     W.ccount[nw] = no;
     W.cur = nw;

@@ -1,0 +1,176 @@
+// rs_kernels.cuh -- device buffers, env load/store and the static-topology step kernel template.
+// Included by rs_step.cu (ABI + runtime-topology kernels) and by rs_static_inst.cu, which is compiled once per
+// (topology, profiling) pair so that the instantiations build in parallel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include "rs_pooled.cuh"
+
+using namespace rs;
+
+struct DevBuf {
+    float* state; int* ccount; int* ckey; float* cdat;
+    double* potential; float* initial_z; float* feet; int* frame; uint32_t* episode;
+    float* rows; float* tau; float* rewards5; int* nrows; int* ncontacts;
+    int N, S, MCcap, rec, maxr;
+};
+
+// ----------------------------------------------------------------------------------------------
+template <int NL, int MC, bool SL>
+__device__ __forceinline__ void load_env(const DevModel& M, const DevBuf& B, int e, Work<NL, MC, SL>& W, Episode& E) {
+    const int N = B.N;
+    const float* s = B.state + e;
+    int f = 0;
+    if (!M.fixed_base) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) W.bpos[k] = s[(size_t)(f++) * N];
+#pragma unroll
+        for (int k = 0; k < 4; k++) W.bquat[k] = s[(size_t)(f++) * N];
+#pragma unroll
+        for (int k = 0; k < 3; k++) W.bw[k] = s[(size_t)(f++) * N];
+#pragma unroll
+        for (int k = 0; k < 3; k++) W.bv[k] = s[(size_t)(f++) * N];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { W.bpos[k] = 0; W.bw[k] = 0; W.bv[k] = 0; W.bquat[k] = 0; }
+        W.bquat[3] = 1.f;
+    }
+    for (int d = 0; d < M.n_dof; d++) W.q[d] = s[(size_t)(f + d) * N];
+    for (int d = 0; d < M.n_dof; d++) W.qd[d] = s[(size_t)(f + M.n_dof + d) * N];
+    int nc = B.ccount[e];
+    W.cur = 0; W.ccount[0] = nc; W.ccount[1] = 0;
+    for (int i = 0; i < nc; i++) {
+        W.ckey[0][i] = B.ckey[(size_t)i * N + e];
+#pragma unroll
+        for (int k = 0; k < CDAT; k++) W.cdat[0][i][k] = B.cdat[((size_t)i * CDAT + k) * N + e];
+    }
+    E.potential = B.potential[e]; E.initial_z = B.initial_z[e]; E.frame = B.frame[e]; E.episode = B.episode[e];
+    for (int k = 0; k < M.n_feet; k++) E.feet_contact[k] = B.feet[(size_t)k * N + e];
+    W.n_rows = 0; W.n_contacts = 0;
+}
+
+template <int NL, int MC, bool SL>
+__device__ __forceinline__ void store_env(const DevModel& M, const DevBuf& B, int e, const Work<NL, MC, SL>& W, const Episode& E) {
+    const int N = B.N;
+    float* s = B.state + e;
+    int f = 0;
+    if (!M.fixed_base) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) s[(size_t)(f++) * N] = W.bpos[k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) s[(size_t)(f++) * N] = W.bquat[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) s[(size_t)(f++) * N] = W.bw[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) s[(size_t)(f++) * N] = W.bv[k];
+    }
+    for (int d = 0; d < M.n_dof; d++) s[(size_t)(f + d) * N] = W.q[d];
+    for (int d = 0; d < M.n_dof; d++) s[(size_t)(f + M.n_dof + d) * N] = W.qd[d];
+    const int cur = W.cur, nc = W.ccount[cur];
+    B.ccount[e] = nc;
+    for (int i = 0; i < nc; i++) {
+        B.ckey[(size_t)i * N + e] = W.ckey[cur][i];
+#pragma unroll
+        for (int k = 0; k < CDAT; k++) B.cdat[((size_t)i * CDAT + k) * N + e] = W.cdat[cur][i][k];
+    }
+    B.potential[e] = E.potential; B.initial_z[e] = E.initial_z; B.frame[e] = E.frame; B.episode[e] = E.episode;
+    for (int k = 0; k < M.n_feet; k++) B.feet[(size_t)k * N + e] = E.feet_contact[k];
+    B.nrows[e] = W.n_rows; B.ncontacts[e] = W.n_contacts;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Step kernel specialised on a compile-time topology: one warp per CTA (32 envs), link cache in shared memory,
+// constraint rows built by the whole warp (rs_pooled.cuh).  Every lane runs the kernel to the end: the spare lanes of
+// the tail warp own no env (valid == false) but still help with the warp's row tasks.
+// PROF: also accumulate clock64() deltas per phase into cyc[8] (profiling twin).
+template <class T, int MC, bool PROF, int WPC>
+__global__ void __launch_bounds__(32 * WPC) k_step_static(const __grid_constant__ DevModel M, const DevBuf B, const float* __restrict__ actions,
+                                                    float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
+                                                    int auto_reset, uint32_t seed, uint32_t env_id0, double* __restrict__ stats,
+                                                    unsigned long long* __restrict__ cyc) {
+    extern __shared__ float s_lc[];
+    const int e = blockIdx.x * (32 * WPC) + threadIdx.x;
+    const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;   // warp in CTA, lane
+    const bool valid = e < B.N;
+    double st_rew = 0, st_ep = 0, st_len = 0, st_nf = 0, st_rows = 0, st_con = 0, st_steps = 0;
+    long long t0 = 0, t1 = 0, t2 = 0;
+    if (PROF) t0 = clock64();
+    Work<T::NL, MC, true> W;
+    Episode E;
+    float* const lc0 = s_lc + wic * (32 * lc_size<T>());   // this warp's link caches, [slot][lane]
+    LinkCache<32> lc{lc0 + lane};
+    float a[MA];
+    if (valid) {
+        load_env(M, B, e, W, E);
+        if (actions) { for (int k = 0; k < M.n_act; k++) a[k] = actions[(size_t)e * M.n_act + k]; }
+        else { for (int k = 0; k < M.n_act; k++) a[k] = 2.f * rs_uniform(seed ^ 0xA5A5A5A5u, env_id0 + e, E.episode * 1024u + (uint32_t)E.frame, (uint32_t)k) - 1.f; }
+        apply_action(M, W, a, 1);
+    }
+    const RowPool pool{B.rows + (size_t)(blockIdx.x * WPC + wic) * ((size_t)32 * B.maxr * B.rec), 32 * B.maxr};
+    const WarpDev<WPC> warp;
+    PhaseClock pc;
+    if (PROF) { for (int k = 0; k < 6; k++) pc.t[k] = 0; t1 = clock64(); }
+    for (int s = 0; s < M.frame_skip; s++) substep_pooled<T>(warp, valid, M, W, pool, lc, lc0, PROF ? &pc : nullptr);
+    if (PROF) t2 = clock64();
+    if (valid) {
+        float* o = obs + (size_t)e * M.obs_dim;
+        StepOut out;
+        auto cs = [&](float* oo, int os, double* dist, float* pitch, int* al) { static_calc_state<T>(M, W, lc, E, oo, os, dist, pitch, al); };
+        epilogue_with(M, W, E, a, 1, o, 1, out, cs);
+        int dn = out.done;
+        bool finite = true;
+        for (int k = 0; k < M.obs_dim; k++) finite = finite && isfinite(o[k]);
+        int finished = dn || E.frame >= M.max_episode_steps;
+        st_rew = out.reward; st_rows = W.n_rows; st_con = W.n_contacts; st_steps = 1; st_nf = finite ? 0 : 1;
+        if (finished) { st_ep = 1; st_len = E.frame; }
+        if (auto_reset && finished) { env_reset_with(M, W, E, seed, env_id0 + e, o, 1, cs); dn = 1; }
+        rew[e] = out.reward; done[e] = (uint8_t)dn;
+        if (B.rewards5) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) B.rewards5[(size_t)e * 5 + k] = out.rewards5[k];
+        }
+        store_env(M, B, e, W, E);
+    }
+    if (PROF && lane == 0) {
+        long long t3 = clock64();
+        for (int k = 0; k < 5; k++) atomicAdd(cyc + k, (unsigned long long)pc.t[k]);
+        atomicAdd(cyc + 5, (unsigned long long)(t3 - t2));
+        atomicAdd(cyc + 6, (unsigned long long)(t1 - t0));
+        atomicAdd(cyc + 7, (unsigned long long)(t3 - t0));
+    }
+    if (stats) {
+        st_rew = warp_sum(st_rew); st_ep = warp_sum(st_ep); st_len = warp_sum(st_len); st_nf = warp_sum(st_nf);
+        st_rows = warp_sum(st_rows); st_con = warp_sum(st_con); st_steps = warp_sum(st_steps);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(stats + 0, st_rew); atomicAdd(stats + 1, st_ep); atomicAdd(stats + 2, st_len); atomicAdd(stats + 3, st_nf);
+            atomicAdd(stats + 4, st_rows); atomicAdd(stats + 5, st_con); atomicAdd(stats + 6, st_steps);
+        }
+    }
+}
+
+// arguments of one static-topology step launch (plain struct: the instantiations live in other translation units)
+struct StaticLaunch {
+    const DevModel* M; const DevBuf* B; int n;
+    const float* actions; float* obs; float* rew; uint8_t* done;
+    int auto_reset; uint32_t seed, env_id0; double* stats; unsigned long long* cyc; cudaStream_t st;
+};
+
+template <class T, int MC, bool PROF, int WPC>
+static int launch_static(const StaticLaunch& a) {
+    constexpr int per = 32 * WPC;
+    const size_t smem = sizeof(float) * per * lc_size<T>();
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_step_static<T, MC, PROF, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    k_step_static<T, MC, PROF, WPC><<<(a.n + per - 1) / per, per, smem, a.st>>>(*a.M, *a.B, a.actions, a.obs, a.rew, a.done, a.auto_reset, a.seed, a.env_id0, a.stats, a.cyc);
+    return 0;
+}
+
+// registry of the static-topology instantiations (each lives in its own translation unit, rs_static_inst.cu)
+typedef int (*StaticLaunchFn)(const StaticLaunch&);
+void rs_register_static(int topo, int prof, int wpc, StaticLaunchFn fn);

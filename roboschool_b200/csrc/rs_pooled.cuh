@@ -43,10 +43,19 @@ struct WarpHost {
     RS_HD int lane() const { return 0; }
     RS_HD int excl_scan(int v, int& total) const { total = v; return 0; }
     RS_HD void sync() const {}
+    RS_HD void cta_sync() const {}
 };
 #ifdef __CUDACC__
+// WPC: warps per CTA.  With WPC > 1 the warps of a CTA are re-aligned at the phase boundaries of the sub-step
+// (cta_sync), so that they walk the (large, fully unrolled) instruction stream together and share instruction fetches.
+template <int WPC>
 struct WarpDev {
     static constexpr int WIDTH = 32;
+    RS_HD void cta_sync() const {
+#ifdef __CUDA_ARCH__
+        if (WPC > 1) __syncthreads();
+#endif
+    }
     RS_HD int lane() const {
 #ifdef __CUDA_ARCH__
         return threadIdx.x & 31;
@@ -93,9 +102,9 @@ RS_HD void xf_force_inv(float* out, const float* R, const float* r, const float*
 //   Rows go to pool slots slot0 .. slot0+NR-1.  first: overwrite; else accumulate (second body of a pair).
 //   denom[rr] = J . M^-1 J^T of THIS side.
 // ---------------------------------------------------------------------------------------------
-template <class T, int NR, bool HASW, int STRIDE>
+template <class T, int NR, bool HASW, bool first, int STRIDE>
 RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*wr)[6], float jdir,
-                           const RowPool& pool, int slot0, bool first, float* denom) {
+                           const RowPool& pool, int slot0, float* denom) {
     constexpr int n = T::NL, nd = 6 + T::ND;
     float F[HASW ? NR : 1][6], Z[NR][6], Y[NR][n];
 #pragma unroll
@@ -131,7 +140,7 @@ RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*
 #pragma unroll
                     for (int k = 0; k < 6; k++) Z[rr][k] += h[k] * kk;
                     float& J = pool.at(slot0 + rr, 6 + d);
-                    J = first ? j : J + j;
+                    if constexpr (first) J = j; else J += j;
                 }
             }
 #pragma unroll
@@ -150,7 +159,7 @@ RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*
         } else {
             if constexpr (d >= 0) {
 #pragma unroll
-                for (int rr = 0; rr < NR; rr++) { Y[rr][i] = 0.f; if (first) pool.at(slot0 + rr, 6 + d) = 0.f; }
+                for (int rr = 0; rr < NR; rr++) { Y[rr][i] = 0.f; if constexpr (first) pool.at(slot0 + rr, 6 + d) = 0.f; }
             }
         }
     });
@@ -161,7 +170,7 @@ RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*
 #pragma unroll
             for (int k = 0; k < 6; k++) {
                 acc[rr][0][k] = 0.f;
-                if (first) { pool.at(slot0 + rr, k) = 0.f; pool.at(slot0 + rr, nd + k) = 0.f; }
+                if constexpr (first) { pool.at(slot0 + rr, k) = 0.f; pool.at(slot0 + rr, nd + k) = 0.f; }
             }
         }
     } else {
@@ -182,7 +191,7 @@ RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*
             for (int k = 0; k < 3; k++) {
                 float& J0 = pool.at(slot0 + rr, k); float& J1 = pool.at(slot0 + rr, 3 + k);
                 float& U0 = pool.at(slot0 + rr, nd + k); float& U1 = pool.at(slot0 + rr, nd + 3 + k);
-                if (first) { J0 = jw[k]; J1 = jv[k]; U0 = uw[k]; U1 = uv[k]; }
+                if constexpr (first) { J0 = jw[k]; J1 = jv[k]; U0 = uw[k]; U1 = uv[k]; }
                 else { J0 += jw[k]; J1 += jv[k]; U0 += uw[k]; U1 += uv[k]; }
             }
             if constexpr (HASW) { if (body == 0) denom[rr] = dot6(wr[rr], acc[rr][0]); }
@@ -206,12 +215,18 @@ RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*
                 const float a = invD * (Y[rr][i] - dot6(acc[rr][i + 1], h));
                 saxpy<T, i>(acc[rr][i + 1], a);
                 float& U = pool.at(slot0 + rr, nd + 6 + d);
-                U = first ? a : U + a;
+                if constexpr (first) U = a; else U += a;
                 if constexpr (!HASW) { if (body == i + 1) denom[rr] = a * jdir; }
             }
             if constexpr (HASW) { if (body == i + 1) denom[rr] = dot6(wr[rr], acc[rr][i + 1]); }
         }
     });
+}
+
+// second body of a two-body contact: accumulate variant, kept out of line (rare; keeps the hot instruction stream short)
+template <class T, int STRIDE>
+RS_HDN void pooled_response_second(const LinkCache<STRIDE>& lc, int body, const float (*wr)[6], const RowPool& pool, int slot0, float* denom) {
+    pooled_response<T, 3, true, false>(lc, body, wr, 0.f, pool, slot0, denom);
 }
 
 // resolveSingleConstraintRowGeneric on a pooled row record
@@ -311,7 +326,7 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
             const float dir = (code >> 16) ? -1.f : 1.f;
             LinkCache<STRIDE> lco{lc_lane0 + o};
             float dn[1];
-            pooled_response<T, 1, false>(lco, body, (const float (*)[6]) nullptr, dir, pool, t, true, dn);
+            pooled_response<T, 1, false, true>(lco, body, (const float (*)[6]) nullptr, dir, pool, t, dn);
             pool.at(t, 2 * nd) = dn[0];
         }
     }
@@ -330,17 +345,24 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
                 for (int k = 13; k < POOL_DESC_WORDS; k++) desc[k] = pool.at(slot, k);
             }
             LinkCache<STRIDE> lco{lc_lane0 + o};
-            float dsum[3] = {0.f, 0.f, 0.f};
-            const int nside = bB >= 0 ? 2 : 1;
-            for (int side = 0; side < nside; side++) {
-                const float* ds = desc + 1 + 12 * side;
+            float dsum[3];
+            {
+                float wr[3][6];
+#pragma unroll
+                for (int w = 0; w < 3; w++) {
+                    cross3(wr[w], desc + 1, desc + 4 + 3 * w);
+                    wr[w][3] = desc[4 + 3 * w]; wr[w][4] = desc[5 + 3 * w]; wr[w][5] = desc[6 + 3 * w];
+                }
+                pooled_response<T, 3, true, true>(lco, bA, (const float (*)[6]) wr, 0.f, pool, slot, dsum);
+            }
+            if (bB >= 0) {   // second body of a self-collision pair: rare, accumulates into the same rows
                 float wr[3][6], dn[3];
 #pragma unroll
                 for (int w = 0; w < 3; w++) {
-                    cross3(wr[w], ds, ds + 3 + 3 * w);
-                    wr[w][3] = ds[3 + 3 * w]; wr[w][4] = ds[4 + 3 * w]; wr[w][5] = ds[5 + 3 * w];
+                    cross3(wr[w], desc + 13, desc + 16 + 3 * w);
+                    wr[w][3] = desc[16 + 3 * w]; wr[w][4] = desc[17 + 3 * w]; wr[w][5] = desc[18 + 3 * w];
                 }
-                pooled_response<T, 3, true>(lco, side == 0 ? bA : bB, (const float (*)[6]) wr, 0.f, pool, slot, side == 0, dn);
+                pooled_response_second<T>(lco, bB, (const float (*)[6]) wr, pool, slot, dn);
                 dsum[0] += dn[0]; dsum[1] += dn[1]; dsum[2] += dn[2];
             }
 #pragma unroll
@@ -436,13 +458,19 @@ RS_HD void substep_pooled(const Warp& warp, bool valid, const DevModel& M, Work<
                           const LinkCache<STRIDE>& lc, float* lc_lane0, PhaseClock* pc = nullptr) {
     const float dt = M.timestep;
     long long c0 = 0, c1 = 0;
+    warp.cta_sync();
     if (pc) c0 = RS_CLOCK();
-    if (valid) static_kinematics<T>(W, lc);
-    if (pc) { c1 = RS_CLOCK(); pc->t[0] += c1 - c0; c0 = c1; }
-    if (valid) collide(M, W);
+    if (valid) {
+        float gwr[T::NG][6];
+        static_kinematics<T, true>(W, lc, gwr);
+        if (pc) { c1 = RS_CLOCK(); pc->t[0] += c1 - c0; c0 = c1; }
+        static_collide<T>(M, W, gwr);
+    }
     if (pc) { c1 = RS_CLOCK(); pc->t[1] += c1 - c0; c0 = c1; }
+    warp.cta_sync();
     if (valid) static_aba<T>(M, W, lc, dt);
     if (pc) { c1 = RS_CLOCK(); pc->t[2] += c1 - c0; c0 = c1; }
+    warp.cta_sync();
     warp.sync();   // link caches complete before other lanes read them
     solve_pooled<T, Warp, NL, MC, SL, STRIDE>(warp, valid, M, W, dt, pool, lc_lane0);
     warp.sync();   // all helpers done with this sub-step's caches before kinematics overwrites them

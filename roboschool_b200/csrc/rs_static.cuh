@@ -100,8 +100,31 @@ RS_HD void cached_xform(const LinkCache<STRIDE>& lc, float* R, float* r) {
 // kinematics: fills the (cos, sin) cache and the world transforms W.Rwl / W.pos (thread-private,
 // read by the narrowphase / contact rows / epilogue by dynamic body index)
 // ---------------------------------------------------------------------------------------------
-template <class T, int NL, int MC, bool SL, int STRIDE>
-RS_HD void static_kinematics(Work<NL, MC, SL>& W, const LinkCache<STRIDE>& lc) {
+// world end points of the geoms attached to body B (0 = base), while that body's transform is still in registers
+template <class T, int B, int NL, int MC, bool SL>
+RS_HD void static_body_geoms(const Work<NL, MC, SL>& W, float (*gwr)[6]) {
+    static_for<T::NG>([&](auto gc) {
+        constexpr int g = decltype(gc)::value;
+        if constexpr (T::g_link[g] + 1 == B) {
+            const float* R = W.Rwl[B];
+            const float* p = W.pos[B];
+            constexpr float a0 = T::g_p0[3 * g], a1 = T::g_p0[3 * g + 1], a2 = T::g_p0[3 * g + 2];
+            gwr[g][0] = p[0] + (RS_CM(a0, R[0]) + RS_CM(a1, R[3]) + RS_CM(a2, R[6]));
+            gwr[g][1] = p[1] + (RS_CM(a0, R[1]) + RS_CM(a1, R[4]) + RS_CM(a2, R[7]));
+            gwr[g][2] = p[2] + (RS_CM(a0, R[2]) + RS_CM(a1, R[5]) + RS_CM(a2, R[8]));
+            if constexpr (T::g_type[g] == RS_GEOM_CAPSULE) {
+                constexpr float b0 = T::g_p1[3 * g], b1 = T::g_p1[3 * g + 1], b2 = T::g_p1[3 * g + 2];
+                gwr[g][3] = p[0] + (RS_CM(b0, R[0]) + RS_CM(b1, R[3]) + RS_CM(b2, R[6]));
+                gwr[g][4] = p[1] + (RS_CM(b0, R[1]) + RS_CM(b1, R[4]) + RS_CM(b2, R[7]));
+                gwr[g][5] = p[2] + (RS_CM(b0, R[2]) + RS_CM(b1, R[5]) + RS_CM(b2, R[8]));
+            } else { gwr[g][3] = gwr[g][0]; gwr[g][4] = gwr[g][1]; gwr[g][5] = gwr[g][2]; }
+        }
+    });
+}
+
+// GEOMS: also produce the world end points of every collision geom into gwr[NG][6] (statically indexed => registers)
+template <class T, bool GEOMS = false, int NL, int MC, bool SL, int STRIDE>
+RS_HD void static_kinematics(Work<NL, MC, SL>& W, const LinkCache<STRIDE>& lc, float (*gwr)[6] = nullptr) {
     float Rbw[9];
     quat_to_mat(Rbw, W.bquat[0], W.bquat[1], W.bquat[2], W.bquat[3]);
 #pragma unroll
@@ -111,6 +134,7 @@ RS_HD void static_kinematics(Work<NL, MC, SL>& W, const LinkCache<STRIDE>& lc) {
     W.pos[0][0] = W.bpos[0]; W.pos[0][1] = W.bpos[1]; W.pos[0][2] = W.bpos[2];
 #pragma unroll
     for (int k = 0; k < 9; k++) lc.at(lc_rb<T>() + k) = W.Rwl[0][k];
+    if constexpr (GEOMS) static_body_geoms<T, 0>(W, gwr);
     static_for<T::NL>([&](auto ic) {
         constexpr int i = decltype(ic)::value;
         constexpr int p = T::parent[i], jt = T::jtype[i], dI = T::dof[i];
@@ -126,7 +150,65 @@ RS_HD void static_kinematics(Work<NL, MC, SL>& W, const LinkCache<STRIDE>& lc) {
         float rw[3];
         tmulv(rw, W.Rwl[i + 1], r);
         W.pos[i + 1][0] = W.pos[p + 1][0] + rw[0]; W.pos[i + 1][1] = W.pos[p + 1][1] + rw[1]; W.pos[i + 1][2] = W.pos[p + 1][2] + rw[2];
+        if constexpr (GEOMS) static_body_geoms<T, i + 1>(W, gwr);
     });
+}
+
+// ---------------------------------------------------------------------------------------------
+// narrowphase driver with a compile-time broadphase: the floor test of every geom and the bounding-sphere test of
+// every self-collision pair run on registers (gwr, from static_kinematics<T, true>) and set one bit per manifold;
+// only manifolds whose bit is set -- or that still hold cached points -- reach collide_manifold().
+// Same rejects as collide() (they are conservative: a manifold skipped here has no point within its threshold).
+// ---------------------------------------------------------------------------------------------
+template <class T, int NL, int MC, bool SL>
+RS_HD void static_collide(const DevModel& M, Work<NL, MC, SL>& W, const float (*gwr)[6]) {
+    constexpr int NG = T::NG, NP = T::NP, NMAN = NG + NP, NW = (NMAN + 31) / 32;
+    uint32_t cand[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) cand[w] = 0u;
+    static_for<NG>([&](auto gc) {
+        constexpr int g = decltype(gc)::value;
+#pragma unroll
+        for (int k = 0; k < 6; k++) W.gw[g][k] = gwr[g][k];
+        if constexpr (T::g_floor[g] != 0) {
+            constexpr float rad = T::g_radius[g], thr = T::g_thresh[g];
+            const float zmin = fminf(gwr[g][2], gwr[g][5]) - rad;
+            if (zmin < thr) cand[g >> 5] |= 1u << (g & 31);
+        }
+    });
+    if constexpr (NP > 0) {
+        float sm[NG][3];   // end-point sums (2 x midpoint)
+        static_for<NG>([&](auto gc) {
+            constexpr int g = decltype(gc)::value;
+            sm[g][0] = gwr[g][0] + gwr[g][3]; sm[g][1] = gwr[g][1] + gwr[g][4]; sm[g][2] = gwr[g][2] + gwr[g][5];
+        });
+        static_for<NP>([&](auto pc) {
+            constexpr int pk = decltype(pc)::value;
+            constexpr int ga = T::pair_a[pk], gb = T::pair_b[pk], k = NG + pk;
+            constexpr float reach = T::pair_reach[pk];
+            const float dx = 0.5f * (sm[ga][0] - sm[gb][0]), dy = 0.5f * (sm[ga][1] - sm[gb][1]), dz = 0.5f * (sm[ga][2] - sm[gb][2]);
+            if (!(dx * dx + dy * dy + dz * dz > reach * reach)) cand[k >> 5] |= 1u << (k & 31);
+        });
+    }
+    const int old = W.cur, nw = 1 - W.cur;
+    const int nold = W.ccount[old];
+    for (int i = 0; i < nold; i++) {
+        const int k = W.ckey[old][i];
+#pragma unroll
+        for (int w = 0; w < NW; w++) if ((k >> 5) == w) cand[w] |= 1u << (k & 31);
+    }
+    int oi = 0, no = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        uint32_t m = cand[w];
+        while (m) {
+            const int k = w * 32 + rs_ctz(m);
+            m &= m - 1u;
+            collide_manifold(M, W, W.gw, k, old, nw, nold, oi, no);
+        }
+    }
+    W.ccount[nw] = no;
+    W.cur = nw;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -447,6 +529,16 @@ inline bool topo_matches(const DevModel& D) {
                 !eq(D.Sw[i][k], T::Sw[3 * i + k]) || !eq(D.Sv[i][k], T::Sv[3 * i + k]) || !eq(D.inertia[i][k], T::inertia[3 * i + k])) return false;
         }
         for (int k = 0; k < 9; k++) if (!eq(D.R0[i][k], T::R0[9 * i + k])) return false;
+    }
+    if (D.n_geoms != T::NG || D.n_pairs != T::NP) return false;
+    for (int g = 0; g < T::NG; g++) {
+        if (D.g_link[g] != T::g_link[g] || D.g_type[g] != T::g_type[g] || (D.g_floor[g] != 0) != (T::g_floor[g] != 0)) return false;
+        if (!eq(D.g_radius[g], T::g_radius[g]) || !eq(D.break_thresh[D.g_link[g] + 1], T::g_thresh[g])) return false;
+        for (int k = 0; k < 3; k++) if (!eq(D.g_p0[g][k], T::g_p0[3 * g + k]) || !eq(D.g_p1[g][k], T::g_p1[3 * g + k])) return false;
+    }
+    for (int k = 0; k < T::NP; k++) {
+        if (D.pair_a[k] != T::pair_a[k] || D.pair_b[k] != T::pair_b[k]) return false;
+        if (!eq(D.g_bound[D.pair_a[k]] + D.g_bound[D.pair_b[k]] + D.pair_thresh[k], T::pair_reach[k])) return false;
     }
     if (!T::FIXED_BASE) {
         if (!eq(D.base_mass, T::base_mass)) return false;

@@ -15,9 +15,7 @@
 #include <vector>
 #include "../../include/roboschool_b200.h"
 #include "rs_devmodel.h"
-#include "rs_pooled.cuh"
-
-using namespace rs;
+#include "rs_kernels.cuh"
 
 static thread_local std::string g_err;
 static int fail(const std::string& s) { g_err = s; return 1; }
@@ -27,18 +25,26 @@ int rs_set_error(const char* s) { g_err = s; return 1; }   // shared with rs_mlp
 extern "C" const char* rs_last_error(void) { return g_err.c_str(); }
 extern "C" int rs_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 
-struct DevBuf {
-    float* state; int* ccount; int* ckey; float* cdat;
-    double* potential; float* initial_z; float* feet; int* frame; uint32_t* episode;
-    float* rows; float* tau; float* rewards5; int* nrows; int* ncontacts;
-    int N, S, MCcap, rec, maxr;
-};
+// static-topology instantiations register themselves here (rs_static_inst.cu, one object file each)
+static StaticLaunchFn g_static[8][2][9];   // [topology id][profiling][warps per CTA]
+void rs_register_static(int topo, int prof, int wpc, StaticLaunchFn fn) {
+    if (topo >= 0 && topo < 8 && wpc >= 0 && wpc < 9) g_static[topo][prof ? 1 : 0][wpc] = fn;
+}
+// warps per CTA of the step kernel: RS_WPC (tuning knob) if that instantiation exists, else the per-topology default
+static StaticLaunchFn pick_static(int topo, int prof, int def_wpc) {
+    int wpc = def_wpc;
+    if (const char* e = getenv("RS_WPC")) wpc = atoi(e);
+    if (wpc < 0 || wpc > 8 || !g_static[topo][prof][wpc]) wpc = def_wpc;
+    if (!g_static[topo][prof][wpc]) wpc = 1;
+    return g_static[topo][prof][wpc];
+}
 
 struct rs_world {
     rs_model_desc desc;
     DevModel M;
     DevBuf B;
     int device, n, family;   // family: 0 (NL<=6), 1 (NL<=12), 2 (NL<=24)
+    int wpc;                 // warps per CTA of the static-topology kernel
     int topo;                // 0: runtime-topology kernel; 1..4: kernel specialised on a generated topology (rs_topo_gen.h)
     cudaStream_t stream;
     // pinned staging + device staging for the host-buffer entry point
@@ -47,75 +53,6 @@ struct rs_world {
     double* d_stats;
     uint32_t rollout_seed, env_id0;
 };
-
-// ----------------------------------------------------------------------------------------------
-template <int NL, int MC, bool SL>
-__device__ __forceinline__ void load_env(const DevModel& M, const DevBuf& B, int e, Work<NL, MC, SL>& W, Episode& E) {
-    const int N = B.N;
-    const float* s = B.state + e;
-    int f = 0;
-    if (!M.fixed_base) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) W.bpos[k] = s[(size_t)(f++) * N];
-#pragma unroll
-        for (int k = 0; k < 4; k++) W.bquat[k] = s[(size_t)(f++) * N];
-#pragma unroll
-        for (int k = 0; k < 3; k++) W.bw[k] = s[(size_t)(f++) * N];
-#pragma unroll
-        for (int k = 0; k < 3; k++) W.bv[k] = s[(size_t)(f++) * N];
-    } else {
-#pragma unroll
-        for (int k = 0; k < 3; k++) { W.bpos[k] = 0; W.bw[k] = 0; W.bv[k] = 0; W.bquat[k] = 0; }
-        W.bquat[3] = 1.f;
-    }
-    for (int d = 0; d < M.n_dof; d++) W.q[d] = s[(size_t)(f + d) * N];
-    for (int d = 0; d < M.n_dof; d++) W.qd[d] = s[(size_t)(f + M.n_dof + d) * N];
-    int nc = B.ccount[e];
-    W.cur = 0; W.ccount[0] = nc; W.ccount[1] = 0;
-    for (int i = 0; i < nc; i++) {
-        W.ckey[0][i] = B.ckey[(size_t)i * N + e];
-#pragma unroll
-        for (int k = 0; k < CDAT; k++) W.cdat[0][i][k] = B.cdat[((size_t)i * CDAT + k) * N + e];
-    }
-    E.potential = B.potential[e]; E.initial_z = B.initial_z[e]; E.frame = B.frame[e]; E.episode = B.episode[e];
-    for (int k = 0; k < M.n_feet; k++) E.feet_contact[k] = B.feet[(size_t)k * N + e];
-    W.n_rows = 0; W.n_contacts = 0;
-}
-
-template <int NL, int MC, bool SL>
-__device__ __forceinline__ void store_env(const DevModel& M, const DevBuf& B, int e, const Work<NL, MC, SL>& W, const Episode& E) {
-    const int N = B.N;
-    float* s = B.state + e;
-    int f = 0;
-    if (!M.fixed_base) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) s[(size_t)(f++) * N] = W.bpos[k];
-#pragma unroll
-        for (int k = 0; k < 4; k++) s[(size_t)(f++) * N] = W.bquat[k];
-#pragma unroll
-        for (int k = 0; k < 3; k++) s[(size_t)(f++) * N] = W.bw[k];
-#pragma unroll
-        for (int k = 0; k < 3; k++) s[(size_t)(f++) * N] = W.bv[k];
-    }
-    for (int d = 0; d < M.n_dof; d++) s[(size_t)(f + d) * N] = W.q[d];
-    for (int d = 0; d < M.n_dof; d++) s[(size_t)(f + M.n_dof + d) * N] = W.qd[d];
-    const int cur = W.cur, nc = W.ccount[cur];
-    B.ccount[e] = nc;
-    for (int i = 0; i < nc; i++) {
-        B.ckey[(size_t)i * N + e] = W.ckey[cur][i];
-#pragma unroll
-        for (int k = 0; k < CDAT; k++) B.cdat[((size_t)i * CDAT + k) * N + e] = W.cdat[cur][i][k];
-    }
-    B.potential[e] = E.potential; B.initial_z[e] = E.initial_z; B.frame[e] = E.frame; B.episode[e] = E.episode;
-    for (int k = 0; k < M.n_feet; k++) B.feet[(size_t)k * N + e] = E.feet_contact[k];
-    B.nrows[e] = W.n_rows; B.ncontacts[e] = W.n_contacts;
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    return v;
-}
 
 // One env step per thread.  actions == nullptr: uniform random actions from the counter-based RNG.
 template <int NL, int MC>
@@ -159,83 +96,6 @@ __global__ void __launch_bounds__(64) k_step(const __grid_constant__ DevModel M,
             atomicAdd(stats + 4, st_rows); atomicAdd(stats + 5, st_con); atomicAdd(stats + 6, st_steps);
         }
     }
-}
-
-// Step kernel specialised on a compile-time topology: one warp per CTA (32 envs), link cache in shared memory,
-// constraint rows built by the whole warp (rs_pooled.cuh).  Every lane runs the kernel to the end: the spare lanes of
-// the tail warp own no env (valid == false) but still help with the warp's row tasks.
-// PROF: also accumulate clock64() deltas per phase into cyc[8] (profiling twin).
-template <class T, int MC, bool PROF>
-__global__ void __launch_bounds__(32) k_step_static(const __grid_constant__ DevModel M, const DevBuf B, const float* __restrict__ actions,
-                                                    float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
-                                                    int auto_reset, uint32_t seed, uint32_t env_id0, double* __restrict__ stats,
-                                                    unsigned long long* __restrict__ cyc) {
-    extern __shared__ float s_lc[];
-    const int e = blockIdx.x * 32 + threadIdx.x;
-    const bool valid = e < B.N;
-    double st_rew = 0, st_ep = 0, st_len = 0, st_nf = 0, st_rows = 0, st_con = 0, st_steps = 0;
-    long long t0 = 0, t1 = 0, t2 = 0;
-    if (PROF) t0 = clock64();
-    Work<T::NL, MC, true> W;
-    Episode E;
-    LinkCache<32> lc{s_lc + threadIdx.x};
-    float a[MA];
-    if (valid) {
-        load_env(M, B, e, W, E);
-        if (actions) { for (int k = 0; k < M.n_act; k++) a[k] = actions[(size_t)e * M.n_act + k]; }
-        else { for (int k = 0; k < M.n_act; k++) a[k] = 2.f * rs_uniform(seed ^ 0xA5A5A5A5u, env_id0 + e, E.episode * 1024u + (uint32_t)E.frame, (uint32_t)k) - 1.f; }
-        apply_action(M, W, a, 1);
-    }
-    const RowPool pool{B.rows + (size_t)blockIdx.x * ((size_t)32 * B.maxr * B.rec), 32 * B.maxr};
-    const WarpDev warp;
-    PhaseClock pc;
-    if (PROF) { for (int k = 0; k < 6; k++) pc.t[k] = 0; t1 = clock64(); }
-    for (int s = 0; s < M.frame_skip; s++) substep_pooled<T>(warp, valid, M, W, pool, lc, s_lc, PROF ? &pc : nullptr);
-    if (PROF) t2 = clock64();
-    if (valid) {
-        float* o = obs + (size_t)e * M.obs_dim;
-        StepOut out;
-        auto cs = [&](float* oo, int os, double* dist, float* pitch, int* al) { static_calc_state<T>(M, W, lc, E, oo, os, dist, pitch, al); };
-        epilogue_with(M, W, E, a, 1, o, 1, out, cs);
-        int dn = out.done;
-        bool finite = true;
-        for (int k = 0; k < M.obs_dim; k++) finite = finite && isfinite(o[k]);
-        int finished = dn || E.frame >= M.max_episode_steps;
-        st_rew = out.reward; st_rows = W.n_rows; st_con = W.n_contacts; st_steps = 1; st_nf = finite ? 0 : 1;
-        if (finished) { st_ep = 1; st_len = E.frame; }
-        if (auto_reset && finished) { env_reset_with(M, W, E, seed, env_id0 + e, o, 1, cs); dn = 1; }
-        rew[e] = out.reward; done[e] = (uint8_t)dn;
-        if (B.rewards5) {
-#pragma unroll
-            for (int k = 0; k < 5; k++) B.rewards5[(size_t)e * 5 + k] = out.rewards5[k];
-        }
-        store_env(M, B, e, W, E);
-    }
-    if (PROF && threadIdx.x == 0) {
-        long long t3 = clock64();
-        for (int k = 0; k < 5; k++) atomicAdd(cyc + k, (unsigned long long)pc.t[k]);
-        atomicAdd(cyc + 5, (unsigned long long)(t3 - t2));
-        atomicAdd(cyc + 6, (unsigned long long)(t1 - t0));
-        atomicAdd(cyc + 7, (unsigned long long)(t3 - t0));
-    }
-    if (stats) {
-        st_rew = warp_sum(st_rew); st_ep = warp_sum(st_ep); st_len = warp_sum(st_len); st_nf = warp_sum(st_nf);
-        st_rows = warp_sum(st_rows); st_con = warp_sum(st_con); st_steps = warp_sum(st_steps);
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(stats + 0, st_rew); atomicAdd(stats + 1, st_ep); atomicAdd(stats + 2, st_len); atomicAdd(stats + 3, st_nf);
-            atomicAdd(stats + 4, st_rows); atomicAdd(stats + 5, st_con); atomicAdd(stats + 6, st_steps);
-        }
-    }
-}
-
-template <class T, int MC, bool PROF>
-static int launch_static(rs_world* w, const float* actions, float* obs, float* rew, uint8_t* done, int auto_reset, uint32_t seed,
-                         uint32_t env_id0, double* stats, unsigned long long* cyc, cudaStream_t st) {
-    const size_t smem = sizeof(float) * 32 * lc_size<T>();
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_step_static<T, MC, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-    k_step_static<T, MC, PROF><<<(w->n + 31) / 32, 32, smem, st>>>(w->M, w->B, actions, obs, rew, done, auto_reset, seed, env_id0, stats, cyc);
-    return 0;
 }
 
 // Profiling twin of k_step: same work, plus clock64() deltas per phase summed over threads into cyc[8].
@@ -357,6 +217,8 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
         else if (topo_matches<TopoWalker2d>(w->M) && model->max_contacts <= 16) w->topo = 4;
     }
     w->device = device; w->n = n_envs;
+    // warps per CTA (measured on B200, profiles/): one CTA per SM at 32768 Humanoid envs; 4 for Ant; 1 otherwise
+    w->wpc = w->topo == 1 ? 7 : (w->topo == 2 ? 4 : 1);
     DevBuf& B = w->B;
     B.N = n_envs; B.S = (model->fixed_base ? 0 : 13) + 2 * model->n_dof; B.MCcap = MC;
     B.rec = 2 * (6 + model->n_dof) + 1; B.maxr = NL + 3 * MC;   // +1: pooled rows keep their denominator in the record
@@ -370,7 +232,7 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
     CK(cudaMalloc(&B.feet, sizeof(float) * N * MF));
     CK(cudaMalloc(&B.frame, sizeof(int) * N));
     CK(cudaMalloc(&B.episode, sizeof(uint32_t) * N));
-    CK(cudaMalloc(&B.rows, sizeof(float) * (size_t)((n_envs + 31) / 32 * 32) * B.rec * B.maxr));   // one pool per warp of 32 envs
+    CK(cudaMalloc(&B.rows, sizeof(float) * (size_t)((n_envs + 127) / 128 * 128) * B.rec * B.maxr));   // one pool per warp of 32 envs
     CK(cudaMalloc(&B.tau, sizeof(float) * N * (model->n_dof > 0 ? model->n_dof : 1)));
     CK(cudaMalloc(&B.rewards5, sizeof(float) * N * 5));
     CK(cudaMalloc(&B.nrows, sizeof(int) * N));
@@ -440,12 +302,13 @@ extern "C" int rs_world_reset(rs_world* w, uint32_t seed, uint32_t env_id0, cons
 
 static int launch_step(rs_world* w, const float* actions, float* obs, float* rew, uint8_t* done, int auto_reset, uint32_t seed,
                        uint32_t env_id0, double* stats, cudaStream_t st) {
-    switch (w->topo) {
-        case 1: launch_static<TopoHumanoid, 16, false>(w, actions, obs, rew, done, auto_reset, seed, env_id0, stats, nullptr, st); CK(cudaGetLastError()); return 0;
-        case 2: launch_static<TopoAnt, 16, false>(w, actions, obs, rew, done, auto_reset, seed, env_id0, stats, nullptr, st); CK(cudaGetLastError()); return 0;
-        case 3: launch_static<TopoHopper, 8, false>(w, actions, obs, rew, done, auto_reset, seed, env_id0, stats, nullptr, st); CK(cudaGetLastError()); return 0;
-        case 4: launch_static<TopoWalker2d, 16, false>(w, actions, obs, rew, done, auto_reset, seed, env_id0, stats, nullptr, st); CK(cudaGetLastError()); return 0;
-        default: break;
+    if (w->topo) {
+        StaticLaunch a{&w->M, &w->B, w->n, actions, obs, rew, done, auto_reset, seed, env_id0, stats, nullptr, st};
+        StaticLaunchFn fn = pick_static(w->topo, 0, w->wpc);
+        if (!fn) return fail("static-topology kernel not linked");
+        fn(a);
+        CK(cudaGetLastError());
+        return 0;
     }
     FAMILY_DISPATCH(w, (k_step<NL, MC><<<nblocks(w->n), 64, 0, st>>>(w->M, w->B, actions, obs, rew, done, auto_reset, seed, env_id0, stats)));
     CK(cudaGetLastError());
@@ -475,11 +338,13 @@ extern "C" int rs_world_step_profile(rs_world* w, const float* actions_dev, floa
     CK(cudaMalloc(&d, 8 * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), (cudaStream_t)stream));
     cudaStream_t st = (cudaStream_t)stream;
+    StaticLaunch sl{&w->M, &w->B, w->n, actions_dev, obs_dev, reward_dev, done_dev, 1, w->rollout_seed, w->env_id0, nullptr, d, st};
     switch (w->topo) {
-        case 1: launch_static<TopoHumanoid, 16, true>(w, actions_dev, obs_dev, reward_dev, done_dev, 1, w->rollout_seed, w->env_id0, nullptr, d, st); break;
-        case 2: launch_static<TopoAnt, 16, true>(w, actions_dev, obs_dev, reward_dev, done_dev, 1, w->rollout_seed, w->env_id0, nullptr, d, st); break;
-        case 3: launch_static<TopoHopper, 8, true>(w, actions_dev, obs_dev, reward_dev, done_dev, 1, w->rollout_seed, w->env_id0, nullptr, d, st); break;
-        case 4: launch_static<TopoWalker2d, 16, true>(w, actions_dev, obs_dev, reward_dev, done_dev, 1, w->rollout_seed, w->env_id0, nullptr, d, st); break;
+        case 1: case 2: case 3: case 4: {
+            StaticLaunchFn fn = pick_static(w->topo, 1, 1);
+            if (!fn) { cudaFree(d); return fail("profiling kernel not linked"); }
+            fn(sl);
+        } break;
         default:
             FAMILY_DISPATCH(w, (k_step_prof<NL, MC><<<nblocks(w->n), 64, 0, st>>>(w->M, w->B, actions_dev, obs_dev, reward_dev, done_dev,
                                                                                   w->rollout_seed, w->env_id0, d)));

@@ -80,6 +80,27 @@ def emit(env_id, cname):
     s += arr("mass", [m.mass[i] for i in range(n)]) + arr("inertia", inert)
     s += "    static constexpr float base_mass = %s;\n" % f(m.base_mass)
     s += arr("base_inertia", list(m.base_inertia))
+    # collision geoms / self-collision pairs (static broadphase, rs_static.cuh static_collide)
+    ng, npair = m.n_geoms, m.n_pairs
+    s += "    static constexpr int NG = %d, NP = %d;\n" % (ng, npair)
+    s += arr("g_link", [m.g_link[g] for g in range(ng)], "int", I)
+    s += arr("g_type", [m.g_type[g] for g in range(ng)], "int", I)
+    s += arr("g_floor", [m.g_floor[g] for g in range(ng)], "int", I)
+    s += arr("g_p0", snap([m.g_p0[g][k] for g in range(ng) for k in range(3)]))
+    s += arr("g_p1", snap([m.g_p1[g][k] for g in range(ng) for k in range(3)]))
+    s += arr("g_radius", [m.g_radius[g] for g in range(ng)])
+    s += arr("g_thresh", [m.break_thresh[m.g_link[g] + 1] for g in range(ng)])
+    def bound(g):
+        d = np.array([m.g_p1[g][k] - m.g_p0[g][k] for k in range(3)])
+        return float(np.float32(0.5 * np.sqrt((d * d).sum()) + m.g_radius[g]) * np.float32(1.0001) + np.float32(1e-6))
+    s += arr("pair_a", [m.pair_a[k] for k in range(npair)], "int", I)
+    s += arr("pair_b", [m.pair_b[k] for k in range(npair)], "int", I)
+    reach = []
+    for k in range(npair):
+        a, b = m.pair_a[k], m.pair_b[k]
+        thr = min(m.break_thresh[m.g_link[a] + 1], m.break_thresh[m.g_link[b] + 1])
+        reach.append(float(np.float32(bound(a)) + np.float32(bound(b)) + np.float32(thr)))
+    s += arr("pair_reach", reach)
     s += "};\n\n"
     sig = "%d:%d:%d:" % (n, m.n_dof, m.fixed_base) + ",".join(str(m.parent[i]) for i in range(n))
     return s, sig
