@@ -264,7 +264,7 @@ def main():
 
     st = stats.cpu().numpy()
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC.replace(ENV_ID, args.env), "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s, %d envs/GPU (%d total), agent_zoo v1 MLP policy on tensor cores, frame_skip 4, on-device auto-reset" % (args.env, n, total_envs),

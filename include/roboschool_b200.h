@@ -99,6 +99,10 @@ int rs_world_get_state(rs_world* w, float* state_host);
 /* potential float64[n], initial_z float32[n], feet_contact float32[n][n_feet], frame int32[n] */
 int rs_world_set_episode(rs_world* w, const double* potential, const float* initial_z, const float* feet_contact, const int* frame);
 int rs_world_get_episode(rs_world* w, double* potential, float* initial_z, float* feet_contact, int* frame);
+/* Flagrun (gym_humanoid_flagrun.py:21-45): per-env flag position float64[n][2] (walk_target_x/y), env steps until it
+ * moves int32[n] (flag_timeout) and RNG draws consumed by flag_reposition uint32[n].  NULL pointers are skipped. */
+int rs_world_set_flags(rs_world* w, const double* target_xy, const int* timeout, const uint32_t* draws);
+int rs_world_get_flags(rs_world* w, double* target_xy, int* timeout, uint32_t* draws);
 
 /* World::query_body_position (physics-bullet.cpp:440-495): per env, per body (base first, then
  * links): COM position3, quaternion4 (xyzw), linear velocity3  -> out_host[n_envs][1+L][10]. */

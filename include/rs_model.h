@@ -128,6 +128,11 @@ typedef struct rs_model_desc {
     double reset_base_quat[4];
     int    reset_set_base;               /* Humanoid: set_pose_and_speed at reset          */
     int    pad1;
+    /* moving walk target (RoboschoolHumanoidFlagrun, gym_humanoid_flagrun.py:6-45) */
+    int    flag_task;                    /* 0: fixed walk target; 1: flag repositioned when reached / timed out */
+    int    flag_timeout_steps;           /* 600/frame_skip env steps (gym_humanoid_flagrun.py:35)               */
+    double flag_halflen;                 /* StadiumScene.stadium_halflen   (scene_stadium.py:6)                 */
+    double flag_halfwidth;               /* StadiumScene.stadium_halfwidth (scene_stadium.py:7)                 */
 } rs_model_desc;
 
 #ifdef __cplusplus

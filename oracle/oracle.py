@@ -56,6 +56,8 @@ def lib():
         L.oracle_energy.argtypes = [P, I]
         L.oracle_energy.restype = D
         L.oracle_foot_flags.argtypes = [P, I, ip, ip]
+        L.oracle_set_flag.argtypes = [P, I, D, D, I, U]
+        L.oracle_get_flag.argtypes = [P, I, dp, dp, ip, ctypes.POINTER(U)]
         L.oracle_hash.argtypes = [U, U, U, U]
         L.oracle_hash.restype = U
         _LIB = L
@@ -111,7 +113,17 @@ class OracleWorld:
         return pot.value, iz.value, fc[:self.model.n_feet].copy(), fr.value
 
     def reset(self, seed=0, env_id0=0):
+        self.seed, self.env_id0 = seed, env_id0     # the flag RNG stream of later steps continues from these
         self.L.oracle_reset_all(self.h, seed, env_id0)
+
+    def set_flag(self, env, tx, ty, timeout, draws):
+        self.L.oracle_set_flag(self.h, env, tx, ty, int(timeout), int(draws))
+
+    def get_flag(self, env):
+        tx, ty = ctypes.c_double(), ctypes.c_double()
+        to, dr = ctypes.c_int(), ctypes.c_uint32()
+        self.L.oracle_get_flag(self.h, env, ctypes.byref(tx), ctypes.byref(ty), ctypes.byref(to), ctypes.byref(dr))
+        return tx.value, ty.value, to.value, dr.value
 
     def set_tau(self, env, tau):
         t = np.zeros(self.model.n_dof)
@@ -121,7 +133,9 @@ class OracleWorld:
     def substeps(self, env, n=1):
         self.L.oracle_substeps(self.h, env, n)
 
-    def step(self, actions, auto_reset=False, seed=0, env_id0=0, threads=0):
+    def step(self, actions, auto_reset=False, seed=None, env_id0=None, threads=0):
+        seed = getattr(self, "seed", 0) if seed is None else seed
+        env_id0 = getattr(self, "env_id0", 0) if env_id0 is None else env_id0
         a = np.ascontiguousarray(actions, dtype=np.float64).reshape(self.n, self.model.n_act)
         self.L.oracle_step(self.h, _dp(a), int(auto_reset), seed, env_id0, threads)
         return self.obs()

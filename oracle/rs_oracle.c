@@ -74,6 +74,10 @@ typedef struct {
     int frame;
     int done_latch;
     uint32_t episode;
+    /* walk target: the model's constant, or the Flagrun flag (gym_humanoid_flagrun.py:21-45) */
+    double target_x, target_y;
+    int flag_timeout;
+    uint32_t flag_draws;
     /* outputs of the last env step */
     double obs[8 + 2 * RS_MAX_ACT + RS_MAX_FEET];
     double reward, rewards5[5];
@@ -853,8 +857,8 @@ static void calc_state(const rs_model_desc *m, oenv *e, double *body_xy_dist) {
     double z = bp[2], r, p, yaw;
     quat_rpy(bq, &r, &p, &yaw);
     if (e->initial_z < 0) e->initial_z = z;
-    double theta = atan2(m->walk_target_y - my, m->walk_target_x - mx);
-    double dy = m->walk_target_y - my, dx = m->walk_target_x - mx;
+    double theta = atan2(e->target_y - my, e->target_x - mx);
+    double dy = e->target_y - my, dx = e->target_x - mx;
     *body_xy_dist = sqrt(dy * dy + dx * dx);
     double ang = theta - yaw;
     double cy = cos(-yaw), sy = sin(-yaw);
@@ -869,10 +873,44 @@ static void calc_state(const rs_model_desc *m, oenv *e, double *body_xy_dist) {
     e->rewards5[0] = p; /* temporarily */
 }
 
+static double rs_uniform(uint32_t seed, uint32_t env, uint32_t episode, uint32_t k);
+
+/* RoboschoolHumanoidFlagrun.flag_reposition (gym_humanoid_flagrun.py:21-35).  The reference draws from
+ * np_random in this order: [randint(2) if first,] uniform x [, uniform y]; here the draws are the counter-based
+ * stream (seed, env, episode, 2000 + n). */
+static void flag_reposition(const rs_model_desc *m, oenv *e, uint32_t seed, uint32_t env_id, int first) {
+    int straight = 0;
+    if (first) straight = rs_uniform(seed, env_id, e->episode, 2000u + e->flag_draws++) < 0.5;
+    if (straight) {
+        double u = rs_uniform(seed, env_id, e->episode, 2000u + e->flag_draws++);
+        e->target_x = 0.5 * m->flag_halflen + (m->flag_halflen - 0.5 * m->flag_halflen) * u;
+        e->target_y = 0.0;
+    } else {
+        double ux = rs_uniform(seed, env_id, e->episode, 2000u + e->flag_draws++);
+        double uy = rs_uniform(seed, env_id, e->episode, 2000u + e->flag_draws++);
+        double x = -m->flag_halflen + (m->flag_halflen - -m->flag_halflen) * ux;
+        double y = -m->flag_halfwidth + (m->flag_halfwidth - -m->flag_halfwidth) * uy;
+        e->target_x = x * 0.5; e->target_y = y * 0.5;
+    }
+    e->flag_timeout = m->flag_timeout_steps;
+}
+
+/* RoboschoolHumanoidFlagrun.calc_state (gym_humanoid_flagrun.py:37-44) */
+static void calc_state_flag(const rs_model_desc *m, oenv *e, double *dist, uint32_t seed, uint32_t env_id) {
+    if (!m->flag_task) { calc_state(m, e, dist); return; }
+    e->flag_timeout -= 1;
+    calc_state(m, e, dist);
+    if (*dist < 1.0 || e->flag_timeout <= 0) {
+        flag_reposition(m, e, seed, env_id, 0);
+        calc_state(m, e, dist);
+        e->potential = -*dist / m->dt_env;
+    }
+}
+
 /* RoboschoolForwardWalker.step epilogue (gym_forward_walker.py:94-133) */
-static void epilogue(const rs_model_desc *m, oenv *e, const double *a) {
+static void epilogue(const rs_model_desc *m, oenv *e, const double *a, uint32_t seed, uint32_t env_id) {
     double dist;
-    calc_state(m, e, &dist);
+    calc_state_flag(m, e, &dist, seed, env_id);
     double pitch = e->rewards5[0];
     double z = e->obs[0] + e->initial_z;   /* state[0]+initial_z, state already float32 & clipped */
     double alive;
@@ -943,8 +981,11 @@ static void env_reset(const rs_model_desc *m, oenv *e, int nman, uint32_t seed, 
     memset(e->feet_contact, 0, sizeof e->feet_contact);
     e->initial_z = m->initial_z;
     e->frame = 0; e->done = 0;
+    e->target_x = m->walk_target_x; e->target_y = m->walk_target_y;
+    e->flag_timeout = 0; e->flag_draws = 0;
+    if (m->flag_task) flag_reposition(m, e, seed, env_id, 1);
     double dist;
-    calc_state(m, e, &dist);
+    calc_state_flag(m, e, &dist, seed, env_id);
     e->potential = -dist / m->dt_env;
 }
 
@@ -957,6 +998,7 @@ oracle_world *oracle_create(const rs_model_desc *m, int n_envs) {
         w->env[i].man = (manifold *)calloc((size_t)(w->nman > 0 ? w->nman : 1), sizeof(manifold));
         w->env[i].base_quat[3] = 1;
         w->env[i].initial_z = m->initial_z;
+        w->env[i].target_x = m->walk_target_x; w->env[i].target_y = m->walk_target_y;
     }
     return w;
 }
@@ -988,6 +1030,14 @@ void oracle_get_episode(const oracle_world *w, int env, double *potential, doubl
     *potential = e->potential; *initial_z = e->initial_z; *frame = e->frame;
     for (int k = 0; k < w->m.n_feet; k++) feet_contact[k] = e->feet_contact[k];
 }
+void oracle_set_flag(oracle_world *w, int env, double tx, double ty, int timeout, uint32_t draws) {
+    oenv *e = &w->env[env];
+    e->target_x = tx; e->target_y = ty; e->flag_timeout = timeout; e->flag_draws = draws;
+}
+void oracle_get_flag(const oracle_world *w, int env, double *tx, double *ty, int *timeout, uint32_t *draws) {
+    const oenv *e = &w->env[env];
+    *tx = e->target_x; *ty = e->target_y; *timeout = e->flag_timeout; *draws = e->flag_draws;
+}
 void oracle_reset(oracle_world *w, int env, uint32_t seed, uint32_t env_id) { env_reset(&w->m, &w->env[env], w->nman, seed, env_id); }
 void oracle_reset_all(oracle_world *w, uint32_t seed, uint32_t env_id0) {
     for (int i = 0; i < w->n_envs; i++) env_reset(&w->m, &w->env[i], w->nman, seed, env_id0 + (uint32_t)i);
@@ -1012,7 +1062,7 @@ static void step_one(oracle_world *w, int i, const double *actions, int auto_res
     /* applyJointDamping: once per stepSimulation, from the velocities at its start */
     for (int l = 0; l < m->n_links; l++) if (m->dof_idx[l] >= 0 && m->jdamping[l] != 0) e->tau[m->dof_idx[l]] += -m->jdamping[l] * e->qd[m->dof_idx[l]];
     for (int s = 0; s < m->frame_skip; s++) substep(m, e);
-    epilogue(m, e, a);
+    epilogue(m, e, a, seed, env_id0 + (uint32_t)i);
     if (auto_reset && (e->done || e->frame >= m->max_episode_steps)) {
         /* obs returned for a finished env is the first obs of the next episode (vector-env convention) */
         double rew = e->reward;

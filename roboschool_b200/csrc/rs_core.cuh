@@ -61,6 +61,8 @@ struct DevModel {
     double walk_target_x, walk_target_y, dt_env;
     float reset_joint_spread, reset_yaw_spread, reset_base_pos[3], reset_base_quat[4];
     int reset_set_base;
+    int flag_task, flag_timeout_steps;
+    double flag_halflen, flag_halfwidth;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -992,10 +994,13 @@ RS_HD void body_pose(const Work<NL, MC, SL>& W, int b, float* pos, float* quat, 
 
 struct Episode {
     double potential;
+    double target_x, target_y;   // walk target (constant 1 km ahead, or the Flagrun flag)
     float initial_z;
     float feet_contact[MF];
     int frame;
     uint32_t episode;
+    int flag_timeout;            // Flagrun: env steps until the flag moves
+    uint32_t flag_draws;         // Flagrun: RNG draws consumed by flag_reposition in this episode
 };
 
 struct StepOut {
@@ -1042,7 +1047,7 @@ RS_HD void calc_state_core(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, c
     float z = bp[2];
     if (E.initial_z < 0.f) E.initial_z = z;
     // target bearing / distance: the target is 1 km away, so these run in double (a handful of ops)
-    double dy = M.walk_target_y - (double)my, dx = M.walk_target_x - (double)mx;
+    double dy = E.target_y - (double)my, dx = E.target_x - (double)mx;
     *dist = sqrt(dy * dy + dx * dx);
     float ang = (float)(atan2(dy, dx) - (double)yaw);
     float cy = cosf(-yaw), sy = sinf(-yaw);
@@ -1063,11 +1068,46 @@ RS_HD void calc_state(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, float*
     calc_state_core(M, W, E, bp, bq, bv, obs, ostride, dist, pitch, at_limit);
 }
 
+// RoboschoolHumanoidFlagrun.flag_reposition (gym_humanoid_flagrun.py:21-35); draws come from the counter-based RNG
+// in the reference's order: [randint(2) if first,] uniform x [, uniform y]
+RS_HD void flag_reposition(const DevModel& M, Episode& E, uint32_t seed, uint32_t env_id, bool first) {
+    auto draw = [&]() { return (double)rs_uniform(seed, env_id, E.episode, 2000u + E.flag_draws++); };
+    bool straight = false;
+    if (first) straight = draw() < 0.5;     // np_random.randint(2) == 0
+    if (straight) {
+        E.target_x = 0.5 * M.flag_halflen + (M.flag_halflen - 0.5 * M.flag_halflen) * draw();
+        E.target_y = 0.0;
+    } else {
+        double x = -M.flag_halflen + (M.flag_halflen - -M.flag_halflen) * draw();
+        double y = -M.flag_halfwidth + (M.flag_halfwidth - -M.flag_halfwidth) * draw();
+        E.target_x = x * 0.5; E.target_y = y * 0.5;   // more_compact = 0.5
+    }
+    E.flag_timeout = M.flag_timeout_steps;
+}
+
+// RoboschoolHumanoidFlagrun.calc_state (gym_humanoid_flagrun.py:37-44) around the plain calc_state `cs`.
+// Returns true if the flag moved (the caller must then not count a potential jump as progress).
+template <class CS>
+RS_HD bool calc_state_flag(const DevModel& M, Episode& E, uint32_t seed, uint32_t env_id, float* obs, int ostride,
+                           double* dist, float* pitch, int* at_limit, CS&& cs) {
+    if (!M.flag_task) { cs(obs, ostride, dist, pitch, at_limit); return false; }
+    E.flag_timeout -= 1;
+    cs(obs, ostride, dist, pitch, at_limit);
+    if (*dist < 1.0 || E.flag_timeout <= 0) {
+        flag_reposition(M, E, seed, env_id, false);
+        cs(obs, ostride, dist, pitch, at_limit);   // state again, against the new flag
+        E.potential = -*dist / M.dt_env;           // avoid reward jump
+        return true;
+    }
+    return false;
+}
+
 // `cs(obs, ostride, &dist, &pitch, &at_limit)` computes the observation (generic or static kinematics)
 template <int NL, int MC, bool SL, class CS>
-RS_HD void epilogue_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, const float* act, int astride, float* obs, int ostride, StepOut& out, CS&& cs) {
+RS_HD void epilogue_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, const float* act, int astride, float* obs, int ostride, StepOut& out, CS&& cs,
+                         uint32_t seed = 0, uint32_t env_id = 0) {
     double dist; float pitch; int at_limit;
-    cs(obs, ostride, &dist, &pitch, &at_limit);
+    calc_state_flag(M, E, seed, env_id, obs, ostride, &dist, &pitch, &at_limit, cs);
     float z = obs[0] + E.initial_z;
     float alive;
     if (M.alive_rule == RS_ALIVE_Z_AND_PITCH) alive = (z > M.alive_z && fabsf(pitch) < 1.0f) ? M.alive_bonus : -1.f;
@@ -1108,10 +1148,11 @@ RS_HD void epilogue_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, con
 }
 
 template <int NL, int MC, bool SL>
-RS_HD void epilogue(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, const float* act, int astride, float* obs, int ostride, StepOut& out) {
+RS_HD void epilogue(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, const float* act, int astride, float* obs, int ostride, StepOut& out,
+                    uint32_t seed = 0, uint32_t env_id = 0) {
     epilogue_with(M, W, E, act, astride, obs, ostride, out, [&](float* o, int os, double* dist, float* pitch, int* al) {
         calc_state(M, W, E, o, os, dist, pitch, al);
-    });
+    }, seed, env_id);
 }
 
 // reset to the reference's reset distribution (gym_forward_walker.py:24-30, gym_mujoco_walkers.py:106-128)
@@ -1136,8 +1177,11 @@ RS_HD void env_reset_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, ui
     for (int k = 0; k < M.n_feet; k++) E.feet_contact[k] = 0.f;
     E.initial_z = M.initial_z;
     E.frame = 0;
+    E.target_x = M.walk_target_x; E.target_y = M.walk_target_y;
+    E.flag_timeout = 0; E.flag_draws = 0;
+    if (M.flag_task) flag_reposition(M, E, seed, env_id, true);     // humanoid_task() (gym_humanoid_flagrun.py:17-19)
     double dist; float pitch; int al;
-    cs(obs, ostride, &dist, &pitch, &al);
+    calc_state_flag(M, E, seed, env_id, obs, ostride, &dist, &pitch, &al, cs);
     E.potential = -dist / M.dt_env;
 }
 template <int NL, int MC, bool SL>

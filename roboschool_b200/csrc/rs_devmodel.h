@@ -82,6 +82,8 @@ inline int build_dev_model(const rs_model_desc* m, DevModel* D, const char** err
     for (int k = 0; k < 3; k++) D->reset_base_pos[k] = (float)m->reset_base_pos[k];
     for (int k = 0; k < 4; k++) D->reset_base_quat[k] = (float)m->reset_base_quat[k];
     D->reset_set_base = m->reset_set_base;
+    D->flag_task = m->flag_task; D->flag_timeout_steps = m->flag_timeout_steps;
+    D->flag_halflen = m->flag_halflen; D->flag_halfwidth = m->flag_halfwidth;
     return 0;
 }
 

@@ -12,6 +12,7 @@ using namespace rs;
 struct DevBuf {
     float* state; int* ccount; int* ckey; float* cdat;
     double* potential; float* initial_z; float* feet; int* frame; uint32_t* episode;
+    double* target; int* flag_timeout; uint32_t* flag_draws;   // Flagrun: target [2][N], steps left, RNG draws used
     float* rows; float* tau; float* rewards5; int* nrows; int* ncontacts;
     int N, S, MCcap, rec, maxr;
 };
@@ -47,6 +48,8 @@ __device__ __forceinline__ void load_env(const DevModel& M, const DevBuf& B, int
     }
     E.potential = B.potential[e]; E.initial_z = B.initial_z[e]; E.frame = B.frame[e]; E.episode = B.episode[e];
     for (int k = 0; k < M.n_feet; k++) E.feet_contact[k] = B.feet[(size_t)k * N + e];
+    if (M.flag_task) { E.target_x = B.target[e]; E.target_y = B.target[(size_t)N + e]; E.flag_timeout = B.flag_timeout[e]; E.flag_draws = B.flag_draws[e]; }
+    else { E.target_x = M.walk_target_x; E.target_y = M.walk_target_y; E.flag_timeout = 0; E.flag_draws = 0; }
     W.n_rows = 0; W.n_contacts = 0;
 }
 
@@ -76,6 +79,7 @@ __device__ __forceinline__ void store_env(const DevModel& M, const DevBuf& B, in
     }
     B.potential[e] = E.potential; B.initial_z[e] = E.initial_z; B.frame[e] = E.frame; B.episode[e] = E.episode;
     for (int k = 0; k < M.n_feet; k++) B.feet[(size_t)k * N + e] = E.feet_contact[k];
+    if (M.flag_task) { B.target[e] = E.target_x; B.target[(size_t)N + e] = E.target_y; B.flag_timeout[e] = E.flag_timeout; B.flag_draws[e] = E.flag_draws; }
     B.nrows[e] = W.n_rows; B.ncontacts[e] = W.n_contacts;
 }
 
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__(32 * WPC) k_step_static(const __grid_constant_
         float* o = obs + (size_t)e * M.obs_dim;
         StepOut out;
         auto cs = [&](float* oo, int os, double* dist, float* pitch, int* al) { static_calc_state<T>(M, W, lc, E, oo, os, dist, pitch, al); };
-        epilogue_with(M, W, E, a, 1, o, 1, out, cs);
+        epilogue_with(M, W, E, a, 1, o, 1, out, cs, seed, env_id0 + e);
         int dn = out.done;
         bool finite = true;
         for (int k = 0; k < M.obs_dim; k++) finite = finite && isfinite(o[k]);

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(64) k_step(const __grid_constant__ DevModel M,
         for (int s = 0; s < M.frame_skip; s++) substep(M, W, ws);
         float* o = obs + (size_t)e * M.obs_dim;
         StepOut out;
-        epilogue(M, W, E, a, 1, o, 1, out);
+        epilogue(M, W, E, a, 1, o, 1, out, seed, env_id0 + e);
         int dn = out.done;
         bool finite = true;
         for (int k = 0; k < M.obs_dim; k++) finite = finite && isfinite(o[k]);
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(64) k_step_prof(const __grid_constant__ DevMod
     long long t2 = clock64();
     float* o = obs + (size_t)e * M.obs_dim;
     StepOut out;
-    epilogue(M, W, E, a, 1, o, 1, out);
+    epilogue(M, W, E, a, 1, o, 1, out, seed, env_id0 + e);
     int dn = out.done;
     if (dn || E.frame >= M.max_episode_steps) { env_reset(M, W, E, seed, env_id0 + e, o, 1); dn = 1; }
     rew[e] = out.reward; done[e] = (uint8_t)dn;
@@ -232,6 +232,12 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
     CK(cudaMalloc(&B.feet, sizeof(float) * N * MF));
     CK(cudaMalloc(&B.frame, sizeof(int) * N));
     CK(cudaMalloc(&B.episode, sizeof(uint32_t) * N));
+    CK(cudaMalloc(&B.target, sizeof(double) * N * 2));
+    CK(cudaMalloc(&B.flag_timeout, sizeof(int) * N));
+    CK(cudaMalloc(&B.flag_draws, sizeof(uint32_t) * N));
+    CK(cudaMemset(B.target, 0, sizeof(double) * N * 2));
+    CK(cudaMemset(B.flag_timeout, 0, sizeof(int) * N));
+    CK(cudaMemset(B.flag_draws, 0, sizeof(uint32_t) * N));
     CK(cudaMalloc(&B.rows, sizeof(float) * (size_t)((n_envs + 127) / 128 * 128) * B.rec * B.maxr));   // one pool per warp of 32 envs
     CK(cudaMalloc(&B.tau, sizeof(float) * N * (model->n_dof > 0 ? model->n_dof : 1)));
     CK(cudaMalloc(&B.rewards5, sizeof(float) * N * 5));
@@ -274,7 +280,7 @@ extern "C" int rs_world_destroy(rs_world* w) {
     DevBuf& B = w->B;
     cudaFree(B.state); cudaFree(B.ccount); cudaFree(B.ckey); cudaFree(B.cdat); cudaFree(B.potential); cudaFree(B.initial_z);
     cudaFree(B.feet); cudaFree(B.frame); cudaFree(B.episode); cudaFree(B.rows); cudaFree(B.tau); cudaFree(B.rewards5);
-    cudaFree(B.nrows); cudaFree(B.ncontacts);
+    cudaFree(B.nrows); cudaFree(B.ncontacts); cudaFree(B.target); cudaFree(B.flag_timeout); cudaFree(B.flag_draws);
     cudaFreeHost(w->h_act); cudaFreeHost(w->h_obs); cudaFreeHost(w->h_rew); cudaFreeHost(w->h_done);
     cudaFree(w->d_act); cudaFree(w->d_obs); cudaFree(w->d_rew); cudaFree(w->d_done); cudaFree(w->d_stats);
     cudaStreamDestroy(w->stream);
@@ -436,6 +442,34 @@ extern "C" int rs_world_get_episode(rs_world* w, double* potential, float* initi
         CK(cudaMemcpy(f.data(), w->B.feet, sizeof(float) * f.size(), cudaMemcpyDeviceToHost));
         for (size_t e = 0; e < N; e++) for (int k = 0; k < F; k++) feet_contact[e * F + k] = f[(size_t)k * N + e];
     }
+    return 0;
+}
+
+extern "C" int rs_world_set_flags(rs_world* w, const double* target_xy, const int* timeout, const uint32_t* draws) {
+    CK(cudaSetDevice(w->device));
+    size_t N = (size_t)w->n;
+    CK(cudaDeviceSynchronize());
+    if (target_xy) {
+        std::vector<double> t(2 * N);
+        for (size_t e = 0; e < N; e++) { t[e] = target_xy[2 * e]; t[N + e] = target_xy[2 * e + 1]; }
+        CK(cudaMemcpy(w->B.target, t.data(), sizeof(double) * 2 * N, cudaMemcpyHostToDevice));
+    }
+    if (timeout) CK(cudaMemcpy(w->B.flag_timeout, timeout, sizeof(int) * N, cudaMemcpyHostToDevice));
+    if (draws) CK(cudaMemcpy(w->B.flag_draws, draws, sizeof(uint32_t) * N, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int rs_world_get_flags(rs_world* w, double* target_xy, int* timeout, uint32_t* draws) {
+    CK(cudaSetDevice(w->device));
+    size_t N = (size_t)w->n;
+    CK(cudaDeviceSynchronize());
+    if (target_xy) {
+        std::vector<double> t(2 * N);
+        CK(cudaMemcpy(t.data(), w->B.target, sizeof(double) * 2 * N, cudaMemcpyDeviceToHost));
+        for (size_t e = 0; e < N; e++) { target_xy[2 * e] = t[e]; target_xy[2 * e + 1] = t[N + e]; }
+    }
+    if (timeout) CK(cudaMemcpy(timeout, w->B.flag_timeout, sizeof(int) * N, cudaMemcpyDeviceToHost));
+    if (draws) CK(cudaMemcpy(draws, w->B.flag_draws, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -43,6 +43,20 @@ ENV_SPECS = {
               "right_shoulder1": 75, "right_shoulder2": 75, "right_elbow": 75,
               "left_shoulder1": 75, "left_shoulder2": 75, "left_elbow": 75},
         reset_base=dict(z=1.4, yaw_spread=math.pi / 16), reward_threshold=3500.0),
+    # Humanoid running to a flag that moves when reached or after 150 steps (gym_humanoid_flagrun.py:6-45):
+    # same model and physics; electricity cost halved (:14); stadium-centred target box (scene_stadium.py:6-7)
+    "RoboschoolHumanoidFlagrun-v1": dict(
+        xml="humanoid_symmetric.xml", robot="torso", A=17, O=44, power=0.41,
+        feet=["right_foot", "left_foot"],
+        alive_rule=RS_ALIVE_Z, alive_z=0.78, alive_bonus=2.0, cost_scale=4.25, electricity_scale=0.5,
+        initial_z=0.8,
+        coef={"abdomen_z": 100, "abdomen_y": 100, "abdomen_x": 100,
+              "right_hip_x": 100, "right_hip_z": 100, "right_hip_y": 300, "right_knee": 200,
+              "left_hip_x": 100, "left_hip_z": 100, "left_hip_y": 300, "left_knee": 200,
+              "right_shoulder1": 75, "right_shoulder2": 75, "right_elbow": 75,
+              "left_shoulder1": 75, "left_shoulder2": 75, "left_elbow": 75},
+        reset_base=dict(z=1.4, yaw_spread=math.pi / 16), reward_threshold=2000.0,
+        flag=dict(halflen=105 * 0.25, halfwidth=50 * 0.25, timeout=600)),
     # plumbing config (BASELINE.json configs[0]); obs/reward computed by the Python facade
     "RoboschoolInvertedPendulum-v1": dict(
         xml="inverted_pendulum.xml", robot="cart", A=1, O=5, power=1.0, feet=[],
@@ -91,7 +105,7 @@ def apply_task(m: ModelDesc, spec: dict) -> ModelDesc:
     m.alive_rule = spec["alive_rule"]
     m.alive_z = spec["alive_z"]
     m.alive_bonus = spec["alive_bonus"]
-    m.electricity_cost = -2.0 * spec["cost_scale"]       # gym_forward_walker.py:83, gym_mujoco_walkers.py:86
+    m.electricity_cost = -2.0 * spec["cost_scale"] * spec.get("electricity_scale", 1.0)   # gym_forward_walker.py:83, gym_mujoco_walkers.py:86, gym_humanoid_flagrun.py:14
     m.stall_torque_cost = -0.1 * spec["cost_scale"]      # :84 / :87
     m.foot_collision_cost = -1.0                         # :85
     m.joints_at_limit_cost = -0.2                        # :87
@@ -104,6 +118,11 @@ def apply_task(m: ModelDesc, spec: dict) -> ModelDesc:
         m.arr("reset_base_pos")[:] = [0.0, 0.0, rb["z"]]
         m.arr("reset_base_quat")[:] = [0, 0, 0, 1]
         m.reset_yaw_spread = rb["yaw_spread"]
+    fl = spec.get("flag")
+    if fl:
+        m.flag_task = 1
+        m.flag_timeout_steps = int(fl["timeout"] // m.frame_skip)   # 600/frame_skip (gym_humanoid_flagrun.py:35)
+        m.flag_halflen, m.flag_halfwidth = fl["halflen"], fl["halfwidth"]
     m.max_episode_steps = 1000
     m.max_contacts = spec.get("max_contacts", 16)
     m.meta["env_id"] = spec.get("env_id", "")

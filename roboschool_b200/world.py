@@ -99,6 +99,20 @@ class BatchedWorld:
         _lib.check(self.L.rs_world_get_episode(self.h, p.ctypes.data, z.ctypes.data, f.ctypes.data, fr.ctypes.data))
         return p, z, f[:, :self.model.n_feet], fr
 
+    def set_flags(self, target_xy=None, timeout=None, draws=None):
+        """Flagrun: per-env flag position [n,2] (float64), steps until it moves, RNG draws consumed."""
+        t = None if target_xy is None else np.ascontiguousarray(target_xy, dtype=np.float64).reshape(self.n, 2)
+        to = None if timeout is None else np.ascontiguousarray(timeout, dtype=np.int32).reshape(self.n)
+        d = None if draws is None else np.ascontiguousarray(draws, dtype=np.uint32).reshape(self.n)
+        _lib.check(self.L.rs_world_set_flags(self.h, _ptr(t), _ptr(to), _ptr(d)))
+
+    def get_flags(self):
+        t = np.empty((self.n, 2), dtype=np.float64)
+        to = np.empty(self.n, dtype=np.int32)
+        d = np.empty(self.n, dtype=np.uint32)
+        _lib.check(self.L.rs_world_get_flags(self.h, t.ctypes.data, to.ctypes.data, d.ctypes.data))
+        return t, to, d
+
     def link_poses(self):
         out = np.empty((self.n, self.model.n_links + 1, 10), dtype=np.float32)
         _lib.check(self.L.rs_world_link_poses(self.h, out.ctypes.data))

@@ -33,7 +33,7 @@ static void step_env_static(Emul* e, int i, const float* a, int auto_reset, uint
     for (int s = 0; s < M.frame_skip; s++) substep_pooled<T>(WarpHost(), true, M, W, pool, lc, lc.p);
     float* obs = &e->obs[(size_t)i * M.obs_dim];
     auto cs = [&](float* o, int os, double* dist, float* pitch, int* al) { static_calc_state<T>(M, W, lc, e->ep[i], o, os, dist, pitch, al); };
-    epilogue_with(M, W, e->ep[i], a, 1, obs, 1, e->out[i], cs);
+    epilogue_with(M, W, e->ep[i], a, 1, obs, 1, e->out[i], cs, seed, env0 + i);
     int done = e->out[i].done;
     if (auto_reset && (done || e->ep[i].frame >= M.max_episode_steps)) { env_reset_with(M, W, e->ep[i], seed, env0 + i, obs, 1, cs); done = 1; }
     e->rew[i] = e->out[i].reward; e->done[i] = done;
@@ -51,7 +51,7 @@ void* emul_create(const rs_model_desc* m, int n) {
     const char* err = nullptr;
     if (build_dev_model(m, &e->M, &err)) { delete e; return nullptr; }
     e->n = n; e->w.resize(n); e->ep.resize(n); e->out.resize(n);
-    for (int i = 0; i < n; i++) { memset(&e->w[i], 0, sizeof(W_t)); e->w[i].bquat[3] = 1; memset(&e->ep[i], 0, sizeof(Episode)); e->ep[i].initial_z = e->M.initial_z; }
+    for (int i = 0; i < n; i++) { memset(&e->w[i], 0, sizeof(W_t)); e->w[i].bquat[3] = 1; memset(&e->ep[i], 0, sizeof(Episode)); e->ep[i].initial_z = e->M.initial_z; e->ep[i].target_x = e->M.walk_target_x; e->ep[i].target_y = e->M.walk_target_y; }
     e->rec = 2 * (6 + e->M.n_dof) + 1; e->maxr = NL + 3 * MC;
     e->ws.resize((size_t)e->rec * e->maxr);
     e->obs.resize((size_t)n * e->M.obs_dim); e->rew.resize(n); e->done.resize(n);
@@ -103,6 +103,12 @@ void emul_set_episode(void* h, int env, double potential, double initial_z, cons
     E.potential = potential; E.initial_z = (float)initial_z; E.frame = frame;
     for (int k = 0; k < e->M.n_feet; k++) E.feet_contact[k] = (float)fc[k];
 }
+void emul_set_flag(void* h, int env, double tx, double ty, int timeout, uint32_t draws) {
+    Emul* e = (Emul*)h; Episode& E = e->ep[env]; E.target_x = tx; E.target_y = ty; E.flag_timeout = timeout; E.flag_draws = draws;
+}
+void emul_get_flag(void* h, int env, double* out) {
+    Emul* e = (Emul*)h; Episode& E = e->ep[env]; out[0] = E.target_x; out[1] = E.target_y; out[2] = E.flag_timeout; out[3] = E.flag_draws;
+}
 void emul_step(void* h, const double* actions, int auto_reset, uint32_t seed, uint32_t env0) {
     Emul* e = (Emul*)h; RowWS ws{e->ws.data(), 1};
     const DevModel& M = e->M;
@@ -122,7 +128,7 @@ void emul_step(void* h, const double* actions, int auto_reset, uint32_t seed, ui
         apply_action(M, W, a, 1);
         for (int s = 0; s < M.frame_skip; s++) substep(M, W, ws);
         float* obs = &e->obs[(size_t)i * M.obs_dim];
-        epilogue(M, W, e->ep[i], a, 1, obs, 1, e->out[i]);
+        epilogue(M, W, e->ep[i], a, 1, obs, 1, e->out[i], seed, env0 + i);
         int done = e->out[i].done;
         if (auto_reset && (done || e->ep[i].frame >= M.max_episode_steps)) { env_reset(M, W, e->ep[i], seed, env0 + i, obs, 1); done = 1; }
         e->rew[i] = e->out[i].reward; e->done[i] = done;

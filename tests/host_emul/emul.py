@@ -44,6 +44,8 @@ def lib():
         L.emul_get_contacts.argtypes = [P, I, dp, I]; L.emul_get_contacts.restype = I
         L.emul_counts.argtypes = [P, I, ip, ip]
         L.emul_link_poses.argtypes = [P, I, dp]
+        L.emul_set_flag.argtypes = [P, I, D, D, I, U]
+        L.emul_get_flag.argtypes = [P, I, dp]
         _LIB = L
     return _LIB
 
@@ -80,13 +82,22 @@ class EmulWorld:
 
     def substeps(self, env, n=1): self.L.emul_substeps(self.h, env, n)
 
-    def reset(self, seed=0, env_id0=0): self.L.emul_reset_all(self.h, seed, env_id0)
+    def reset(self, seed=0, env_id0=0):
+        self.seed, self.env_id0 = seed, env_id0
+        self.L.emul_reset_all(self.h, seed, env_id0)
+
+    def set_flag(self, env, tx, ty, timeout, draws): self.L.emul_set_flag(self.h, env, tx, ty, int(timeout), int(draws))
+
+    def get_flag(self, env):
+        o = np.zeros(4); self.L.emul_get_flag(self.h, env, _dp(o)); return o[0], o[1], int(o[2]), int(o[3])
 
     def set_episode(self, env, potential, initial_z, feet_contact, frame=0):
         fc = np.zeros(8); fc[:len(feet_contact)] = feet_contact
         self.L.emul_set_episode(self.h, env, potential, initial_z, _dp(fc), frame)
 
-    def step(self, actions, auto_reset=False, seed=0, env_id0=0):
+    def step(self, actions, auto_reset=False, seed=None, env_id0=None):
+        seed = getattr(self, "seed", 0) if seed is None else seed
+        env_id0 = getattr(self, "env_id0", 0) if env_id0 is None else env_id0
         a = np.ascontiguousarray(actions, dtype=np.float64).reshape(self.n, self.model.n_act)
         self.L.emul_step(self.h, _dp(a), int(auto_reset), seed, env_id0)
         return self.obs()

@@ -8,7 +8,9 @@ from roboschool_b200.envspec import load_env_model
 
 pytestmark = pytest.mark.gpu
 
-ENVS = ["RoboschoolHopper-v1", "RoboschoolAnt-v1", "RoboschoolHumanoid-v1", "RoboschoolInvertedPendulum-v1"]
+ENVS = ["RoboschoolHopper-v1", "RoboschoolAnt-v1", "RoboschoolHumanoid-v1", "RoboschoolInvertedPendulum-v1",
+        "RoboschoolHumanoidFlagrun-v1"]
+STEP_ENVS = ENVS[:3] + ENVS[4:]
 # Per env-step (= 4 sub-steps) error of the fp32 CUDA path against the fp64 oracle, relative to
 # max(1, |state|_inf), over seeded random-action rollouts.  The dynamics are non-smooth (contact
 # make/break, friction-cone and limit clamps), so a clamp that flips in one sub-step gives an outlier:
@@ -39,7 +41,7 @@ def test_reset_matches_oracle(env_id, oracle_lib):
     assert np.abs(w.get_state() - o.get_state()).max() < 1e-6
 
 
-@pytest.mark.parametrize("env_id", ENVS[:3])
+@pytest.mark.parametrize("env_id", STEP_ENVS)
 def test_step_teacher_forced(env_id, oracle_lib):
     """Each step starts from the oracle's state (teacher forcing) so the per-step error is isolated:
     state within STEP_RTOL, identical contact manifolds (ids and per-manifold slots), same done flags."""
@@ -55,6 +57,9 @@ def test_step_teacher_forced(env_id, oracle_lib):
         ep = [o.get_episode(i) for i in range(n)]
         w.set_episode(potential=[e[0] for e in ep], initial_z=[e[1] for e in ep],
                       feet_contact=np.array([e[2] for e in ep]).reshape(n, m.n_feet), frame=[e[3] for e in ep])
+        if m.flag_task:
+            fl = [o.get_flag(i) for i in range(n)]
+            w.set_flags(target_xy=[[f[0], f[1]] for f in fl], timeout=[f[2] for f in fl], draws=[f[3] for f in fl])
         for i in range(n):   # the oracle starts from the float32-rounded state as well
             o.set_state(i, so[i].astype(np.float32).astype(np.float64), clear_contacts=False)
         obs_g, rew_g, done_g = w.step_host(a.astype(np.float32))
@@ -73,6 +78,11 @@ def test_step_teacher_forced(env_id, oracle_lib):
             errs.append(r)
             if r < STEP_RTOL:
                 assert np.abs(obs_g[i] - obs_o[i]).max() < 2e-3
+        if m.flag_task:   # same flag bookkeeping (position, timeout, RNG draws) on both sides
+            tg, tog, dg = w.get_flags()
+            fo = np.array([o.get_flag(i) for i in range(n)])
+            ok = alive
+            assert np.abs(tg[ok] - fo[ok, :2]).max() < 1e-9 and (tog[ok] == fo[ok, 2]).all() and (dg[ok] == fo[ok, 3]).all()
     errs = np.array(errs)
     assert np.median(errs) <= 1e-5, np.median(errs)
     assert (errs <= STEP_RTOL).mean() >= 0.95, (errs <= STEP_RTOL).mean()
@@ -80,7 +90,7 @@ def test_step_teacher_forced(env_id, oracle_lib):
     assert alive.mean() >= 0.97, "contact manifolds diverged in %d of %d envs" % ((~alive).sum(), n)
 
 
-@pytest.mark.parametrize("env_id", ENVS[:3])
+@pytest.mark.parametrize("env_id", STEP_ENVS)
 def test_free_running_bounded_divergence(env_id, oracle_lib):
     """No teacher forcing: fp32 GPU vs fp64 oracle over a short horizon; divergence stays bounded and
     observations/rewards agree early in the rollout."""

@@ -15,7 +15,7 @@ def emul():
 
 
 @pytest.mark.parametrize("static", [False, True], ids=["generic", "static-pooled"])
-@pytest.mark.parametrize("env_id", ["RoboschoolHopper-v1", "RoboschoolAnt-v1", "RoboschoolHumanoid-v1"])
+@pytest.mark.parametrize("env_id", ["RoboschoolHopper-v1", "RoboschoolAnt-v1", "RoboschoolHumanoid-v1", "RoboschoolHumanoidFlagrun-v1"])
 def test_emul_teacher_forced(env_id, static, emul, oracle_lib):
     """static=True runs the compile-time-topology sweeps with the pooled row builder (rs_static.cuh,
     rs_pooled.cuh) -- the code the shipped models run on the GPU; False the runtime-topology twin."""
@@ -36,6 +36,8 @@ def test_emul_teacher_forced(env_id, static, emul, oracle_lib):
             s32 = so[i].astype(np.float32).astype(np.float64)
             o.set_state(i, s32, clear_contacts=False); e.set_state(i, s32, clear_contacts=False)
             ep = o.get_episode(i); e.set_episode(i, ep[0], ep[1], ep[2], ep[3])
+            if m.flag_task:
+                e.set_flag(i, *o.get_flag(i))
         oo, orw, od = o.step(a)
         eo, erw, ed = e.step(a)
         for i in range(n):
@@ -51,6 +53,9 @@ def test_emul_teacher_forced(env_id, static, emul, oracle_lib):
             if r < 1e-4:
                 assert np.abs(oo[i] - eo[i]).max() < 2e-3
                 assert abs(orw[i] - erw[i]) < 5e-2
+                if m.flag_task:
+                    fo, fe = o.get_flag(i), e.get_flag(i)
+                    assert fo[2:] == fe[2:] and abs(fo[0] - fe[0]) < 1e-9 and abs(fo[1] - fe[1]) < 1e-9
     errs = np.array(errs)
     assert alive.mean() >= 0.9
     assert np.median(errs) <= 1e-5 and (errs <= 1e-4).mean() >= 0.95 and errs.max() < 0.2

@@ -84,7 +84,7 @@ def test_determinism_and_thread_independence(oracle_lib):
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
 
 
-@pytest.mark.parametrize("env_id", ["RoboschoolHopper-v1", "RoboschoolAnt-v1", "RoboschoolHumanoid-v1"])
+@pytest.mark.parametrize("env_id", ["RoboschoolHopper-v1", "RoboschoolAnt-v1", "RoboschoolHumanoid-v1", "RoboschoolHumanoidFlagrun-v1"])
 def test_epilogue_matches_reference_python(env_id, oracle_lib):
     """Golden vectors made by the reference's own gym_forward_walker.py (tools/gen_golden_epilogue.py)."""
     g = np.load(os.path.join(GOLDEN, "epilogue_%s.npz" % env_id))
@@ -102,6 +102,39 @@ def test_epilogue_matches_reference_python(env_id, oracle_lib):
         assert abs(rew[0] - g["ref_rew"][t]) < 1e-6
         assert bool(done[0]) == bool(g["ref_done"][t])
         assert np.abs(w.rewards5(0) - g["ref_rewards5"][t]).max() < 1e-6
+        if m.flag_task:   # flag position and timeout as kept by the reference's flag_reposition / calc_state
+            tx, ty, to, _ = w.get_flag(0)
+            assert abs(tx - g["ref_flags"][t][0]) < 1e-12 and abs(ty - g["ref_flags"][t][1]) < 1e-12
+            assert to == int(g["ref_flags"][t][2])
+    if m.flag_task:
+        assert len(np.unique(g["ref_flags"][:, 0])) >= 2, "fixture must contain a flag reposition"
+
+
+def test_behavioural_fixture_flagrun_chases_flags(oracle_lib):
+    """The reference's pretrained Flagrun policy on the restated physics: weaker pin than the Humanoid one -- the
+    policy runs towards the moving flag (reward/step well above the alive bonus alone would give a faller, flags are
+    reached before their 150-step timeout) but it does NOT reach the registered reward_threshold 2000
+    (roboschool/__init__.py:78-84) in most episodes: turning makes it fall.  Recorded as a gap in DESIGN.md."""
+    m = envspec.load_env_model("RoboschoolHumanoidFlagrun-v1")
+    wts = load_zoo_weights("RoboschoolHumanoidFlagrun-v1")
+    n = 16
+    w = oracle_lib.OracleWorld(m, n)
+    w.reset(seed=2)
+    obs = w.obs()[0]
+    tot = np.zeros(n); alive = np.ones(n, bool); reached = np.zeros(n); length = np.zeros(n)
+    prev = [w.get_flag(i) for i in range(n)]
+    for t in range(1000):
+        obs, rew, done = w.step(oracle_lib.mlp_forward(wts, obs), threads=4)
+        tot += rew * alive; length += alive
+        alive &= ~done.astype(bool)
+        for i in range(n):
+            f = w.get_flag(i)
+            if f[3] != prev[i][3] and prev[i][2] > 1 and alive[i]:
+                reached[i] += 1          # moved although the timeout had not run out: the robot got within 1 m
+            prev[i] = f
+    assert np.median(length) >= 150, length
+    assert (tot / length).mean() > 1.0, tot / length
+    assert reached.sum() >= 3, reached
 
 
 def test_mlp_known_answers(oracle_lib):

@@ -169,6 +169,7 @@ def make_cpp_household(model, replay, foot_names):
         def test_window(self): return True
         def load_thingy(self, *a): return Thingy("stadium", -1, replay)
         def new_camera_free_float(self, *a): return None
+        def debug_sphere(self, *a): return None
 
         def load_mjcf(self, fn):
             if fn.endswith("ground_plane.xml"):
@@ -191,7 +192,31 @@ def make_cpp_household(model, replay, foot_names):
     return mod
 
 
-def generate(env_id, cls_name, n_steps=60, seed=3):
+class CounterRNG(object):
+    """np_random stand-in for the reference classes: replays the counter-based stream the oracle / CUDA path draw from
+    (oracle/rs_oracle.c rs_uniform), in the order the reference consumes np_random at reset and in flag_reposition:
+    A joint draws (k = 0..A-1), the yaw draw (k = 1000), then the flag draws (k = 2000, 2001, ...)."""
+    def __init__(self, seed, env_id, episode, n_act):
+        from oracle.oracle import lib
+        self.h = lib().oracle_hash
+        self.seed, self.env_id, self.episode, self.A, self.calls = seed, env_id, episode, n_act, 0
+
+    def _u(self):
+        c = self.calls
+        self.calls += 1
+        k = c if c < self.A else (1000 if c == self.A else 2000 + (c - self.A - 1))
+        return float(self.h(self.seed, self.env_id, self.episode, k) >> 8) * (1.0 / 16777216.0)
+
+    def uniform(self, low=0.0, high=1.0, size=None):
+        assert size is None
+        return low + (high - low) * self._u()
+
+    def randint(self, n):
+        assert n == 2
+        return 0 if self._u() < 0.5 else 1
+
+
+def generate(env_id, cls_name, n_steps=60, seed=3, counter_rng=False):
     from roboschool_b200 import envspec
     from oracle.oracle import OracleWorld
     m = envspec.compile_env(env_id, os.path.join(REF, "roboschool", "mujoco_assets"))
@@ -237,17 +262,21 @@ def generate(env_id, cls_name, n_steps=60, seed=3):
         max_episode_steps = 1000
     env.spec = Spec()
     R.t = 0
+    if counter_rng:
+        env.np_random = CounterRNG(seed, 0, 1, m.n_act)
+    ref_flags = []
     ref_obs0 = env.reset()
     ref_obs, ref_rew, ref_done, ref_r5 = [], [], [], []
     for t in range(n_steps):
         ob, rw, dn, _ = env.step(acts[t])
         ref_obs.append(np.asarray(ob, dtype=np.float64)); ref_rew.append(rw); ref_done.append(dn); ref_r5.append(list(env.rewards))
+        ref_flags.append([env.walk_target_x, env.walk_target_y, getattr(env, "flag_timeout", 0)])
     out = os.path.join(ROOT, "tests", "golden", "epilogue_%s.npz" % env_id)
     os.makedirs(os.path.dirname(out), exist_ok=True)
     np.savez_compressed(out, seed=seed, actions=acts, poses=np.array(R.poses), q=np.array(R.q), qd=np.array(R.qd),
                         foot_flags=np.array(R.foot_flags, dtype=np.int32).reshape(n_steps + 1, -1, 2),
                         ref_obs0=np.asarray(ref_obs0, dtype=np.float64), ref_obs=np.array(ref_obs), ref_rew=np.array(ref_rew),
-                        ref_done=np.array(ref_done), ref_rewards5=np.array(ref_r5))
+                        ref_done=np.array(ref_done), ref_rewards5=np.array(ref_r5), ref_flags=np.array(ref_flags, dtype=np.float64))
     d_obs = np.abs(np.array(ref_obs) - np.array(oracle_obs)).max()
     d_rew = np.abs(np.array(ref_rew) - np.array(oracle_rew)).max()
     print("%-26s steps=%d  |ref-oracle| obs %.2e rew %.2e obs0 %.2e done equal=%s" % (
@@ -258,3 +287,5 @@ if __name__ == "__main__":
     generate("RoboschoolHopper-v1", "RoboschoolHopper")
     generate("RoboschoolAnt-v1", "RoboschoolAnt")
     generate("RoboschoolHumanoid-v1", "RoboschoolHumanoid")
+    # Flagrun: 170 steps so that the 150-step flag timeout (and the reposition after it) is part of the fixture
+    generate("RoboschoolHumanoidFlagrun-v1", "RoboschoolHumanoidFlagrun", n_steps=170, counter_rng=True)
