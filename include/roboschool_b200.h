@@ -138,6 +138,14 @@ int rs_world_rollout(rs_world* w, rs_policy* p, int n_steps, uint32_t seed, uint
 int rs_world_rollout_reset(rs_world* w, uint32_t seed, uint32_t env_id0, void* stream);
 /* device pointers of the world-owned rollout buffers: obs [n][O], act [n][A], reward [n], done [n] (uint8) */
 int rs_world_rollout_buffers(rs_world* w, float** obs_dev, float** act_dev, float** rew_dev, uint8_t** done_dev);
+/* Rollout recorder for trainers: n_steps policy+env steps written into the caller's time-major DEVICE
+ * tensors obs_T [n_steps+1][n][O], act_T [n_steps][n][A], rew_T [n_steps][n], done_T [n_steps][n] (uint8); obs_T[0] is
+ * filled from obs0_dev [n][O], or, if that is NULL, with the world's own current observations (after
+ * rs_world_rollout_reset or a previous rollout).  Finished envs are
+ * reset on the device (done=1, next obs = first obs of the new episode).  policy == NULL replays the actions in act_T. */
+int rs_world_rollout_record(rs_world* w, rs_policy* policy, int n_steps, const float* obs0_dev, float* obs_T, float* act_T,
+                            float* rew_T, uint8_t* done_T, double* stats_dev, void* stream);
+
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,8 @@ extern "C" {
 #define RS_ALIVE_Z_AND_PITCH 0 /* Hopper/Walker2d: +1 if z>alive_z and |pitch|<1 else -1 */
 #define RS_ALIVE_Z           1 /* Ant (+1), Humanoid (+2): bonus if z>alive_z else -1     */
 #define RS_ALIVE_ALWAYS      2 /* pendulum-style plumbing envs: never done from alive      */
+#define RS_ALIVE_CHEETAH     3 /* HalfCheetah: +1 if |pitch|<1 and none of feet 1,2,4,5 (shins, thighs) touched the
+                                  floor in the PREVIOUS step, else -1 (gym_mujoco_walkers.py:50-52)            */
 
 typedef struct rs_model_desc {
     /* ---- sizes ---- */

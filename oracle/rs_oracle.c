@@ -916,6 +916,8 @@ static void epilogue(const rs_model_desc *m, oenv *e, const double *a, uint32_t 
     double alive;
     if (m->alive_rule == RS_ALIVE_Z_AND_PITCH) alive = (z > m->alive_z && fabs(pitch) < 1.0) ? m->alive_bonus : -1;
     else if (m->alive_rule == RS_ALIVE_Z) alive = (z > m->alive_z) ? m->alive_bonus : -1;
+    else if (m->alive_rule == RS_ALIVE_CHEETAH)   /* gym_mujoco_walkers.py:50-52: stale feet_contact of shins and thighs */
+        alive = (fabs(pitch) < 1.0 && !e->feet_contact[1] && !e->feet_contact[2] && !e->feet_contact[4] && !e->feet_contact[5]) ? m->alive_bonus : -1;
     else alive = m->alive_bonus;
     int done = alive < 0;
     for (int k = 0; k < m->obs_dim; k++) if (!isfinite(e->obs[k])) done = 1;

@@ -56,6 +56,7 @@ def lib():
     L.rs_world_rollout.argtypes = [P, P, I, U, U, P, P]
     L.rs_world_rollout_reset.argtypes = [P, U, U, P]
     L.rs_world_rollout_buffers.argtypes = [P, PP, PP, PP, PP]
+    L.rs_world_rollout_record.argtypes = [P, P, I, P, P, P, P, P, P, P]
     _LIB = L
     return L
 
@@ -72,5 +73,5 @@ EXPORTED_SYMBOLS = [
     "rs_world_set_episode", "rs_world_get_episode", "rs_world_set_flags", "rs_world_get_flags", "rs_world_link_poses", "rs_world_get_contacts",
     "rs_world_get_counts", "rs_world_get_rewards5", "rs_world_state_dev", "rs_policy_create",
     "rs_policy_destroy", "rs_policy_forward", "rs_world_rollout", "rs_world_rollout_reset",
-    "rs_world_rollout_buffers",
+    "rs_world_rollout_buffers", "rs_world_rollout_record",
 ]

@@ -1112,6 +1112,8 @@ RS_HD void epilogue_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, con
     float alive;
     if (M.alive_rule == RS_ALIVE_Z_AND_PITCH) alive = (z > M.alive_z && fabsf(pitch) < 1.0f) ? M.alive_bonus : -1.f;
     else if (M.alive_rule == RS_ALIVE_Z) alive = (z > M.alive_z) ? M.alive_bonus : -1.f;
+    else if (M.alive_rule == RS_ALIVE_CHEETAH)   // feet_contact still holds the previous step's flags here
+        alive = (fabsf(pitch) < 1.0f && E.feet_contact[1] == 0.f && E.feet_contact[2] == 0.f && E.feet_contact[4] == 0.f && E.feet_contact[5] == 0.f) ? M.alive_bonus : -1.f;
     else alive = M.alive_bonus;
     int done = alive < 0.f;
     for (int k = 0; k < M.obs_dim; k++) if (!isfinite(obs[k * ostride])) done = 1;

@@ -215,6 +215,7 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
         else if (topo_matches<TopoAnt>(w->M) && model->max_contacts <= 16) w->topo = 2;
         else if (topo_matches<TopoHopper>(w->M) && model->max_contacts <= 8) w->topo = 3;
         else if (topo_matches<TopoWalker2d>(w->M) && model->max_contacts <= 16) w->topo = 4;
+        else if (topo_matches<TopoHalfCheetah>(w->M) && model->max_contacts <= 16) w->topo = 5;
     }
     w->device = device; w->n = n_envs;
     // warps per CTA (measured on B200, profiles/): one CTA per SM at 32768 Humanoid envs; 4 for Ant; 1 otherwise
@@ -346,7 +347,7 @@ extern "C" int rs_world_step_profile(rs_world* w, const float* actions_dev, floa
     cudaStream_t st = (cudaStream_t)stream;
     StaticLaunch sl{&w->M, &w->B, w->n, actions_dev, obs_dev, reward_dev, done_dev, 1, w->rollout_seed, w->env_id0, nullptr, d, st};
     switch (w->topo) {
-        case 1: case 2: case 3: case 4: {
+        case 1: case 2: case 3: case 4: case 5: {
             StaticLaunchFn fn = pick_static(w->topo, 1, 1);
             if (!fn) { cudaFree(d); return fail("profiling kernel not linked"); }
             fn(sl);
@@ -534,6 +535,29 @@ extern "C" int rs_world_rollout(rs_world* w, rs_policy* p, int n_steps, uint32_t
         }
         if (launch_step(w, act, w->d_obs, w->d_rew, w->d_done, 1, seed, env_id0, stats_dev, st)) return 1;
     }
+    return 0;
+}
+
+// Rollout recorder (the caller side of step for PPO-style trainers): T policy+env steps written straight
+// into the caller's time-major tensors -- obs [T+1][N][O] (obs[0] = current observations, filled here from the world's
+// buffer, or from obs0_dev if given), act [T][N][A], rew [T][N], done [T][N].  No staging copies: the policy reads obs[t] and writes act[t]; the
+// step kernel reads act[t] and writes obs[t+1], rew[t], done[t]; finished envs auto-reset (done[t]=1, obs[t+1] is the
+// first observation of the new episode).  p == NULL: act[t] must already hold the actions to replay.
+extern "C" int rs_world_rollout_record(rs_world* w, rs_policy* p, int n_steps, const float* obs0_dev, float* obs_T, float* act_T, float* rew_T,
+                                       uint8_t* done_T, double* stats_dev, void* stream) {
+    if (!obs_T || !act_T || !rew_T || !done_T || n_steps <= 0) return fail("rs_world_rollout_record: bad arguments");
+    CK(cudaSetDevice(w->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t N = (size_t)w->n, O = (size_t)w->desc.obs_dim, A = (size_t)w->desc.n_act;
+    CK(cudaMemcpyAsync(obs_T, obs0_dev ? obs0_dev : w->d_obs, sizeof(float) * N * O, cudaMemcpyDeviceToDevice, st));
+    for (int t = 0; t < n_steps; t++) {
+        float* a = act_T + (size_t)t * N * A;
+        if (p && rs_policy_forward(p, obs_T + (size_t)t * N * O, a, w->n, stream)) return 1;
+        if (launch_step(w, a, obs_T + (size_t)(t + 1) * N * O, rew_T + (size_t)t * N, done_T + (size_t)t * N, 1, w->rollout_seed, w->env_id0,
+                        stats_dev, st)) return 1;
+    }
+    // keep the world's own observation buffer current so that rollouts can be chained
+    CK(cudaMemcpyAsync(w->d_obs, obs_T + (size_t)n_steps * N * O, sizeof(float) * N * O, cudaMemcpyDeviceToDevice, st));
     return 0;
 }
 

@@ -15,7 +15,7 @@ from . import mjcf
 _HERE = os.path.dirname(os.path.abspath(__file__))
 MODEL_DIR = os.path.join(_HERE, "models")
 
-RS_ALIVE_Z_AND_PITCH, RS_ALIVE_Z, RS_ALIVE_ALWAYS = 0, 1, 2
+RS_ALIVE_Z_AND_PITCH, RS_ALIVE_Z, RS_ALIVE_ALWAYS, RS_ALIVE_CHEETAH = 0, 1, 2, 3
 
 ENV_SPECS = {
     # id: xml, robot_name, A, O, power, foot_list, alive rule/params, per-joint coef overrides
@@ -27,6 +27,12 @@ ENV_SPECS = {
         xml="walker2d.xml", robot="torso", A=6, O=22, power=0.40, feet=["foot", "foot_left"],
         alive_rule=RS_ALIVE_Z_AND_PITCH, alive_z=0.8, alive_bonus=1.0, cost_scale=1.0,
         initial_z=None, coef={"foot_joint": 30.0, "foot_left_joint": 30.0}, reward_threshold=2500.0),
+    "RoboschoolHalfCheetah-v1": dict(      # gym_mujoco_walkers.py:40-59
+        xml="half_cheetah.xml", robot="torso", A=6, O=26, power=0.90,
+        feet=["ffoot", "fshin", "fthigh", "bfoot", "bshin", "bthigh"],
+        alive_rule=RS_ALIVE_CHEETAH, alive_z=0.0, alive_bonus=1.0, cost_scale=1.0, initial_z=None,
+        coef={"bthigh": 120.0, "bshin": 90.0, "bfoot": 60.0, "fthigh": 140.0, "fshin": 60.0, "ffoot": 30.0},
+        reward_threshold=3000.0),
     "RoboschoolAnt-v1": dict(
         xml="ant.xml", robot="torso", A=8, O=28, power=2.5,
         feet=["front_left_foot", "front_right_foot", "left_back_foot", "right_back_foot"],

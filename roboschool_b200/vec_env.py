@@ -59,5 +59,23 @@ class VecEnv:
         self.world.step(a, self.obs, self.rew, self.done, self.auto_reset, self._stream())
         return self.obs, self.rew, self.done
 
+    def rollout(self, policy, n_steps, actions=None):
+        """Collect n_steps transitions on the device for a trainer: returns time-major tensors
+        (obs [T+1,N,O], act [T,N,A], rew [T,N], done [T,N] uint8).  `policy` is a ZooPolicy-like object (MLP on the
+        tensor cores); with policy=None the given `actions` [T,N,A] are replayed.  Continues from the current state
+        (call reset() first); finished envs auto-reset inside the rollout."""
+        T, N, O, A = int(n_steps), self.n, self.model.obs_dim, self.model.n_act
+        obs_T = torch.empty((T + 1, N, O), dtype=torch.float32, device=self.device)
+        rew_T = torch.empty((T, N), dtype=torch.float32, device=self.device)
+        done_T = torch.empty((T, N), dtype=torch.uint8, device=self.device)
+        if policy is None:
+            assert actions is not None and tuple(actions.shape) == (T, N, A)
+            act_T = actions.to(device=self.device, dtype=torch.float32).contiguous()
+        else:
+            act_T = torch.empty((T, N, A), dtype=torch.float32, device=self.device)
+        self.world.rollout_record(policy, T, obs_T, act_T, rew_T, done_T, obs0=self.obs, stream=self._stream())
+        self.obs.copy_(obs_T[T])
+        return obs_T, act_T, rew_T, done_T
+
     def close(self):
         self.world.close()

@@ -144,6 +144,12 @@ class BatchedWorld:
         ph = policy.h if policy is not None else None
         _lib.check(self.L.rs_world_rollout(self.h, ph, int(n_steps), seed, env_id0, _ptr(stats), stream))
 
+    def rollout_record(self, policy, n_steps, obs_T, act_T, rew_T, done_T, obs0=None, stats=None, stream=None):
+        """T steps into time-major device tensors (raw pointers or torch tensors); see rs_world_rollout_record."""
+        ph = policy.h if policy is not None else None
+        q = lambda t: t if (t is None or isinstance(t, int)) else t.data_ptr()
+        _lib.check(self.L.rs_world_rollout_record(self.h, ph, int(n_steps), q(obs0), q(obs_T), q(act_T), q(rew_T), q(done_T), _ptr(stats), stream))
+
     def rollout_buffers(self):
         ptrs = [ctypes.c_void_p() for _ in range(4)]
         _lib.check(self.L.rs_world_rollout_buffers(self.h, *[ctypes.byref(p) for p in ptrs]))

@@ -67,6 +67,7 @@ int emul_use_static(void* h, int on) {
         else if (topo_matches<TopoAnt>(e->M)) e->topo = 2;
         else if (topo_matches<TopoHopper>(e->M)) e->topo = 3;
         else if (topo_matches<TopoWalker2d>(e->M)) e->topo = 4;
+        else if (topo_matches<TopoHalfCheetah>(e->M)) e->topo = 5;
     }
     return e->topo;
 }
@@ -91,6 +92,7 @@ void emul_substeps(void* h, int env, int n) {
         case 2: substeps_static<TopoAnt>(e, env, n); return;
         case 3: substeps_static<TopoHopper>(e, env, n); return;
         case 4: substeps_static<TopoWalker2d>(e, env, n); return;
+        case 5: substeps_static<TopoHalfCheetah>(e, env, n); return;
     }
     for (int s = 0; s < n; s++) substep(e->M, e->w[env], ws);
 }
@@ -121,7 +123,8 @@ void emul_step(void* h, const double* actions, int auto_reset, uint32_t seed, ui
                 case 1: step_env_static<TopoHumanoid>(e, i, a, auto_reset, seed, env0); break;
                 case 2: step_env_static<TopoAnt>(e, i, a, auto_reset, seed, env0); break;
                 case 3: step_env_static<TopoHopper>(e, i, a, auto_reset, seed, env0); break;
-                default: step_env_static<TopoWalker2d>(e, i, a, auto_reset, seed, env0); break;
+                case 4: step_env_static<TopoWalker2d>(e, i, a, auto_reset, seed, env0); break;
+                default: step_env_static<TopoHalfCheetah>(e, i, a, auto_reset, seed, env0); break;
             }
             continue;
         }

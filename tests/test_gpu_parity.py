@@ -9,7 +9,7 @@ from roboschool_b200.envspec import load_env_model
 pytestmark = pytest.mark.gpu
 
 ENVS = ["RoboschoolHopper-v1", "RoboschoolAnt-v1", "RoboschoolHumanoid-v1", "RoboschoolInvertedPendulum-v1",
-        "RoboschoolHumanoidFlagrun-v1"]
+        "RoboschoolHumanoidFlagrun-v1", "RoboschoolWalker2d-v1", "RoboschoolHalfCheetah-v1"]
 STEP_ENVS = ENVS[:3] + ENVS[4:]
 # Per env-step (= 4 sub-steps) error of the fp32 CUDA path against the fp64 oracle, relative to
 # max(1, |state|_inf), over seeded random-action rollouts.  The dynamics are non-smooth (contact
@@ -183,3 +183,32 @@ def test_vec_env_full_size_properties():
     for a, (o, r, d) in zip(acts, outs):
         o3, r3, d3 = env3.step(a[1000:1256].contiguous())
         assert torch.equal(o3, o[1000:1256]) and torch.equal(r3, r[1000:1256])
+
+
+def test_rollout_record_matches_stepping():
+    """Rollout recorder (time-major tensors for trainers) == the same steps taken one by one through VecEnv.step
+    with the zoo policy: bit-identical observations, actions, rewards, dones, across an auto-reset."""
+    import torch
+    from roboschool_b200.vec_env import VecEnv
+    from roboschool_b200.policy import ZooPolicy, load_zoo_weights
+    env_id, n, T = "RoboschoolHopper-v1", 512, 48      # Hopper under its zoo policy falls within ~30 steps here: resets are covered
+    pol = ZooPolicy(load_zoo_weights(env_id), 0)
+    a_env = VecEnv(env_id, n, 0)
+    a_env.reset(seed=4)
+    obs_T, act_T, rew_T, done_T = a_env.rollout(pol, T)
+    torch.cuda.synchronize()
+    b_env = VecEnv(env_id, n, 0)
+    obs = b_env.reset(seed=4)
+    assert torch.equal(obs_T[0], obs)
+    act = torch.empty((n, b_env.act_dim), device="cuda")
+    for t in range(T):
+        pol.forward(obs, act)
+        assert torch.equal(act, act_T[t])
+        obs, rew, done = b_env.step(act)
+        assert torch.equal(obs, obs_T[t + 1]) and torch.equal(rew, rew_T[t]) and torch.equal(done, done_T[t])
+    assert done_T.sum().item() > 0
+    # replaying the recorded actions without a policy reproduces the rollout
+    c_env = VecEnv(env_id, n, 0)
+    c_env.reset(seed=4)
+    o2, a2, r2, d2 = c_env.rollout(None, T, actions=act_T)
+    assert torch.equal(o2, obs_T) and torch.equal(r2, rew_T) and torch.equal(d2, done_T)

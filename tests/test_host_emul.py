@@ -15,7 +15,8 @@ def emul():
 
 
 @pytest.mark.parametrize("static", [False, True], ids=["generic", "static-pooled"])
-@pytest.mark.parametrize("env_id", ["RoboschoolHopper-v1", "RoboschoolAnt-v1", "RoboschoolHumanoid-v1", "RoboschoolHumanoidFlagrun-v1"])
+@pytest.mark.parametrize("env_id", ["RoboschoolHopper-v1", "RoboschoolWalker2d-v1", "RoboschoolHalfCheetah-v1", "RoboschoolAnt-v1",
+                                    "RoboschoolHumanoid-v1", "RoboschoolHumanoidFlagrun-v1"])
 def test_emul_teacher_forced(env_id, static, emul, oracle_lib):
     """static=True runs the compile-time-topology sweeps with the pooled row builder (rs_static.cuh,
     rs_pooled.cuh) -- the code the shipped models run on the GPU; False the runtime-topology twin."""

@@ -285,6 +285,8 @@ def generate(env_id, cls_name, n_steps=60, seed=3, counter_rng=False):
 
 if __name__ == "__main__":
     generate("RoboschoolHopper-v1", "RoboschoolHopper")
+    generate("RoboschoolWalker2d-v1", "RoboschoolWalker2d")
+    generate("RoboschoolHalfCheetah-v1", "RoboschoolHalfCheetah")
     generate("RoboschoolAnt-v1", "RoboschoolAnt")
     generate("RoboschoolHumanoid-v1", "RoboschoolHumanoid")
     # Flagrun: 170 steps so that the 150-step flag timeout (and the reposition after it) is part of the fixture

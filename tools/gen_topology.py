@@ -107,7 +107,7 @@ def emit(env_id, cname):
 
 
 MODELS = [("RoboschoolHumanoid-v1", "TopoHumanoid"), ("RoboschoolAnt-v1", "TopoAnt"), ("RoboschoolHopper-v1", "TopoHopper"),
-          ("RoboschoolWalker2d-v1", "TopoWalker2d")]
+          ("RoboschoolWalker2d-v1", "TopoWalker2d"), ("RoboschoolHalfCheetah-v1", "TopoHalfCheetah")]
 
 if __name__ == "__main__":
     out = "// GENERATED by tools/gen_topology.py from roboschool_b200/models/*.json -- do not edit.\n#pragma once\nnamespace rs {\n\n"
