@@ -37,6 +37,11 @@ extern "C" {
 #define RS_GEOM_SPHERE  0
 #define RS_GEOM_CAPSULE 1
 
+/* task kinds */
+#define RS_TASK_WALKER          0 /* RoboschoolForwardWalker family (gym_forward_walker.py)                  */
+#define RS_TASK_PENDULUM        1 /* RoboschoolInvertedPendulum[Swingup] (gym_pendulums.py:70-127)            */
+#define RS_TASK_DOUBLE_PENDULUM 2 /* RoboschoolInvertedDoublePendulum (gym_pendulums.py:7-65)                 */
+
 /* alive rules (gym_mujoco_walkers.py alive_bonus variants) */
 #define RS_ALIVE_Z_AND_PITCH 0 /* Hopper/Walker2d: +1 if z>alive_z and |pitch|<1 else -1 */
 #define RS_ALIVE_Z           1 /* Ant (+1), Humanoid (+2): bonus if z>alive_z else -1     */
@@ -135,6 +140,14 @@ typedef struct rs_model_desc {
     int    flag_timeout_steps;           /* 600/frame_skip env steps (gym_humanoid_flagrun.py:35)               */
     double flag_halflen;                 /* StadiumScene.stadium_halflen   (scene_stadium.py:6)                 */
     double flag_halfwidth;               /* StadiumScene.stadium_halfwidth (scene_stadium.py:7)                 */
+    /* task kind: which obs/reward/done epilogue runs after the sub-steps */
+    int    task_kind;                    /* RS_TASK_*                                                            */
+    int    task_swingup;                 /* InvertedPendulumSwingup: reward cos(theta), never done (gym_pendulums.py:107-112) */
+    int    task_link;                    /* InvertedDoublePendulum: link "pole2" whose pose enters obs/reward   */
+    int    n_reset;                      /* joints randomised at reset: q = center + U(-spread, spread), draw k */
+    int    reset_dof[RS_MAX_ACT];
+    int    task_dof[4];                  /* pendulums: slider, hinge, hinge2 dofs                                */
+    double reset_center[RS_MAX_ACT];
 } rs_model_desc;
 
 #ifdef __cplusplus

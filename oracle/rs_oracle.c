@@ -834,6 +834,19 @@ static void foot_contacts(const rs_model_desc *m, const oenv *e, int foot, int *
 /* calc_state (gym_forward_walker.py:45-76), float32 squeezes where the reference has them */
 static void calc_state(const rs_model_desc *m, oenv *e, double *body_xy_dist) {
     kinematics(m, e); velocities(m, e);
+    if (m->task_kind != RS_TASK_WALKER) {
+        /* gym_pendulums.py calc_state (:35-47, :97-105): current_position() returns floats */
+        int ds = m->task_dof[0], d1 = m->task_dof[1], k = 0;
+        e->obs[k++] = (float)e->q[ds]; e->obs[k++] = (float)e->qd[ds];
+        if (m->task_kind == RS_TASK_DOUBLE_PENDULUM) e->obs[k++] = e->pos[m->task_link + 1][0];
+        e->obs[k++] = cos((double)(float)e->q[d1]); e->obs[k++] = sin((double)(float)e->q[d1]); e->obs[k++] = (float)e->qd[d1];
+        if (m->task_kind == RS_TASK_DOUBLE_PENDULUM) {
+            int d2 = m->task_dof[2];
+            e->obs[k++] = cos((double)(float)e->q[d2]); e->obs[k++] = sin((double)(float)e->q[d2]); e->obs[k++] = (float)e->qd[d2];
+        }
+        *body_xy_dist = 0;
+        return;
+    }
     int A = m->n_act;
     float j[2 * RS_MAX_ACT];
     int at_limit = 0;
@@ -911,6 +924,24 @@ static void calc_state_flag(const rs_model_desc *m, oenv *e, double *dist, uint3
 static void epilogue(const rs_model_desc *m, oenv *e, const double *a, uint32_t seed, uint32_t env_id) {
     double dist;
     calc_state_flag(m, e, &dist, seed, env_id);
+    if (m->task_kind != RS_TASK_WALKER) {
+        /* gym_pendulums.py step (:49-65, :107-123) */
+        double reward; int dn;
+        memset(e->rewards5, 0, sizeof e->rewards5);
+        if (m->task_kind == RS_TASK_PENDULUM) {
+            double th = (double)(float)e->q[m->task_dof[1]];
+            if (m->task_swingup) { reward = cos(th); dn = 0; } else { reward = 1.0; dn = fabs(th) > 0.2; }
+            e->rewards5[0] = reward;
+        } else {
+            double px = e->pos[m->task_link + 1][0], py = e->pos[m->task_link + 1][2];
+            double pen = 0.01 * px * px + (py + 0.3 - 2.0) * (py + 0.3 - 2.0);
+            e->rewards5[0] = 10.0; e->rewards5[1] = -pen;
+            reward = 10.0 - pen; dn = (py + 0.3) <= 1.0;
+        }
+        for (int k = 0; k < m->obs_dim; k++) if (!isfinite(e->obs[k])) dn = 1;
+        e->reward = reward; e->done = dn; e->frame++;
+        return;
+    }
     double pitch = e->rewards5[0];
     double z = e->obs[0] + e->initial_z;   /* state[0]+initial_z, state already float32 & clipped */
     double alive;
@@ -966,9 +997,9 @@ static double rs_uniform(uint32_t seed, uint32_t env, uint32_t episode, uint32_t
 static void env_reset(const rs_model_desc *m, oenv *e, int nman, uint32_t seed, uint32_t env_id) {
     e->episode++;
     memset(e->q, 0, sizeof e->q); memset(e->qd, 0, sizeof e->qd); memset(e->tau, 0, sizeof e->tau);
-    for (int k = 0; k < m->n_act; k++) {
+    for (int k = 0; k < m->n_reset; k++) {
         double u = rs_uniform(seed, env_id, e->episode, (uint32_t)k);
-        e->q[m->act_dof[k]] = (double)(float)(m->reset_joint_spread * (2.0 * u - 1.0)); /* reset_current_position(float,..) */
+        e->q[m->reset_dof[k]] = (double)(float)(m->reset_center[k] + m->reset_joint_spread * (2.0 * u - 1.0)); /* reset_current_position(float,..) */
     }
     v3cpy(e->base_pos, m->reset_base_pos);
     memcpy(e->base_quat, m->reset_base_quat, sizeof e->base_quat);

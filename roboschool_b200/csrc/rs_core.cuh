@@ -63,6 +63,9 @@ struct DevModel {
     int reset_set_base;
     int flag_task, flag_timeout_steps;
     double flag_halflen, flag_halfwidth;
+    int task_kind, task_swingup, task_link, n_reset;
+    int reset_dof[MA], task_dof[4];
+    float reset_center[MA];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1022,6 +1025,20 @@ RS_HD void rel_joint(const DevModel& M, int li, float q, float qd, float* pos, f
 template <int NL, int MC, bool SL>
 RS_HD void calc_state_core(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, const float* bp, const float* bq, const float* bv,
                            float* obs, int ostride, double* dist, float* pitch, int* at_limit) {
+    if (M.task_kind != RS_TASK_WALKER) {
+        // gym_pendulums.py calc_state (:35-47, :97-105): Joint::current_position returns floats; cos/sin in double
+        const int ds = M.task_dof[0], d1 = M.task_dof[1];
+        int k = 0;
+        obs[(k++) * ostride] = W.q[ds]; obs[(k++) * ostride] = W.qd[ds];
+        if (M.task_kind == RS_TASK_DOUBLE_PENDULUM) obs[(k++) * ostride] = W.pos[M.task_link + 1][0];
+        obs[(k++) * ostride] = (float)cos((double)W.q[d1]); obs[(k++) * ostride] = (float)sin((double)W.q[d1]); obs[(k++) * ostride] = W.qd[d1];
+        if (M.task_kind == RS_TASK_DOUBLE_PENDULUM) {
+            const int d2 = M.task_dof[2];
+            obs[(k++) * ostride] = (float)cos((double)W.q[d2]); obs[(k++) * ostride] = (float)sin((double)W.q[d2]); obs[(k++) * ostride] = W.qd[d2];
+        }
+        *dist = 0.0; *pitch = 0.f; *at_limit = 0;
+        return;
+    }
     const int A = M.n_act;
     int nlim = 0;
     for (int k = 0; k < A; k++) {
@@ -1108,6 +1125,26 @@ RS_HD void epilogue_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, con
                          uint32_t seed = 0, uint32_t env_id = 0) {
     double dist; float pitch; int at_limit;
     calc_state_flag(M, E, seed, env_id, obs, ostride, &dist, &pitch, &at_limit, cs);
+    if (M.task_kind != RS_TASK_WALKER) {
+        // gym_pendulums.py step (:49-65, :107-123)
+        float reward; int dn;
+        out.rewards5[1] = out.rewards5[2] = out.rewards5[3] = out.rewards5[4] = 0.f;
+        if (M.task_kind == RS_TASK_PENDULUM) {
+            const float th = W.q[M.task_dof[1]];
+            if (M.task_swingup) { reward = (float)cos((double)th); dn = 0; }
+            else { reward = 1.0f; dn = fabsf(th) > 0.2f; }
+            out.rewards5[0] = reward;
+        } else {
+            const double px = (double)W.pos[M.task_link + 1][0], py = (double)W.pos[M.task_link + 1][2];
+            const double pen = 0.01 * px * px + (py + 0.3 - 2.0) * (py + 0.3 - 2.0);
+            out.rewards5[0] = 10.f; out.rewards5[1] = (float)(-pen);
+            reward = (float)(10.0 - pen); dn = (py + 0.3) <= 1.0;
+        }
+        for (int k = 0; k < M.obs_dim; k++) if (!isfinite(obs[k * ostride])) dn = 1;
+        out.reward = reward; out.done = dn;
+        E.frame++;
+        return;
+    }
     float z = obs[0] + E.initial_z;
     float alive;
     if (M.alive_rule == RS_ALIVE_Z_AND_PITCH) alive = (z > M.alive_z && fabsf(pitch) < 1.0f) ? M.alive_bonus : -1.f;
@@ -1162,9 +1199,9 @@ template <int NL, int MC, bool SL, class CS>
 RS_HD void env_reset_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, uint32_t seed, uint32_t env_id, float* obs, int ostride, CS&& cs) {
     E.episode++;
     for (int d = 0; d < M.n_dof; d++) { W.q[d] = 0.f; W.qd[d] = 0.f; W.tau[d] = 0.f; }
-    for (int k = 0; k < M.n_act; k++) {
+    for (int k = 0; k < M.n_reset; k++) {
         float u = rs_uniform(seed, env_id, E.episode, (uint32_t)k);
-        W.q[M.act_dof[k]] = (float)((double)M.reset_joint_spread * (2.0 * (double)u - 1.0));
+        W.q[M.reset_dof[k]] = (float)((double)M.reset_center[k] + (double)M.reset_joint_spread * (2.0 * (double)u - 1.0));
     }
 #pragma unroll
     for (int k = 0; k < 3; k++) { W.bpos[k] = M.reset_base_pos[k]; W.bw[k] = 0.f; W.bv[k] = 0.f; }

@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 MODEL_DIR = os.path.join(_HERE, "models")
 
 RS_ALIVE_Z_AND_PITCH, RS_ALIVE_Z, RS_ALIVE_ALWAYS, RS_ALIVE_CHEETAH = 0, 1, 2, 3
+RS_TASK_WALKER, RS_TASK_PENDULUM, RS_TASK_DOUBLE_PENDULUM = 0, 1, 2
 
 ENV_SPECS = {
     # id: xml, robot_name, A, O, power, foot_list, alive rule/params, per-joint coef overrides
@@ -63,12 +64,30 @@ ENV_SPECS = {
               "left_shoulder1": 75, "left_shoulder2": 75, "left_elbow": 75},
         reset_base=dict(z=1.4, yaw_spread=math.pi / 16), reward_threshold=2000.0,
         flag=dict(halflen=105 * 0.25, halfwidth=50 * 0.25, timeout=600)),
-    # plumbing config (BASELINE.json configs[0]); obs/reward computed by the Python facade
+    # BASELINE.json configs[0] and its siblings (gym_pendulums.py): empty scene, dt 0.0165, frame_skip 1, no contacts
     "RoboschoolInvertedPendulum-v1": dict(
         xml="inverted_pendulum.xml", robot="cart", A=1, O=5, power=1.0, feet=[],
         alive_rule=RS_ALIVE_ALWAYS, alive_z=0.0, alive_bonus=0.0, cost_scale=1.0,
         initial_z=None, coef={"slider": 100.0}, no_floor=True, timestep=0.0165, frame_skip=1,
-        act_joints=["slider"], max_contacts=4, reward_threshold=950.0),
+        act_joints=["slider"], max_contacts=4, reward_threshold=950.0,
+        task=dict(kind=RS_TASK_PENDULUM, dofs=["slider", "hinge"], reset=[("hinge", 0.0)])),
+    "RoboschoolInvertedPendulumSwingup-v1": dict(
+        xml="inverted_pendulum.xml", robot="cart", A=1, O=5, power=1.0, feet=[],
+        alive_rule=RS_ALIVE_ALWAYS, alive_z=0.0, alive_bonus=0.0, cost_scale=1.0,
+        initial_z=None, coef={"slider": 100.0}, no_floor=True, timestep=0.0165, frame_skip=1,
+        act_joints=["slider"], max_contacts=4, reward_threshold=800.0,
+        # As registered, the reference's Swingup class is NOT a swing-up task: `swingup = True` is a class attribute that
+        # RoboschoolInvertedPendulum.__init__(self, swingup=False) overrides on the instance (gym_pendulums.py:77-79,126-127),
+        # so gym.make('RoboschoolInvertedPendulumSwingup-v1') behaves like InvertedPendulum-v1.  The fixture made from the
+        # reference's own class pins that; set task swingup=1 and reset centre 3.1415 on a cloned model for the real thing.
+        task=dict(kind=RS_TASK_PENDULUM, swingup=0, dofs=["slider", "hinge"], reset=[("hinge", 0.0)])),
+    "RoboschoolInvertedDoublePendulum-v1": dict(
+        xml="inverted_double_pendulum.xml", robot="cart", A=1, O=9, power=1.0, feet=[],
+        alive_rule=RS_ALIVE_ALWAYS, alive_z=0.0, alive_bonus=0.0, cost_scale=1.0,
+        initial_z=None, coef={"slider": 200.0}, no_floor=True, timestep=0.0165, frame_skip=1,
+        act_joints=["slider"], max_contacts=4, reward_threshold=9100.0,
+        task=dict(kind=RS_TASK_DOUBLE_PENDULUM, dofs=["slider", "hinge", "hinge2"], link="pole2",
+                  reset=[("hinge", 0.0), ("hinge2", 0.0)])),
 }
 
 
@@ -117,7 +136,24 @@ def apply_task(m: ModelDesc, spec: dict) -> ModelDesc:
     m.joints_at_limit_cost = -0.2                        # :87
     m.initial_z = -1.0 if spec["initial_z"] is None else spec["initial_z"]
     m.walk_target_x, m.walk_target_y = 1e3, 0.0          # gym_forward_walker.py:13-14
-    m.reset_joint_spread = 0.1                           # gym_forward_walker.py:26
+    m.reset_joint_spread = 0.1                           # gym_forward_walker.py:26, gym_pendulums.py:24,89
+    task = spec.get("task")
+    if task:
+        m.task_kind = task["kind"]
+        m.task_swingup = task.get("swingup", 0)
+        for k, n in enumerate(task["dofs"]):
+            m.task_dof[k] = m.dof_idx[jn.index(n)]
+        m.task_link = ln.index(task["link"]) if "link" in task else -1
+        m.n_reset = len(task["reset"])
+        for k, (n, c) in enumerate(task["reset"]):
+            m.reset_dof[k] = m.dof_idx[jn.index(n)]
+            m.reset_center[k] = c
+    else:   # forward walkers: every ordered joint, U(-0.1, 0.1) about 0 (gym_forward_walker.py:25-26)
+        m.task_kind = RS_TASK_WALKER
+        m.n_reset = m.n_act
+        for k in range(m.n_act):
+            m.reset_dof[k] = m.act_dof[k]
+            m.reset_center[k] = 0.0
     rb = spec.get("reset_base")
     if rb:
         m.reset_set_base = 1

@@ -269,8 +269,8 @@ def generate(env_id, cls_name, n_steps=60, seed=3, counter_rng=False):
     ref_obs, ref_rew, ref_done, ref_r5 = [], [], [], []
     for t in range(n_steps):
         ob, rw, dn, _ = env.step(acts[t])
-        ref_obs.append(np.asarray(ob, dtype=np.float64)); ref_rew.append(rw); ref_done.append(dn); ref_r5.append(list(env.rewards))
-        ref_flags.append([env.walk_target_x, env.walk_target_y, getattr(env, "flag_timeout", 0)])
+        ref_obs.append(np.asarray(ob, dtype=np.float64)); ref_rew.append(rw); ref_done.append(dn); ref_r5.append((list(env.rewards) + [0.0] * 5)[:5])
+        ref_flags.append([getattr(env, "walk_target_x", 0.0), getattr(env, "walk_target_y", 0.0), getattr(env, "flag_timeout", 0)])
     out = os.path.join(ROOT, "tests", "golden", "epilogue_%s.npz" % env_id)
     os.makedirs(os.path.dirname(out), exist_ok=True)
     np.savez_compressed(out, seed=seed, actions=acts, poses=np.array(R.poses), q=np.array(R.q), qd=np.array(R.qd),
@@ -284,6 +284,9 @@ def generate(env_id, cls_name, n_steps=60, seed=3, counter_rng=False):
 
 
 if __name__ == "__main__":
+    generate("RoboschoolInvertedPendulum-v1", "RoboschoolInvertedPendulum")
+    generate("RoboschoolInvertedPendulumSwingup-v1", "RoboschoolInvertedPendulumSwingup")
+    generate("RoboschoolInvertedDoublePendulum-v1", "RoboschoolInvertedDoublePendulum")
     generate("RoboschoolHopper-v1", "RoboschoolHopper")
     generate("RoboschoolWalker2d-v1", "RoboschoolWalker2d")
     generate("RoboschoolHalfCheetah-v1", "RoboschoolHalfCheetah")
