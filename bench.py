@@ -214,15 +214,16 @@ def main():
     # host memory, runs policy + step, and copies obs/reward/done back D2H ---
     e2e_steps = max(10, args.steps // 4)
     torch.cuda.synchronize()
-    o_np, r_np, d_np = W.policy_step_host(pol, None)   # continue from the device-resident rollout: same steady-state workload
-    for _ in range(3):
-        o_np, r_np, d_np = W.policy_step_host(pol, o_np)
+    bufs = [W.pinned_host_buffers(), W.pinned_host_buffers()]   # page-locked ping-pong: this step's output is the next step's input
+    o_np, r_np, d_np = W.policy_step_host(pol, None, out=bufs[0])   # continue from the device-resident rollout: same steady-state workload
+    for k in range(3):
+        o_np, r_np, d_np = W.policy_step_host(pol, o_np, out=bufs[(k + 1) & 1])
     if world_size > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        o_np, r_np, d_np = W.policy_step_host(pol, o_np)
+    for k in range(e2e_steps):
+        o_np, r_np, d_np = W.policy_step_host(pol, o_np, out=bufs[k & 1])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -274,7 +275,7 @@ def main():
                      "kernel": "k_step", "algorithmic_bytes_per_env_step": abytes, "kernel_ms": ms_kernel, "peak_source": peak_src},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "rs_world_policy_step_host (host obs in -> policy -> step -> host obs/reward/done out), %d steps, wall clock" % e2e_steps},
+                "api": "rs_world_policy_step_host (pinned host obs in -> policy -> step -> pinned host obs/reward/done out), %d steps, wall clock" % e2e_steps},
         "gpu_launches": 2 * args.steps + 2 * (e2e_steps + 4),
         "clocks": clocks,
         "rollout_stats": {"mean_reward": st[0] / max(st[6], 1), "episodes": st[1], "mean_episode_len": st[2] / max(st[1], 1),

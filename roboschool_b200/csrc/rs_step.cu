@@ -563,24 +563,36 @@ extern "C" int rs_world_rollout_record(rs_world* w, rs_policy* p, int n_steps, c
 
 // End-to-end call for callers whose observations live in HOST memory: H2D obs -> policy on the tensor cores ->
 // env step (auto-reset) -> D2H obs/reward/done, all on the world's stream, one synchronisation at the end.
+// page-locked (cudaHostAlloc / cudaHostRegister) host memory can be the source / target of an async copy directly;
+// pageable memory goes through the world's pinned staging buffers
+static bool host_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 extern "C" int rs_world_policy_step_host(rs_world* w, rs_policy* p, const float* obs_in_host, float* obs_out_host, float* reward_host,
                                          uint8_t* done_host) {
     if (!p || !obs_out_host || !reward_host || !done_host) return fail("rs_world_policy_step_host: null argument");
     CK(cudaSetDevice(w->device));
     size_t N = (size_t)w->n, O = (size_t)w->desc.obs_dim;
     if (obs_in_host) {   // NULL: continue from the observations already on the device (after rs_world_rollout_reset / rollout)
-        memcpy(w->h_obs, obs_in_host, sizeof(float) * N * O);
-        CK(cudaMemcpyAsync(w->d_obs, w->h_obs, sizeof(float) * N * O, cudaMemcpyHostToDevice, w->stream));
+        const float* src = obs_in_host;
+        if (!host_is_pinned(obs_in_host)) { memcpy(w->h_obs, obs_in_host, sizeof(float) * N * O); src = w->h_obs; }
+        CK(cudaMemcpyAsync(w->d_obs, src, sizeof(float) * N * O, cudaMemcpyHostToDevice, w->stream));
     }
     if (rs_policy_forward(p, w->d_obs, w->d_act, w->n, (void*)w->stream)) return 1;
     if (launch_step(w, w->d_act, w->d_obs, w->d_rew, w->d_done, 1, w->rollout_seed, w->env_id0, nullptr, w->stream)) return 1;
-    CK(cudaMemcpyAsync(w->h_obs, w->d_obs, sizeof(float) * N * O, cudaMemcpyDeviceToHost, w->stream));
-    CK(cudaMemcpyAsync(w->h_rew, w->d_rew, sizeof(float) * N, cudaMemcpyDeviceToHost, w->stream));
-    CK(cudaMemcpyAsync(w->h_done, w->d_done, N, cudaMemcpyDeviceToHost, w->stream));
+    const bool direct = host_is_pinned(obs_out_host) && host_is_pinned(reward_host) && host_is_pinned(done_host);
+    CK(cudaMemcpyAsync(direct ? obs_out_host : w->h_obs, w->d_obs, sizeof(float) * N * O, cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaMemcpyAsync(direct ? reward_host : w->h_rew, w->d_rew, sizeof(float) * N, cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaMemcpyAsync(direct ? done_host : w->h_done, w->d_done, N, cudaMemcpyDeviceToHost, w->stream));
     CK(cudaStreamSynchronize(w->stream));
-    memcpy(obs_out_host, w->h_obs, sizeof(float) * N * O);
-    memcpy(reward_host, w->h_rew, sizeof(float) * N);
-    memcpy(done_host, w->h_done, N);
+    if (!direct) {
+        memcpy(obs_out_host, w->h_obs, sizeof(float) * N * O);
+        memcpy(reward_host, w->h_rew, sizeof(float) * N);
+        memcpy(done_host, w->h_done, N);
+    }
     return 0;
 }
 

@@ -60,12 +60,21 @@ class BatchedWorld:
         _lib.check(self.L.rs_world_step_host(self.h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data, int(auto_reset)))
         return obs, rew, done
 
-    def policy_step_host(self, policy, obs_in):
+    def pinned_host_buffers(self):
+        """(obs [n,O] f32, reward [n] f32, done [n] u8) numpy views of page-locked host memory: passed as `out=` (and as
+        the next call's obs_in) they are copied to/from the device directly, without the library's staging memcpy."""
+        import torch
+        t = (torch.empty((self.n, self.O), dtype=torch.float32).pin_memory(), torch.empty(self.n, dtype=torch.float32).pin_memory(),
+             torch.empty(self.n, dtype=torch.uint8).pin_memory())
+        self._pinned = getattr(self, "_pinned", []) + [t]     # keep the torch owners alive
+        return tuple(x.numpy() for x in t)
+
+    def policy_step_host(self, policy, obs_in, out=None):
         """obs (host) -> policy (tensor cores) -> step (auto-reset) -> obs, reward, done (host)."""
         o = None if obs_in is None else np.ascontiguousarray(obs_in, dtype=np.float32).reshape(self.n, self.O)
-        obs = np.empty((self.n, self.O), dtype=np.float32)
-        rew = np.empty(self.n, dtype=np.float32)
-        done = np.empty(self.n, dtype=np.uint8)
+        if out is None:
+            out = (np.empty((self.n, self.O), dtype=np.float32), np.empty(self.n, dtype=np.float32), np.empty(self.n, dtype=np.uint8))
+        obs, rew, done = out
         _lib.check(self.L.rs_world_policy_step_host(self.h, policy.h, _ptr(o), obs.ctypes.data, rew.ctypes.data, done.ctypes.data))
         return obs, rew, done
 

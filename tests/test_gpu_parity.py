@@ -212,3 +212,29 @@ def test_rollout_record_matches_stepping():
     c_env.reset(seed=4)
     o2, a2, r2, d2 = c_env.rollout(None, T, actions=act_T)
     assert torch.equal(o2, obs_T) and torch.equal(r2, rew_T) and torch.equal(d2, done_T)
+
+
+@pytest.mark.parametrize("env_id", ["RoboschoolHumanoid-v1", "RoboschoolAnt-v1", "RoboschoolHopper-v1"])
+def test_ragged_batch_sizes(env_id):
+    """Ragged batches: N = 1, N not a multiple of the warp (32) or of the CTA (7 / 4 warps), tail lanes that own no
+    env but still help build the warp's constraint rows.  Each small world must reproduce, bit for bit, the matching
+    slice of one big world (RNG and physics are keyed by the global env id, never by the position in the batch)."""
+    import torch
+    from roboschool_b200.vec_env import VecEnv
+    big_n = 1200
+    big = VecEnv(env_id, big_n, 0)
+    obs_b = big.reset(seed=7).clone()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    acts = [torch.rand((big_n, big.act_dim), device="cuda", generator=g) * 2 - 1 for _ in range(12)]
+    outs = []
+    for a in acts:
+        o, r, d = big.step(a)
+        outs.append((o.clone(), r.clone(), d.clone()))
+    for n, off in [(1, 0), (1, 1199), (31, 5), (33, 64), (225, 700), (449, 751)]:
+        small = VecEnv(env_id, n, 0, env_id0=off)
+        o0 = small.reset(seed=7)
+        assert torch.equal(o0, obs_b[off:off + n]), (n, off)
+        for a, (o, r, d) in zip(acts, outs):
+            o2, r2, d2 = small.step(a[off:off + n].contiguous())
+            assert torch.equal(o2, o[off:off + n]) and torch.equal(r2, r[off:off + n]) and torch.equal(d2, d[off:off + n]), (n, off)
+        small.close()
