@@ -18,7 +18,7 @@
 //
 // The leaves->root sweep only visits the links between the loaded body and the root (the wrench is zero
 // elsewhere); the root->leaves sweep visits every link.  Arithmetic per row is the same as in
-// static_row_response(); the denominator J.M^-1 J^T is taken as wrench . (spatial response of the body),
+// the single-row sweeps of round 1; the denominator J.M^-1 J^T is taken as wrench . (spatial response of the body),
 // which is the same sum in a different association.
 //
 // The functions are __host__ __device__: tests/host_emul runs them with a 1-lane "warp" (WarpHost).
@@ -86,15 +86,6 @@ struct WarpDev {
 RS_HD float i2f(int v) { union { int i; float f; } u; u.i = v; return u.f; }
 RS_HD int f2i(float v) { union { int i; float f; } u; u.f = v; return u.i; }
 
-// spatial force child->parent (assign): f' = R^T f ; t' = R^T (t + r x f)
-RS_HD void xf_force_inv(float* out, const float* R, const float* r, const float* in) {
-    float c[3], t[3];
-    cross3(c, r, in + 3);
-    t[0] = in[0] + c[0]; t[1] = in[1] + c[1]; t[2] = in[2] + c[2];
-    tmulv(out, R, t);
-    tmulv(out + 3, R, in + 3);
-}
-
 // ---------------------------------------------------------------------------------------------
 // NR simultaneous unit-impulse responses that share the loaded body.
 //   HASW: the right-hand sides are wrenches wr[rr] (torque;force) on body `body` (0 = base, i+1 = link i), in that
@@ -146,11 +137,11 @@ RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*
 #pragma unroll
             for (int rr = 0; rr < NR; rr++) {
                 float t[6];
-                xf_force_inv(t, R, r, Z[rr]);
+                xf_force_inv_k<rot_kind<T, i>()>(t, R, r, Z[rr]);
 #pragma unroll
                 for (int k = 0; k < 6; k++) Z[rr][k] = t[k];
                 if constexpr (HASW) {
-                    xf_force_inv(t, R, r, F[rr]);
+                    xf_force_inv_k<rot_kind<T, i>()>(t, R, r, F[rr]);
 #pragma unroll
                     for (int k = 0; k < 6; k++) F[rr][k] = t[k];
                 }
@@ -210,7 +201,7 @@ RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*
         }
 #pragma unroll
         for (int rr = 0; rr < NR; rr++) {
-            xf_motion(acc[rr][i + 1], R, r, acc[rr][p + 1]);
+            xf_motion_k<rot_kind<T, i>()>(acc[rr][i + 1], R, r, acc[rr][p + 1]);
             if constexpr (d >= 0) {
                 const float a = invD * (Y[rr][i] - dot6(acc[rr][i + 1], h));
                 saxpy<T, i>(acc[rr][i + 1], a);

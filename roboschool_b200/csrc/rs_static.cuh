@@ -86,6 +86,163 @@ RS_HD void link_xform(float c, float s, float q, float* R, float* r) {
     if constexpr (jt == RS_JOINT_PRISMATIC) { r[0] += RS_CM(ax, q); r[1] += RS_CM(ay, q); r[2] += RS_CM(az, q); }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Structure of the parent->link rotation, known at compile time.  For a revolute joint about a principal axis with an
+// identity zero-rotation, R is a planar rotation (4 non-trivial entries); for a fixed joint with identity zero-rotation it
+// is the identity.  IEEE arithmetic forbids the compiler to drop 0*x on its own, so the sweeps call these helpers with
+// the kind as a template argument: a planar R costs 4 instead of 9 multiply-adds per vector, 24 instead of 54 per
+// similarity transform.  (k, a, b) cyclic; rows: R[k] = e_k, R[a] = c e_a + s e_b, R[b] = -s e_a + c e_b with
+// c = R[a][a], s = R[a][b] read from the matrix itself (s carries the sign of the axis).
+// ---------------------------------------------------------------------------------------------
+enum { ROT_X = 0, ROT_Y = 1, ROT_Z = 2, ROT_GEN = 3, ROT_ID = 4 };
+template <class T, int I>
+constexpr int rot_kind() {
+    const bool r0_identity = T::R0[9 * I] == 1.0f && T::R0[9 * I + 4] == 1.0f && T::R0[9 * I + 8] == 1.0f && T::R0[9 * I + 1] == 0.0f &&
+                             T::R0[9 * I + 2] == 0.0f && T::R0[9 * I + 3] == 0.0f && T::R0[9 * I + 5] == 0.0f && T::R0[9 * I + 6] == 0.0f &&
+                             T::R0[9 * I + 7] == 0.0f;
+    if (!r0_identity) return ROT_GEN;
+    if (T::jtype[I] != RS_JOINT_REVOLUTE) return ROT_ID;
+    const float ax = T::axis[3 * I], ay = T::axis[3 * I + 1], az = T::axis[3 * I + 2];
+    if ((ax == 1.0f || ax == -1.0f) && ay == 0.0f && az == 0.0f) return ROT_X;
+    if ((ay == 1.0f || ay == -1.0f) && ax == 0.0f && az == 0.0f) return ROT_Y;
+    if ((az == 1.0f || az == -1.0f) && ax == 0.0f && ay == 0.0f) return ROT_Z;
+    return ROT_GEN;
+}
+template <int K> RS_HD void rot_mulv(float* o, const float* R, const float* v) {   // o = R v   (o must not alias v)
+    if constexpr (K == ROT_GEN) mulv(o, R, v);
+    else if constexpr (K == ROT_ID) { o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; }
+    else {
+        constexpr int k = K, a = (K + 1) % 3, b = (K + 2) % 3;
+        const float c = R[a * 3 + a], s = R[a * 3 + b];
+        o[k] = v[k]; o[a] = c * v[a] + s * v[b]; o[b] = c * v[b] - s * v[a];
+    }
+}
+template <int K> RS_HD void rot_tmulv(float* o, const float* R, const float* v) {  // o = R^T v
+    if constexpr (K == ROT_GEN) tmulv(o, R, v);
+    else if constexpr (K == ROT_ID) { o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; }
+    else {
+        constexpr int k = K, a = (K + 1) % 3, b = (K + 2) % 3;
+        const float c = R[a * 3 + a], s = R[a * 3 + b];
+        o[k] = v[k]; o[a] = c * v[a] - s * v[b]; o[b] = s * v[a] + c * v[b];
+    }
+}
+template <int K> RS_HD void rot_mul33(float* O, const float* R, const float* A) {  // O = R A  (rows of A mixed; O must not alias A)
+    if constexpr (K == ROT_GEN) mul33(O, R, A);
+    else if constexpr (K == ROT_ID) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) O[i] = A[i];
+    } else {
+        constexpr int k = K, a = (K + 1) % 3, b = (K + 2) % 3;
+        const float c = R[a * 3 + a], s = R[a * 3 + b];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            O[k * 3 + j] = A[k * 3 + j];
+            O[a * 3 + j] = c * A[a * 3 + j] + s * A[b * 3 + j];
+            O[b * 3 + j] = c * A[b * 3 + j] - s * A[a * 3 + j];
+        }
+    }
+}
+// O = R^T X R for a full 3x3 X (O must not alias X)
+template <int K> RS_HD void rot_sim(float* O, const float* R, const float* X) {
+    if constexpr (K == ROT_GEN) {
+        float T[9], RT[9];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) RT[i * 3 + j] = R[j * 3 + i];
+        mul33(T, X, R); mul33(O, RT, T);
+    } else if constexpr (K == ROT_ID) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) O[i] = X[i];
+    } else {
+        constexpr int k = K, a = (K + 1) % 3, b = (K + 2) % 3;
+        const float c = R[a * 3 + a], s = R[a * 3 + b];
+        float Y[9];   // Y = R^T X : rows a, b of X mixed
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            Y[k * 3 + j] = X[k * 3 + j];
+            Y[a * 3 + j] = c * X[a * 3 + j] - s * X[b * 3 + j];
+            Y[b * 3 + j] = s * X[a * 3 + j] + c * X[b * 3 + j];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {   // O = Y R : columns a, b of Y mixed
+            O[i * 3 + k] = Y[i * 3 + k];
+            O[i * 3 + a] = c * Y[i * 3 + a] - s * Y[i * 3 + b];
+            O[i * 3 + b] = s * Y[i * 3 + a] + c * Y[i * 3 + b];
+        }
+    }
+}
+// spatial motion parent->child: w' = R w ; v' = R v - r x (R w)
+template <int K> RS_HD void xf_motion_k(float* o, const float* R, const float* r, const float* in) {
+    float w[3], v[3], c[3];
+    rot_mulv<K>(w, R, in); rot_mulv<K>(v, R, in + 3); cross3(c, r, w);
+    o[0] = w[0]; o[1] = w[1]; o[2] = w[2]; o[3] = v[0] - c[0]; o[4] = v[1] - c[1]; o[5] = v[2] - c[2];
+}
+// spatial force child->parent: f' = R^T f ; t' = R^T (t + r x f)
+template <int K> RS_HD void xf_force_inv_k(float* out, const float* R, const float* r, const float* in) {
+    float c[3], t[3];
+    cross3(c, r, in + 3);
+    t[0] = in[0] + c[0]; t[1] = in[1] + c[1]; t[2] = in[2] + c[2];
+    rot_tmulv<K>(out, R, t);
+    rot_tmulv<K>(out + 3, R, in + 3);
+}
+template <int K> RS_HD void xf_force_inv_add_k(float* acc, const float* R, const float* r, const float* in) {
+    float o[6];
+    xf_force_inv_k<K>(o, R, r, in);
+#pragma unroll
+    for (int k = 0; k < 6; k++) acc[k] += o[k];
+}
+// Ip += X^T Ic X for X = motion transform parent->child (R, r).  Same algebra as inertia_to_parent_add(), with the skew
+// products written out (r~ has six non-zeros) and the rotations specialised on K.
+template <int K> RS_HD void inertia_to_parent_add_k(float* Ip, const float* Ic, const float* R, const float* r) {
+    float A[9], M[9];
+    sym_to_full(A, Ic); sym_to_full(M, Ic + 15);
+    const float* B = Ic + 6;
+    const float x = r[0], y = r[1], z = r[2];
+    // r~ M : row0 = -z M1 + y M2 ; row1 = z M0 - x M2 ; row2 = -y M0 + x M1     (Mi = row i of M)
+    float Bp[9], Ap[9];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        Bp[j] = B[j] + (y * M[6 + j] - z * M[3 + j]);
+        Bp[3 + j] = B[3 + j] + (z * M[j] - x * M[6 + j]);
+        Bp[6 + j] = B[6 + j] + (x * M[3 + j] - y * M[j]);
+    }
+    // A' = A - B r~ + r~ Bp^T.   (B r~)[i] = ( z Bi1 - y Bi2 , -z Bi0 + x Bi2 , y Bi0 - x Bi1 )
+    //                            (r~ Bp^T)[0][j] = -z Bp[j][1] + y Bp[j][2] ; [1][j] = z Bp[j][0] - x Bp[j][2] ; [2][j] = -y Bp[j][0] + x Bp[j][1]
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        Ap[i * 3 + 0] = A[i * 3 + 0] - (z * B[i * 3 + 1] - y * B[i * 3 + 2]);
+        Ap[i * 3 + 1] = A[i * 3 + 1] - (x * B[i * 3 + 2] - z * B[i * 3 + 0]);
+        Ap[i * 3 + 2] = A[i * 3 + 2] - (y * B[i * 3 + 0] - x * B[i * 3 + 1]);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        Ap[j] += y * Bp[j * 3 + 2] - z * Bp[j * 3 + 1];
+        Ap[3 + j] += z * Bp[j * 3 + 0] - x * Bp[j * 3 + 2];
+        Ap[6 + j] += x * Bp[j * 3 + 1] - y * Bp[j * 3 + 0];
+    }
+    float Ar[9], Br[9], Mr[9];
+    rot_sim<K>(Ar, R, Ap); rot_sim<K>(Br, R, Bp); rot_sim<K>(Mr, R, M);
+    Ip[0] += Ar[0]; Ip[1] += 0.5f * (Ar[1] + Ar[3]); Ip[2] += 0.5f * (Ar[2] + Ar[6]);
+    Ip[3] += Ar[4]; Ip[4] += 0.5f * (Ar[5] + Ar[7]); Ip[5] += Ar[8];
+#pragma unroll
+    for (int i = 0; i < 9; i++) Ip[6 + i] += Br[i];
+    Ip[15] += Mr[0]; Ip[16] += 0.5f * (Mr[1] + Mr[3]); Ip[17] += 0.5f * (Mr[2] + Mr[6]);
+    Ip[18] += Mr[4]; Ip[19] += 0.5f * (Mr[5] + Mr[7]); Ip[20] += Mr[8];
+}
+// h = I^A S with the constant joint subspace of link I (zero entries of S dropped)
+template <class T, int I>
+RS_HD void inertia_mul_S(float* h, const float* IA) {
+    constexpr float s0 = T::Sw[3 * I], s1 = T::Sw[3 * I + 1], s2 = T::Sw[3 * I + 2], s3 = T::Sv[3 * I], s4 = T::Sv[3 * I + 1], s5 = T::Sv[3 * I + 2];
+    const float* A = IA; const float* B = IA + 6; const float* M = IA + 15;   // A sym(6) B full(9) M sym(6)
+    h[0] = RS_CM(s0, A[0]) + RS_CM(s1, A[1]) + RS_CM(s2, A[2]) + RS_CM(s3, B[0]) + RS_CM(s4, B[1]) + RS_CM(s5, B[2]);
+    h[1] = RS_CM(s0, A[1]) + RS_CM(s1, A[3]) + RS_CM(s2, A[4]) + RS_CM(s3, B[3]) + RS_CM(s4, B[4]) + RS_CM(s5, B[5]);
+    h[2] = RS_CM(s0, A[2]) + RS_CM(s1, A[4]) + RS_CM(s2, A[5]) + RS_CM(s3, B[6]) + RS_CM(s4, B[7]) + RS_CM(s5, B[8]);
+    h[3] = RS_CM(s0, B[0]) + RS_CM(s1, B[3]) + RS_CM(s2, B[6]) + RS_CM(s3, M[0]) + RS_CM(s4, M[1]) + RS_CM(s5, M[2]);
+    h[4] = RS_CM(s0, B[1]) + RS_CM(s1, B[4]) + RS_CM(s2, B[7]) + RS_CM(s3, M[1]) + RS_CM(s4, M[3]) + RS_CM(s5, M[4]);
+    h[5] = RS_CM(s0, B[2]) + RS_CM(s1, B[5]) + RS_CM(s2, B[8]) + RS_CM(s3, M[2]) + RS_CM(s4, M[4]) + RS_CM(s5, M[5]);
+}
+
 // (prismatic joints keep q in the cos slot, so that any lane of the warp can rebuild any env's transforms)
 template <class T, int I, int STRIDE>
 RS_HD void cached_xform(const LinkCache<STRIDE>& lc, float* R, float* r) {
@@ -146,7 +303,7 @@ RS_HD void static_kinematics(Work<NL, MC, SL>& W, const LinkCache<STRIDE>& lc, f
         if constexpr (jt == RS_JOINT_PRISMATIC) { q = W.q[dI]; lc.at(lc_cs<T>() + 2 * i) = q; }
         float R[9], r[3];
         link_xform<T, i>(c, s, q, R, r);
-        mul33(W.Rwl[i + 1], R, W.Rwl[p + 1]);
+        rot_mul33<rot_kind<T, i>()>(W.Rwl[i + 1], R, W.Rwl[p + 1]);
         float rw[3];
         tmulv(rw, W.Rwl[i + 1], r);
         W.pos[i + 1][0] = W.pos[p + 1][0] + rw[0]; W.pos[i + 1][1] = W.pos[p + 1][1] + rw[1]; W.pos[i + 1][2] = W.pos[p + 1][2] + rw[2];
@@ -250,7 +407,7 @@ RS_HD void static_aba(const DevModel& M, Work<NL, MC, SL>& W, const LinkCache<ST
         constexpr float mI = T::mass[i], i0 = T::inertia[3 * i], i1 = T::inertia[3 * i + 1], i2 = T::inertia[3 * i + 2];
         float R[9], r[3];
         cached_xform<T, i>(lc, R, r);
-        xf_motion(vel[i + 1], R, r, vel[p + 1]);
+        xf_motion_k<rot_kind<T, i>()>(vel[i + 1], R, r, vel[p + 1]);
         if constexpr (dI >= 0) {
             float qd = W.qd[dI];
             saxpy<T, i>(vel[i + 1], qd);
@@ -285,9 +442,8 @@ RS_HD void static_aba(const DevModel& M, Work<NL, MC, SL>& W, const LinkCache<ST
         cached_xform<T, i>(lc, R, r);
         float Zt[6];
         if constexpr (dI >= 0) {
-            float S[6] = {s0, s1, s2, s3, s4, s5};
             float h[6];
-            inertia_mul(h, IA[i + 1], S);
+            inertia_mul_S<T, i>(h, IA[i + 1]);
             float D = sdot<T, i>(h);
             float y = W.tau[dI] - sdot<T, i>(Z[i + 1]) - dot6(c[i], h);
             float invD = 1.0f / D;
@@ -318,8 +474,8 @@ RS_HD void static_aba(const DevModel& M, Work<NL, MC, SL>& W, const LinkCache<ST
             if constexpr (p >= 0) init_rigid(IA[p + 1], mP, p0, p1, p2);
             else init_rigid(IA[0], bM, bI0, bI1, bI2);
         }
-        inertia_to_parent_add(IA[p + 1], IA[i + 1], R, r);
-        xf_force_inv_add(Z[p + 1], R, r, Zt);
+        inertia_to_parent_add_k<rot_kind<T, i>()>(IA[p + 1], IA[i + 1], R, r);
+        xf_force_inv_add_k<rot_kind<T, i>()>(Z[p + 1], R, r, Zt);
     });
     // ---- base acceleration + root -> leaves joint accelerations ----
     float acc[n + 1][6];
@@ -341,7 +497,7 @@ RS_HD void static_aba(const DevModel& M, Work<NL, MC, SL>& W, const LinkCache<ST
         constexpr int p = T::parent[i];
         float R[9], r[3];
         cached_xform<T, i>(lc, R, r);
-        xf_motion(acc[i + 1], R, r, acc[p + 1]);
+        xf_motion_k<rot_kind<T, i>()>(acc[i + 1], R, r, acc[p + 1]);
         constexpr int dI = T::dof[i];
         if constexpr (dI >= 0) {
             float h[6];
@@ -367,119 +523,8 @@ RS_HD void static_aba(const DevModel& M, Work<NL, MC, SL>& W, const LinkCache<ST
 }
 
 // ---------------------------------------------------------------------------------------------
-// unit-impulse response (fillContactJacobianMultiDof + calcAccelerationDeltasMultiDof), static sweeps.
-// Same contract as the generic row_response().
+// observation with the static sweeps (the constraint-row responses live in rs_pooled.cuh)
 // ---------------------------------------------------------------------------------------------
-// HASW=false: pure joint-space row (joint limit): no wrench to walk up the tree, J is the unit vector e_jdof
-template <class T, bool HASW, int NL, int MC, bool SL, int STRIDE>
-RS_HDN float static_row_response(const Work<NL, MC, SL>& W, const LinkCache<STRIDE>& lc, int body, const float* wrench, int jdof, float jdir,
-                                const RowWS& ws, int row, int rec, bool first, const float* vel, float* relvel) {
-    constexpr int n = T::NL, nd = 6 + T::ND;
-    float F[HASW ? n + 1 : 1][6], Z[n + 1][6], Y[n], jd[n];
-    static_for<n + 1>([&](auto bc) {
-        constexpr int b = decltype(bc)::value;
-        if constexpr (HASW) {
-            const bool hit = (b == body);
-#pragma unroll
-            for (int k = 0; k < 6; k++) { float w = hit ? wrench[k] : 0.f; F[b][k] = w; Z[b][k] = -w; }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 6; k++) Z[b][k] = 0.f;
-        }
-    });
-    float denom = 0.f;
-    static_rfor<n>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
-        constexpr int p = T::parent[i];
-        float R[9], r[3];
-        cached_xform<T, i>(lc, R, r);
-        float Zt[6];
-#pragma unroll
-        for (int k = 0; k < 6; k++) Zt[k] = Z[i + 1][k];
-        constexpr int d = T::dof[i];
-        if constexpr (d >= 0) {
-            const float jj = (d == jdof) ? jdir : 0.f;
-            float j = jj;
-            if constexpr (HASW) j += sdot<T, i>(F[i + 1]);
-            float y = jj - sdot<T, i>(Z[i + 1]);
-            Y[i] = y; jd[i] = j;
-            float kk = lc.at(lc_invd<T>() + i) * y;
-#pragma unroll
-            for (int k = 0; k < 6; k++) Zt[k] += lc.at(lc_h<T>() + 6 * i + k) * kk;
-            float& J = ws.at(row, rec, 6 + d);
-            J = first ? j : J + j;
-            *relvel += j * vel[6 + d];
-        }
-        xf_force_inv_add(Z[p + 1], R, r, Zt);
-        if constexpr (HASW) xf_force_inv_add(F[p + 1], R, r, F[i + 1]);
-    });
-    float acc[n + 1][6];
-    if constexpr (T::FIXED_BASE) {
-#pragma unroll
-        for (int k = 0; k < 6; k++) { acc[0][k] = 0.f; if (first) { ws.at(row, rec, k) = 0.f; ws.at(row, rec, nd + k) = 0.f; } }
-    } else {
-        float jw[3] = {0.f, 0.f, 0.f}, jv[3] = {0.f, 0.f, 0.f}, rr[6], uw[3], uv[3], Lb[21];
-#pragma unroll
-        for (int k = 0; k < 21; k++) Lb[k] = lc.at(lc_lb<T>() + k);
-        if constexpr (HASW) { tmulv(jw, W.Rwl[0], F[0]); tmulv(jv, W.Rwl[0], F[0] + 3); }
-        chol6_solve(rr, Lb, Z[0]);
-#pragma unroll
-        for (int k = 0; k < 6; k++) acc[0][k] = -rr[k];
-        tmulv(uw, W.Rwl[0], acc[0]); tmulv(uv, W.Rwl[0], acc[0] + 3);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            float& J0 = ws.at(row, rec, k); float& J1 = ws.at(row, rec, 3 + k);
-            float& U0 = ws.at(row, rec, nd + k); float& U1 = ws.at(row, rec, nd + 3 + k);
-            if (first) { J0 = jw[k]; J1 = jv[k]; U0 = uw[k]; U1 = uv[k]; }
-            else { J0 += jw[k]; J1 += jv[k]; U0 += uw[k]; U1 += uv[k]; }
-            denom += jw[k] * uw[k] + jv[k] * uv[k];
-            *relvel += jw[k] * vel[k] + jv[k] * vel[3 + k];
-        }
-    }
-    static_for<n>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
-        constexpr int p = T::parent[i];
-        float R[9], r[3];
-        cached_xform<T, i>(lc, R, r);
-        xf_motion(acc[i + 1], R, r, acc[p + 1]);
-        constexpr int d = T::dof[i];
-        if constexpr (d >= 0) {
-            float h[6];
-#pragma unroll
-            for (int k = 0; k < 6; k++) h[k] = lc.at(lc_h<T>() + 6 * i + k);
-            float a = lc.at(lc_invd<T>() + i) * (Y[i] - dot6(acc[i + 1], h));
-            saxpy<T, i>(acc[i + 1], a);
-            float& U = ws.at(row, rec, nd + 6 + d);
-            U = first ? a : U + a;
-            denom += jd[i] * a;
-        }
-    });
-    return denom;
-}
-
-// ---------------------------------------------------------------------------------------------
-// sub-step / observation with the static sweeps
-// ---------------------------------------------------------------------------------------------
-template <class T, int NL, int MC, bool SL, int STRIDE>
-RS_HD void substep_static(const DevModel& M, Work<NL, MC, SL>& W, const RowWS& ws, const LinkCache<STRIDE>& lc, PhaseClock* pc = nullptr) {
-    float dt = M.timestep;
-    long long c0 = 0, c1 = 0;
-    if (pc) c0 = RS_CLOCK();
-    static_kinematics<T>(W, lc);
-    if (pc) { c1 = RS_CLOCK(); pc->t[0] += c1 - c0; c0 = c1; }
-    collide(M, W);
-    if (pc) { c1 = RS_CLOCK(); pc->t[1] += c1 - c0; c0 = c1; }
-    static_aba<T>(M, W, lc, dt);
-    if (pc) { c1 = RS_CLOCK(); pc->t[2] += c1 - c0; c0 = c1; }
-    solve_with(M, W, dt, ws, [&](int body, const float* wr, int jdof, float jdir, int row, int rec, bool first, const float* vel, float* relvel) {
-        if (body < 0) return static_row_response<T, false>(W, lc, body, wr, jdof, jdir, ws, row, rec, first, vel, relvel);
-        return static_row_response<T, true>(W, lc, body, wr, jdof, jdir, ws, row, rec, first, vel, relvel);
-    });
-    if (pc) { c1 = RS_CLOCK(); pc->t[3] += c1 - c0; c0 = c1; }
-    integrate(M, W, dt);
-    if (pc) { c1 = RS_CLOCK(); pc->t[4] += c1 - c0; }
-}
-
 template <class T, int NL, int MC, bool SL, int STRIDE>
 RS_HD void static_calc_state(const DevModel& M, Work<NL, MC, SL>& W, const LinkCache<STRIDE>& lc, Episode& E, float* obs, int ostride,
                              double* dist, float* pitch, int* at_limit) {
@@ -497,7 +542,7 @@ RS_HD void static_calc_state(const DevModel& M, Work<NL, MC, SL>& W, const LinkC
         constexpr int p = T::parent[i];
         float R[9], r[3];
         cached_xform<T, i>(lc, R, r);
-        xf_motion(vel[i + 1], R, r, vel[p + 1]);
+        xf_motion_k<rot_kind<T, i>()>(vel[i + 1], R, r, vel[p + 1]);
         constexpr int dI = T::dof[i];
         if constexpr (dI >= 0) saxpy<T, i>(vel[i + 1], W.qd[dI]);
         if (body == i + 1) { vl[0] = vel[i + 1][3]; vl[1] = vel[i + 1][4]; vl[2] = vel[i + 1][5]; }
