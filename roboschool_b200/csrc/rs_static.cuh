@@ -52,6 +52,29 @@ RS_HD void saxpy(float* x, float a) {
     x[3] += RS_CM(s3, a); x[4] += RS_CM(s4, a); x[5] += RS_CM(s5, a);
 }
 
+// sin and cos of a joint angle: Cody-Waite reduction by pi/2 (three constants, exact product for |x| < ~1e5 rad -- joint
+// angles are a few rad) and the minimax polynomials on [-pi/4, pi/4]; ~1 ulp.  Straight-line: unlike sincosf() there is
+// no large-argument slow path to branch around (17 joints x 4 sub-steps of taken branches in the instruction stream).
+RS_HD void rs_sincos(float x, float* sn, float* cs) {
+    const float j = rintf(x * 0.636619772f);
+    const int q = (int)j;
+    float r = fmaf(j, -1.57079601e+00f, x);
+    r = fmaf(j, -3.13916473e-07f, r);
+    r = fmaf(j, -5.39030253e-15f, r);
+    const float s = r * r;
+    float ps = fmaf(2.86567956e-6f, s, -1.98559923e-4f);
+    ps = fmaf(ps, s, 8.33338592e-3f);
+    ps = fmaf(ps, s, -1.66666672e-1f);
+    const float sr = fmaf(r * s, ps, r);
+    float pc = fmaf(2.44677067e-5f, s, -1.38877297e-3f);
+    pc = fmaf(pc, s, 4.16666567e-2f);
+    pc = fmaf(pc, s, -0.5f);
+    const float cr = fmaf(s, pc, 1.0f);
+    const float a = (q & 1) ? cr : sr, b = (q & 1) ? sr : cr;     // sin, cos before the sign of the quadrant
+    *sn = (q & 2) ? -a : a;
+    *cs = ((q + 1) & 2) ? -b : b;
+}
+
 // rotation parent->link coords and COM offset of link I from (cos q, sin q, q)
 template <class T, int I>
 RS_HD void link_xform(float c, float s, float q, float* R, float* r) {
@@ -297,7 +320,7 @@ RS_HD void static_kinematics(Work<NL, MC, SL>& W, const LinkCache<STRIDE>& lc, f
         constexpr int p = T::parent[i], jt = T::jtype[i], dI = T::dof[i];
         float c = 1.0f, s = 0.0f, q = 0.0f;
         if constexpr (jt == RS_JOINT_REVOLUTE) {
-            sincosf(W.q[dI], &s, &c);
+            rs_sincos(W.q[dI], &s, &c);
             lc.at(lc_cs<T>() + 2 * i) = c; lc.at(lc_cs<T>() + 2 * i + 1) = s;
         }
         if constexpr (jt == RS_JOINT_PRISMATIC) { q = W.q[dI]; lc.at(lc_cs<T>() + 2 * i) = q; }
@@ -420,8 +443,14 @@ RS_HD void static_aba(const DevModel& M, Work<NL, MC, SL>& W, const LinkCache<ST
             cross3(t1, v, jv + 3); cross3(t2, v + 3, jv);
             c[i][3] = t1[0] + t2[0]; c[i][4] = t1[1] + t2[1]; c[i][5] = t1[2] + t2[2];
         }
-        const float I3[3] = {i0, i1, i2};
-        bias(vel[i + 1], mI, I3, W.Rwl[i + 1], Z[i + 1]);
+        if constexpr (mI == 0.0f && i0 == 0.0f && i1 == 0.0f && i2 == 0.0f) {
+            // massless link (importer-generated dummy of a multi-joint body): no gravity, damping or gyroscopic force
+#pragma unroll
+            for (int k = 0; k < 6; k++) Z[i + 1][k] = 0.f;
+        } else {
+            const float I3[3] = {i0, i1, i2};
+            bias(vel[i + 1], mI, I3, W.Rwl[i + 1], Z[i + 1]);
+        }
     });
     // ---- leaves -> root: articulated inertias, h, D, Y ----
     float IA[n + 1][21];

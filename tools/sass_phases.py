@@ -9,35 +9,43 @@ import csv, re, sys, collections
 dis, kname = sys.argv[1], sys.argv[2]
 src_csv = sys.argv[3] if len(sys.argv) > 3 else None
 
+import os
+CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "roboschool_b200", "csrc")
+
+def _anchors(fname, items):
+    """[(first line of the text anchor, phase)] sorted; phase None = ambiguous helper region."""
+    lines = open(os.path.join(CSRC, fname)).read().split("\n")
+    out = []
+    for text, nth, phase in items:
+        hits = [i + 1 for i, l in enumerate(lines) if text in l]
+        if len(hits) > nth:
+            out.append((hits[nth], phase))
+    return sorted(out)
+
+RANGES = {
+    "rs_kernels.cuh": [(1, "load/store/kernel-glue")],
+    "rs_static.cuh": _anchors("rs_static.cuh", [
+        ("namespace rs {", 0, None), ("RS_HD void static_body_geoms", 0, "kinematics"), ("RS_HD void static_collide", 0, "collide_broadphase"),
+        ("RS_HD void static_aba", 0, "aba"), ("RS_HD void static_calc_state", 0, "calc_state")]),
+    "rs_pooled.cuh": _anchors("rs_pooled.cuh", [
+        ("namespace rs {", 0, None), ("RS_HD void pooled_response", 0, "resp_up"), ("float acc[NR][n + 1][6];", 0, "resp_root"),
+        ("static_for<n>([&](auto ic) {", 0, "resp_down"), ("RS_HD void resolve_pooled", 0, "pgs_row"),
+        ("RS_HD void solve_pooled", 0, "solve_owner_setup"), ("// ---- all lanes: limit-row tasks ----", 0, "solve_tasks_glue"),
+        ("// ---- owner: right-hand sides", 0, "solve_owner_rhs+pgs"), ("RS_HD void substep_pooled", 0, "substep-glue")]),
+    "rs_core.cuh": _anchors("rs_core.cuh", [
+        ("namespace rs {", 0, None), ("RS_HD void kinematics(", 0, "generic_kin"), ("RS_HD void clamp_vel", 0, "clamp_vel"),
+        ("RS_HD void aba(", 0, "generic_aba"), ("RS_HD void to_world", 0, None), ("RS_HD void seg_seg_closest", 0, "collide_narrow"),
+        ("RS_HD void resolve_row", 0, "generic_solve"), ("RS_HD void integrate", 0, "integrate"), ("RS_HD void mat_to_quat", 0, "epilogue"),
+        ("RS_HD void env_reset_with", 0, "reset"), ("RS_HD void apply_action", 0, "apply_action")]),
+}
+
 def phase_of(f, ln):
     f = f.split("/")[-1]
-    if f == "rs_kernels.cuh":
-        return "load/store/epilogue-glue"
-    if f == "rs_static.cuh":
-        if ln < 100: return None
-        if ln < 131: return "kinematics"
-        if ln < 290: return "aba"
-        if ln < 385: return "old_response"
-        return "calc_state"
-    if f == "rs_pooled.cuh":
-        if ln < 98: return None
-        if ln < 166: return "resp_up"
-        if ln < 205: return "resp_root"
-        if ln < 235: return "resp_down"
-        if ln < 250: return "resolve_row"
-        if ln < 330: return "solve_owner_setup"
-        if ln < 372: return "solve_tasks_glue"
-        return "solve_owner_pgs"
-    if f == "rs_core.cuh":
-        if ln < 276: return None
-        if ln < 346: return "generic_kin"
-        if ln < 555: return "clamp/aba_generic"
-        if ln < 762: return "collide"
-        if ln < 905: return "solve_generic"
-        if ln < 926: return "integrate"
-        if ln < 1102: return "epilogue"
-        return "reset/apply_action"
-    return None
+    ph = None
+    for start, name in RANGES.get(f, []):
+        if ln >= start:
+            ph = name
+    return ph
 
 cur_fn, phase, in_fn = None, "prologue", False
 count = collections.Counter()
