@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(32 * WPC) k_step_static(const __grid_constant_
         else { for (int k = 0; k < M.n_act; k++) a[k] = 2.f * rs_uniform(seed ^ 0xA5A5A5A5u, env_id0 + e, E.episode * 1024u + (uint32_t)E.frame, (uint32_t)k) - 1.f; }
         apply_action(M, W, a, 1);
     }
-    const RowPool pool{B.rows + (size_t)(blockIdx.x * WPC + wic) * ((size_t)32 * B.maxr * B.rec), 32 * B.maxr};
+    constexpr int CAP = pool_cap<T, MC, 32>();      // <= 32 * B.maxr: the allocation covers it
+    const RowPool<CAP> pool{B.rows + (size_t)(blockIdx.x * WPC + wic) * ((size_t)CAP * pool_rec<T>())};
     const WarpDev<WPC> warp;
     PhaseClock pc;
     if (PROF) { for (int k = 0; k < 6; k++) pc.t[k] = 0; t1 = clock64(); }

@@ -28,11 +28,14 @@
 namespace rs {
 
 // pool of row records shared by the lanes of a warp: word k of slot s at p[k * cap + s]
+// CAP (slots per pool) is a compile-time constant so that the word index k becomes an immediate offset
+template <int CAP>
 struct RowPool {
     float* p;
-    int cap;
-    RS_HD float& at(int slot, int k) const { return p[(size_t)k * cap + slot]; }
+    RS_HD float& at(int slot, int k) const { return p[k * CAP + slot]; }
 };
+// slots a warp of WIDTH envs can need: every env at its row capacity
+template <class T, int MC, int WIDTH> constexpr int pool_cap() { return WIDTH * (T::NL + 3 * MC); }
 // words of a row record: [0,nd) J ; [nd,2nd) M^-1 J^T ; [2nd] denominator.  A task descriptor lives in
 // words [0,25) of the task's first row slot until the task is executed (needs 2*nd+1 >= 25).
 constexpr int POOL_DESC_WORDS = 25;
@@ -93,9 +96,9 @@ RS_HD int f2i(float v) { union { int i; float f; } u; u.f = v; return u.i; }
 //   Rows go to pool slots slot0 .. slot0+NR-1.  first: overwrite; else accumulate (second body of a pair).
 //   denom[rr] = J . M^-1 J^T of THIS side.
 // ---------------------------------------------------------------------------------------------
-template <class T, int NR, bool HASW, bool first, int STRIDE>
+template <class T, int NR, bool HASW, bool first, int STRIDE, class Pool>
 RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*wr)[6], float jdir,
-                           const RowPool& pool, int slot0, float* denom) {
+                           const Pool& pool, int slot0, float* denom) {
     constexpr int n = T::NL, nd = 6 + T::ND;
     float F[HASW ? NR : 1][6], Z[NR][6], Y[NR][n];
 #pragma unroll
@@ -215,14 +218,14 @@ RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*
 }
 
 // second body of a two-body contact: accumulate variant, kept out of line (rare; keeps the hot instruction stream short)
-template <class T, int STRIDE>
-RS_HDN void pooled_response_second(const LinkCache<STRIDE>& lc, int body, const float (*wr)[6], const RowPool& pool, int slot0, float* denom) {
+template <class T, int STRIDE, class Pool>
+RS_HDN void pooled_response_second(const LinkCache<STRIDE>& lc, int body, const float (*wr)[6], const Pool& pool, int slot0, float* denom) {
     pooled_response<T, 3, true, false>(lc, body, wr, 0.f, pool, slot0, denom);
 }
 
 // resolveSingleConstraintRowGeneric on a pooled row record
-template <int ND>
-RS_HD void resolve_pooled(const RowPool& pool, int slot, float* dv, float rhs, float invd, float lo, float hi, float& applied) {
+template <int ND, class Pool>
+RS_HD void resolve_pooled(const Pool& pool, int slot, float* dv, float rhs, float invd, float lo, float hi, float& applied) {
     float j[ND], u[ND];
 #pragma unroll
     for (int k = 0; k < ND; k++) { j[k] = pool.at(slot, k); u[k] = pool.at(slot, ND + k); }
@@ -243,8 +246,8 @@ RS_HD void resolve_pooled(const RowPool& pool, int slot, float* dv, float rhs, f
 //   valid   : this lane owns a live env (the tail warp's spare lanes only help)
 //   lc_lane0: link cache of lane 0 of this warp; the cache of lane o is lc_lane0 + o (host: o == 0)
 // ---------------------------------------------------------------------------------------------
-template <class T, class Warp, int NL, int MC, bool SL, int STRIDE>
-RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL, MC, SL>& W, float dt, const RowPool& pool, float* lc_lane0) {
+template <class T, class Warp, int NL, int MC, bool SL, int STRIDE, class Pool>
+RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL, MC, SL>& W, float dt, const Pool& pool, float* lc_lane0) {
     static_assert(pool_rec<T>() >= POOL_DESC_WORDS, "row record too small to hold a task descriptor");
     constexpr int nd = 6 + T::ND, n = T::NL;
     const int lane = warp.lane();
@@ -444,8 +447,8 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
 }
 
 // one sub-step with the pooled solver; every lane of the warp must call it (valid == false: helper only)
-template <class T, class Warp, int NL, int MC, bool SL, int STRIDE>
-RS_HD void substep_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL, MC, SL>& W, const RowPool& pool,
+template <class T, class Warp, int NL, int MC, bool SL, int STRIDE, class Pool>
+RS_HD void substep_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL, MC, SL>& W, const Pool& pool,
                           const LinkCache<STRIDE>& lc, float* lc_lane0, PhaseClock* pc = nullptr) {
     const float dt = M.timestep;
     long long c0 = 0, c1 = 0;
@@ -463,7 +466,7 @@ RS_HD void substep_pooled(const Warp& warp, bool valid, const DevModel& M, Work<
     if (pc) { c1 = RS_CLOCK(); pc->t[2] += c1 - c0; c0 = c1; }
     warp.cta_sync();
     warp.sync();   // link caches complete before other lanes read them
-    solve_pooled<T, Warp, NL, MC, SL, STRIDE>(warp, valid, M, W, dt, pool, lc_lane0);
+    solve_pooled<T, Warp, NL, MC, SL, STRIDE, Pool>(warp, valid, M, W, dt, pool, lc_lane0);
     warp.sync();   // all helpers done with this sub-step's caches before kinematics overwrites them
     if (pc) { c1 = RS_CLOCK(); pc->t[3] += c1 - c0; c0 = c1; }
     if (valid) integrate(M, W, dt);

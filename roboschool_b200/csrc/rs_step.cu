@@ -239,7 +239,7 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
     CK(cudaMemset(B.target, 0, sizeof(double) * N * 2));
     CK(cudaMemset(B.flag_timeout, 0, sizeof(int) * N));
     CK(cudaMemset(B.flag_draws, 0, sizeof(uint32_t) * N));
-    CK(cudaMalloc(&B.rows, sizeof(float) * (size_t)((n_envs + 127) / 128 * 128) * B.rec * B.maxr));   // one pool per warp of 32 envs
+    CK(cudaMalloc(&B.rows, sizeof(float) * (size_t)((n_envs + 255) / 256 * 256 + 256) * B.rec * B.maxr));   // one pool per warp of 32 envs, incl. the spare warps of the last CTA (up to 8 warps per CTA)
     CK(cudaMalloc(&B.tau, sizeof(float) * N * (model->n_dof > 0 ? model->n_dof : 1)));
     CK(cudaMalloc(&B.rewards5, sizeof(float) * N * 5));
     CK(cudaMalloc(&B.nrows, sizeof(int) * N));

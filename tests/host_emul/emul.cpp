@@ -27,7 +27,7 @@ struct Emul {
 
 template <class T>
 static void step_env_static(Emul* e, int i, const float* a, int auto_reset, uint32_t seed, uint32_t env0) {
-    const DevModel& M = e->M; W_t& W = e->w[i]; RowPool pool{e->ws.data(), e->maxr};
+    const DevModel& M = e->M; W_t& W = e->w[i]; RowPool<pool_cap<T, MC, 1>()> pool{e->ws.data()};
     LinkCache<1> lc{e->lcbuf.data() + (size_t)i * e->lcsize};
     apply_action(M, W, a, 1);
     for (int s = 0; s < M.frame_skip; s++) substep_pooled<T>(WarpHost(), true, M, W, pool, lc, lc.p);
@@ -40,7 +40,7 @@ static void step_env_static(Emul* e, int i, const float* a, int auto_reset, uint
 }
 template <class T>
 static void substeps_static(Emul* e, int env, int n) {
-    RowPool pool{e->ws.data(), e->maxr};
+    RowPool<pool_cap<T, MC, 1>()> pool{e->ws.data()};
     LinkCache<1> lc{e->lcbuf.data() + (size_t)env * e->lcsize};
     for (int s = 0; s < n; s++) substep_pooled<T>(WarpHost(), true, e->M, e->w[env], pool, lc, lc.p);
 }
