@@ -627,13 +627,33 @@ RS_HD int sort_cached_points(const Manifold4& mf, const float* np) {
     return best;
 }
 
+// world transform of one body, fetched once per manifold (the per-body arrays are thread-private scratch: every
+// dynamic-index access is a local-memory load)
+struct BodyXf {
+    float R[9], p[3];   // R: world -> body coords ; p: COM in world
+};
 template <int NL, int MC, bool SL>
-RS_HD void manifold_add(Manifold4& mf, const Work<NL, MC, SL>& W, int bA, int bB, const float* n, const float* pOnB, float depth, float thresh) {
+RS_HD void load_xf(const Work<NL, MC, SL>& W, int b, BodyXf& X) {
+#pragma unroll
+    for (int k = 0; k < 9; k++) X.R[k] = W.Rwl[b][k];
+    X.p[0] = W.pos[b][0]; X.p[1] = W.pos[b][1]; X.p[2] = W.pos[b][2];
+}
+RS_HD void xf_to_world(const BodyXf& X, const float* l, float* w) {
+    float t[3]; tmulv(t, X.R, l);
+    w[0] = X.p[0] + t[0]; w[1] = X.p[1] + t[1]; w[2] = X.p[2] + t[2];
+}
+RS_HD void xf_to_local(const BodyXf& X, const float* w, float* l) {
+    float t[3] = {w[0] - X.p[0], w[1] - X.p[1], w[2] - X.p[2]};
+    mulv(l, X.R, t);
+}
+
+// bB < 0: the other body is the world (floor)
+RS_HD void manifold_add(Manifold4& mf, const BodyXf& XA, const BodyXf& XB, int bB, const float* n, const float* pOnB, float depth, float thresh) {
     if (depth > thresh) return;
     float np[CDAT];
     float pA[3] = {pOnB[0] + n[0] * depth, pOnB[1] + n[1] * depth, pOnB[2] + n[2] * depth};
-    to_local(W, bA, pA, np);
-    if (bB >= 0) to_local(W, bB, pOnB, np + 3); else { np[3] = pOnB[0]; np[4] = pOnB[1]; np[5] = pOnB[2]; }
+    xf_to_local(XA, pA, np);
+    if (bB >= 0) xf_to_local(XB, pOnB, np + 3); else { np[3] = pOnB[0]; np[4] = pOnB[1]; np[5] = pOnB[2]; }
     np[6] = n[0]; np[7] = n[1]; np[8] = n[2]; np[9] = depth;
     float shortest = thresh * thresh; int nearest = -1;
 #pragma unroll
@@ -651,16 +671,15 @@ RS_HD void manifold_add(Manifold4& mf, const Work<NL, MC, SL>& W, int bA, int bB
     }
 }
 
-template <int NL, int MC, bool SL>
-RS_HD void manifold_refresh(Manifold4& mf, const Work<NL, MC, SL>& W, int bA, int bB, float thresh) {
+RS_HD void manifold_refresh(Manifold4& mf, const BodyXf& XA, const BodyXf& XB, int bB, float thresh) {
     bool rem[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         rem[i] = false;
         if (i < mf.n) {
             float pA[3], pB[3];
-            to_world(W, bA, mf.d[i], pA);
-            if (bB >= 0) to_world(W, bB, mf.d[i] + 3, pB); else { pB[0] = mf.d[i][3]; pB[1] = mf.d[i][4]; pB[2] = mf.d[i][5]; }
+            xf_to_world(XA, mf.d[i], pA);
+            if (bB >= 0) xf_to_world(XB, mf.d[i] + 3, pB); else { pB[0] = mf.d[i][3]; pB[1] = mf.d[i][4]; pB[2] = mf.d[i][5]; }
             float df[3] = {pA[0] - pB[0], pA[1] - pB[1], pA[2] - pB[2]};
             float dist = dot3(df, mf.d[i] + 6);
             mf.d[i][9] = dist;
@@ -704,15 +723,17 @@ RS_HD void collide_manifold(const DevModel& M, Work<NL, MC, SL>& W, const float 
         if (!M.g_floor[k]) return;
         int b = M.g_link[k] + 1;
         float thr = M.break_thresh[b];
+        BodyXf XA;
+        load_xf(W, b, XA);
         // support vertex in -z: lower end sphere, first end wins ties
         const float* c = (M.g_type[k] == RS_GEOM_CAPSULE && gw[k][5] < gw[k][2]) ? gw[k] + 3 : gw[k];
         float dist = c[2] - M.g_radius[k];
         if (dist < thr) {
             const float nz[3] = {0.f, 0.f, 1.f};
             float pOnB[3] = {c[0], c[1], 0.f};
-            manifold_add(mf, W, b, -1, nz, pOnB, dist, thr);
+            manifold_add(mf, XA, XA, -1, nz, pOnB, dist, thr);
         }
-        if (mf.n) manifold_refresh(mf, W, b, -1, thr);
+        if (mf.n) manifold_refresh(mf, XA, XA, -1, thr);
     } else {
         int pk = k - M.n_geoms;
         int ga = M.pair_a[pk], gb = M.pair_b[pk];
@@ -728,9 +749,15 @@ RS_HD void collide_manifold(const DevModel& M, Work<NL, MC, SL>& W, const float 
             float nn[3] = {1.f, 0.f, 0.f};
             if (len > 1e-12f) { float il = 1.0f / len; nn[0] = d[0] * il; nn[1] = d[1] * il; nn[2] = d[2] * il; }
             float pOnB[3] = {cB[0] + nn[0] * rB, cB[1] + nn[1] * rB, cB[2] + nn[2] * rB};
-            manifold_add(mf, W, bA, bB, nn, pOnB, dist, thr);
+            BodyXf XA, XB;
+            load_xf(W, bA, XA); load_xf(W, bB, XB);
+            manifold_add(mf, XA, XB, bB, nn, pOnB, dist, thr);
+            if (mf.n) manifold_refresh(mf, XA, XB, bB, thr);
+        } else if (mf.n) {
+            BodyXf XA, XB;
+            load_xf(W, bA, XA); load_xf(W, bB, XB);
+            manifold_refresh(mf, XA, XB, bB, thr);
         }
-        if (mf.n) manifold_refresh(mf, W, bA, bB, thr);
     }
 #pragma unroll
     for (int s = 0; s < 4; s++) if (s < mf.n && no < MC && no < M.max_contacts) {

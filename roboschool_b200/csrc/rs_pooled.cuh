@@ -291,20 +291,25 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
         pool.at(slot, 0) = i2f(lane | (bA << 8) | ((bB + 1) << 16));
 #pragma unroll
         for (int k = 0; k < 3; k++) pool.at(slot, 1 + k) = cd[k];
+        float Rb[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Rb[k] = W.Rwl[bA][k];
 #pragma unroll
         for (int w = 0; w < 3; w++) {
             float dl[3];
-            mulv(dl, W.Rwl[bA], dirs[w]);
+            mulv(dl, Rb, dirs[w]);
 #pragma unroll
             for (int k = 0; k < 3; k++) pool.at(slot, 4 + 3 * w + k) = dl[k];
         }
         if (bB >= 0) {
 #pragma unroll
+            for (int k = 0; k < 9; k++) Rb[k] = W.Rwl[bB][k];
+#pragma unroll
             for (int k = 0; k < 3; k++) pool.at(slot, 13 + k) = cd[3 + k];
 #pragma unroll
             for (int w = 0; w < 3; w++) {
                 float dl[3];
-                mulv(dl, W.Rwl[bB], dirs[w]);
+                mulv(dl, Rb, dirs[w]);
 #pragma unroll
                 for (int k = 0; k < 3; k++) pool.at(slot, 16 + 3 * w + k) = -dl[k];
             }
