@@ -41,6 +41,8 @@ extern "C" {
 #define RS_TASK_WALKER          0 /* RoboschoolForwardWalker family (gym_forward_walker.py)                  */
 #define RS_TASK_PENDULUM        1 /* RoboschoolInvertedPendulum[Swingup] (gym_pendulums.py:70-127)            */
 #define RS_TASK_DOUBLE_PENDULUM 2 /* RoboschoolInvertedDoublePendulum (gym_pendulums.py:7-65)                 */
+#define RS_TASK_REACHER         3 /* RoboschoolReacher (gym_reacher.py): task_dof = joint0, joint1, target_x, target_y;
+                                     task_link = fingertip, task_link2 = target                               */
 
 /* alive rules (gym_mujoco_walkers.py alive_bonus variants) */
 #define RS_ALIVE_Z_AND_PITCH 0 /* Hopper/Walker2d: +1 if z>alive_z and |pitch|<1 else -1 */
@@ -148,6 +150,9 @@ typedef struct rs_model_desc {
     int    reset_dof[RS_MAX_ACT];
     int    task_dof[4];                  /* pendulums: slider, hinge, hinge2 dofs                                */
     double reset_center[RS_MAX_ACT];
+    double reset_spread[RS_MAX_ACT];     /* per reset joint: q = center + U(-spread, spread)                       */
+    int    task_link2;                   /* Reacher: link "target"                                                */
+    int    pad2;
 } rs_model_desc;
 
 #ifdef __cplusplus

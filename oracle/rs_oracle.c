@@ -834,6 +834,28 @@ static void foot_contacts(const rs_model_desc *m, const oenv *e, int foot, int *
 /* calc_state (gym_forward_walker.py:45-76), float32 squeezes where the reference has them */
 static void calc_state(const rs_model_desc *m, oenv *e, double *body_xy_dist) {
     kinematics(m, e); velocities(m, e);
+    if (m->task_kind == RS_TASK_REACHER) {
+        /* gym_reacher.py calc_state (:38-55) */
+        int dd[2] = {m->task_dof[0], m->task_dof[1]};
+        float rel[4];
+        for (int k = 0; k < 2; k++) {
+            int li = -1;
+            for (int i = 0; i < m->n_links; i++) if (m->dof_idx[i] == dd[k]) li = i;
+            float pos = (float)e->q[dd[k]], spd = (float)e->qd[dd[k]];
+            float l1 = (float)m->lim_lo[li], l2 = (float)m->lim_hi[li];
+            if (l1 < l2) { float mid = (float)(0.5 * (l1 + l2)); pos = 2 * (pos - mid) / (l2 - l1); }
+            if (m->max_vel[li] > 0) spd /= (float)m->max_vel[li]; else spd *= (m->jtype[li] == RS_JOINT_REVOLUTE) ? 0.1f : 0.5f;
+            rel[2 * k] = pos; rel[2 * k + 1] = spd;
+        }
+        const double *pf = e->pos[m->task_link + 1], *pt = e->pos[m->task_link2 + 1];
+        double v[3] = {pf[0] - pt[0], pf[1] - pt[1], pf[2] - pt[2]};
+        e->obs[0] = (float)e->q[m->task_dof[2]]; e->obs[1] = (float)e->q[m->task_dof[3]];
+        e->obs[2] = v[0]; e->obs[3] = v[1];
+        e->obs[4] = cos((double)rel[0]); e->obs[5] = sin((double)rel[0]); e->obs[6] = rel[1];
+        e->obs[7] = rel[2]; e->obs[8] = rel[3];
+        *body_xy_dist = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        return;
+    }
     if (m->task_kind != RS_TASK_WALKER) {
         /* gym_pendulums.py calc_state (:35-47, :97-105): current_position() returns floats */
         int ds = m->task_dof[0], d1 = m->task_dof[1], k = 0;
@@ -924,6 +946,18 @@ static void calc_state_flag(const rs_model_desc *m, oenv *e, double *dist, uint3
 static void epilogue(const rs_model_desc *m, oenv *e, const double *a, uint32_t seed, uint32_t env_id) {
     double dist;
     calc_state_flag(m, e, &dist, seed, env_id);
+    if (m->task_kind == RS_TASK_REACHER) {
+        /* gym_reacher.py step (:60-79) */
+        double pot_old = e->potential;
+        e->potential = -100.0 * dist;
+        double thd = e->obs[6], ga = e->obs[7], gad = e->obs[8];
+        double elec = -0.10 * (fabs(a[0] * thd) + fabs(a[1] * gad)) - 0.01 * (fabs(a[0]) + fabs(a[1]));
+        double stuck = fabs(fabs(ga) - 1) < 0.01 ? -0.1 : 0.0;
+        memset(e->rewards5, 0, sizeof e->rewards5);
+        e->rewards5[0] = e->potential - pot_old; e->rewards5[1] = elec; e->rewards5[2] = stuck;
+        e->reward = e->rewards5[0] + elec + stuck; e->done = 0; e->frame++;
+        return;
+    }
     if (m->task_kind != RS_TASK_WALKER) {
         /* gym_pendulums.py step (:49-65, :107-123) */
         double reward; int dn;
@@ -999,7 +1033,7 @@ static void env_reset(const rs_model_desc *m, oenv *e, int nman, uint32_t seed, 
     memset(e->q, 0, sizeof e->q); memset(e->qd, 0, sizeof e->qd); memset(e->tau, 0, sizeof e->tau);
     for (int k = 0; k < m->n_reset; k++) {
         double u = rs_uniform(seed, env_id, e->episode, (uint32_t)k);
-        e->q[m->reset_dof[k]] = (double)(float)(m->reset_center[k] + m->reset_joint_spread * (2.0 * u - 1.0)); /* reset_current_position(float,..) */
+        e->q[m->reset_dof[k]] = (double)(float)(m->reset_center[k] + m->reset_spread[k] * (2.0 * u - 1.0)); /* reset_current_position(float,..) */
     }
     v3cpy(e->base_pos, m->reset_base_pos);
     memcpy(e->base_quat, m->reset_base_quat, sizeof e->base_quat);
@@ -1019,7 +1053,7 @@ static void env_reset(const rs_model_desc *m, oenv *e, int nman, uint32_t seed, 
     if (m->flag_task) flag_reposition(m, e, seed, env_id, 1);
     double dist;
     calc_state_flag(m, e, &dist, seed, env_id);
-    e->potential = -dist / m->dt_env;
+    e->potential = m->task_kind == RS_TASK_REACHER ? -100.0 * dist : -dist / m->dt_env;
 }
 
 /* =========================== exported API =========================== */

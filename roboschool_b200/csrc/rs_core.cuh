@@ -63,9 +63,9 @@ struct DevModel {
     int reset_set_base;
     int flag_task, flag_timeout_steps;
     double flag_halflen, flag_halfwidth;
-    int task_kind, task_swingup, task_link, n_reset;
+    int task_kind, task_swingup, task_link, task_link2, n_reset;
     int reset_dof[MA], task_dof[4];
-    float reset_center[MA];
+    float reset_center[MA], reset_spread[MA];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1052,6 +1052,23 @@ RS_HD void rel_joint(const DevModel& M, int li, float q, float qd, float* pos, f
 template <int NL, int MC, bool SL>
 RS_HD void calc_state_core(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, const float* bp, const float* bq, const float* bv,
                            float* obs, int ostride, double* dist, float* pitch, int* at_limit) {
+    if (M.task_kind == RS_TASK_REACHER) {
+        // gym_reacher.py calc_state (:38-55): relative joint positions (floats), target joint positions (floats),
+        // fingertip - target from the part poses; the potential uses the 3-D distance
+        const int d0 = M.task_dof[0], d1 = M.task_dof[1];
+        float th, thd, ga, gad;
+        rel_joint(M, M.dof_link[d0], W.q[d0], W.qd[d0], &th, &thd);
+        rel_joint(M, M.dof_link[d1], W.q[d1], W.qd[d1], &ga, &gad);
+        const float* pf = W.pos[M.task_link + 1];
+        const float* pt = W.pos[M.task_link2 + 1];
+        const double vx = (double)pf[0] - (double)pt[0], vy = (double)pf[1] - (double)pt[1], vz = (double)pf[2] - (double)pt[2];
+        obs[0] = W.q[M.task_dof[2]]; obs[ostride] = W.q[M.task_dof[3]];
+        obs[2 * ostride] = (float)vx; obs[3 * ostride] = (float)vy;
+        obs[4 * ostride] = (float)cos((double)th); obs[5 * ostride] = (float)sin((double)th); obs[6 * ostride] = thd;
+        obs[7 * ostride] = ga; obs[8 * ostride] = gad;
+        *dist = sqrt(vx * vx + vy * vy + vz * vz); *pitch = 0.f; *at_limit = 0;
+        return;
+    }
     if (M.task_kind != RS_TASK_WALKER) {
         // gym_pendulums.py calc_state (:35-47, :97-105): Joint::current_position returns floats; cos/sin in double
         const int ds = M.task_dof[0], d1 = M.task_dof[1];
@@ -1152,6 +1169,20 @@ RS_HD void epilogue_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, con
                          uint32_t seed = 0, uint32_t env_id = 0) {
     double dist; float pitch; int at_limit;
     calc_state_flag(M, E, seed, env_id, obs, ostride, &dist, &pitch, &at_limit, cs);
+    if (M.task_kind == RS_TASK_REACHER) {
+        // gym_reacher.py step (:60-79): potential = -100 |fingertip - target|; never done
+        const double pot_old = E.potential;
+        E.potential = -100.0 * dist;
+        const float a0 = act[0], a1 = act[astride];
+        const float thd = obs[6 * ostride], ga = obs[7 * ostride], gad = obs[8 * ostride];
+        const float elec = -0.10f * (fabsf(a0 * thd) + fabsf(a1 * gad)) - 0.01f * (fabsf(a0) + fabsf(a1));
+        const float stuck = fabsf(fabsf(ga) - 1.f) < 0.01f ? -0.1f : 0.f;
+        out.rewards5[0] = (float)(E.potential - pot_old); out.rewards5[1] = elec; out.rewards5[2] = stuck; out.rewards5[3] = out.rewards5[4] = 0.f;
+        out.reward = out.rewards5[0] + elec + stuck;
+        out.done = 0;
+        E.frame++;
+        return;
+    }
     if (M.task_kind != RS_TASK_WALKER) {
         // gym_pendulums.py step (:49-65, :107-123)
         float reward; int dn;
@@ -1228,7 +1259,7 @@ RS_HD void env_reset_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, ui
     for (int d = 0; d < M.n_dof; d++) { W.q[d] = 0.f; W.qd[d] = 0.f; W.tau[d] = 0.f; }
     for (int k = 0; k < M.n_reset; k++) {
         float u = rs_uniform(seed, env_id, E.episode, (uint32_t)k);
-        W.q[M.reset_dof[k]] = (float)((double)M.reset_center[k] + (double)M.reset_joint_spread * (2.0 * (double)u - 1.0));
+        W.q[M.reset_dof[k]] = (float)((double)M.reset_center[k] + (double)M.reset_spread[k] * (2.0 * (double)u - 1.0));
     }
 #pragma unroll
     for (int k = 0; k < 3; k++) { W.bpos[k] = M.reset_base_pos[k]; W.bw[k] = 0.f; W.bv[k] = 0.f; }
@@ -1248,7 +1279,7 @@ RS_HD void env_reset_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, ui
     if (M.flag_task) flag_reposition(M, E, seed, env_id, true);     // humanoid_task() (gym_humanoid_flagrun.py:17-19)
     double dist; float pitch; int al;
     calc_state_flag(M, E, seed, env_id, obs, ostride, &dist, &pitch, &al, cs);
-    E.potential = -dist / M.dt_env;
+    E.potential = M.task_kind == RS_TASK_REACHER ? -100.0 * dist : -dist / M.dt_env;
 }
 template <int NL, int MC, bool SL>
 RS_HD void env_reset(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, uint32_t seed, uint32_t env_id, float* obs, int ostride) {

@@ -82,8 +82,8 @@ inline int build_dev_model(const rs_model_desc* m, DevModel* D, const char** err
     for (int k = 0; k < 3; k++) D->reset_base_pos[k] = (float)m->reset_base_pos[k];
     for (int k = 0; k < 4; k++) D->reset_base_quat[k] = (float)m->reset_base_quat[k];
     D->reset_set_base = m->reset_set_base;
-    D->task_kind = m->task_kind; D->task_swingup = m->task_swingup; D->task_link = m->task_link; D->n_reset = m->n_reset;
-    for (int k = 0; k < m->n_reset && k < MA; k++) { D->reset_dof[k] = m->reset_dof[k]; D->reset_center[k] = (float)m->reset_center[k]; }
+    D->task_kind = m->task_kind; D->task_swingup = m->task_swingup; D->task_link = m->task_link; D->task_link2 = m->task_link2; D->n_reset = m->n_reset;
+    for (int k = 0; k < m->n_reset && k < MA; k++) { D->reset_dof[k] = m->reset_dof[k]; D->reset_center[k] = (float)m->reset_center[k]; D->reset_spread[k] = (float)m->reset_spread[k]; }
     for (int k = 0; k < 4; k++) D->task_dof[k] = m->task_dof[k];
     D->flag_task = m->flag_task; D->flag_timeout_steps = m->flag_timeout_steps;
     D->flag_halflen = m->flag_halflen; D->flag_halfwidth = m->flag_halfwidth;

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 MODEL_DIR = os.path.join(_HERE, "models")
 
 RS_ALIVE_Z_AND_PITCH, RS_ALIVE_Z, RS_ALIVE_ALWAYS, RS_ALIVE_CHEETAH = 0, 1, 2, 3
-RS_TASK_WALKER, RS_TASK_PENDULUM, RS_TASK_DOUBLE_PENDULUM = 0, 1, 2
+RS_TASK_WALKER, RS_TASK_PENDULUM, RS_TASK_DOUBLE_PENDULUM, RS_TASK_REACHER = 0, 1, 2, 3
 
 ENV_SPECS = {
     # id: xml, robot_name, A, O, power, foot_list, alive rule/params, per-joint coef overrides
@@ -28,6 +28,13 @@ ENV_SPECS = {
         xml="walker2d.xml", robot="torso", A=6, O=22, power=0.40, feet=["foot", "foot_left"],
         alive_rule=RS_ALIVE_Z_AND_PITCH, alive_z=0.8, alive_bonus=1.0, cost_scale=1.0,
         initial_z=None, coef={"foot_joint": 30.0, "foot_left_joint": 30.0}, reward_threshold=2500.0),
+    "RoboschoolReacher-v1": dict(          # gym_reacher.py: zero gravity, arm + target (two top-level bodies), never done
+        xml="reacher.xml", robot="body0", A=2, O=9, power=1.0, feet=[],
+        alive_rule=RS_ALIVE_ALWAYS, alive_z=0.0, alive_bonus=0.0, cost_scale=1.0,
+        initial_z=None, coef={"joint0": 0.05, "joint1": 0.05}, no_floor=True, timestep=0.0165, frame_skip=1, gravity=0.0,
+        act_joints=["joint0", "joint1"], max_contacts=4, reward_threshold=18.0, max_episode_steps=150,
+        task=dict(kind=RS_TASK_REACHER, dofs=["joint0", "joint1", "target_x", "target_y"], link="fingertip", link2="target",
+                  reset=[("target_x", 0.0, 0.27), ("target_y", 0.0, 0.27), ("joint0", 0.0, 3.14), ("joint1", 0.0, 3.14)])),
     "RoboschoolHalfCheetah-v1": dict(      # gym_mujoco_walkers.py:40-59
         xml="half_cheetah.xml", robot="torso", A=6, O=26, power=0.90,
         feet=["ffoot", "fshin", "fthigh", "bfoot", "bshin", "bthigh"],
@@ -144,16 +151,19 @@ def apply_task(m: ModelDesc, spec: dict) -> ModelDesc:
         for k, n in enumerate(task["dofs"]):
             m.task_dof[k] = m.dof_idx[jn.index(n)]
         m.task_link = ln.index(task["link"]) if "link" in task else -1
+        m.task_link2 = ln.index(task["link2"]) if "link2" in task else -1
         m.n_reset = len(task["reset"])
-        for k, (n, c) in enumerate(task["reset"]):
-            m.reset_dof[k] = m.dof_idx[jn.index(n)]
-            m.reset_center[k] = c
+        for k, r in enumerate(task["reset"]):
+            m.reset_dof[k] = m.dof_idx[jn.index(r[0])]
+            m.reset_center[k] = r[1]
+            m.reset_spread[k] = r[2] if len(r) > 2 else 0.1
     else:   # forward walkers: every ordered joint, U(-0.1, 0.1) about 0 (gym_forward_walker.py:25-26)
         m.task_kind = RS_TASK_WALKER
         m.n_reset = m.n_act
         for k in range(m.n_act):
             m.reset_dof[k] = m.act_dof[k]
             m.reset_center[k] = 0.0
+            m.reset_spread[k] = 0.1
     rb = spec.get("reset_base")
     if rb:
         m.reset_set_base = 1
@@ -165,7 +175,7 @@ def apply_task(m: ModelDesc, spec: dict) -> ModelDesc:
         m.flag_task = 1
         m.flag_timeout_steps = int(fl["timeout"] // m.frame_skip)   # 600/frame_skip (gym_humanoid_flagrun.py:35)
         m.flag_halflen, m.flag_halfwidth = fl["halflen"], fl["halfwidth"]
-    m.max_episode_steps = 1000
+    m.max_episode_steps = spec.get("max_episode_steps", 1000)
     m.max_contacts = spec.get("max_contacts", 16)
     m.meta["env_id"] = spec.get("env_id", "")
     m.meta["reward_threshold"] = spec.get("reward_threshold")
@@ -177,7 +187,7 @@ def compile_env(env_id, assets_dir, **kw):
     spec = dict(ENV_SPECS[env_id], env_id=env_id)
     m = mjcf.compile_mjcf(os.path.join(assets_dir, spec["xml"]),
                           has_floor=not spec.get("no_floor", False),
-                          timestep=spec.get("timestep", 0.0165 / 4),
+                          timestep=spec.get("timestep", 0.0165 / 4), gravity=spec.get("gravity", 9.8),
                           frame_skip=spec.get("frame_skip", 4), **kw)
     return apply_task(m, spec)
 

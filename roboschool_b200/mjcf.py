@@ -288,9 +288,12 @@ def compile_mjcf(xml_path, honour_density=False, honour_damping=False, has_floor
             defaults[ch.tag] = dict(ch.attrib)
     wb = root.find("worldbody")
     bodies = [ch for ch in wb if ch.tag == "body"]
-    if len(bodies) != 1:
-        raise NotImplementedError("expected exactly one top-level body, got %d" % len(bodies))
-    top = _parse_body(bodies[0], defaults, degrees)
+    if len(bodies) == 0:
+        raise NotImplementedError("no top-level body")
+    tops = [_parse_body(b, defaults, degrees) for b in bodies]
+    if len(tops) > 1 and not all(t.joints for t in tops):
+        raise NotImplementedError("several top-level bodies are supported only when each hangs from the world by joints")
+    top = tops[0]
 
     m = ModelDesc()
     links = []   # dicts
@@ -307,8 +310,9 @@ def compile_mjcf(xml_path, honour_density=False, honour_damping=False, has_floor
         m.base_mass = 0.0
         base_name = "world"
         base_thresh = CONTACT_BREAKING_THRESHOLD
-        # anchor frame = world; the top body is attached by its own joints
-        pending = [(top, -1, np.zeros(3), np.eye(3), True)]
+        # anchor frame = world; each top body is attached by its own joints.  (Bullet makes one multibody per top-level
+        # body -- reacher.xml: arm and target; hung from one fixed anchor they stay dynamically independent.)
+        pending = [(t, -1, np.zeros(3), np.eye(3), True) for t in tops]
         base_pos = np.zeros(3)
         base_rot = np.eye(3)
     else:

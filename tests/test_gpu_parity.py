@@ -9,7 +9,7 @@ from roboschool_b200.envspec import load_env_model
 pytestmark = pytest.mark.gpu
 
 ENVS = ["RoboschoolHopper-v1", "RoboschoolAnt-v1", "RoboschoolHumanoid-v1", "RoboschoolInvertedPendulum-v1",
-        "RoboschoolHumanoidFlagrun-v1", "RoboschoolWalker2d-v1", "RoboschoolHalfCheetah-v1", "RoboschoolInvertedDoublePendulum-v1"]
+        "RoboschoolHumanoidFlagrun-v1", "RoboschoolWalker2d-v1", "RoboschoolHalfCheetah-v1", "RoboschoolInvertedDoublePendulum-v1", "RoboschoolReacher-v1"]
 STEP_ENVS = ENVS
 # Per env-step (= 4 sub-steps) error of the fp32 CUDA path against the fp64 oracle, relative to
 # max(1, |state|_inf), over seeded random-action rollouts.  The dynamics are non-smooth (contact

@@ -15,7 +15,7 @@ def emul():
 
 
 @pytest.mark.parametrize("static", [False, True], ids=["generic", "static-pooled"])
-@pytest.mark.parametrize("env_id", ["RoboschoolInvertedPendulum-v1", "RoboschoolInvertedDoublePendulum-v1", "RoboschoolHopper-v1", "RoboschoolWalker2d-v1", "RoboschoolHalfCheetah-v1", "RoboschoolAnt-v1",
+@pytest.mark.parametrize("env_id", ["RoboschoolInvertedPendulum-v1", "RoboschoolInvertedDoublePendulum-v1", "RoboschoolReacher-v1", "RoboschoolHopper-v1", "RoboschoolWalker2d-v1", "RoboschoolHalfCheetah-v1", "RoboschoolAnt-v1",
                                     "RoboschoolHumanoid-v1", "RoboschoolHumanoidFlagrun-v1"])
 def test_emul_teacher_forced(env_id, static, emul, oracle_lib):
     """static=True runs the compile-time-topology sweeps with the pooled row builder (rs_static.cuh,

@@ -85,7 +85,7 @@ def test_determinism_and_thread_independence(oracle_lib):
 
 
 @pytest.mark.parametrize("env_id", ["RoboschoolInvertedPendulum-v1", "RoboschoolInvertedPendulumSwingup-v1",
-                                    "RoboschoolInvertedDoublePendulum-v1", "RoboschoolHopper-v1", "RoboschoolWalker2d-v1",
+                                    "RoboschoolInvertedDoublePendulum-v1", "RoboschoolReacher-v1", "RoboschoolHopper-v1", "RoboschoolWalker2d-v1",
                                     "RoboschoolHalfCheetah-v1", "RoboschoolAnt-v1", "RoboschoolHumanoid-v1", "RoboschoolHumanoidFlagrun-v1"])
 def test_epilogue_matches_reference_python(env_id, oracle_lib):
     """Golden vectors made by the reference's own gym_forward_walker.py (tools/gen_golden_epilogue.py)."""

@@ -287,6 +287,7 @@ if __name__ == "__main__":
     generate("RoboschoolInvertedPendulum-v1", "RoboschoolInvertedPendulum")
     generate("RoboschoolInvertedPendulumSwingup-v1", "RoboschoolInvertedPendulumSwingup")
     generate("RoboschoolInvertedDoublePendulum-v1", "RoboschoolInvertedDoublePendulum")
+    generate("RoboschoolReacher-v1", "RoboschoolReacher")
     generate("RoboschoolHopper-v1", "RoboschoolHopper")
     generate("RoboschoolWalker2d-v1", "RoboschoolWalker2d")
     generate("RoboschoolHalfCheetah-v1", "RoboschoolHalfCheetah")
