@@ -39,7 +39,11 @@ class _Spec:
 
 
 @pytest.mark.parametrize("cls,env_id", [("RoboschoolHopper", "RoboschoolHopper-v1"), ("RoboschoolAnt", "RoboschoolAnt-v1"),
-                                        ("RoboschoolHumanoid", "RoboschoolHumanoid-v1")])
+                                        ("RoboschoolHumanoid", "RoboschoolHumanoid-v1"), ("RoboschoolWalker2d", "RoboschoolWalker2d-v1"),
+                                        ("RoboschoolHalfCheetah", "RoboschoolHalfCheetah-v1"),
+                                        ("RoboschoolInvertedPendulum", "RoboschoolInvertedPendulum-v1"),
+                                        ("RoboschoolInvertedDoublePendulum", "RoboschoolInvertedDoublePendulum-v1"),
+                                        ("RoboschoolReacher", "RoboschoolReacher-v1")])
 def test_reference_env_runs_on_shim_and_matches_fused_path(cls, env_id, ref_roboschool, oracle_lib):
     from roboschool_b200 import envspec
     env = getattr(ref_roboschool, cls)()
@@ -47,14 +51,17 @@ def test_reference_env_runs_on_shim_and_matches_fused_path(cls, env_id, ref_robo
     env.seed(3)
     obs0 = env.reset()
     m = envspec.load_env_model(env_id)
-    assert obs0.shape == (m.obs_dim,) and obs0.dtype == np.float32
-    assert [j.name for j in env.ordered_joints] == m.meta["ordered_joints"]
+    assert obs0.shape == (m.obs_dim,)
+    if m.task_kind == 0:
+        assert obs0.dtype == np.float32
+        assert [j.name for j in env.ordered_joints] == m.meta["ordered_joints"]
     # take the shim's post-reset state as the start of a fused (batched-path) oracle rollout
     robot = env.cpp_robot
     s0 = robot._backend.get_state()[0]
     o = oracle_lib.OracleWorld(m, 1)
     o.set_state(0, s0)
-    o.set_episode(0, env.potential, env.initial_z if env.initial_z is not None else -1.0, np.zeros(m.n_feet), 0)
+    iz = getattr(env, "initial_z", None)
+    o.set_episode(0, env.potential, iz if iz is not None else -1.0, np.zeros(m.n_feet), 0)
     rng = np.random.RandomState(0)
     for t in range(30):
         a = rng.uniform(-1, 1, m.n_act).astype(np.float32)
