@@ -270,7 +270,6 @@ struct Work {
     float cdat[2][MC][CDAT];
     int ccount[2];
     int cur;
-    float gw[MG][6];             // world end points of the collision geoms (this sub-step)
     int n_rows, n_contacts;      // of the last solve (reported)
 };
 
@@ -706,10 +705,19 @@ RS_HD void manifold_refresh(Manifold4& mf, const BodyXf& XA, const BodyXf& XB, i
     }
 }
 
+// world end points of geom g from its body's transform (sphere: both ends coincide)
+RS_HD void geom_ends(const DevModel& M, int g, const BodyXf& X, float* e) {
+    xf_to_world(X, M.g_p0[g], e);
+    if (M.g_type[g] == RS_GEOM_CAPSULE) xf_to_world(X, M.g_p1[g], e + 3);
+    else { e[3] = e[0]; e[4] = e[1]; e[5] = e[2]; }
+}
+
 // one manifold (floor geom k < n_geoms, or self pair k - n_geoms): cached points of the old list, narrowphase,
-// refresh, append to the new list.  gw: world end points of every geom.  oi / no: cursors into the old / new list.
+// refresh, append to the new list.  The geom end points are rebuilt from the body transform, which is fetched once
+// (a manifold reaches this function only if the broadphase flagged it or it still holds points: a handful per env).
+// oi / no: cursors into the old / new list.
 template <int NL, int MC, bool SL>
-RS_HD void collide_manifold(const DevModel& M, Work<NL, MC, SL>& W, const float (*gw)[6], int k, int old, int nw, int nold, int& oi, int& no) {
+RS_HD void collide_manifold(const DevModel& M, Work<NL, MC, SL>& W, int k, int old, int nw, int nold, int& oi, int& no) {
     Manifold4 mf; mf.n = 0;
     while (oi < nold && W.ckey[old][oi] == k) {
 #pragma unroll
@@ -725,8 +733,10 @@ RS_HD void collide_manifold(const DevModel& M, Work<NL, MC, SL>& W, const float 
         float thr = M.break_thresh[b];
         BodyXf XA;
         load_xf(W, b, XA);
+        float ge[6];
+        geom_ends(M, k, XA, ge);
         // support vertex in -z: lower end sphere, first end wins ties
-        const float* c = (M.g_type[k] == RS_GEOM_CAPSULE && gw[k][5] < gw[k][2]) ? gw[k] + 3 : gw[k];
+        const float* c = (M.g_type[k] == RS_GEOM_CAPSULE && ge[5] < ge[2]) ? ge + 3 : ge;
         float dist = c[2] - M.g_radius[k];
         if (dist < thr) {
             const float nz[3] = {0.f, 0.f, 1.f};
@@ -739,8 +749,12 @@ RS_HD void collide_manifold(const DevModel& M, Work<NL, MC, SL>& W, const float 
         int ga = M.pair_a[pk], gb = M.pair_b[pk];
         int bA = M.g_link[ga] + 1, bB = M.g_link[gb] + 1;
         float thr = M.pair_thresh[pk];
+        BodyXf XA, XB;
+        load_xf(W, bA, XA); load_xf(W, bB, XB);
+        float ea[6], eb[6];
+        geom_ends(M, ga, XA, ea); geom_ends(M, gb, XB, eb);
         float cA[3], cB[3];
-        seg_seg_closest(gw[ga], gw[ga] + 3, gw[gb], gw[gb] + 3, cA, cB);
+        seg_seg_closest(ea, ea + 3, eb, eb + 3, cA, cB);
         float d[3] = {cA[0] - cB[0], cA[1] - cB[1], cA[2] - cB[2]};
         float len = sqrtf(dot3(d, d)), rB = M.g_radius[gb];
         float dist = len - M.g_radius[ga] - rB;
@@ -749,15 +763,9 @@ RS_HD void collide_manifold(const DevModel& M, Work<NL, MC, SL>& W, const float 
             float nn[3] = {1.f, 0.f, 0.f};
             if (len > 1e-12f) { float il = 1.0f / len; nn[0] = d[0] * il; nn[1] = d[1] * il; nn[2] = d[2] * il; }
             float pOnB[3] = {cB[0] + nn[0] * rB, cB[1] + nn[1] * rB, cB[2] + nn[2] * rB};
-            BodyXf XA, XB;
-            load_xf(W, bA, XA); load_xf(W, bB, XB);
             manifold_add(mf, XA, XB, bB, nn, pOnB, dist, thr);
-            if (mf.n) manifold_refresh(mf, XA, XB, bB, thr);
-        } else if (mf.n) {
-            BodyXf XA, XB;
-            load_xf(W, bA, XA); load_xf(W, bB, XB);
-            manifold_refresh(mf, XA, XB, bB, thr);
         }
+        if (mf.n) manifold_refresh(mf, XA, XB, bB, thr);
     }
 #pragma unroll
     for (int s = 0; s < 4; s++) if (s < mf.n && no < MC && no < M.max_contacts) {
@@ -775,7 +783,7 @@ RS_HD void collide(const DevModel& M, Work<NL, MC, SL>& W) {
     const int nold = W.ccount[old];
     const int nman = M.n_geoms + M.n_pairs;
     // world end points of every geom, once per sub-step (each geom takes part in many pairs)
-    float (*gw)[6] = W.gw;
+    float gw[MG][6];
     for (int g = 0; g < M.n_geoms; g++) {
         int b = M.g_link[g] + 1;
         to_world(W, b, M.g_p0[g], gw[g]);
@@ -799,7 +807,7 @@ RS_HD void collide(const DevModel& M, Work<NL, MC, SL>& W) {
                 if (dx * dx + dy * dy + dz * dz > reach * reach) continue;
             }
         }
-        collide_manifold(M, W, gw, k, old, nw, nold, oi, no);
+        collide_manifold(M, W, k, old, nw, nold, oi, no);
     }
     W.ccount[nw] = no;
     W.cur = nw;

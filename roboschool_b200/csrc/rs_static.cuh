@@ -348,8 +348,6 @@ RS_HD void static_collide(const DevModel& M, Work<NL, MC, SL>& W, const float (*
     for (int w = 0; w < NW; w++) cand[w] = 0u;
     static_for<NG>([&](auto gc) {
         constexpr int g = decltype(gc)::value;
-#pragma unroll
-        for (int k = 0; k < 6; k++) W.gw[g][k] = gwr[g][k];
         if constexpr (T::g_floor[g] != 0) {
             constexpr float rad = T::g_radius[g], thr = T::g_thresh[g];
             const float zmin = fminf(gwr[g][2], gwr[g][5]) - rad;
@@ -384,7 +382,7 @@ RS_HD void static_collide(const DevModel& M, Work<NL, MC, SL>& W, const float (*
         while (m) {
             const int k = w * 32 + rs_ctz(m);
             m &= m - 1u;
-            collide_manifold(M, W, W.gw, k, old, nw, nold, oi, no);
+            collide_manifold(M, W, k, old, nw, nold, oi, no);
         }
     }
     W.ccount[nw] = no;
