@@ -1,6 +1,10 @@
 // rs_mlp.cu -- agent_zoo v1 policy forward: relu(relu(x W1 + b1) W2 + b2) W3 + b3
 // (agent_zoo/RoboschoolHumanoid_v1_2017jul.py:21-34,63-68), batched over envs on the tensor cores.
 //
+// The default kernel is the tcgen05 / TMEM one in rs_mlp_tc5.cu.  This file holds the policy object, the C ABI and the
+// round-1 mma.sync kernel, kept selectable (RS_MLP_TC5=0) as the measured baseline the tcgen05 kernel is compared with.
+//
+// mma.sync kernel:
 // Design: persistent CTAs (one per SM).  The whole weight set is staged ONCE per CTA in shared memory as
 // fp16, transposed (N-major) so a B fragment is one conflict-free 32-bit load.  Each warp owns 16 envs and
 // runs them through the three layers with mma.sync.m16n8k16 (fp16 in, fp32 accumulate).  The accumulator
@@ -13,6 +17,8 @@
 #include <string>
 #include <vector>
 #include "../../include/roboschool_b200.h"
+#include "rs_mlp_tc5.h"
+#include <stdlib.h>
 
 int rs_set_error(const char* s);
 static int mfail(const std::string& s) { rs_set_error(s.c_str()); return 1; }
@@ -23,6 +29,10 @@ struct rs_policy {
     int in_p, out_p, variant;
     void* w;                 // packed fp16 transposed weights + fp32 biases (device)
     size_t bytes;
+    // tcgen05 / TMEM kernel (rs_mlp_tc5.cu): operand-layout weight image
+    int tc5_variant, n_sm, use_tc5;
+    void* tc5_image;
+    size_t tc5_smem;
 };
 
 __device__ __forceinline__ void mma_f16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
@@ -158,6 +168,16 @@ extern "C" int rs_policy_create(int in_dim, int h1, int h2, int out_dim, const f
     else if (h1 == 128 && h2 == 64 && p->in_p == 32 && p->out_p == 8) { p->variant = 2; rc = create_variant<32, 128, 64, 8>(p, w1, b1, w2, b2, w3, b3); }
     else { delete p; return mfail("rs_policy_create: unsupported layer sizes (agent_zoo v1 shapes only: 44-256-128-17, {15,22,26,28}-128-64-{3,6,8})"); }
     if (rc) { delete p; return 1; }
+    p->tc5_variant = rs_tc5_supported(in_dim, h1, h2, out_dim);
+    p->tc5_image = nullptr; p->use_tc5 = 0;
+    if (p->tc5_variant) {
+        cudaDeviceProp prop;
+        MCK(cudaGetDeviceProperties(&prop, device));
+        p->n_sm = prop.multiProcessorCount;
+        if (rs_tc5_pack(p->tc5_variant, in_dim, out_dim, w1, b1, w2, b2, w3, b3, &p->tc5_image, &p->tc5_smem)) { cudaGetLastError(); p->tc5_variant = 0; }
+        const char* e = getenv("RS_MLP_TC5");       // RS_MLP_TC5=0 selects the mma.sync kernel below (A/B measurements)
+        p->use_tc5 = p->tc5_variant && !(e && atoi(e) == 0);
+    }
     *out = p;
     return 0;
 }
@@ -166,6 +186,7 @@ extern "C" int rs_policy_destroy(rs_policy* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     cudaFree(p->w);
+    if (p->tc5_image) cudaFree(p->tc5_image);
     delete p;
     return 0;
 }
@@ -176,6 +197,11 @@ extern "C" int rs_policy_forward(rs_policy* p, const float* obs_dev, float* act_
     int tiles = (n + 16 * MLP_WARPS - 1) / (16 * MLP_WARPS);
     int grid = tiles < 148 ? tiles : 148;
     cudaStream_t st = (cudaStream_t)stream;
+    if (p->use_tc5) {
+        if (rs_tc5_forward(p->tc5_variant, p->tc5_image, p->tc5_smem, obs_dev, act_dev, n, p->in_dim, p->out_dim, p->n_sm, st))
+            return mfail("rs_policy_forward: tcgen05 kernel launch failed");
+        return 0;
+    }
     const unsigned char* w = (const unsigned char*)p->w;
     switch (p->variant) {
         case 0: k_mlp<48, 256, 128, 24><<<grid, 32 * MLP_WARPS, p->bytes, st>>>(w, obs_dev, act_dev, n, p->in_dim, p->out_dim); break;
