@@ -103,6 +103,11 @@ int rs_world_get_episode(rs_world* w, double* potential, float* initial_z, float
  * moves int32[n] (flag_timeout) and RNG draws consumed by flag_reposition uint32[n].  NULL pointers are skipped. */
 int rs_world_set_flags(rs_world* w, const double* target_xy, const int* timeout, const uint32_t* draws);
 int rs_world_get_flags(rs_world* w, double* target_xy, int* timeout, uint32_t* draws);
+/* FlagrunHarder (gym_humanoid_flagrun.py:73-169) per-env task state, float64[n][8]: task (0 walk, 1 stand up, 2 roll over),
+ * on_ground_frame_counter, crawl_start_potential is set (0/1), crawl_start_potential, crawl_ignored_potential, and the
+ * RepeatUnderlearnedTasks history of each task (bits 0-9 = last outcomes, newest in bit 0; bits 16+ = how many). */
+int rs_world_set_task_state(rs_world* w, const double* state_host);
+int rs_world_get_task_state(rs_world* w, double* state_host);
 
 /* World::query_body_position (physics-bullet.cpp:440-495): per env, per body (base first, then
  * links): COM position3, quaternion4 (xyzw), linear velocity3  -> out_host[n_envs][1+L][10]. */

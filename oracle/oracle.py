@@ -58,6 +58,8 @@ def lib():
         L.oracle_foot_flags.argtypes = [P, I, ip, ip]
         L.oracle_set_flag.argtypes = [P, I, D, D, I, U]
         L.oracle_get_flag.argtypes = [P, I, dp, dp, ip, ctypes.POINTER(U)]
+        L.oracle_get_task_state.argtypes = [P, I, dp]
+        L.oracle_set_task_state.argtypes = [P, I, dp]
         L.oracle_hash.argtypes = [U, U, U, U]
         L.oracle_hash.restype = U
         _LIB = L
@@ -118,6 +120,12 @@ class OracleWorld:
 
     def set_flag(self, env, tx, ty, timeout, draws):
         self.L.oracle_set_flag(self.h, env, tx, ty, int(timeout), int(draws))
+
+    def get_task_state(self, env):
+        s = np.zeros(8); self.L.oracle_get_task_state(self.h, env, _dp(s)); return s
+
+    def set_task_state(self, env, s):
+        s = np.ascontiguousarray(s, dtype=np.float64); self.L.oracle_set_task_state(self.h, env, _dp(s))
 
     def get_flag(self, env):
         tx, ty = ctypes.c_double(), ctypes.c_double()

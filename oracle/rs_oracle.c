@@ -78,6 +78,13 @@ typedef struct {
     double target_x, target_y;
     int flag_timeout;
     uint32_t flag_draws;
+    /* FlagrunHarder (gym_humanoid_flagrun.py:73-160): task of this episode, frames spent on the ground, crawl bookkeeping
+     * of calc_potential, per-task history of the last <=10 episode outcomes (bits 0-9 newest first, length in bits 16+) */
+    int task, on_ground;
+    int crawl_valid;
+    double crawl_start, crawl_ignored;
+    uint32_t hist[3];
+    double elec_cost;
     /* outputs of the last env step */
     double obs[8 + 2 * RS_MAX_ACT + RS_MAX_FEET];
     double reward, rewards5[5];
@@ -930,6 +937,67 @@ static void flag_reposition(const rs_model_desc *m, oenv *e, uint32_t seed, uint
     e->flag_timeout = m->flag_timeout_steps;
 }
 
+/* FlagrunHarder.potential_leak (gym_humanoid_flagrun.py:141-147); valid after calc_state (kinematics) */
+static double harder_leak(const rs_model_desc *m, const oenv *e) {
+    double z1 = e->pos[m->body_link + 1][2], z2 = e->pos[m->task_link + 1][2];
+    double z = 0.7 * z1 + 0.3 * z2;
+    z = z < 0 ? 0 : (z > 0.7 ? 0.7 : z);
+    return 0.5 + 1.5 * (z / 0.7);
+}
+/* FlagrunHarder.calc_potential (gym_humanoid_flagrun.py:149-169): progress towards the flag does not count while crawling */
+static double harder_potential(const rs_model_desc *m, oenv *e, double dist) {
+    double frp = -dist / m->dt_env;
+    if (e->pos[m->body_link + 1][2] < 0.8) {
+        if (!e->crawl_valid) { e->crawl_start = frp - e->crawl_ignored; e->crawl_valid = 1; }
+        e->crawl_ignored = frp - e->crawl_start;
+        frp = e->crawl_start;
+    } else {
+        frp -= e->crawl_ignored;
+        e->crawl_valid = 0;
+    }
+    return frp + harder_leak(m, e) * 100;
+}
+static double task_potential(const rs_model_desc *m, oenv *e, double dist) {
+    if (m->task_kind == RS_TASK_REACHER) return -100.0 * dist;
+    if (m->flag_task == 2) return harder_potential(m, e, dist);
+    return -dist / m->dt_env;
+}
+/* FlagrunHarder.alive_bonus (gym_humanoid_flagrun.py:101-139).  The flying cube itself is not simulated;
+ * its five np_random draws are still consumed so that the flag positions drawn later stay on the reference's stream. */
+static double harder_alive(const rs_model_desc *m, oenv *e, double z) {
+    if (e->frame % 30 == 0 && e->frame > 100 && e->on_ground == 0) e->flag_draws += 5;
+    if (z < 0.8) {
+        if (e->task == 0) e->on_ground = 10000;      /* TASK_WALK: ends the episode immediately */
+        e->on_ground += 1;
+        e->elec_cost = -2.0 / 5.0;                   /* RoboschoolHumanoid.electricity_cost (class attribute, -2.0) / 5 */
+    } else if (e->on_ground > 0) {
+        e->on_ground -= 1;
+        e->elec_cost = -2.0 / 2.0;
+    } else {
+        e->elec_cost = -2.0 / 2.0;
+    }
+    return e->on_ground < 170 ? harder_leak(m, e) : -1;
+}
+/* RepeatUnderlearnedTasks (gym_humanoid_flagrun.py:47-64) */
+static int harder_pick_task(oenv *e, double u) {
+    double prob[3], sum = 0, cdf[3];
+    for (int i = 0; i < 3; i++) {
+        int len = (int)(e->hist[i] >> 16), nz = __builtin_popcount(e->hist[i] & 0x3FFu);
+        prob[i] = 1 - nz / (1.0 + len);
+        sum += prob[i];
+    }
+    double acc = 0;
+    for (int i = 0; i < 3; i++) { acc += prob[i] / sum; cdf[i] = acc; }
+    int idx = 0;
+    for (int i = 0; i < 3; i++) if (cdf[i] / cdf[2] <= u) idx++;
+    return idx > 2 ? 2 : idx;
+}
+static void harder_task_completed(oenv *e, int completed) {
+    uint32_t h = e->hist[e->task];
+    uint32_t len = h >> 16; if (len < 10) len++;
+    e->hist[e->task] = (((h << 1) | (completed ? 1u : 0u)) & 0x3FFu) | (len << 16);
+}
+
 /* RoboschoolHumanoidFlagrun.calc_state (gym_humanoid_flagrun.py:37-44) */
 static void calc_state_flag(const rs_model_desc *m, oenv *e, double *dist, uint32_t seed, uint32_t env_id) {
     if (!m->flag_task) { calc_state(m, e, dist); return; }
@@ -938,7 +1006,7 @@ static void calc_state_flag(const rs_model_desc *m, oenv *e, double *dist, uint3
     if (*dist < 1.0 || e->flag_timeout <= 0) {
         flag_reposition(m, e, seed, env_id, 0);
         calc_state(m, e, dist);
-        e->potential = -*dist / m->dt_env;
+        e->potential = task_potential(m, e, *dist);
     }
 }
 
@@ -980,6 +1048,7 @@ static void epilogue(const rs_model_desc *m, oenv *e, const double *a, uint32_t 
     double z = e->obs[0] + e->initial_z;   /* state[0]+initial_z, state already float32 & clipped */
     double alive;
     if (m->alive_rule == RS_ALIVE_Z_AND_PITCH) alive = (z > m->alive_z && fabs(pitch) < 1.0) ? m->alive_bonus : -1;
+    else if (m->flag_task == 2) alive = harder_alive(m, e, z);
     else if (m->alive_rule == RS_ALIVE_Z) alive = (z > m->alive_z) ? m->alive_bonus : -1;
     else if (m->alive_rule == RS_ALIVE_CHEETAH)   /* gym_mujoco_walkers.py:50-52: stale feet_contact of shins and thighs */
         alive = (fabs(pitch) < 1.0 && !e->feet_contact[1] && !e->feet_contact[2] && !e->feet_contact[4] && !e->feet_contact[5]) ? m->alive_bonus : -1;
@@ -987,7 +1056,7 @@ static void epilogue(const rs_model_desc *m, oenv *e, const double *a, uint32_t 
     int done = alive < 0;
     for (int k = 0; k < m->obs_dim; k++) if (!isfinite(e->obs[k])) done = 1;
     double pot_old = e->potential;
-    e->potential = -dist / m->dt_env;
+    e->potential = task_potential(m, e, dist);
     double progress = e->potential - pot_old;
     double feet_cost = 0;
     for (int f = 0; f < m->n_feet; f++) {
@@ -1006,12 +1075,15 @@ static void epilogue(const rs_model_desc *m, oenv *e, const double *a, uint32_t 
         if (m->max_vel[li] > 0) spd /= (float)m->max_vel[li]; else spd *= (m->jtype[li] == RS_JOINT_REVOLUTE) ? 0.1f : 0.5f;
         s1 += fabs(a[k] * (double)spd);
     }
-    double elec = m->electricity_cost * (s1 / A) + m->stall_torque_cost * (s2 / A);
+    double elec = (m->flag_task == 2 ? e->elec_cost : m->electricity_cost) * (s1 / A) + m->stall_torque_cost * (s2 / A);
     double jl = e->rewards5[3];
     e->rewards5[0] = alive; e->rewards5[1] = progress; e->rewards5[2] = elec; e->rewards5[3] = jl; e->rewards5[4] = feet_cost;
     e->reward = alive + progress + elec + jl + feet_cost;
     e->done = done;
     e->frame++;
+    if (m->flag_task == 2 && ((done && !e->done_latch) || e->frame == m->max_episode_steps))   /* episode_over (gym_forward_walker.py:127-128) */
+        harder_task_completed(e, e->frame == m->max_episode_steps);
+    e->done_latch |= done;
 }
 
 /* counter-based RNG shared bit-for-bit with the CUDA path (integer hash -> 24-bit uniform) */
@@ -1037,23 +1109,34 @@ static void env_reset(const rs_model_desc *m, oenv *e, int nman, uint32_t seed, 
     }
     v3cpy(e->base_pos, m->reset_base_pos);
     memcpy(e->base_quat, m->reset_base_quat, sizeof e->base_quat);
+    e->task = 0;
+    if (m->flag_task == 2) e->task = harder_pick_task(e, rs_uniform(seed, env_id, e->episode, 1500u));   /* humanoid_task(): decide_best_task() */
     if (m->reset_set_base && m->reset_yaw_spread > 0) {
         double u = rs_uniform(seed, env_id, e->episode, 1000u);
         double yaw = m->reset_yaw_spread * (2.0 * u - 1.0);
-        /* Pose::set_rpy(0,0,yaw) python-binding.cpp:42-55 */
-        e->base_quat[0] = 0; e->base_quat[1] = 0; e->base_quat[2] = sin(0.5 * yaw); e->base_quat[3] = cos(0.5 * yaw);
+        /* set_initial_orientation (gym_mujoco_walkers.py:106-128): TASK_WALK upright at z+1.4, TASK_STAND_UP lying face down
+         * (pitch pi/2, z+0.45), TASK_ROLL_OVER on the back (pitch 3pi/2-0.15, z+0.22); Pose::set_rpy python-binding.cpp:42-55 */
+        double pitch = 0, roll = 0;
+        if (e->task == 1) { pitch = M_PI / 2; e->base_pos[2] = m->reset_base_pos[2] - 1.4 + 0.45; }
+        else if (e->task == 2) { pitch = M_PI * 3 / 2 - 0.15; e->base_pos[2] = m->reset_base_pos[2] - 1.4 + 0.22; }
+        double t0 = cos(yaw * 0.5), t1 = sin(yaw * 0.5), t2 = cos(roll * 0.5), t3 = sin(roll * 0.5), t4 = cos(pitch * 0.5), t5 = sin(pitch * 0.5);
+        e->base_quat[3] = t0 * t2 * t4 + t1 * t3 * t5;
+        e->base_quat[0] = t0 * t3 * t4 - t1 * t2 * t5;
+        e->base_quat[1] = t0 * t2 * t5 + t1 * t3 * t4;
+        e->base_quat[2] = t1 * t2 * t4 - t0 * t3 * t5;
     }
     v3set(e->base_w, 0, 0, 0); v3set(e->base_v, 0, 0, 0);
     for (int k = 0; k < nman; k++) e->man[k].n = 0;
     memset(e->feet_contact, 0, sizeof e->feet_contact);
     e->initial_z = m->initial_z;
-    e->frame = 0; e->done = 0;
+    e->frame = 0; e->done = 0; e->done_latch = 0;
     e->target_x = m->walk_target_x; e->target_y = m->walk_target_y;
     e->flag_timeout = 0; e->flag_draws = 0;
+    e->on_ground = 0; e->crawl_valid = 0; e->crawl_start = 0; e->crawl_ignored = 0; e->elec_cost = m->electricity_cost;
     if (m->flag_task) flag_reposition(m, e, seed, env_id, 1);
     double dist;
     calc_state_flag(m, e, &dist, seed, env_id);
-    e->potential = m->task_kind == RS_TASK_REACHER ? -100.0 * dist : -dist / m->dt_env;
+    e->potential = task_potential(m, e, dist);
 }
 
 /* =========================== exported API =========================== */
@@ -1104,6 +1187,17 @@ void oracle_set_flag(oracle_world *w, int env, double tx, double ty, int timeout
 void oracle_get_flag(const oracle_world *w, int env, double *tx, double *ty, int *timeout, uint32_t *draws) {
     const oenv *e = &w->env[env];
     *tx = e->target_x; *ty = e->target_y; *timeout = e->flag_timeout; *draws = e->flag_draws;
+}
+/* FlagrunHarder task state as 8 doubles: task, on_ground, crawl_valid, crawl_start, crawl_ignored, hist[0..2] */
+void oracle_get_task_state(const oracle_world *w, int env, double *out) {
+    const oenv *e = &w->env[env];
+    out[0] = e->task; out[1] = e->on_ground; out[2] = e->crawl_valid; out[3] = e->crawl_start; out[4] = e->crawl_ignored;
+    out[5] = e->hist[0]; out[6] = e->hist[1]; out[7] = e->hist[2];
+}
+void oracle_set_task_state(oracle_world *w, int env, const double *in) {
+    oenv *e = &w->env[env];
+    e->task = (int)in[0]; e->on_ground = (int)in[1]; e->crawl_valid = (int)in[2]; e->crawl_start = in[3]; e->crawl_ignored = in[4];
+    e->hist[0] = (uint32_t)in[5]; e->hist[1] = (uint32_t)in[6]; e->hist[2] = (uint32_t)in[7];
 }
 void oracle_reset(oracle_world *w, int env, uint32_t seed, uint32_t env_id) { env_reset(&w->m, &w->env[env], w->nman, seed, env_id); }
 void oracle_reset_all(oracle_world *w, uint32_t seed, uint32_t env_id0) {

@@ -1039,6 +1039,12 @@ struct Episode {
     uint32_t episode;
     int flag_timeout;            // Flagrun: env steps until the flag moves
     uint32_t flag_draws;         // Flagrun: RNG draws consumed by flag_reposition in this episode
+    // FlagrunHarder (gym_humanoid_flagrun.py:73-169): task of this episode (0 walk, 1 stand up, 2 roll over), frames on the
+    // ground, crawl bookkeeping of calc_potential, per-task history of the last <= 10 outcomes (bits 0-9, length in bits 16+)
+    int task, on_ground, crawl_valid, done_latch;
+    double crawl_start, crawl_ignored;
+    uint32_t hist[3];
+    float elec_cost;
 };
 
 struct StepOut {
@@ -1154,10 +1160,80 @@ RS_HD void flag_reposition(const DevModel& M, Episode& E, uint32_t seed, uint32_
     E.flag_timeout = M.flag_timeout_steps;
 }
 
+// ---- FlagrunHarder ----
+// potential_leak (gym_humanoid_flagrun.py:141-147); z1 torso, z2 pelvis (world), valid after the kinematics of calc_state
+RS_HD double harder_leak(float z1, float z2) {
+    double z = 0.7 * (double)z1 + 0.3 * (double)z2;
+    z = z < 0.0 ? 0.0 : (z > 0.7 ? 0.7 : z);
+    return 0.5 + 1.5 * (z / 0.7);
+}
+// calc_potential (:149-169): progress towards the flag does not count while crawling (torso below 0.8)
+RS_HD double harder_potential(const DevModel& M, Episode& E, double dist, float z1, float z2) {
+    double frp = -dist / M.dt_env;
+    if ((double)z1 < 0.8) {
+        if (!E.crawl_valid) { E.crawl_start = frp - E.crawl_ignored; E.crawl_valid = 1; }
+        E.crawl_ignored = frp - E.crawl_start;
+        frp = E.crawl_start;
+    } else {
+        frp -= E.crawl_ignored;
+        E.crawl_valid = 0;
+    }
+    return frp + harder_leak(z1, z2) * 100.0;
+}
+// alive_bonus (:101-139).  The flying cube is not simulated; its five np_random draws are still consumed.
+RS_HD float harder_alive(Episode& E, float z, float z1, float z2) {
+    if (E.frame % 30 == 0 && E.frame > 100 && E.on_ground == 0) E.flag_draws += 5;
+    if (z < 0.8f) {
+        if (E.task == 0) E.on_ground = 10000;
+        E.on_ground += 1;
+        E.elec_cost = -2.0f / 5.0f;
+    } else if (E.on_ground > 0) {
+        E.on_ground -= 1;
+        E.elec_cost = -2.0f / 2.0f;
+    } else {
+        E.elec_cost = -2.0f / 2.0f;
+    }
+    return E.on_ground < 170 ? (float)harder_leak(z1, z2) : -1.f;
+}
+// RepeatUnderlearnedTasks.decide_best_task / task_completed (:47-64)
+RS_HD int harder_pick_task(const Episode& E, double u) {
+    double prob[3], sum = 0.0, cdf[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const uint32_t bits = E.hist[i] & 0x3FFu;
+        int nz = 0;
+#pragma unroll
+        for (int b = 0; b < 10; b++) nz += (bits >> b) & 1u;
+        const int len = (int)(E.hist[i] >> 16);
+        prob[i] = 1.0 - (double)nz / (1.0 + (double)len);
+        sum += prob[i];
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { acc += prob[i] / sum; cdf[i] = acc; }
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) if (cdf[i] / cdf[2] <= u) idx++;
+    return idx > 2 ? 2 : idx;
+}
+RS_HD void harder_task_completed(Episode& E, bool completed) {
+    const uint32_t h = E.hist[E.task];
+    uint32_t len = h >> 16; if (len < 10u) len++;
+    E.hist[E.task] = (((h << 1) | (completed ? 1u : 0u)) & 0x3FFu) | (len << 16);
+}
+
+// the potential the reward's progress term differentiates: distance to the target, or FlagrunHarder's / Reacher's variant.
+// z1 / z2: world z of the robot body and of link M.task_link (FlagrunHarder: pelvis)
+RS_HD double task_potential(const DevModel& M, Episode& E, double dist, float z1, float z2) {
+    if (M.task_kind == RS_TASK_REACHER) return -100.0 * dist;
+    if (M.flag_task == 2) return harder_potential(M, E, dist, z1, z2);
+    return -dist / M.dt_env;
+}
+
 // RoboschoolHumanoidFlagrun.calc_state (gym_humanoid_flagrun.py:37-44) around the plain calc_state `cs`.
 // Returns true if the flag moved (the caller must then not count a potential jump as progress).
-template <class CS>
-RS_HD bool calc_state_flag(const DevModel& M, Episode& E, uint32_t seed, uint32_t env_id, float* obs, int ostride,
+template <int NL, int MC, bool SL, class CS>
+RS_HD bool calc_state_flag(const DevModel& M, const Work<NL, MC, SL>& W, Episode& E, uint32_t seed, uint32_t env_id, float* obs, int ostride,
                            double* dist, float* pitch, int* at_limit, CS&& cs) {
     if (!M.flag_task) { cs(obs, ostride, dist, pitch, at_limit); return false; }
     E.flag_timeout -= 1;
@@ -1165,7 +1241,7 @@ RS_HD bool calc_state_flag(const DevModel& M, Episode& E, uint32_t seed, uint32_
     if (*dist < 1.0 || E.flag_timeout <= 0) {
         flag_reposition(M, E, seed, env_id, false);
         cs(obs, ostride, dist, pitch, at_limit);   // state again, against the new flag
-        E.potential = -*dist / M.dt_env;           // avoid reward jump
+        E.potential = task_potential(M, E, *dist, W.pos[M.body_link + 1][2], W.pos[(M.task_link >= 0 ? M.task_link : M.body_link) + 1][2]);   // avoid reward jump
         return true;
     }
     return false;
@@ -1176,7 +1252,7 @@ template <int NL, int MC, bool SL, class CS>
 RS_HD void epilogue_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, const float* act, int astride, float* obs, int ostride, StepOut& out, CS&& cs,
                          uint32_t seed = 0, uint32_t env_id = 0) {
     double dist; float pitch; int at_limit;
-    calc_state_flag(M, E, seed, env_id, obs, ostride, &dist, &pitch, &at_limit, cs);
+    calc_state_flag(M, W, E, seed, env_id, obs, ostride, &dist, &pitch, &at_limit, cs);
     if (M.task_kind == RS_TASK_REACHER) {
         // gym_reacher.py step (:60-79): potential = -100 |fingertip - target|; never done
         const double pot_old = E.potential;
@@ -1212,8 +1288,10 @@ RS_HD void epilogue_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, con
         return;
     }
     float z = obs[0] + E.initial_z;
+    const float z_body = W.pos[M.body_link + 1][2], z_aux = W.pos[(M.task_link >= 0 ? M.task_link : M.body_link) + 1][2];
     float alive;
-    if (M.alive_rule == RS_ALIVE_Z_AND_PITCH) alive = (z > M.alive_z && fabsf(pitch) < 1.0f) ? M.alive_bonus : -1.f;
+    if (M.flag_task == 2) alive = harder_alive(E, z, z_body, z_aux);
+    else if (M.alive_rule == RS_ALIVE_Z_AND_PITCH) alive = (z > M.alive_z && fabsf(pitch) < 1.0f) ? M.alive_bonus : -1.f;
     else if (M.alive_rule == RS_ALIVE_Z) alive = (z > M.alive_z) ? M.alive_bonus : -1.f;
     else if (M.alive_rule == RS_ALIVE_CHEETAH)   // feet_contact still holds the previous step's flags here
         alive = (fabsf(pitch) < 1.0f && E.feet_contact[1] == 0.f && E.feet_contact[2] == 0.f && E.feet_contact[4] == 0.f && E.feet_contact[5] == 0.f) ? M.alive_bonus : -1.f;
@@ -1221,7 +1299,7 @@ RS_HD void epilogue_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, con
     int done = alive < 0.f;
     for (int k = 0; k < M.obs_dim; k++) if (!isfinite(obs[k * ostride])) done = 1;
     double pot_old = E.potential;
-    E.potential = -dist / M.dt_env;
+    E.potential = task_potential(M, E, dist, z_body, z_aux);
     float progress = (float)(E.potential - pot_old);
     // feet: World::bullet_contact_list(foot) -> floor / other parts (gym_forward_walker.py:106-112)
     float feet_cost = 0.f;
@@ -1244,12 +1322,16 @@ RS_HD void epilogue_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, con
         rel_joint(M, li, W.q[d], W.qd[d], &p, &s);
         s1 += fabsf(a * s); s2 += a * a;
     }
-    float elec = M.electricity_cost * (s1 / (float)A) + M.stall_torque_cost * (s2 / (float)A);
+    float elec = (M.flag_task == 2 ? E.elec_cost : M.electricity_cost) * (s1 / (float)A) + M.stall_torque_cost * (s2 / (float)A);
     float jl = M.joints_at_limit_cost * (float)at_limit;
     out.rewards5[0] = alive; out.rewards5[1] = progress; out.rewards5[2] = elec; out.rewards5[3] = jl; out.rewards5[4] = feet_cost;
     out.reward = alive + progress + elec + jl + feet_cost;
     out.done = done;
     E.frame++;
+    if (M.flag_task == 2) {   // episode_over (gym_forward_walker.py:127-128) -> RepeatUnderlearnedTasks.task_completed
+        if ((done && !E.done_latch) || E.frame == M.max_episode_steps) harder_task_completed(E, E.frame == M.max_episode_steps);
+        E.done_latch |= done;
+    }
 }
 
 template <int NL, int MC, bool SL>
@@ -1273,10 +1355,17 @@ RS_HD void env_reset_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, ui
     for (int k = 0; k < 3; k++) { W.bpos[k] = M.reset_base_pos[k]; W.bw[k] = 0.f; W.bv[k] = 0.f; }
 #pragma unroll
     for (int k = 0; k < 4; k++) W.bquat[k] = M.reset_base_quat[k];
+    E.task = 0;
+    if (M.flag_task == 2) E.task = harder_pick_task(E, (double)rs_uniform(seed, env_id, E.episode, 1500u));   // humanoid_task()
     if (M.reset_set_base && M.reset_yaw_spread > 0.f) {
         float u = rs_uniform(seed, env_id, E.episode, 1000u);
         double yaw = (double)M.reset_yaw_spread * (2.0 * (double)u - 1.0);
-        W.bquat[0] = 0.f; W.bquat[1] = 0.f; W.bquat[2] = (float)sin(0.5 * yaw); W.bquat[3] = (float)cos(0.5 * yaw);
+        // set_initial_orientation (gym_mujoco_walkers.py:106-128) + Pose::set_rpy (python-binding.cpp:42-55), roll = 0
+        double pitch = 0.0;
+        if (E.task == 1) { pitch = 1.5707963267948966; W.bpos[2] = M.reset_base_pos[2] - 1.4f + 0.45f; }
+        else if (E.task == 2) { pitch = 3.141592653589793 * 3 / 2 - 0.15; W.bpos[2] = M.reset_base_pos[2] - 1.4f + 0.22f; }
+        const double t0 = cos(yaw * 0.5), t1 = sin(yaw * 0.5), t4 = cos(pitch * 0.5), t5 = sin(pitch * 0.5);
+        W.bquat[3] = (float)(t0 * t4); W.bquat[0] = (float)(-t1 * t5); W.bquat[1] = (float)(t0 * t5); W.bquat[2] = (float)(t1 * t4);
     }
     W.ccount[0] = W.ccount[1] = 0; W.cur = 0;
     for (int k = 0; k < M.n_feet; k++) E.feet_contact[k] = 0.f;
@@ -1284,10 +1373,11 @@ RS_HD void env_reset_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, ui
     E.frame = 0;
     E.target_x = M.walk_target_x; E.target_y = M.walk_target_y;
     E.flag_timeout = 0; E.flag_draws = 0;
+    E.on_ground = 0; E.crawl_valid = 0; E.done_latch = 0; E.crawl_start = 0.0; E.crawl_ignored = 0.0; E.elec_cost = M.electricity_cost;
     if (M.flag_task) flag_reposition(M, E, seed, env_id, true);     // humanoid_task() (gym_humanoid_flagrun.py:17-19)
     double dist; float pitch; int al;
-    calc_state_flag(M, E, seed, env_id, obs, ostride, &dist, &pitch, &al, cs);
-    E.potential = M.task_kind == RS_TASK_REACHER ? -100.0 * dist : -dist / M.dt_env;
+    calc_state_flag(M, W, E, seed, env_id, obs, ostride, &dist, &pitch, &al, cs);
+    E.potential = task_potential(M, E, dist, W.pos[M.body_link + 1][2], W.pos[(M.task_link >= 0 ? M.task_link : M.body_link) + 1][2]);
 }
 template <int NL, int MC, bool SL>
 RS_HD void env_reset(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, uint32_t seed, uint32_t env_id, float* obs, int ostride) {

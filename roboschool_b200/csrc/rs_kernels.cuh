@@ -13,6 +13,7 @@ struct DevBuf {
     float* state; int* ccount; int* ckey; float* cdat;
     double* potential; float* initial_z; float* feet; int* frame; uint32_t* episode;
     double* target; int* flag_timeout; uint32_t* flag_draws;   // Flagrun: target [2][N], steps left, RNG draws used
+    int* hx_i; double* hx_d;   // FlagrunHarder: [7][N] task, on_ground, crawl_valid, done_latch, hist[3] ; [2][N] crawl_start, crawl_ignored
     float* rows; float* tau; float* rewards5; int* nrows; int* ncontacts;
     int N, S, MCcap, rec, maxr;
 };
@@ -50,6 +51,15 @@ __device__ __forceinline__ void load_env(const DevModel& M, const DevBuf& B, int
     for (int k = 0; k < M.n_feet; k++) E.feet_contact[k] = B.feet[(size_t)k * N + e];
     if (M.flag_task) { E.target_x = B.target[e]; E.target_y = B.target[(size_t)N + e]; E.flag_timeout = B.flag_timeout[e]; E.flag_draws = B.flag_draws[e]; }
     else { E.target_x = M.walk_target_x; E.target_y = M.walk_target_y; E.flag_timeout = 0; E.flag_draws = 0; }
+    if (M.flag_task == 2) {
+        E.task = B.hx_i[e]; E.on_ground = B.hx_i[(size_t)N + e]; E.crawl_valid = B.hx_i[(size_t)2 * N + e]; E.done_latch = B.hx_i[(size_t)3 * N + e];
+#pragma unroll
+        for (int k = 0; k < 3; k++) E.hist[k] = (uint32_t)B.hx_i[(size_t)(4 + k) * N + e];
+        E.crawl_start = B.hx_d[e]; E.crawl_ignored = B.hx_d[(size_t)N + e];
+    } else {
+        E.task = 0; E.on_ground = 0; E.crawl_valid = 0; E.done_latch = 0; E.hist[0] = E.hist[1] = E.hist[2] = 0u; E.crawl_start = 0.0; E.crawl_ignored = 0.0;
+    }
+    E.elec_cost = M.electricity_cost;
     W.n_rows = 0; W.n_contacts = 0;
 }
 
@@ -80,6 +90,12 @@ __device__ __forceinline__ void store_env(const DevModel& M, const DevBuf& B, in
     B.potential[e] = E.potential; B.initial_z[e] = E.initial_z; B.frame[e] = E.frame; B.episode[e] = E.episode;
     for (int k = 0; k < M.n_feet; k++) B.feet[(size_t)k * N + e] = E.feet_contact[k];
     if (M.flag_task) { B.target[e] = E.target_x; B.target[(size_t)N + e] = E.target_y; B.flag_timeout[e] = E.flag_timeout; B.flag_draws[e] = E.flag_draws; }
+    if (M.flag_task == 2) {
+        B.hx_i[e] = E.task; B.hx_i[(size_t)N + e] = E.on_ground; B.hx_i[(size_t)2 * N + e] = E.crawl_valid; B.hx_i[(size_t)3 * N + e] = E.done_latch;
+#pragma unroll
+        for (int k = 0; k < 3; k++) B.hx_i[(size_t)(4 + k) * N + e] = (int)E.hist[k];
+        B.hx_d[e] = E.crawl_start; B.hx_d[(size_t)N + e] = E.crawl_ignored;
+    }
     B.nrows[e] = W.n_rows; B.ncontacts[e] = W.n_contacts;
 }
 

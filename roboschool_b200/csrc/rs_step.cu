@@ -239,6 +239,10 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
     CK(cudaMemset(B.target, 0, sizeof(double) * N * 2));
     CK(cudaMemset(B.flag_timeout, 0, sizeof(int) * N));
     CK(cudaMemset(B.flag_draws, 0, sizeof(uint32_t) * N));
+    CK(cudaMalloc(&B.hx_i, sizeof(int) * N * 7));
+    CK(cudaMalloc(&B.hx_d, sizeof(double) * N * 2));
+    CK(cudaMemset(B.hx_i, 0, sizeof(int) * N * 7));
+    CK(cudaMemset(B.hx_d, 0, sizeof(double) * N * 2));
     CK(cudaMalloc(&B.rows, sizeof(float) * (size_t)((n_envs + 255) / 256 * 256 + 256) * B.rec * B.maxr));   // one pool per warp of 32 envs, incl. the spare warps of the last CTA (up to 8 warps per CTA)
     CK(cudaMalloc(&B.tau, sizeof(float) * N * (model->n_dof > 0 ? model->n_dof : 1)));
     CK(cudaMalloc(&B.rewards5, sizeof(float) * N * 5));
@@ -281,7 +285,7 @@ extern "C" int rs_world_destroy(rs_world* w) {
     DevBuf& B = w->B;
     cudaFree(B.state); cudaFree(B.ccount); cudaFree(B.ckey); cudaFree(B.cdat); cudaFree(B.potential); cudaFree(B.initial_z);
     cudaFree(B.feet); cudaFree(B.frame); cudaFree(B.episode); cudaFree(B.rows); cudaFree(B.tau); cudaFree(B.rewards5);
-    cudaFree(B.nrows); cudaFree(B.ncontacts); cudaFree(B.target); cudaFree(B.flag_timeout); cudaFree(B.flag_draws);
+    cudaFree(B.nrows); cudaFree(B.ncontacts); cudaFree(B.target); cudaFree(B.flag_timeout); cudaFree(B.flag_draws); cudaFree(B.hx_i); cudaFree(B.hx_d);
     cudaFreeHost(w->h_act); cudaFreeHost(w->h_obs); cudaFreeHost(w->h_rew); cudaFreeHost(w->h_done);
     cudaFree(w->d_act); cudaFree(w->d_obs); cudaFree(w->d_rew); cudaFree(w->d_done); cudaFree(w->d_stats);
     cudaStreamDestroy(w->stream);
@@ -471,6 +475,38 @@ extern "C" int rs_world_get_flags(rs_world* w, double* target_xy, int* timeout, 
     }
     if (timeout) CK(cudaMemcpy(timeout, w->B.flag_timeout, sizeof(int) * N, cudaMemcpyDeviceToHost));
     if (draws) CK(cudaMemcpy(draws, w->B.flag_draws, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// FlagrunHarder task state, 8 doubles per env: task, on_ground, crawl_valid, crawl_start, crawl_ignored, hist[0..2]
+extern "C" int rs_world_set_task_state(rs_world* w, const double* in_host) {
+    CK(cudaSetDevice(w->device));
+    size_t N = (size_t)w->n;
+    std::vector<int> hi(7 * N); std::vector<double> hd(2 * N);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(hi.data(), w->B.hx_i, sizeof(int) * 7 * N, cudaMemcpyDeviceToHost));   // keeps done_latch
+    for (size_t e = 0; e < N; e++) {
+        const double* s = in_host + 8 * e;
+        hi[e] = (int)s[0]; hi[N + e] = (int)s[1]; hi[2 * N + e] = (int)s[2];
+        for (int k = 0; k < 3; k++) hi[(4 + k) * N + e] = (int)(uint32_t)s[5 + k];
+        hd[e] = s[3]; hd[N + e] = s[4];
+    }
+    CK(cudaMemcpy(w->B.hx_i, hi.data(), sizeof(int) * 7 * N, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(w->B.hx_d, hd.data(), sizeof(double) * 2 * N, cudaMemcpyHostToDevice));
+    return 0;
+}
+extern "C" int rs_world_get_task_state(rs_world* w, double* out_host) {
+    CK(cudaSetDevice(w->device));
+    size_t N = (size_t)w->n;
+    std::vector<int> hi(7 * N); std::vector<double> hd(2 * N);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(hi.data(), w->B.hx_i, sizeof(int) * 7 * N, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hd.data(), w->B.hx_d, sizeof(double) * 2 * N, cudaMemcpyDeviceToHost));
+    for (size_t e = 0; e < N; e++) {
+        double* s = out_host + 8 * e;
+        s[0] = hi[e]; s[1] = hi[N + e]; s[2] = hi[2 * N + e]; s[3] = hd[e]; s[4] = hd[N + e];
+        for (int k = 0; k < 3; k++) s[5 + k] = (double)(uint32_t)hi[(4 + k) * N + e];
+    }
     return 0;
 }
 

@@ -71,6 +71,21 @@ ENV_SPECS = {
               "left_shoulder1": 75, "left_shoulder2": 75, "left_elbow": 75},
         reset_base=dict(z=1.4, yaw_spread=math.pi / 16), reward_threshold=2000.0,
         flag=dict(halflen=105 * 0.25, halfwidth=50 * 0.25, timeout=600)),
+    # Flagrun + stand-up / roll-over starts chosen by a per-env curriculum, potential "leak" alive bonus, crawl-proof potential
+    # (gym_humanoid_flagrun.py:73-169).  The flying cube that pelts the robot is NOT simulated (box narrowphase + a second
+    # free body per env: DESIGN.md section 7); its RNG draws are consumed so the flag stream matches the reference.
+    "RoboschoolHumanoidFlagrunHarder-v1": dict(
+        xml="humanoid_symmetric.xml", robot="torso", A=17, O=44, power=0.41,
+        feet=["right_foot", "left_foot"],
+        alive_rule=RS_ALIVE_Z, alive_z=0.78, alive_bonus=2.0, cost_scale=4.25, electricity_scale=0.5,
+        initial_z=0.8,
+        coef={"abdomen_z": 100, "abdomen_y": 100, "abdomen_x": 100,
+              "right_hip_x": 100, "right_hip_z": 100, "right_hip_y": 300, "right_knee": 200,
+              "left_hip_x": 100, "left_hip_z": 100, "left_hip_y": 300, "left_knee": 200,
+              "right_shoulder1": 75, "right_shoulder2": 75, "right_elbow": 75,
+              "left_shoulder1": 75, "left_shoulder2": 75, "left_elbow": 75},
+        reset_base=dict(z=1.4, yaw_spread=math.pi / 16), reward_threshold=None,
+        flag=dict(halflen=105 * 0.25, halfwidth=50 * 0.25, timeout=600, harder=True, pelvis="pelvis")),
     # BASELINE.json configs[0] and its siblings (gym_pendulums.py): empty scene, dt 0.0165, frame_skip 1, no contacts
     "RoboschoolInvertedPendulum-v1": dict(
         xml="inverted_pendulum.xml", robot="cart", A=1, O=5, power=1.0, feet=[],
@@ -172,7 +187,9 @@ def apply_task(m: ModelDesc, spec: dict) -> ModelDesc:
         m.reset_yaw_spread = rb["yaw_spread"]
     fl = spec.get("flag")
     if fl:
-        m.flag_task = 1
+        m.flag_task = 2 if fl.get("harder") else 1
+        if fl.get("harder"):
+            m.task_link = ln.index(fl["pelvis"])
         m.flag_timeout_steps = int(fl["timeout"] // m.frame_skip)   # 600/frame_skip (gym_humanoid_flagrun.py:35)
         m.flag_halflen, m.flag_halfwidth = fl["halflen"], fl["halfwidth"]
     m.max_episode_steps = spec.get("max_episode_steps", 1000)

@@ -122,6 +122,16 @@ class BatchedWorld:
         _lib.check(self.L.rs_world_get_flags(self.h, t.ctypes.data, to.ctypes.data, d.ctypes.data))
         return t, to, d
 
+    def set_task_state(self, state):
+        """FlagrunHarder task state [n,8] float64 (see rs_world_set_task_state)."""
+        s = np.ascontiguousarray(state, dtype=np.float64).reshape(self.n, 8)
+        _lib.check(self.L.rs_world_set_task_state(self.h, s.ctypes.data))
+
+    def get_task_state(self):
+        s = np.empty((self.n, 8), dtype=np.float64)
+        _lib.check(self.L.rs_world_get_task_state(self.h, s.ctypes.data))
+        return s
+
     def link_poses(self):
         out = np.empty((self.n, self.model.n_links + 1, 10), dtype=np.float32)
         _lib.check(self.L.rs_world_link_poses(self.h, out.ctypes.data))

@@ -111,6 +111,16 @@ void emul_set_flag(void* h, int env, double tx, double ty, int timeout, uint32_t
 void emul_get_flag(void* h, int env, double* out) {
     Emul* e = (Emul*)h; Episode& E = e->ep[env]; out[0] = E.target_x; out[1] = E.target_y; out[2] = E.flag_timeout; out[3] = E.flag_draws;
 }
+void emul_set_task_state(void* h, int env, const double* s) {
+    Emul* e = (Emul*)h; Episode& E = e->ep[env];
+    E.task = (int)s[0]; E.on_ground = (int)s[1]; E.crawl_valid = (int)s[2]; E.crawl_start = s[3]; E.crawl_ignored = s[4];
+    for (int k = 0; k < 3; k++) E.hist[k] = (uint32_t)s[5 + k];
+}
+void emul_get_task_state(void* h, int env, double* s) {
+    Emul* e = (Emul*)h; Episode& E = e->ep[env];
+    s[0] = E.task; s[1] = E.on_ground; s[2] = E.crawl_valid; s[3] = E.crawl_start; s[4] = E.crawl_ignored;
+    for (int k = 0; k < 3; k++) s[5 + k] = E.hist[k];
+}
 void emul_step(void* h, const double* actions, int auto_reset, uint32_t seed, uint32_t env0) {
     Emul* e = (Emul*)h; RowWS ws{e->ws.data(), 1};
     const DevModel& M = e->M;

@@ -46,6 +46,8 @@ def lib():
         L.emul_link_poses.argtypes = [P, I, dp]
         L.emul_set_flag.argtypes = [P, I, D, D, I, U]
         L.emul_get_flag.argtypes = [P, I, dp]
+        L.emul_set_task_state.argtypes = [P, I, dp]
+        L.emul_get_task_state.argtypes = [P, I, dp]
         _LIB = L
     return _LIB
 
@@ -87,6 +89,12 @@ class EmulWorld:
         self.L.emul_reset_all(self.h, seed, env_id0)
 
     def set_flag(self, env, tx, ty, timeout, draws): self.L.emul_set_flag(self.h, env, tx, ty, int(timeout), int(draws))
+
+    def set_task_state(self, env, s):
+        s = np.ascontiguousarray(s, dtype=np.float64); self.L.emul_set_task_state(self.h, env, _dp(s))
+
+    def get_task_state(self, env):
+        s = np.zeros(8); self.L.emul_get_task_state(self.h, env, _dp(s)); return s
 
     def get_flag(self, env):
         o = np.zeros(4); self.L.emul_get_flag(self.h, env, _dp(o)); return o[0], o[1], int(o[2]), int(o[3])

@@ -9,7 +9,8 @@ from roboschool_b200.envspec import load_env_model
 pytestmark = pytest.mark.gpu
 
 ENVS = ["RoboschoolHopper-v1", "RoboschoolAnt-v1", "RoboschoolHumanoid-v1", "RoboschoolInvertedPendulum-v1",
-        "RoboschoolHumanoidFlagrun-v1", "RoboschoolWalker2d-v1", "RoboschoolHalfCheetah-v1", "RoboschoolInvertedDoublePendulum-v1", "RoboschoolReacher-v1"]
+        "RoboschoolHumanoidFlagrun-v1", "RoboschoolWalker2d-v1", "RoboschoolHalfCheetah-v1", "RoboschoolInvertedDoublePendulum-v1", "RoboschoolReacher-v1",
+        "RoboschoolHumanoidFlagrunHarder-v1"]
 STEP_ENVS = ENVS
 # Per env-step (= 4 sub-steps) error of the fp32 CUDA path against the fp64 oracle, relative to
 # max(1, |state|_inf), over seeded random-action rollouts.  The dynamics are non-smooth (contact
@@ -60,6 +61,8 @@ def test_step_teacher_forced(env_id, oracle_lib):
         if m.flag_task:
             fl = [o.get_flag(i) for i in range(n)]
             w.set_flags(target_xy=[[f[0], f[1]] for f in fl], timeout=[f[2] for f in fl], draws=[f[3] for f in fl])
+        if m.flag_task == 2:
+            w.set_task_state(np.stack([o.get_task_state(i) for i in range(n)]))
         for i in range(n):   # the oracle starts from the float32-rounded state as well
             o.set_state(i, so[i].astype(np.float32).astype(np.float64), clear_contacts=False)
         obs_g, rew_g, done_g = w.step_host(a.astype(np.float32))
@@ -83,6 +86,11 @@ def test_step_teacher_forced(env_id, oracle_lib):
             fo = np.array([o.get_flag(i) for i in range(n)])
             ok = alive
             assert np.abs(tg[ok] - fo[ok, :2]).max() < 1e-9 and (tog[ok] == fo[ok, 2]).all() and (dg[ok] == fo[ok, 3]).all()
+        if m.flag_task == 2:
+            tsg = w.get_task_state()
+            tso = np.stack([o.get_task_state(i) for i in range(n)])
+            ok = alive
+            assert (tsg[ok][:, [0, 1, 2, 5, 6, 7]] == tso[ok][:, [0, 1, 2, 5, 6, 7]]).all()
     errs = np.array(errs)
     assert np.median(errs) <= 1e-5, np.median(errs)
     assert (errs <= STEP_RTOL).mean() >= 0.95, (errs <= STEP_RTOL).mean()

@@ -16,7 +16,7 @@ def emul():
 
 @pytest.mark.parametrize("static", [False, True], ids=["generic", "static-pooled"])
 @pytest.mark.parametrize("env_id", ["RoboschoolInvertedPendulum-v1", "RoboschoolInvertedDoublePendulum-v1", "RoboschoolReacher-v1", "RoboschoolHopper-v1", "RoboschoolWalker2d-v1", "RoboschoolHalfCheetah-v1", "RoboschoolAnt-v1",
-                                    "RoboschoolHumanoid-v1", "RoboschoolHumanoidFlagrun-v1"])
+                                    "RoboschoolHumanoid-v1", "RoboschoolHumanoidFlagrun-v1", "RoboschoolHumanoidFlagrunHarder-v1"])
 def test_emul_teacher_forced(env_id, static, emul, oracle_lib):
     """static=True runs the compile-time-topology sweeps with the pooled row builder (rs_static.cuh,
     rs_pooled.cuh) -- the code the shipped models run on the GPU; False the runtime-topology twin."""
@@ -41,6 +41,8 @@ def test_emul_teacher_forced(env_id, static, emul, oracle_lib):
             ep = o.get_episode(i); e.set_episode(i, ep[0], ep[1], ep[2], ep[3])
             if m.flag_task:
                 e.set_flag(i, *o.get_flag(i))
+            if m.flag_task == 2:
+                e.set_task_state(i, o.get_task_state(i))
         oo, orw, od = o.step(a)
         eo, erw, ed = e.step(a)
         for i in range(n):
@@ -59,6 +61,9 @@ def test_emul_teacher_forced(env_id, static, emul, oracle_lib):
                 if m.flag_task:
                     fo, fe = o.get_flag(i), e.get_flag(i)
                     assert fo[2:] == fe[2:] and abs(fo[0] - fe[0]) < 1e-9 and abs(fo[1] - fe[1]) < 1e-9
+                if m.flag_task == 2:
+                    to, te = o.get_task_state(i), e.get_task_state(i)
+                    assert (to[[0, 1, 2, 5, 6, 7]] == te[[0, 1, 2, 5, 6, 7]]).all() and np.abs(to[3:5] - te[3:5]).max() < 1e-2
     errs = np.array(errs)
     assert alive.mean() >= 0.9
     assert np.median(errs) <= 1e-5 and (errs <= 1e-4).mean() >= 0.95 and errs.max() < 0.2

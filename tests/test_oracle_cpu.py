@@ -86,7 +86,8 @@ def test_determinism_and_thread_independence(oracle_lib):
 
 @pytest.mark.parametrize("env_id", ["RoboschoolInvertedPendulum-v1", "RoboschoolInvertedPendulumSwingup-v1",
                                     "RoboschoolInvertedDoublePendulum-v1", "RoboschoolReacher-v1", "RoboschoolHopper-v1", "RoboschoolWalker2d-v1",
-                                    "RoboschoolHalfCheetah-v1", "RoboschoolAnt-v1", "RoboschoolHumanoid-v1", "RoboschoolHumanoidFlagrun-v1"])
+                                    "RoboschoolHalfCheetah-v1", "RoboschoolAnt-v1", "RoboschoolHumanoid-v1", "RoboschoolHumanoidFlagrun-v1",
+                                    "RoboschoolHumanoidFlagrunHarder-v1"])
 def test_epilogue_matches_reference_python(env_id, oracle_lib):
     """Golden vectors made by the reference's own gym_forward_walker.py (tools/gen_golden_epilogue.py)."""
     g = np.load(os.path.join(GOLDEN, "epilogue_%s.npz" % env_id))
@@ -95,11 +96,13 @@ def test_epilogue_matches_reference_python(env_id, oracle_lib):
     w.reset(seed=int(g["seed"]))
     assert np.abs(w.obs()[0][0] - g["ref_obs0"]).max() < 1e-6
     nd = m.n_dof
+    row = 0     # index into the recorded frames (one per step, plus one per reset of a multi-episode fixture)
     for t in range(g["actions"].shape[0]):
         obs, rew, done = w.step(g["actions"][t:t + 1])
         s = w.get_state(0)
+        row += 1
         # the replayed trajectory must be the one the fixture was recorded from
-        assert np.abs(s[-2 * nd:-nd] - g["q"][t + 1]).max() < 1e-9, "fixture stale: rerun tools/gen_golden_epilogue.py"
+        assert np.abs(s[-2 * nd:-nd] - g["q"][row]).max() < 1e-9, "fixture stale: rerun tools/gen_golden_epilogue.py"
         assert np.abs(obs[0] - g["ref_obs"][t]).max() < 1e-6
         assert abs(rew[0] - g["ref_rew"][t]) < 1e-6
         assert bool(done[0]) == bool(g["ref_done"][t])
@@ -108,6 +111,13 @@ def test_epilogue_matches_reference_python(env_id, oracle_lib):
             tx, ty, to, _ = w.get_flag(0)
             assert abs(tx - g["ref_flags"][t][0]) < 1e-12 and abs(ty - g["ref_flags"][t][1]) < 1e-12
             assert to == int(g["ref_flags"][t][2])
+        if m.flag_task == 2:   # FlagrunHarder: the task the reference's curriculum chose for this episode
+            assert int(w.get_task_state(0)[0]) == int(g["ref_task"][t])
+        if "reset_after" in g and t in g["reset_after"]:   # multi-episode fixture: the reference called env.reset() here
+            k = list(g["reset_after"]).index(t)
+            w.L.oracle_reset(w.h, 0, int(g["seed"]), 0)
+            assert np.abs(w.obs()[0][0] - g["ref_reset_obs"][k]).max() < 1e-6
+            row += 1
     if m.flag_task:
         assert len(np.unique(g["ref_flags"][:, 0])) >= 2, "fixture must contain a flag reposition"
 

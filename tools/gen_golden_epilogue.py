@@ -170,6 +170,7 @@ def make_cpp_household(model, replay, foot_names):
         def load_thingy(self, *a): return Thingy("stadium", -1, replay)
         def new_camera_free_float(self, *a): return None
         def debug_sphere(self, *a): return None
+        def load_urdf(self, *a): return Robot(Thingy("cube", -1, replay), [], [])
 
         def load_mjcf(self, fn):
             if fn.endswith("ground_plane.xml"):
@@ -208,15 +209,21 @@ class CounterRNG(object):
         return float(self.h(self.seed, self.env_id, self.episode, k) >> 8) * (1.0 / 16777216.0)
 
     def uniform(self, low=0.0, high=1.0, size=None):
-        assert size is None
+        if size is not None:      # FlagrunHarder's cube noise: consumes one draw per element
+            n = int(np.prod(size))
+            return np.array([low + (high - low) * self._u() for _ in range(n)]).reshape(size)
         return low + (high - low) * self._u()
+
+    def choice_u(self):
+        """the draw RepeatUnderlearnedTasks.decide_best_task takes (np.random.choice in the reference): stream slot 1500"""
+        return float(self.h(self.seed, self.env_id, self.episode, 1500) >> 8) * (1.0 / 16777216.0)
 
     def randint(self, n):
         assert n == 2
         return 0 if self._u() < 0.5 else 1
 
 
-def generate(env_id, cls_name, n_steps=60, seed=3, counter_rng=False):
+def generate(env_id, cls_name, n_steps=60, seed=3, counter_rng=False, multi_episode=False):
     from roboschool_b200 import envspec
     from oracle.oracle import OracleWorld
     m = envspec.compile_env(env_id, os.path.join(REF, "roboschool", "mujoco_assets"))
@@ -240,10 +247,17 @@ def generate(env_id, cls_name, n_steps=60, seed=3, counter_rng=False):
 
     record()
     obs0 = o.obs()[0][0].copy()
+    reset_after = []          # steps after which the env was reset (multi_episode): the next frame is the reset state
+    oracle_reset_obs = {}
     for t in range(n_steps):
         ob, rw, dn = o.step(acts[t:t + 1])
         record()
         oracle_obs.append(ob[0].copy()); oracle_rew.append(rw[0]); oracle_done.append(dn[0]); oracle_r5.append(o.rewards5(0))
+        if multi_episode and dn[0]:
+            o.L.oracle_reset(o.h, 0, seed, 0)
+            record()
+            reset_after.append(t)
+            oracle_reset_obs[t] = o.obs()[0][0].copy()
 
     # ---- run the reference's Python over the recorded trajectory
     install_stub_gym()
@@ -262,21 +276,39 @@ def generate(env_id, cls_name, n_steps=60, seed=3, counter_rng=False):
         max_episode_steps = 1000
     env.spec = Spec()
     R.t = 0
+    episode = 1
     if counter_rng:
-        env.np_random = CounterRNG(seed, 0, 1, m.n_act)
-    ref_flags = []
+        env.np_random = CounterRNG(seed, 0, episode, m.n_act)
+    if multi_episode:     # RepeatUnderlearnedTasks draws from the global numpy RNG: route it to the counter stream
+        def choice(rng, p):
+            cdf = np.cumsum(np.asarray(p, dtype=np.float64)); cdf = cdf / cdf[-1]
+            return min(int(np.count_nonzero(cdf <= env.np_random.choice_u())), len(cdf) - 1)
+        np_choice, np.random.choice = np.random.choice, choice
+    ref_flags, ref_task, ref_reset_obs = [], [], {}
     ref_obs0 = env.reset()
     ref_obs, ref_rew, ref_done, ref_r5 = [], [], [], []
     for t in range(n_steps):
         ob, rw, dn, _ = env.step(acts[t])
         ref_obs.append(np.asarray(ob, dtype=np.float64)); ref_rew.append(rw); ref_done.append(dn); ref_r5.append((list(env.rewards) + [0.0] * 5)[:5])
         ref_flags.append([getattr(env, "walk_target_x", 0.0), getattr(env, "walk_target_y", 0.0), getattr(env, "flag_timeout", 0)])
+        ref_task.append(getattr(env, "task", 0))
+        if multi_episode and t in reset_after:
+            episode += 1
+            env.np_random = CounterRNG(seed, 0, episode, m.n_act)
+            R.t += 1                       # the frame recorded right after the oracle's reset
+            ref_reset_obs[t] = np.asarray(env.reset(), dtype=np.float64)
+    if multi_episode:
+        np.random.choice = np_choice
+        for t in reset_after:
+            assert np.abs(ref_reset_obs[t] - oracle_reset_obs[t]).max() < 1e-6, ("reset obs", t)
     out = os.path.join(ROOT, "tests", "golden", "epilogue_%s.npz" % env_id)
     os.makedirs(os.path.dirname(out), exist_ok=True)
     np.savez_compressed(out, seed=seed, actions=acts, poses=np.array(R.poses), q=np.array(R.q), qd=np.array(R.qd),
-                        foot_flags=np.array(R.foot_flags, dtype=np.int32).reshape(n_steps + 1, -1, 2),
+                        foot_flags=np.array(R.foot_flags, dtype=np.int32).reshape(len(R.foot_flags), -1, 2),
                         ref_obs0=np.asarray(ref_obs0, dtype=np.float64), ref_obs=np.array(ref_obs), ref_rew=np.array(ref_rew),
-                        ref_done=np.array(ref_done), ref_rewards5=np.array(ref_r5), ref_flags=np.array(ref_flags, dtype=np.float64))
+                        ref_done=np.array(ref_done), ref_rewards5=np.array(ref_r5), ref_flags=np.array(ref_flags, dtype=np.float64),
+                        ref_task=np.array(ref_task, dtype=np.int32), reset_after=np.array(reset_after, dtype=np.int32),
+                        ref_reset_obs=np.array([ref_reset_obs[t] for t in reset_after]).reshape(len(reset_after), m.obs_dim))
     d_obs = np.abs(np.array(ref_obs) - np.array(oracle_obs)).max()
     d_rew = np.abs(np.array(ref_rew) - np.array(oracle_rew)).max()
     print("%-26s steps=%d  |ref-oracle| obs %.2e rew %.2e obs0 %.2e done equal=%s" % (
@@ -295,3 +327,5 @@ if __name__ == "__main__":
     generate("RoboschoolHumanoid-v1", "RoboschoolHumanoid")
     # Flagrun: 170 steps so that the 150-step flag timeout (and the reposition after it) is part of the fixture
     generate("RoboschoolHumanoidFlagrun-v1", "RoboschoolHumanoidFlagrun", n_steps=170, counter_rng=True)
+    # FlagrunHarder: several episodes (the task curriculum and the stand-up / roll-over starts are part of the fixture)
+    generate("RoboschoolHumanoidFlagrunHarder-v1", "RoboschoolHumanoidFlagrunHarder", n_steps=420, counter_rng=True, multi_episode=True)
