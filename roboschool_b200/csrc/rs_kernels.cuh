@@ -186,8 +186,14 @@ template <class T, int MC, bool PROF, int WPC>
 static int launch_static(const StaticLaunch& a) {
     constexpr int per = 32 * WPC;
     const size_t smem = sizeof(float) * per * lc_size<T>();
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_step_static<T, MC, PROF, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    // the opt-in to > 48 KB of dynamic shared memory is per device: remember which devices have it
+    static unsigned attr_devices = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((attr_devices >> (dev & 31)) & 1u)) {
+        cudaFuncSetAttribute(k_step_static<T, MC, PROF, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_devices |= 1u << (dev & 31);
+    }
     k_step_static<T, MC, PROF, WPC><<<(a.n + per - 1) / per, per, smem, a.st>>>(*a.M, *a.B, a.actions, a.obs, a.rew, a.done, a.auto_reset, a.seed, a.env_id0, a.stats, a.cyc);
     return 0;
 }
