@@ -84,7 +84,9 @@ int rs_world_step_host(rs_world* w, const float* actions_host, float* obs_host, 
 
 /* policy + step for callers whose observations live in HOST memory (numpy): H2D obs_in -> policy forward on the
  * tensor cores -> env step with auto-reset -> D2H obs_out/reward/done; one stream synchronisation.
- * obs_in_host == NULL continues from the observations already on the device. */
+ * obs_in_host == NULL continues from the observations already on the device.  Page-locked host buffers (cudaHostAlloc /
+ * cudaHostRegister, e.g. pinned torch tensors) are the source / target of the async copies directly; pageable ones go
+ * through the world's pinned staging buffers. */
 int rs_world_policy_step_host(rs_world* w, rs_policy* p, const float* obs_in_host, float* obs_out_host, float* reward_host,
                               uint8_t* done_host);
 
@@ -131,7 +133,7 @@ int rs_world_state_dev(rs_world* w, float** state_dev);
 int rs_policy_create(int in_dim, int h1, int h2, int out_dim, const float* w1, const float* b1, const float* w2,
                      const float* b2, const float* w3, const float* b3, int device, rs_policy** out);
 int rs_policy_destroy(rs_policy* p);
-/* act_dev[n][out] = policy(obs_dev[n][in]) on the tensor cores */
+/* act_dev[n][out] = policy(obs_dev[n][in]) on the tensor cores (tcgen05.mma, fp16 operands, fp32 accumulation in TMEM) */
 int rs_policy_forward(rs_policy* p, const float* obs_dev, float* act_dev, int n, void* stream);
 
 /* Fused rollout: n_steps x { act = policy(obs) ; step(auto_reset) } with no host round trip; the

@@ -463,7 +463,6 @@ RS_HD void static_aba(const DevModel& M, Work<NL, MC, SL>& W, const LinkCache<ST
         constexpr bool is_leaf = T::leaf[i] != 0, is_first = T::first_fold[i] != 0;
         constexpr float mI = T::mass[i], i0 = T::inertia[3 * i], i1 = T::inertia[3 * i + 1], i2 = T::inertia[3 * i + 2];
         constexpr float mP = T::mass[pp], p0 = T::inertia[3 * pp], p1 = T::inertia[3 * pp + 1], p2 = T::inertia[3 * pp + 2];
-        constexpr float s0 = T::Sw[3 * i], s1 = T::Sw[3 * i + 1], s2 = T::Sw[3 * i + 2], s3 = T::Sv[3 * i], s4 = T::Sv[3 * i + 1], s5 = T::Sv[3 * i + 2];
         if constexpr (is_leaf) init_rigid(IA[i + 1], mI, i0, i1, i2);
         float R[9], r[3];
         cached_xform<T, i>(lc, R, r);
