@@ -246,3 +246,25 @@ def test_ragged_batch_sizes(env_id):
             o2, r2, d2 = small.step(a[off:off + n].contiguous())
             assert torch.equal(o2, o[off:off + n]) and torch.equal(r2, r[off:off + n]) and torch.equal(d2, d[off:off + n]), (n, off)
         small.close()
+
+
+def test_behavioural_fixture_on_gpu_humanoid_walks():
+    """The behavioural pin of the oracle (tests/test_oracle_cpu.py) on the CUDA path, at scale: the reference's pretrained
+    Humanoid policy -- trained on the Bullet path -- walks on the fp32 batched stepper: over 1000 steps of 4096 envs the
+    mean reward per step is above reward_threshold/1000 = 3.5 (roboschool/__init__.py:71-77), nearly every episode reaches
+    the 1000-step time limit, and nothing goes non-finite."""
+    import torch
+    from roboschool_b200.world import BatchedWorld
+    from roboschool_b200.policy import ZooPolicy, load_zoo_weights
+    env_id, n = "RoboschoolHumanoid-v1", 4096
+    W = BatchedWorld(load_env_model(env_id), n, 0)
+    pol = ZooPolicy(load_zoo_weights(env_id), 0)
+    st = torch.cuda.current_stream().cuda_stream
+    stats = torch.zeros(8, dtype=torch.float64, device="cuda")
+    W.rollout_reset(seed=11, stream=st)
+    W.rollout(pol, 1000, seed=11, stats=stats, stream=st)
+    torch.cuda.synchronize()
+    s = stats.cpu().numpy()
+    assert s[3] == 0, "non-finite observations"
+    assert s[0] / s[6] > 3.5, s[0] / s[6]
+    assert s[1] >= 0.97 * n and s[2] / s[1] > 990, (s[1], s[2] / max(s[1], 1))
