@@ -268,3 +268,36 @@ def test_behavioural_fixture_on_gpu_humanoid_walks():
     assert s[3] == 0, "non-finite observations"
     assert s[0] / s[6] > 3.5, s[0] / s[6]
     assert s[1] >= 0.97 * n and s[2] / s[1] > 990, (s[1], s[2] / max(s[1], 1))
+
+
+@pytest.mark.parametrize("env_id,n", [("RoboschoolHopper-v1", 4096), ("RoboschoolAnt-v1", 65536)])
+def test_baseline_config_sizes_properties(env_id, n):
+    """BASELINE.json configs[1] (Hopper, 4096 envs) and configs[2] (Ant, 65536 envs) at full size, through the
+    size-independent properties: finite outputs, bit-identical reruns, independence of the position in the batch
+    (a slice stepped in its own small world with the matching env_id0), contact pools consistent with feet flags."""
+    import torch
+    from roboschool_b200.vec_env import VecEnv
+    env = VecEnv(env_id, n, 0)
+    obs0 = env.reset(seed=2).clone()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    acts = [torch.rand((n, env.act_dim), device="cuda", generator=g) * 2 - 1 for _ in range(8)]
+    outs = []
+    for a in acts:
+        o, r, d = env.step(a)
+        outs.append((o.clone(), r.clone(), d.clone()))
+    assert all(torch.isfinite(o).all() and torch.isfinite(r).all() for o, r, d in outs)
+    env2 = VecEnv(env_id, n, 0)
+    assert torch.equal(env2.reset(seed=2), obs0)
+    for a, (o, r, d) in zip(acts, outs):
+        o2, r2, d2 = env2.step(a)
+        assert torch.equal(o, o2) and torch.equal(r, r2) and torch.equal(d, d2)
+    off = n - 300
+    env3 = VecEnv(env_id, 300, 0, env_id0=off)
+    assert torch.equal(env3.reset(seed=2), obs0[off:])
+    for a, (o, r, d) in zip(acts, outs):
+        o3, r3, d3 = env3.step(a[off:].contiguous())
+        assert torch.equal(o3, o[off:]) and torch.equal(r3, r[off:]) and torch.equal(d3, d[off:])
+    # feet_contact observations are 0/1 flags
+    F = env.model.n_feet
+    feet = outs[-1][0][:, -F:]
+    assert ((feet == 0) | (feet == 1)).all()
