@@ -218,8 +218,10 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
         else if (topo_matches<TopoHalfCheetah>(w->M) && model->max_contacts <= 16) w->topo = 5;
     }
     w->device = device; w->n = n_envs;
-    // warps per CTA (measured on B200, profiles/): one CTA per SM at 32768 Humanoid envs; 4 for Ant; 1 otherwise
-    w->wpc = w->topo == 1 ? 7 : (w->topo == 2 ? 4 : 1);
+    // warps per CTA (measured on B200): 7-warp CTAs that re-align at the phase barriers once the batch
+    // gives every SM several warps (Humanoid 32768: +13 %, Ant 65536: +16 %, HalfCheetah 65536: +67 %); single-warp CTAs for
+    // small batches, which would otherwise occupy only a few SMs
+    w->wpc = n_envs >= 16384 ? 7 : 1;
     DevBuf& B = w->B;
     B.N = n_envs; B.S = (model->fixed_base ? 0 : 13) + 2 * model->n_dof; B.MCcap = MC;
     B.rec = 2 * (6 + model->n_dof) + 1; B.maxr = NL + 3 * MC;   // +1: pooled rows keep their denominator in the record
