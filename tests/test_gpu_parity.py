@@ -301,3 +301,42 @@ def test_baseline_config_sizes_properties(env_id, n):
     F = env.model.n_feet
     feet = outs[-1][0][:, -F:]
     assert ((feet == 0) | (feet == 1)).all()
+
+
+@pytest.mark.parametrize("variant", ["static-pooled", "generic"])
+def test_free_flight_momentum_converges_on_gpu(variant, monkeypatch):
+    """Physics invariant on the CUDA kernels themselves (no oracle involved): a floating Humanoid tumbling in zero
+    gravity with internal joint motion, no damping / limits / floor.  Linear momentum is an invariant of the continuous
+    dynamics, so its drift under the semi-implicit integrator must shrink ~linearly with dt -- a check of the ABA
+    sweeps, Coriolis and bias terms of the step kernel (the compile-time-topology one and the runtime-topology twin)."""
+    from roboschool_b200.world import BatchedWorld
+    if variant == "generic":
+        monkeypatch.setenv("RS_FORCE_GENERIC", "1")
+    drift = []
+    n = 64
+    for div in (1, 4, 16):
+        m = load_env_model("RoboschoolHumanoid-v1").clone()
+        m.lin_damping = 0; m.ang_damping = 0; m.gravity = 0.0
+        m.timestep = m.timestep / div
+        for i in range(m.n_links):
+            m.has_limit[i] = 0
+        for k in range(m.n_act):
+            m.act_gain[k] = 0.0          # actions produce no torque: free motion
+        w = BatchedWorld(m, n, 0)
+        assert (w.L.rs_world_kernel_variant(w.h) > 0) == (variant == "static-pooled")
+        w.reset(seed=2)
+        s = w.get_state()
+        rng = np.random.RandomState(0)
+        s[:, 13 + 17:] = rng.uniform(-3, 3, (n, 17))
+        s[:, 7:13] = rng.uniform(-1, 1, (n, 6))
+        s[:, 2] = 10.0                   # far above the floor plane (the geoms keep their floor flags: same topology)
+        w.set_state(s)
+        mass = np.array([m.base_mass] + [m.mass[i] for i in range(m.n_links)])
+        p0 = (mass[None, :, None] * w.link_poses()[:, :, 7:10]).sum(1)
+        a = np.zeros((n, m.n_act), dtype=np.float32)
+        for _ in range(20 * div):
+            w.step_host(a, auto_reset=False)
+        p1 = (mass[None, :, None] * w.link_poses()[:, :, 7:10]).sum(1)
+        drift.append(np.median(np.abs(p1 - p0).max(axis=1)))
+        w.close()
+    assert drift[1] < drift[0] / 2.5 and drift[2] < drift[1] / 2.0, drift
