@@ -159,6 +159,25 @@ extern "C" int rs_policy_create(int in_dim, int h1, int h2, int out_dim, const f
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return mfail("rs_policy_create: no CUDA device (there is no CPU fallback)");
     MCK(cudaSetDevice(device));
+    // Narrower hidden layers (the May-2017 pendulum policies are 64-32, agent_zoo/RoboschoolInvertedPendulum_v0_2017may.py:8-10)
+    // run on the next wider kernel shape with zero-padded weights: relu(0) = 0 and the extra products are exact zeros, so
+    // the result is unchanged.
+    std::vector<float> pw1, pb1, pw2, pb2, pw3;
+    {
+        int H1 = 0, H2 = 0;
+        if (h1 <= 128 && h2 <= 64) { H1 = 128; H2 = 64; } else if (h1 <= 256 && h2 <= 128) { H1 = 256; H2 = 128; }
+        if (H1 && (H1 != h1 || H2 != h2) && h1 > 0 && h2 > 0) {
+            pw1.assign((size_t)in_dim * H1, 0.f); pb1.assign(H1, 0.f); pw2.assign((size_t)H1 * H2, 0.f); pb2.assign(H2, 0.f);
+            pw3.assign((size_t)H2 * out_dim, 0.f);
+            for (int i = 0; i < in_dim; i++) for (int j = 0; j < h1; j++) pw1[(size_t)i * H1 + j] = w1[(size_t)i * h1 + j];
+            for (int j = 0; j < h1; j++) pb1[j] = b1[j];
+            for (int i = 0; i < h1; i++) for (int j = 0; j < h2; j++) pw2[(size_t)i * H2 + j] = w2[(size_t)i * h2 + j];
+            for (int j = 0; j < h2; j++) pb2[j] = b2[j];
+            for (int i = 0; i < h2; i++) for (int j = 0; j < out_dim; j++) pw3[(size_t)i * out_dim + j] = w3[(size_t)i * out_dim + j];
+            w1 = pw1.data(); b1 = pb1.data(); w2 = pw2.data(); b2 = pb2.data(); w3 = pw3.data();
+            h1 = H1; h2 = H2;
+        }
+    }
     rs_policy* p = new rs_policy();
     p->in_dim = in_dim; p->h1 = h1; p->h2 = h2; p->out_dim = out_dim; p->device = device; p->w = nullptr;
     p->in_p = pad_to(in_dim, 16); p->out_p = pad_to(out_dim, 8);

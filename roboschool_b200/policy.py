@@ -9,10 +9,11 @@ from . import _lib
 ZOO_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "zoo")
 
 
-def load_zoo_weights(env_id):
-    """Weights of the reference's pretrained policy for `env_id` (converted by tools/convert_zoo_weights.py)."""
+def load_zoo_weights(env_id, version="v1"):
+    """Weights of the reference's pretrained policy for `env_id` (converted by tools/convert_zoo_weights.py).
+    version "v1": agent_zoo/*_v1_2017jul.weights; "v0": the independently trained agent_zoo/*_v0_2017may.py."""
     name = env_id.replace("-v1", "")
-    z = np.load(os.path.join(ZOO_DIR, name + "_v1.npz"))
+    z = np.load(os.path.join(ZOO_DIR, name + "_" + version + ".npz"))
     return [z[k] for k in ("dense1_w", "dense1_b", "dense2_w", "dense2_b", "final_w", "final_b")]
 
 

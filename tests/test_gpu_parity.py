@@ -270,6 +270,36 @@ def test_behavioural_fixture_on_gpu_humanoid_walks():
     assert s[1] >= 0.97 * n and s[2] / s[1] > 990, (s[1], s[2] / max(s[1], 1))
 
 
+@pytest.mark.parametrize("env_id,min_return,min_len", [
+    ("RoboschoolInvertedPendulum-v1", 950.0, 990), ("RoboschoolInvertedDoublePendulum-v1", 7000.0, 750),
+    ("RoboschoolReacher-v1", 15.0, 150), ("RoboschoolHopper-v1", 2000.0, 950)])
+def test_behavioural_fixture_on_gpu_v0_policies(env_id, min_return, min_len):
+    """The second behavioural pin (tests/test_oracle_cpu.py::test_behavioural_fixture_v0_policies) on the CUDA path:
+    the reference's independently trained May-2017 policies over one full episode of 2048 envs.  Mean return per
+    finished episode against the registered reward_threshold (roboschool/__init__.py:11-47: 950 / 9100 / 18 / 2500);
+    the double pendulum and the hopper are held to what the oracle reaches (a quarter of the double-pendulum starts
+    fall early, the hopper runs the full episode at ~2250)."""
+    import torch
+    from roboschool_b200.world import BatchedWorld
+    from roboschool_b200.policy import ZooPolicy, load_zoo_weights
+    m = load_env_model(env_id)
+    n, T = 2048, m.max_episode_steps
+    W = BatchedWorld(m, n, 0)
+    pol = ZooPolicy(load_zoo_weights(env_id, "v0"), 0)
+    st = torch.cuda.current_stream().cuda_stream
+    stats = torch.zeros(8, dtype=torch.float64, device="cuda")
+    W.rollout_reset(seed=5, stream=st)
+    W.rollout(pol, T, seed=5, stats=stats, stream=st)
+    torch.cuda.synchronize()
+    s = stats.cpu().numpy()
+    assert s[3] == 0, "non-finite observations"
+    assert s[1] >= n, s[1]
+    # return per episode: reward summed over all env-steps / episodes' share of them
+    ret = s[0] / s[6] * (s[2] / s[1])
+    assert s[2] / s[1] >= min_len, s[2] / s[1]
+    assert ret >= min_return, ret
+
+
 @pytest.mark.parametrize("env_id,n", [("RoboschoolHopper-v1", 4096), ("RoboschoolAnt-v1", 65536)])
 def test_baseline_config_sizes_properties(env_id, n):
     """BASELINE.json configs[1] (Hopper, 4096 envs) and configs[2] (Ant, 65536 envs) at full size, through the

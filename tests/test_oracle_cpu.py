@@ -182,3 +182,37 @@ def test_behavioural_fixture_humanoid_walks(oracle_lib):
         alive &= ~done.astype(bool)
     assert alive.all(), "humanoid fell"
     assert tot.min() > 3500.0, tot
+
+
+def _score_v0(oracle_lib, env_id, n, seed, T=None):
+    m = envspec.load_env_model(env_id)
+    wts = load_zoo_weights(env_id, "v0")
+    w = oracle_lib.OracleWorld(m, n)
+    w.reset(seed=seed)
+    obs = w.obs()[0]
+    tot = np.zeros(n); alive = np.ones(n, bool); length = np.zeros(n)
+    for t in range(T or m.max_episode_steps):
+        obs, rew, done = w.step(oracle_lib.mlp_forward(wts, obs), threads=4)
+        tot += rew * alive; length += alive
+        alive &= ~done.astype(bool)
+        if not alive.any():
+            break
+    return tot, length
+
+
+def test_behavioural_fixture_v0_policies(oracle_lib):
+    """A second, independent behavioural pin: the reference's May-2017 policies (agent_zoo/*_v0_2017may.py, trained on
+    the Bullet path months before the v1 ones) on the restated physics, against the registered reward_threshold of each
+    env (roboschool/__init__.py:11-47).  The cart-pole, the double pendulum and the reacher reach their thresholds, so the
+    fixed-base slide/hinge chains, the contact-free tasks and their epilogues behave like the reference's.  Hopper runs
+    the full 1000 steps at ~2250 (threshold 2500): the planar dummy-joint chain, foot contact and friction are close.
+    Walker2d and HalfCheetah fall under both generations of policies -- see DESIGN.md "Known gaps"."""
+    tot, length = _score_v0(oracle_lib, "RoboschoolInvertedPendulum-v1", 8, 1)
+    assert tot.min() >= 950.0, tot
+    tot, length = _score_v0(oracle_lib, "RoboschoolInvertedDoublePendulum-v1", 8, 1)
+    assert np.median(tot) >= 9100.0, tot
+    tot, length = _score_v0(oracle_lib, "RoboschoolReacher-v1", 16, 1)
+    assert tot.mean() >= 18.0, tot
+    tot, length = _score_v0(oracle_lib, "RoboschoolHopper-v1", 8, 1)
+    assert (length == 1000).all(), length
+    assert tot.min() > 2000.0, tot
