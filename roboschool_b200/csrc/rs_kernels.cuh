@@ -113,9 +113,10 @@ template <class T, int MC, bool PROF, int WPC>
 __global__ void __launch_bounds__(32 * WPC) k_step_static(const __grid_constant__ DevModel M, const DevBuf B, const float* __restrict__ actions,
                                                     float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
                                                     int auto_reset, uint32_t seed, uint32_t env_id0, double* __restrict__ stats,
-                                                    unsigned long long* __restrict__ cyc) {
+                                                    unsigned long long* __restrict__ cyc, int cta0) {
     extern __shared__ float s_lc[];
-    const int e = blockIdx.x * (32 * WPC) + threadIdx.x;
+    const int cta = blockIdx.x + cta0;             // a launch may cover a slice of the CTAs (pipelined host entry point)
+    const int e = cta * (32 * WPC) + threadIdx.x;
     const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;   // warp in CTA, lane
     const bool valid = e < B.N;
     double st_rew = 0, st_ep = 0, st_len = 0, st_nf = 0, st_rows = 0, st_con = 0, st_steps = 0;
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(32 * WPC) k_step_static(const __grid_constant_
         apply_action(M, W, a, 1);
     }
     constexpr int CAP = pool_cap<T, MC, 32>();      // <= 32 * B.maxr: the allocation covers it
-    const RowPool<CAP> pool{B.rows + (size_t)(blockIdx.x * WPC + wic) * ((size_t)CAP * pool_rec<T>())};
+    const RowPool<CAP> pool{B.rows + (size_t)(cta * WPC + wic) * ((size_t)CAP * pool_rec<T>())};
     const WarpDev<WPC> warp;
     PhaseClock pc;
     if (PROF) { for (int k = 0; k < 6; k++) pc.t[k] = 0; t1 = clock64(); }
@@ -180,11 +181,14 @@ struct StaticLaunch {
     const DevModel* M; const DevBuf* B; int n;
     const float* actions; float* obs; float* rew; uint8_t* done;
     int auto_reset; uint32_t seed, env_id0; double* stats; unsigned long long* cyc; cudaStream_t st;
+    int cta0 = 0, ncta = 0;      // slice of the grid to launch (ncta == 0: all CTAs)
+    int* per_out = nullptr;      // query: receives envs per CTA, nothing is launched
 };
 
 template <class T, int MC, bool PROF, int WPC>
 static int launch_static(const StaticLaunch& a) {
     constexpr int per = 32 * WPC;
+    if (a.per_out) { *a.per_out = per; return 0; }
     const size_t smem = sizeof(float) * per * lc_size<T>();
     // the opt-in to > 48 KB of dynamic shared memory is per device: remember which devices have it
     static unsigned attr_devices = 0;
@@ -194,7 +198,8 @@ static int launch_static(const StaticLaunch& a) {
         cudaFuncSetAttribute(k_step_static<T, MC, PROF, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_devices |= 1u << (dev & 31);
     }
-    k_step_static<T, MC, PROF, WPC><<<(a.n + per - 1) / per, per, smem, a.st>>>(*a.M, *a.B, a.actions, a.obs, a.rew, a.done, a.auto_reset, a.seed, a.env_id0, a.stats, a.cyc);
+    const int grid = a.ncta > 0 ? a.ncta : (a.n + per - 1) / per;
+    k_step_static<T, MC, PROF, WPC><<<grid, per, smem, a.st>>>(*a.M, *a.B, a.actions, a.obs, a.rew, a.done, a.auto_reset, a.seed, a.env_id0, a.stats, a.cyc, a.cta0);
     return 0;
 }
 

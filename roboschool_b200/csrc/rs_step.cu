@@ -39,6 +39,7 @@ static StaticLaunchFn pick_static(int topo, int prof, int def_wpc) {
     return g_static[topo][prof][wpc];
 }
 
+#define RS_MAX_CHUNKS 8
 struct rs_world {
     rs_model_desc desc;
     DevModel M;
@@ -47,6 +48,9 @@ struct rs_world {
     int wpc;                 // warps per CTA of the static-topology kernel
     int topo;                // 0: runtime-topology kernel; 1..4: kernel specialised on a generated topology (rs_topo_gen.h)
     cudaStream_t stream;
+    cudaStream_t chunk_stream[RS_MAX_CHUNKS];   // pipelined host entry point: one stream per env slice (created on first use)
+    cudaEvent_t chunk_ev;
+    int n_chunk_streams;
     // pinned staging + device staging for the host-buffer entry point
     float *h_act, *h_obs, *h_rew; uint8_t* h_done;
     float *d_act, *d_obs, *d_rew; uint8_t* d_done;
@@ -291,6 +295,8 @@ extern "C" int rs_world_destroy(rs_world* w) {
     cudaFreeHost(w->h_act); cudaFreeHost(w->h_obs); cudaFreeHost(w->h_rew); cudaFreeHost(w->h_done);
     cudaFree(w->d_act); cudaFree(w->d_obs); cudaFree(w->d_rew); cudaFree(w->d_done); cudaFree(w->d_stats);
     cudaStreamDestroy(w->stream);
+    for (int k = 0; k < w->n_chunk_streams; k++) cudaStreamDestroy(w->chunk_stream[k]);
+    if (w->n_chunk_streams) cudaEventDestroy(w->chunk_ev);
     delete w;
     return 0;
 }
@@ -314,9 +320,10 @@ extern "C" int rs_world_reset(rs_world* w, uint32_t seed, uint32_t env_id0, cons
 }
 
 static int launch_step(rs_world* w, const float* actions, float* obs, float* rew, uint8_t* done, int auto_reset, uint32_t seed,
-                       uint32_t env_id0, double* stats, cudaStream_t st) {
+                       uint32_t env_id0, double* stats, cudaStream_t st, int cta0 = 0, int ncta = 0) {
     if (w->topo) {
         StaticLaunch a{&w->M, &w->B, w->n, actions, obs, rew, done, auto_reset, seed, env_id0, stats, nullptr, st};
+        a.cta0 = cta0; a.ncta = ncta;
         StaticLaunchFn fn = pick_static(w->topo, 0, w->wpc);
         if (!fn) return fail("static-topology kernel not linked");
         fn(a);
@@ -609,11 +616,60 @@ static bool host_is_pinned(const void* p) {
     return a.type == cudaMemoryTypeHost;
 }
 
+// Pipelined form of the host entry point for worlds on a static-topology kernel and page-locked caller buffers: the envs are cut
+// into slices of whole CTAs, each slice runs H2D -> policy -> step -> D2H on its own stream, so the copies of one slice overlap
+// the kernels of the others (one copy engine per direction keeps the copies themselves in issue order).  Slices touch disjoint
+// envs, constraint-row pools and output rows, so the result is bit-identical to the single-stream form.
+static int policy_step_host_pipelined(rs_world* w, rs_policy* p, const float* obs_in_host, float* obs_out_host, float* reward_host,
+                                      uint8_t* done_host, int n_chunks) {
+    int per = 0;
+    {
+        StaticLaunch q{&w->M, &w->B, w->n, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, nullptr, nullptr, nullptr};
+        q.per_out = &per;
+        StaticLaunchFn fn = pick_static(w->topo, 0, w->wpc);
+        if (!fn) return fail("static-topology kernel not linked");
+        fn(q);
+    }
+    const int ncta = (w->n + per - 1) / per;
+    if (n_chunks > ncta) n_chunks = ncta;
+    while (w->n_chunk_streams < n_chunks) {
+        if (!w->n_chunk_streams) CK(cudaEventCreateWithFlags(&w->chunk_ev, cudaEventDisableTiming));
+        CK(cudaStreamCreateWithFlags(&w->chunk_stream[w->n_chunk_streams], cudaStreamNonBlocking));
+        w->n_chunk_streams++;
+    }
+    const size_t O = (size_t)w->desc.obs_dim, A = (size_t)w->desc.n_act;
+    CK(cudaEventRecord(w->chunk_ev, w->stream));            // everything queued on the world's stream so far comes first
+    const int cta_per_chunk = (ncta + n_chunks - 1) / n_chunks;
+    for (int c = 0; c < n_chunks; c++) {
+        const int c0 = c * cta_per_chunk, c1 = (c0 + cta_per_chunk < ncta) ? c0 + cta_per_chunk : ncta;
+        if (c0 >= c1) break;
+        const size_t e0 = (size_t)c0 * per, e1 = ((size_t)c1 * per < (size_t)w->n) ? (size_t)c1 * per : (size_t)w->n, ne = e1 - e0;
+        cudaStream_t st = w->chunk_stream[c];
+        CK(cudaStreamWaitEvent(st, w->chunk_ev, 0));
+        if (obs_in_host) CK(cudaMemcpyAsync(w->d_obs + e0 * O, obs_in_host + e0 * O, sizeof(float) * ne * O, cudaMemcpyHostToDevice, st));
+        if (rs_policy_forward(p, w->d_obs + e0 * O, w->d_act + e0 * A, (int)ne, (void*)st)) return 1;
+        if (launch_step(w, w->d_act, w->d_obs, w->d_rew, w->d_done, 1, w->rollout_seed, w->env_id0, nullptr, st, c0, c1 - c0)) return 1;
+        CK(cudaMemcpyAsync(obs_out_host + e0 * O, w->d_obs + e0 * O, sizeof(float) * ne * O, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(reward_host + e0, w->d_rew + e0, sizeof(float) * ne, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(done_host + e0, w->d_done + e0, ne, cudaMemcpyDeviceToHost, st));
+    }
+    for (int c = 0; c < n_chunks; c++) CK(cudaStreamSynchronize(w->chunk_stream[c]));
+    return 0;
+}
+
 extern "C" int rs_world_policy_step_host(rs_world* w, rs_policy* p, const float* obs_in_host, float* obs_out_host, float* reward_host,
                                          uint8_t* done_host) {
     if (!p || !obs_out_host || !reward_host || !done_host) return fail("rs_world_policy_step_host: null argument");
     CK(cudaSetDevice(w->device));
     size_t N = (size_t)w->n, O = (size_t)w->desc.obs_dim;
+    const bool direct = host_is_pinned(obs_out_host) && host_is_pinned(reward_host) && host_is_pinned(done_host);
+    {
+        int n_chunks = 4;                                   // RS_E2E_CHUNKS=1 selects the single-stream form (A/B measurements)
+        if (const char* e = getenv("RS_E2E_CHUNKS")) n_chunks = atoi(e);
+        if (n_chunks > RS_MAX_CHUNKS) n_chunks = RS_MAX_CHUNKS;
+        if (n_chunks > 1 && w->topo && direct && w->n >= 8192 && (!obs_in_host || host_is_pinned(obs_in_host)))
+            return policy_step_host_pipelined(w, p, obs_in_host, obs_out_host, reward_host, done_host, n_chunks);
+    }
     if (obs_in_host) {   // NULL: continue from the observations already on the device (after rs_world_rollout_reset / rollout)
         const float* src = obs_in_host;
         if (!host_is_pinned(obs_in_host)) { memcpy(w->h_obs, obs_in_host, sizeof(float) * N * O); src = w->h_obs; }
@@ -621,7 +677,6 @@ extern "C" int rs_world_policy_step_host(rs_world* w, rs_policy* p, const float*
     }
     if (rs_policy_forward(p, w->d_obs, w->d_act, w->n, (void*)w->stream)) return 1;
     if (launch_step(w, w->d_act, w->d_obs, w->d_rew, w->d_done, 1, w->rollout_seed, w->env_id0, nullptr, w->stream)) return 1;
-    const bool direct = host_is_pinned(obs_out_host) && host_is_pinned(reward_host) && host_is_pinned(done_host);
     CK(cudaMemcpyAsync(direct ? obs_out_host : w->h_obs, w->d_obs, sizeof(float) * N * O, cudaMemcpyDeviceToHost, w->stream));
     CK(cudaMemcpyAsync(direct ? reward_host : w->h_rew, w->d_rew, sizeof(float) * N, cudaMemcpyDeviceToHost, w->stream));
     CK(cudaMemcpyAsync(direct ? done_host : w->h_done, w->d_done, N, cudaMemcpyDeviceToHost, w->stream));

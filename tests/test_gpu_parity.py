@@ -270,6 +270,45 @@ def test_behavioural_fixture_on_gpu_humanoid_walks():
     assert s[1] >= 0.97 * n and s[2] / s[1] > 990, (s[1], s[2] / max(s[1], 1))
 
 
+@pytest.mark.parametrize("env_id,n", [("RoboschoolHumanoid-v1", 17000), ("RoboschoolHopper-v1", 9000), ("RoboschoolAnt-v1", 33152)])
+def test_policy_step_host_pipelined_matches_single_stream(env_id, n, monkeypatch):
+    """rs_world_policy_step_host with page-locked buffers cuts the envs into CTA-aligned slices on separate streams (copies of
+    one slice overlap the kernels of the others).  Bit-identical to the single-stream form (RS_E2E_CHUNKS=1) and to pageable
+    buffers (staged path), over steps that include auto-resets; n is ragged on purpose (partial tail CTA, partial tail slice)."""
+    import torch
+    from roboschool_b200.world import BatchedWorld
+    from roboschool_b200.policy import ZooPolicy, load_zoo_weights
+    m = load_env_model(env_id)
+    pol = ZooPolicy(load_zoo_weights(env_id), 0)
+    st = torch.cuda.current_stream().cuda_stream
+    def run(chunks, pinned):
+        monkeypatch.setenv("RS_E2E_CHUNKS", str(chunks))
+        W = BatchedWorld(m, n, 0)
+        obs0 = torch.empty((n, m.obs_dim), dtype=torch.float32, device="cuda")
+        W.reset(seed=9, obs=obs0, stream=st)
+        torch.cuda.synchronize()
+        if pinned:
+            a, b = W.pinned_host_buffers(), W.pinned_host_buffers()
+        else:
+            a = (np.empty((n, m.obs_dim), np.float32), np.empty(n, np.float32), np.empty(n, np.uint8))
+            b = (np.empty((n, m.obs_dim), np.float32), np.empty(n, np.float32), np.empty(n, np.uint8))
+        a[0][:] = obs0.cpu().numpy()
+        outs = []
+        cur, nxt = a, b
+        for t in range(40):
+            W.policy_step_host(pol, cur[0], out=nxt)
+            outs.append((nxt[0].copy(), nxt[1].copy(), nxt[2].copy()))
+            cur, nxt = nxt, cur
+        return outs
+    ref = run(1, True)
+    if env_id == "RoboschoolHopper-v1":        # its zoo policy falls within ~30 steps on the restated physics: auto-resets are covered
+        assert sum(int(d.sum()) for _, _, d in ref) > 0
+    for chunks, pinned in [(4, True), (3, True), (4, False)]:
+        got = run(chunks, pinned)
+        for (o, r, d), (o2, r2, d2) in zip(ref, got):
+            assert np.array_equal(o, o2) and np.array_equal(r, r2) and np.array_equal(d, d2), (chunks, pinned)
+
+
 @pytest.mark.parametrize("env_id,min_return,min_len", [
     ("RoboschoolInvertedPendulum-v1", 950.0, 990), ("RoboschoolInvertedDoublePendulum-v1", 7000.0, 750),
     ("RoboschoolReacher-v1", 15.0, 150), ("RoboschoolHopper-v1", 2000.0, 950)])
