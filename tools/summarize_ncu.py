@@ -6,6 +6,10 @@ writes profiles/<tag>_launches.csv (copy), profiles/<tag>_summary.md and profile
 import collections, csv, io, json, os, shutil, subprocess, sys
 
 launches, rep, tag = sys.argv[1:4]
+# optional: algorithmic bytes per env step and envs per launch of the capture (default: the Humanoid bench config)
+alg_bytes = int(sys.argv[4]) if len(sys.argv) > 4 else 628
+n_envs = int(sys.argv[5]) if len(sys.argv) > 5 else 32768
+write_traffic = len(sys.argv) <= 4
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
@@ -55,8 +59,9 @@ def to_bytes(k):
     v, u = float(get(k)), unit(k).lower()
     return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
 traffic = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
-json.dump({"kernel": get("Kernel Name"), "dram_bytes_per_launch": traffic, "source": os.path.basename(rep), "tag": tag},
-          open(os.path.join(out_dir, "k_step_traffic.json"), "w"))
-md += ["", "DRAM traffic per launch: %.3f GB (algorithmic: 628 B x 32768 envs = 0.0206 GB)" % (traffic / 1e9)]
+if write_traffic:    # bench.py reads this file for roofline.traffic of its default (Humanoid) workload
+    json.dump({"kernel": get("Kernel Name"), "dram_bytes_per_launch": traffic, "source": os.path.basename(rep), "tag": tag},
+              open(os.path.join(out_dir, "k_step_traffic.json"), "w"))
+md += ["", "DRAM traffic per launch: %.3f GB (algorithmic: %d B x %d envs = %.4f GB)" % (traffic / 1e9, alg_bytes, n_envs, alg_bytes * n_envs / 1e9)]
 open(os.path.join(out_dir, tag + "_summary.md"), "w").write("\n".join(md) + "\n")
 print("\n".join(md))
