@@ -97,6 +97,13 @@ int rs_world_policy_step_host(rs_world* w, rs_policy* p, const float* obs_in_hos
  * (physics-bullet.cpp:497-508, 358-412). */
 int rs_world_substeps(rs_world* w, int n_substeps, const float* tau_host);
 
+/* Joint::set_servo_target(pos, kp, kd, maxforce) / Joint::set_target_speed(v, kd, maxforce) (physics-bullet.cpp:510-537;
+ * python-binding.cpp:654-665): Bullet's btMultiBodyJointMotor of one joint dof -- a velocity-level row after the joint-limit rows,
+ * target kp (target_pos - q) / dt + kd (target_vel - qd), impulse within -+ max_impulse per sub-step.  max_impulse <= 0 switches
+ * the motor off (what Joint::set_motor_torque does on its first call).  env < 0: every env.  A world that has had a motor set
+ * steps on the runtime-topology kernel (the static-topology kernels build no motor rows). */
+int rs_world_set_joint_motor(rs_world* w, int env, int dof, float kp, float kd, float target_pos, float target_vel, float max_impulse);
+
 /* State exchange with HOST buffers (tests, the single-env cpp_household shim, checkpointing). */
 int rs_world_set_state(rs_world* w, const float* state_host, int clear_contacts);
 int rs_world_get_state(rs_world* w, float* state_host);

@@ -57,6 +57,7 @@ def lib():
         L.oracle_energy.restype = D
         L.oracle_foot_flags.argtypes = [P, I, ip, ip]
         L.oracle_set_flag.argtypes = [P, I, D, D, I, U]
+        L.oracle_set_joint_motor.argtypes = [P, I, I, D, D, D, D, D]
         L.oracle_get_flag.argtypes = [P, I, dp, dp, ip, ctypes.POINTER(U)]
         L.oracle_get_task_state.argtypes = [P, I, dp]
         L.oracle_set_task_state.argtypes = [P, I, dp]
@@ -117,6 +118,10 @@ class OracleWorld:
     def reset(self, seed=0, env_id0=0):
         self.seed, self.env_id0 = seed, env_id0     # the flag RNG stream of later steps continues from these
         self.L.oracle_reset_all(self.h, seed, env_id0)
+
+    def set_joint_motor(self, env, dof, kp, kd, target_pos, target_vel, max_impulse):
+        """btMultiBodyJointMotor of one dof (env < 0: every env); max_impulse per sub-step, 0 = off."""
+        self.L.oracle_set_joint_motor(self.h, env, dof, kp, kd, target_pos, target_vel, max_impulse)
 
     def set_flag(self, env, tx, ty, timeout, draws):
         self.L.oracle_set_flag(self.h, env, tx, ty, int(timeout), int(draws))

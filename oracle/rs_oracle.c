@@ -66,6 +66,9 @@ typedef struct {
     double base_w[3], base_v[3];      /* world frame */
     double q[ML], qd[ML];
     double tau[ML];                   /* joint torques, persist over the sub-steps of one env step */
+    /* btMultiBodyJointMotor per dof (Joint::set_servo_target / set_target_speed, physics-bullet.cpp:510-537):
+     * kp, kd, position / velocity targets and the impulse bound per sub-step; bound 0 = motor off (torque control) */
+    double mot_kp[ML], mot_kd[ML], mot_pos[ML], mot_vel[ML], mot_imp[ML];
     manifold *man;                    /* [n_geoms floor manifolds][n_pairs pair manifolds] */
     /* episode bookkeeping (gym_forward_walker.py) */
     double potential;
@@ -696,6 +699,21 @@ static int setup_rows(const rs_model_desc *m, oenv *e, double dt, crow *nc, int 
             r->lo = 0; r->hi = m->max_limit_impulse; r->cp = NULL; r->friction_index = -1;
         }
     }
+    /* btMultiBodyJointMotor::createConstraintRows.  The motors are added to the world by createJointMotors() after the
+     * import created the limit constraints, so their rows follow the limit rows.  desiredVelocity handed to
+     * fillMultiBodyConstraint = kp * erp * (q* - q) / dt + qd + kd * (qd* - qd) with the motor's erp = 1; the row's
+     * velocity error is that minus J.v (= qd), bounds -+ maxAppliedImpulse, no positional term. */
+    for (int i = 0; i < m->n_links; i++) {
+        int d = m->dof_idx[i];
+        if (d < 0 || !(e->mot_imp[d] > 0)) continue;
+        double jA[MAXDOF]; memset(jA, 0, sizeof jA);
+        jA[6 + d] = 1.0;
+        crow *r = &nc[(*n_nc)++];
+        double relvel = row_finish(m, e, r, jA, NULL, nd);
+        double desired = e->mot_kp[d] * (e->mot_pos[d] - e->q[d]) / dt + e->qd[d] + e->mot_kd[d] * (e->mot_vel[d] - e->qd[d]);
+        r->rhs = (desired - relvel) * r->inv_denom;
+        r->lo = -e->mot_imp[d]; r->hi = e->mot_imp[d]; r->cp = NULL; r->friction_index = -1;
+    }
     /* contacts: btMultiBodyConstraintSolver::convertMultiBodyContact, manifold order, point order */
     int nman = m->n_geoms + m->n_pairs;
     for (int k = 0; k < nman; k++) {
@@ -749,7 +767,7 @@ static inline void resolve_row(crow *c, double *dv, int nd) {
 }
 
 static void solve(const rs_model_desc *m, oenv *e, double dt) {
-    static __thread crow nc[2 * ML], cn[MAXROWS / 4], cf[MAXROWS / 2];
+    static __thread crow nc[3 * ML], cn[MAXROWS / 4], cf[MAXROWS / 2];
     int n_nc, n_cn, n_cf, nd = 6 + m->n_dof;
     int total = setup_rows(m, e, dt, nc, &n_nc, cn, &n_cn, cf, &n_cf);
     e->n_rows_last = total; e->n_contacts_last = n_cn;
@@ -1179,6 +1197,14 @@ void oracle_get_episode(const oracle_world *w, int env, double *potential, doubl
     const oenv *e = &w->env[env];
     *potential = e->potential; *initial_z = e->initial_z; *frame = e->frame;
     for (int k = 0; k < w->m.n_feet; k++) feet_contact[k] = e->feet_contact[k];
+}
+/* Joint motor of one dof of one env (env < 0: every env).  max_impulse is per sub-step: the reference's control commands
+ * set maxForce * physicsDeltaTime with physicsDeltaTime = timestep * frame_skip (physics-bullet.cpp:363,373); 0 = off. */
+void oracle_set_joint_motor(oracle_world *w, int env, int dof, double kp, double kd, double target_pos, double target_vel, double max_impulse) {
+    for (int k = (env < 0 ? 0 : env); k < (env < 0 ? w->n_envs : env + 1); k++) {
+        oenv *e = &w->env[k];
+        e->mot_kp[dof] = kp; e->mot_kd[dof] = kd; e->mot_pos[dof] = target_pos; e->mot_vel[dof] = target_vel; e->mot_imp[dof] = max_impulse;
+    }
 }
 void oracle_set_flag(oracle_world *w, int env, double tx, double ty, int timeout, uint32_t draws) {
     oenv *e = &w->env[env];

@@ -148,19 +148,40 @@ class Joint(object):
         self._l1, self._l2 = np.float32(m.lim_lo[link]), np.float32(m.lim_hi[link])
         self._max_vel = np.float32(m.max_vel[link])
         self._torque = np.float32(0.0)
+        self._first_torque_call, self._torque_need_repeat = True, False
 
     def type(self):
         return "motor" if self._revolute else "linear_motor"
 
     def set_motor_torque(self, q):
-        # first call disables Bullet's default motor (physics-bullet.cpp:502-505): motors are always off here
+        """physics-bullet.cpp:497-508: the first torque call after a motor command (or after loading) switches Bullet's
+        joint motor off with set_servo_target(0, 0.1, 0.1, maxforce 0); the torque is then re-applied every step."""
+        if self._first_torque_call:
+            self.set_servo_target(0, 0.1, 0.1, 0)
+            self._first_torque_call = False
+        self._torque_need_repeat = True
         self._torque = np.float32(q)
 
+    def _server_dt(self):
+        # maxForce is turned into an impulse bound with the physics server's time step, which bullet_step sets to
+        # timestep * skip_frames (physics-bullet.cpp:363-376); before the first step it still has Bullet's default 1/240
+        w = self._robot._world
+        return w._timestep * w._last_repeat if w._last_repeat else 1.0 / 240.0
+
+    def _set_motor(self, kp, kd, target_pos, target_vel, maxforce):
+        b = self._robot._backend
+        if b is not None and self._dof >= 0:
+            b.set_joint_motor(self._dof, kp, kd, target_pos, target_vel, float(np.float32(maxforce)) * self._server_dt())
+        self._first_torque_call = True
+        self._torque_need_repeat = False
+
     def set_servo_target(self, pos, kp, kd, maxforce):
-        raise NotImplementedError("PD servo motor rows are outside the accelerated path (SURVEY.md 8f.3)")
+        """physics-bullet.cpp:524-537 (CONTROL_MODE_POSITION_VELOCITY_PD: position target, velocity target 0)."""
+        self._set_motor(float(np.float32(kp)), float(np.float32(kd)), float(np.float32(pos)), 0.0, maxforce)
 
     def set_target_speed(self, v, kd, maxforce):
-        raise NotImplementedError("velocity motor rows are outside the accelerated path (SURVEY.md 8f.3)")
+        """physics-bullet.cpp:510-522 (CONTROL_MODE_VELOCITY: kp 0)."""
+        self._set_motor(0.0, float(np.float32(kd)), 0.0, float(np.float32(v)), maxforce)
 
     def current_position(self):
         q, qd = self._robot._joint_state(self._dof)
@@ -267,7 +288,8 @@ class Robot(object):
     def _torques(self):
         tau = np.zeros((1, max(self._model.n_dof, 1)), dtype=np.float32)
         for j in self.joints:
-            tau[0, j._dof] = j._torque
+            if j._torque_need_repeat:
+                tau[0, j._dof] = j._torque
         return tau[:, :self._model.n_dof]
 
     # ---- API ----
@@ -314,6 +336,7 @@ class World(object):
         self._gravity = float(np.float32(gravity))
         self._timestep = float(np.float32(timestep))
         self._raw_timestep = timestep
+        self._last_repeat = 0
         self.ts = 0.0
         self._robots = []
         self._floor = None
@@ -373,6 +396,7 @@ class World(object):
         for r in self._robots:
             if r._backend is not None:
                 r._backend.substeps(int(repeat), r._torques())
+        self._last_repeat = int(repeat)
         self.ts += self._timestep * repeat
         for r in self._robots:
             r._refresh()

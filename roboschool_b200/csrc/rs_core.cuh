@@ -271,6 +271,10 @@ struct Work {
     int ccount[2];
     int cur;
     int n_rows, n_contacts;      // of the last solve (reported)
+    // joint motors (btMultiBodyJointMotor) of this env, or nullptr when the world has none: element (field f, dof d) at
+    // motor[(f * n_dof + d) * motor_stride], fields kp, kd, target position, target velocity, impulse bound per sub-step
+    const float* motor = nullptr;
+    int motor_stride = 0;
 };
 
 // row workspace: one record per constraint row, strided so that lane-adjacent envs are address-adjacent
@@ -841,10 +845,12 @@ template <int NL, int MC, bool SL, class Resp>
 RS_HD void solve_with(const DevModel& M, Work<NL, MC, SL>& W, float dt, const RowWS& ws, Resp&& resp) {
     constexpr int NDMAX = 6 + NL;
     const int nd = 6 + M.n_dof, rec = 2 * nd;
-    const int NC0 = 0, CN0 = NL, CF0 = NL + MC;    // row-index bases of the three groups
+    // row-index bases of the three groups; worlds with joint motors reserve a second block of NL non-contact rows
+    const int NCCAP = W.motor ? 2 * NL : NL;
+    const int NC0 = 0, CN0 = NCCAP, CF0 = NCCAP + MC;
     int n_nc = 0, n_cn = 0, n_cf = 0;
     // row scalars stay thread-private; only J and M^-1 J^T (2*nd floats per row) go to the workspace
-    float r_rhs[NL + 3 * MC], r_invd[NL + 3 * MC], r_applied[NL + 3 * MC], r_hi[NL];
+    float r_rhs[2 * NL + 3 * MC], r_invd[2 * NL + 3 * MC], r_applied[2 * NL + 3 * MC], r_hi[2 * NL], r_lo[2 * NL];
     float vel[NDMAX];
 #pragma unroll
     for (int k = 0; k < NDMAX; k++) vel[k] = 0.f;
@@ -871,7 +877,27 @@ RS_HD void solve_with(const DevModel& M, Work<NL, MC, SL>& W, float dt, const Ro
             float invd = denom > RS_FLT_EPS ? 1.0f / denom : 0.f;
             float erp = pen > M.split_thresh ? M.erp : M.erp2;
             r_rhs[row] = pen > M.split_thresh ? (-pen * erp * inv_dt - relvel) * invd : (-relvel) * invd;
-            r_invd[row] = invd; r_applied[row] = 0.f; r_hi[row] = M.max_limit_impulse;
+            r_invd[row] = invd; r_applied[row] = 0.f; r_hi[row] = M.max_limit_impulse; r_lo[row] = 0.f;
+        }
+    }
+    // joint motors (btMultiBodyJointMotor::createConstraintRows; the motors join the world after the limit constraints, so
+    // their rows follow the limit rows): velocity target kp (q* - q) / dt + kd (qd* - qd) relative to the current joint
+    // velocity, impulse within -+ bound, no positional term
+    if (W.motor) {
+        for (int i = 0; i < M.n_links; i++) {
+            int d = M.dof_idx[i];
+            if (d < 0) continue;
+            const float* mp = W.motor + (size_t)d * W.motor_stride;
+            const size_t fs = (size_t)M.n_dof * W.motor_stride;
+            float imp = mp[4 * fs];
+            if (!(imp > 0.f)) continue;
+            float kp = mp[0], kd = mp[fs], tp = mp[2 * fs], tv = mp[3 * fs];
+            int row = NC0 + n_nc++;
+            float relvel = 0.f;
+            float denom = resp(-1, (const float*)nullptr, d, 1.f, row, rec, true, (const float*)vel, &relvel);
+            float invd = denom > RS_FLT_EPS ? 1.0f / denom : 0.f;
+            float desired = kp * (tp - W.q[d]) * inv_dt + W.qd[d] + kd * (tv - W.qd[d]);
+            r_rhs[row] = (desired - relvel) * invd; r_invd[row] = invd; r_applied[row] = 0.f; r_hi[row] = imp; r_lo[row] = -imp;
         }
     }
     // contacts in pool order (manifold id, slot)
@@ -921,7 +947,7 @@ RS_HD void solve_with(const DevModel& M, Work<NL, MC, SL>& W, float dt, const Ro
     for (int it = 0; it < M.n_iter; it++) {
         for (int j = 0; j < n_nc; j++) {
             int row = NC0 + ((it & 1) ? j : n_nc - 1 - j);
-            resolve_row<NDMAX>(ws, row, rec, nd, dv, r_rhs[row], r_invd[row], 0.f, r_hi[row], r_applied[row]);
+            resolve_row<NDMAX>(ws, row, rec, nd, dv, r_rhs[row], r_invd[row], r_lo[row], r_hi[row], r_applied[row]);
         }
         for (int j = 0; j < n_cn; j++) {
             int row = CN0 + j;

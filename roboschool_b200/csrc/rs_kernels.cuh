@@ -15,6 +15,7 @@ struct DevBuf {
     double* target; int* flag_timeout; uint32_t* flag_draws;   // Flagrun: target [2][N], steps left, RNG draws used
     int* hx_i; double* hx_d;   // FlagrunHarder: [7][N] task, on_ground, crawl_valid, done_latch, hist[3] ; [2][N] crawl_start, crawl_ignored
     float* rows; float* tau; float* rewards5; int* nrows; int* ncontacts;
+    float* motor;              // joint motors [5][n_dof][N] (kp, kd, target pos, target vel, impulse bound), nullptr until one is set
     int N, S, MCcap, rec, maxr;
 };
 
@@ -61,6 +62,7 @@ __device__ __forceinline__ void load_env(const DevModel& M, const DevBuf& B, int
     }
     E.elec_cost = M.electricity_cost;
     W.n_rows = 0; W.n_contacts = 0;
+    W.motor = B.motor ? B.motor + e : nullptr; W.motor_stride = N;
 }
 
 template <int NL, int MC, bool SL>

@@ -291,7 +291,7 @@ extern "C" int rs_world_destroy(rs_world* w) {
     DevBuf& B = w->B;
     cudaFree(B.state); cudaFree(B.ccount); cudaFree(B.ckey); cudaFree(B.cdat); cudaFree(B.potential); cudaFree(B.initial_z);
     cudaFree(B.feet); cudaFree(B.frame); cudaFree(B.episode); cudaFree(B.rows); cudaFree(B.tau); cudaFree(B.rewards5);
-    cudaFree(B.nrows); cudaFree(B.ncontacts); cudaFree(B.target); cudaFree(B.flag_timeout); cudaFree(B.flag_draws); cudaFree(B.hx_i); cudaFree(B.hx_d);
+    cudaFree(B.nrows); cudaFree(B.ncontacts); cudaFree(B.target); cudaFree(B.flag_timeout); cudaFree(B.flag_draws); cudaFree(B.hx_i); cudaFree(B.hx_d); cudaFree(B.motor);
     cudaFreeHost(w->h_act); cudaFreeHost(w->h_obs); cudaFreeHost(w->h_rew); cudaFreeHost(w->h_done);
     cudaFree(w->d_act); cudaFree(w->d_obs); cudaFree(w->d_rew); cudaFree(w->d_done); cudaFree(w->d_stats);
     cudaStreamDestroy(w->stream);
@@ -321,7 +321,7 @@ extern "C" int rs_world_reset(rs_world* w, uint32_t seed, uint32_t env_id0, cons
 
 static int launch_step(rs_world* w, const float* actions, float* obs, float* rew, uint8_t* done, int auto_reset, uint32_t seed,
                        uint32_t env_id0, double* stats, cudaStream_t st, int cta0 = 0, int ncta = 0) {
-    if (w->topo) {
+    if (w->topo && !w->B.motor) {      // worlds with joint motors step on the runtime-topology kernel (motor rows live there)
         StaticLaunch a{&w->M, &w->B, w->n, actions, obs, rew, done, auto_reset, seed, env_id0, stats, nullptr, st};
         a.cta0 = cta0; a.ncta = ncta;
         StaticLaunchFn fn = pick_static(w->topo, 0, w->wpc);
@@ -391,6 +391,38 @@ extern "C" int rs_world_step_host(rs_world* w, const float* actions_host, float*
     memcpy(obs_host, w->h_obs, sizeof(float) * N * O);
     memcpy(reward_host, w->h_rew, sizeof(float) * N);
     memcpy(done_host, w->h_done, N);
+    return 0;
+}
+
+// Joint::set_servo_target / set_target_speed (physics-bullet.cpp:510-537) -> btMultiBodyJointMotor of one dof.
+extern "C" int rs_world_set_joint_motor(rs_world* w, int env, int dof, float kp, float kd, float target_pos, float target_vel, float max_impulse) {
+    if (!w) return fail("rs_world_set_joint_motor: null world");
+    const int nd = w->desc.n_dof, N = w->n;
+    if (dof < 0 || dof >= nd || env >= N) return fail("rs_world_set_joint_motor: dof or env out of range");
+    CK(cudaSetDevice(w->device));
+    DevBuf& B = w->B;
+    CK(cudaStreamSynchronize(w->stream));
+    if (!B.motor) {
+        if (!(max_impulse > 0.f)) return 0;                  // switching off a motor of a world that never had one
+        // first motor of this world: motor table (all off) and a row workspace with room for one motor row per dof
+        int NLc = 0, MCc = 0;
+        family_of(&w->desc, &NLc, &MCc);
+        const int maxr = 2 * NLc + 3 * MCc;
+        float* rows = nullptr;
+        CK(cudaMalloc(&rows, sizeof(float) * (size_t)((N + 255) / 256 * 256 + 256) * B.rec * maxr));
+        CK(cudaDeviceSynchronize());
+        cudaFree(B.rows);
+        B.rows = rows; B.maxr = maxr;
+        CK(cudaMalloc(&B.motor, sizeof(float) * 5 * (size_t)nd * N));
+        CK(cudaMemset(B.motor, 0, sizeof(float) * 5 * (size_t)nd * N));
+    }
+    const float v[5] = {kp, kd, target_pos, target_vel, max_impulse > 0.f ? max_impulse : 0.f};
+    const int e0 = env < 0 ? 0 : env, ne = env < 0 ? N : 1;
+    std::vector<float> row((size_t)ne);
+    for (int f = 0; f < 5; f++) {
+        for (int k = 0; k < ne; k++) row[k] = v[f];
+        CK(cudaMemcpy(B.motor + ((size_t)f * nd + dof) * N + e0, row.data(), sizeof(float) * ne, cudaMemcpyHostToDevice));
+    }
     return 0;
 }
 
@@ -667,7 +699,7 @@ extern "C" int rs_world_policy_step_host(rs_world* w, rs_policy* p, const float*
         int n_chunks = 4;                                   // RS_E2E_CHUNKS=1 selects the single-stream form (A/B measurements)
         if (const char* e = getenv("RS_E2E_CHUNKS")) n_chunks = atoi(e);
         if (n_chunks > RS_MAX_CHUNKS) n_chunks = RS_MAX_CHUNKS;
-        if (n_chunks > 1 && w->topo && direct && w->n >= 8192 && (!obs_in_host || host_is_pinned(obs_in_host)))
+        if (n_chunks > 1 && w->topo && !w->B.motor && direct && w->n >= 8192 && (!obs_in_host || host_is_pinned(obs_in_host)))
             return policy_step_host_pipelined(w, p, obs_in_host, obs_out_host, reward_host, done_host, n_chunks);
     }
     if (obs_in_host) {   // NULL: continue from the observations already on the device (after rs_world_rollout_reset / rollout)

@@ -84,6 +84,10 @@ class BatchedWorld:
             t = np.ascontiguousarray(tau, dtype=np.float32).reshape(self.n, self.model.n_dof)
         _lib.check(self.L.rs_world_substeps(self.h, int(n), _ptr(t)))
 
+    def set_joint_motor(self, dof, kp, kd, target_pos, target_vel, max_impulse, env=-1):
+        """btMultiBodyJointMotor of one joint dof (env -1: every env); max_impulse per sub-step, <= 0 switches it off."""
+        _lib.check(self.L.rs_world_set_joint_motor(self.h, int(env), int(dof), float(kp), float(kd), float(target_pos), float(target_vel), float(max_impulse)))
+
     def set_state(self, state, clear_contacts=True):
         s = np.ascontiguousarray(state, dtype=np.float32).reshape(self.n, self.S)
         _lib.check(self.L.rs_world_set_state(self.h, s.ctypes.data, int(clear_contacts)))

@@ -23,6 +23,7 @@ struct Emul {
     int topo;                 // 0 generic, 1 humanoid, 2 ant, 3 hopper, 4 walker2d (static-topology sweeps)
     std::vector<float> lcbuf; // per-env link cache (shared memory on the GPU)
     int lcsize;
+    std::vector<float> motor; // joint motors [n][5][n_dof], allocated by the first emul_set_joint_motor
 };
 
 template <class T>
@@ -85,9 +86,21 @@ void emul_get_state(void* h, int env, double* s) {
     for (int d = 0; d < e->M.n_dof; d++) { s[d] = W.q[d]; s[e->M.n_dof + d] = W.qd[d]; }
 }
 void emul_set_tau(void* h, int env, const double* tau) { Emul* e = (Emul*)h; for (int d = 0; d < e->M.n_dof; d++) e->w[env].tau[d] = (float)tau[d]; }
+// btMultiBodyJointMotor of one dof (rs_world_set_joint_motor); envs with motors run the runtime-topology sweeps, like the library
+void emul_set_joint_motor(void* h, int env, int dof, double kp, double kd, double pos, double vel, double imp) {
+    Emul* e = (Emul*)h; const int nd = e->M.n_dof;
+    if (e->motor.empty()) {
+        e->motor.assign((size_t)e->n * 5 * nd, 0.f);
+        e->ws.resize((size_t)e->rec * (2 * NL + 3 * MC));
+        for (int i = 0; i < e->n; i++) { e->w[i].motor = e->motor.data() + (size_t)i * 5 * nd; e->w[i].motor_stride = 1; }
+    }
+    const double v[5] = {kp, kd, pos, vel, imp > 0 ? imp : 0};
+    for (int i = (env < 0 ? 0 : env); i < (env < 0 ? e->n : env + 1); i++)
+        for (int f = 0; f < 5; f++) e->motor[(size_t)i * 5 * nd + f * nd + dof] = (float)v[f];
+}
 void emul_substeps(void* h, int env, int n) {
     Emul* e = (Emul*)h; RowWS ws{e->ws.data(), 1};
-    switch (e->topo) {
+    switch (e->w[env].motor ? 0 : e->topo) {
         case 1: substeps_static<TopoHumanoid>(e, env, n); return;
         case 2: substeps_static<TopoAnt>(e, env, n); return;
         case 3: substeps_static<TopoHopper>(e, env, n); return;

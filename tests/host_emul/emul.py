@@ -35,6 +35,7 @@ def lib():
         L.emul_set_state.argtypes = [P, I, dp, I]
         L.emul_get_state.argtypes = [P, I, dp]
         L.emul_set_tau.argtypes = [P, I, dp]
+        L.emul_set_joint_motor.argtypes = [P, I, I, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double]
         L.emul_substeps.argtypes = [P, I, I]
         L.emul_reset_all.argtypes = [P, U, U]
         L.emul_set_episode.argtypes = [P, I, D, D, dp, I]
@@ -81,6 +82,9 @@ class EmulWorld:
 
     def set_tau(self, env, tau):
         t = np.zeros(self.model.n_dof); t[:] = tau; self.L.emul_set_tau(self.h, env, _dp(t))
+
+    def set_joint_motor(self, env, dof, kp, kd, target_pos, target_vel, max_impulse):
+        self.L.emul_set_joint_motor(self.h, env, dof, kp, kd, target_pos, target_vel, max_impulse)
 
     def substeps(self, env, n=1): self.L.emul_substeps(self.h, env, n)
 

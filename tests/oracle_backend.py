@@ -27,6 +27,9 @@ class OracleBackend:
             self.o.set_tau(0, np.asarray(tau, dtype=np.float64).reshape(-1))
         self.o.substeps(0, int(n))
 
+    def set_joint_motor(self, dof, kp, kd, target_pos, target_vel, max_impulse, env=-1):
+        self.o.set_joint_motor(0, int(dof), float(kp), float(kd), float(target_pos), float(target_vel), float(max_impulse))
+
     def link_poses(self):
         return self.o.link_poses(0)[None]
 

@@ -95,3 +95,40 @@ def test_load_failure_is_silent_like_reference(capsys):
     assert w.load_mjcf("/nonexistent/robot.xml") == []
     assert "cannot load MJCF" in capsys.readouterr().err
     assert w.step(4) is False
+
+
+def test_joint_motor_state_machine_on_shim(ref_roboschool, oracle_lib):
+    """Joint.set_servo_target / set_target_speed / set_motor_torque (python-binding.cpp:654-665, physics-bullet.cpp:497-537)
+    through the shim on a reference env's own joints: a position servo pulls a knee towards its target, a velocity motor
+    spins a hip at the commanded speed, and the next set_motor_torque switches the motor off again (first_torque_call)
+    so that the joint is torque-controlled as before."""
+    env = ref_roboschool.RoboschoolHumanoid()
+    env.spec = _Spec()
+    env.seed(1)
+    env.reset()
+    world = env.scene.cpp_world
+    knee, hip = env.jdict["right_knee"], env.jdict["left_hip_y"]
+    for j in env.ordered_joints:
+        j.set_motor_torque(0.0)
+    world.step(1)                                        # the server's time step is now timestep * 1
+    q0 = knee.current_position()[0]
+    knee.set_servo_target(-1.0, 0.1, 0.4, 80.0)
+    hip.set_target_speed(-1.5, 0.5, 200.0)
+    assert knee._first_torque_call and not knee._torque_need_repeat
+    for k in range(12):
+        world.step(4)
+    assert knee.current_position()[0] < q0 - 0.3         # moved well towards -1.0
+    assert abs(hip.current_position()[1] + 1.5) < 0.4     # spinning at about the commanded speed
+    knee.set_motor_torque(0.0); hip.set_motor_torque(0.0)
+    assert not knee._first_torque_call and knee._torque_need_repeat
+    b = env.cpp_robot._backend
+    s_before = b.get_state().copy()
+    world.step(1)
+    # same step on a world that never had motors: identical (the motor rows are gone, not merely weak)
+    from tests.oracle_backend import OracleBackend
+    ref = OracleBackend(env.cpp_robot._model, 1)
+    ref.set_state(s_before, clear_contacts=True)
+    b2 = OracleBackend(env.cpp_robot._model, 1); b2.set_state(s_before, clear_contacts=True)
+    b2.set_joint_motor(knee._dof, 0.1, 0.4, -1.0, 0.0, 0.0)
+    ref.substeps(1, np.zeros(env.cpp_robot._model.n_dof)); b2.substeps(1, np.zeros(env.cpp_robot._model.n_dof))
+    assert np.array_equal(ref.get_state(), b2.get_state())

@@ -132,6 +132,42 @@ def test_pendulum_physics_only(oracle_lib):
     assert np.abs(w.get_state() - o.get_state()).max() < 2e-4
 
 
+@pytest.mark.parametrize("env_id", ["RoboschoolInvertedPendulum-v1", "RoboschoolHopper-v1", "RoboschoolHumanoid-v1"])
+def test_joint_motor_rows_match_oracle(env_id, oracle_lib):
+    """rs_world_set_joint_motor (btMultiBodyJointMotor rows behind Joint::set_servo_target / set_target_speed): PD servos with
+    per-env targets on every joint and a velocity motor on the first one, physics-only sub-steps, teacher-forced against the
+    oracle; and the full env step of a world with motors (runtime-topology kernel) against the oracle's."""
+    m, w, o = _worlds(env_id, 16, 2)
+    n, nd, dt = 16, m.n_dof, m.timestep
+    rs = np.random.RandomState(7)
+    for e in range(n):
+        for d in range(nd):
+            args = (0.1, 0.4, float(rs.uniform(-0.3, 0.3)), 0.0, float(rs.choice([0.05, 2.0, 50.0])) * dt)
+            o.set_joint_motor(e, d, *args); w.set_joint_motor(d, *args, env=e)
+    args = (0.0, 0.8, 0.0, 0.5, 20.0 * dt)
+    o.set_joint_motor(-1, 0, *args); w.set_joint_motor(0, *args)           # env -1: every env
+    errs = []
+    for t in range(40):
+        w.set_state(o.get_state().astype(np.float32), clear_contacts=False)
+        for e in range(n):
+            o.substeps(e, 1)
+        w.substeps(1)
+        so, sw = o.get_state(), w.get_state()
+        errs.append(np.abs(so - sw).max(axis=1) / np.maximum(1.0, np.abs(so).max(axis=1)))
+    errs = np.concatenate(errs)
+    assert np.median(errs) <= 1e-5 and np.mean(errs <= 1e-4) >= 0.95 and errs.max() <= 0.2, (np.median(errs), errs.max())
+    # full env step (actions ignored by joints whose motor is on? no: torques still apply, the motor rows come on top)
+    import torch
+    A, O = m.n_act, m.obs_dim
+    act = rs.uniform(-1, 1, (n, A))
+    w.set_state(o.get_state().astype(np.float32), clear_contacts=False)
+    obs = torch.empty((n, O), device="cuda"); rew = torch.empty(n, device="cuda"); done = torch.empty(n, dtype=torch.uint8, device="cuda")
+    w.step(torch.tensor(act, dtype=torch.float32, device="cuda"), obs, rew, done, auto_reset=False)
+    torch.cuda.synchronize()
+    oo, orw, od = o.step(act)
+    assert np.abs(obs.cpu().numpy() - oo).max() < 5e-3
+
+
 def test_link_poses_match(oracle_lib):
     m, w, o = _worlds("RoboschoolHumanoid-v1", 16, 4)
     lp = w.link_poses()

@@ -87,3 +87,28 @@ def test_emul_auto_reset_matches_oracle(emul, oracle_lib):
         if both.any():
             assert np.abs(oo[both] - eo[both]).max() < 1e-6
     assert n_done > 0
+
+
+@pytest.mark.parametrize("env_id", ["RoboschoolInvertedPendulum-v1", "RoboschoolHopper-v1", "RoboschoolHumanoid-v1"])
+def test_emul_joint_motor_rows_match_oracle(env_id, emul, oracle_lib):
+    """Motor rows in the fp32 kernel code against the oracle: PD servos on every joint (impulse bounds between saturating
+    and generous) plus a velocity motor on the first joint, 60 sub-steps from the reset state, teacher-forced."""
+    m = envspec.load_env_model(env_id)
+    o = oracle_lib.OracleWorld(m, 1); o.reset(seed=3)
+    e = emul.EmulWorld(m, 1)
+    e.set_state(0, o.get_state(0))
+    rs = np.random.RandomState(5)
+    dt = m.timestep
+    for d in range(m.n_dof):
+        args = (0.1, 0.4, float(rs.uniform(-0.3, 0.3)), 0.0, float(rs.choice([0.05, 2.0, 50.0])) * dt)
+        o.set_joint_motor(0, d, *args); e.set_joint_motor(0, d, *args)
+    args = (0.0, 0.8, 0.0, 0.5, 20.0 * dt)
+    o.set_joint_motor(0, 0, *args); e.set_joint_motor(0, 0, *args)
+    errs = []
+    for t in range(60):
+        e.set_state(0, o.get_state(0), clear_contacts=False)
+        o.substeps(0, 1); e.substeps(0, 1)
+        so, se = o.get_state(0), e.get_state(0)
+        errs.append(np.abs(so - se).max() / max(1.0, np.abs(so).max()))
+    errs = np.array(errs)
+    assert np.median(errs) <= 1e-5 and errs.max() <= 2e-3, (np.median(errs), errs.max())

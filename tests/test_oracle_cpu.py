@@ -216,3 +216,38 @@ def test_behavioural_fixture_v0_policies(oracle_lib):
     tot, length = _score_v0(oracle_lib, "RoboschoolHopper-v1", 8, 1)
     assert (length == 1000).all(), length
     assert tot.min() > 2000.0, tot
+
+
+def test_joint_motor_rows_closed_forms(oracle_lib):
+    """btMultiBodyJointMotor rows (Joint::set_target_speed / set_servo_target, physics-bullet.cpp:510-537) on the cart-pole:
+    a velocity motor with a generous impulse bound brings the slider to the target speed within one sub-step and holds
+    it whatever the pole does; below saturation the impulse is exactly the bound (velocity change proportional to it);
+    a PD servo on the hinge settles next to its target; bound 0 is torque control (no row)."""
+    m = envspec.load_env_model("RoboschoolInvertedPendulum-v1")
+    nd = m.n_dof
+    w = oracle_lib.OracleWorld(m, 1)
+    w.reset(seed=1)
+    w.set_joint_motor(0, 0, 0.0, 1.0, 0.0, 0.7, 1000.0)
+    for k in range(5):
+        w.substeps(0, 1)
+        assert abs(w.get_state(0)[nd] - 0.7) < 1e-12
+    def fresh():                       # (a second reset of the same world would start episode 1: other joint draws)
+        x = oracle_lib.OracleWorld(m, 1); x.reset(seed=1); return x
+    free = fresh(); free.substeps(0, 1)
+    dv = []
+    for imp in (0.01, 0.02):
+        w = fresh()
+        w.set_joint_motor(0, 0, 0.0, 1.0, 0.0, 0.7, imp)
+        w.substeps(0, 1)
+        dv.append(w.get_state(0)[nd] - free.get_state(0)[nd])
+    assert dv[0] > 0 and abs(dv[1] / dv[0] - 2.0) < 1e-9, dv
+    w = fresh()
+    w.set_joint_motor(0, 1, 0.1, 0.5, 0.3, 0.0, 1000.0)
+    for k in range(300):
+        w.substeps(0, 1)
+    assert abs(w.get_state(0)[1] - 0.3) < 0.03, w.get_state(0)
+    w = fresh()
+    w.set_joint_motor(0, 1, 0.1, 0.5, 0.3, 0.0, 1000.0)
+    w.set_joint_motor(0, 1, 0.1, 0.5, 0.3, 0.0, 0.0)           # off again
+    w.substeps(0, 1)
+    assert np.array_equal(w.get_state(0), free.get_state(0))
