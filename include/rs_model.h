@@ -36,6 +36,8 @@ extern "C" {
 /* geom types */
 #define RS_GEOM_SPHERE  0
 #define RS_GEOM_CAPSULE 1
+#define RS_GEOM_BOX     2 /* btBoxShape: g_p0 = centre, g_p1 = half extents (margin included), g_quat = orientation, g_radius = 0;
+                             collides with the floor plane only (box pairs are dropped by the model compiler)            */
 
 /* task kinds */
 #define RS_TASK_WALKER          0 /* RoboschoolForwardWalker family (gym_forward_walker.py)                  */
@@ -153,6 +155,7 @@ typedef struct rs_model_desc {
     double reset_spread[RS_MAX_ACT];     /* per reset joint: q = center + U(-spread, spread)                       */
     int    task_link2;                   /* Reacher: link "target"                                                */
     int    pad2;
+    double g_quat[RS_MAX_GEOMS][4];      /* box geoms: orientation in the link COM frame, quaternion x,y,z,w (identity otherwise) */
 } rs_model_desc;
 
 #ifdef __cplusplus

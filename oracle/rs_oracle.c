@@ -608,6 +608,18 @@ static void collide(const rs_model_desc *m, oenv *e) {
             if (c1[2] < c0[2]) c = c1;   /* support in -n: first sphere wins ties */
         }
         double vtx[3] = {c[0], c[1], c[2] - m->g_radius[g]};
+        if (m->g_type[g] == RS_GEOM_BOX) {
+            /* btBoxShape::localGetSupportingVertex(R^T (-n)): per box axis +half if the component is >= 0, else -half */
+            double Rb[9], dl[3], db[3], sv[3], vl[3], t[3];
+            const double down[3] = {0, 0, -1};
+            quat_to_mat(Rb, m->g_quat[g]);                  /* box coords -> link coords */
+            m3mulv(dl, e->Rwl[b], down);                    /* -n in link coords */
+            m3tmulv(db, Rb, dl);                            /* -n in box coords */
+            for (int k = 0; k < 3; k++) sv[k] = db[k] >= 0 ? m->g_p1[g][k] : -m->g_p1[g][k];
+            m3mulv(t, Rb, sv);
+            v3add(vl, m->g_p0[g], t);
+            link_to_world(e, b, vl, vtx);
+        }
         double dist = vtx[2];
         if (dist < thr) {
             double pOnB[3] = {vtx[0], vtx[1], 0.0};

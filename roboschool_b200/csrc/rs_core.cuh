@@ -51,6 +51,7 @@ struct DevModel {
     int g_link[MG], g_type[MG], g_floor[MG];
     float g_p0[MG][3], g_p1[MG][3], g_radius[MG], g_fric_floor[MG];
     float g_bound[MG];                // bounding-sphere radius about the segment midpoint (half length + radius)
+    float g_rot[MG][9];               // box geoms: box coords -> link coords (identity otherwise)
     unsigned char pair_a[MP], pair_b[MP], pair_ss[MP];
     float pair_thresh[MP], pair_friction[MP];
     float gravity, timestep, lin_damping, ang_damping, max_coord_vel, erp, erp2, split_thresh, max_limit_impulse, use_gyro;
@@ -741,6 +742,19 @@ RS_HD void collide_manifold(const DevModel& M, Work<NL, MC, SL>& W, int k, int o
         geom_ends(M, k, XA, ge);
         // support vertex in -z: lower end sphere, first end wins ties
         const float* c = (M.g_type[k] == RS_GEOM_CAPSULE && ge[5] < ge[2]) ? ge + 3 : ge;
+        float bv[3];
+        if (M.g_type[k] == RS_GEOM_BOX) {
+            // btBoxShape::localGetSupportingVertex(R^T (-n)): per box axis +half if the component is >= 0, else -half
+            const float down[3] = {0.f, 0.f, -1.f};
+            float dl[3], db[3], sv[3], t[3], vl[3];
+            mulv(dl, XA.R, down); tmulv(db, M.g_rot[k], dl);
+#pragma unroll
+            for (int a = 0; a < 3; a++) sv[a] = db[a] >= 0.f ? M.g_p1[k][a] : -M.g_p1[k][a];
+            mulv(t, M.g_rot[k], sv);
+            vl[0] = M.g_p0[k][0] + t[0]; vl[1] = M.g_p0[k][1] + t[1]; vl[2] = M.g_p0[k][2] + t[2];
+            xf_to_world(XA, vl, bv);
+            c = bv;
+        }
         float dist = c[2] - M.g_radius[k];
         if (dist < thr) {
             const float nz[3] = {0.f, 0.f, 1.f};
@@ -800,7 +814,7 @@ RS_HD void collide(const DevModel& M, Work<NL, MC, SL>& W) {
         if (!has_old) {
             if (k < M.n_geoms) {
                 if (!M.g_floor[k]) continue;
-                float zmin = fminf(gw[k][2], gw[k][5]) - M.g_radius[k];
+                float zmin = fminf(gw[k][2], gw[k][5]) - (M.g_type[k] == RS_GEOM_BOX ? M.g_bound[k] : M.g_radius[k]);
                 if (!(zmin < M.break_thresh[M.g_link[k] + 1])) continue;
             } else {
                 int pk = k - M.n_geoms, ga = M.pair_a[pk], gb = M.pair_b[pk];

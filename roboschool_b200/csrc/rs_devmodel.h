@@ -56,6 +56,17 @@ inline int build_dev_model(const rs_model_desc* m, DevModel* D, const char** err
             double dx = m->g_p1[g][0] - m->g_p0[g][0], dy = m->g_p1[g][1] - m->g_p0[g][1], dz = m->g_p1[g][2] - m->g_p0[g][2];
             D->g_bound[g] = (float)(0.5 * sqrt(dx * dx + dy * dy + dz * dz) + m->g_radius[g]) * 1.0001f + 1e-6f;
         }
+        for (int k = 0; k < 9; k++) D->g_rot[g][k] = (k % 4 == 0) ? 1.f : 0.f;
+        if (m->g_type[g] == RS_GEOM_BOX) {
+            // centre in both end slots (the segment helpers then see a point), bound = half diagonal, rotation from g_quat
+            const double x = m->g_quat[g][0], y = m->g_quat[g][1], z = m->g_quat[g][2], w = m->g_quat[g][3];
+            const double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                                 2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                                 2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)};
+            for (int k = 0; k < 9; k++) D->g_rot[g][k] = (float)R[k];
+            double hx = m->g_p1[g][0], hy = m->g_p1[g][1], hz = m->g_p1[g][2];
+            D->g_bound[g] = (float)sqrt(hx * hx + hy * hy + hz * hz) * 1.0001f + 1e-6f;
+        }
         D->g_fric_floor[g] = (float)(m->g_friction[g] * m->floor_friction);
     }
     for (int k = 0; k < m->n_pairs; k++) {

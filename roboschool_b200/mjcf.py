@@ -27,7 +27,7 @@ build:
    (btCompoundShape::calculateLocalInertia); fromto capsules are
    btMultiSphereShape whose cached AABB carries one extra 0.04 margin;
  * joint ``range`` is converted with ``compiler angle``; damping/stiffness/
-   armature/ref are ignored (``honour_damping=False``);
+   armature/ref are ignored (``honour_damping=False``); box geoms (btBoxShape) collide with the floor plane only;
  * group<-contype, mask<-conaffinity with MuJoCo OR semantics; self-collision
    between links that are not ancestor/descendant.
 """
@@ -39,7 +39,7 @@ import numpy as np
 
 from .model import (ModelDesc, RS_MAX_LINKS, RS_MAX_GEOMS, RS_MAX_PAIRS, RS_MAX_ACT,
                     RS_MAX_FEET, RS_MAX_PARTS, RS_JOINT_FIXED, RS_JOINT_REVOLUTE,
-                    RS_JOINT_PRISMATIC, RS_GEOM_SPHERE, RS_GEOM_CAPSULE)
+                    RS_JOINT_PRISMATIC, RS_GEOM_SPHERE, RS_GEOM_CAPSULE, RS_GEOM_BOX)
 
 CONVEX_DISTANCE_MARGIN = 0.04      # btCollisionMargin.h
 CONTACT_BREAKING_THRESHOLD = 0.02  # gContactBreakingThreshold
@@ -109,7 +109,7 @@ def axisangle_to_mat(aa, degrees):
 
 class _Geom:
     __slots__ = ("name", "type", "p0", "p1", "radius", "fromto", "contype", "conaffinity",
-                 "friction", "density", "volume", "rot", "halflen", "center")
+                 "friction", "density", "volume", "rot", "halflen", "center", "half")
 
 
 class _Joint:
@@ -165,6 +165,16 @@ def _parse_geom(elem, defaults, degrees):
             g.p1 = pos + rot @ np.array([0, 0, +g.halflen])
             h = 2 * g.halflen
         g.volume = math.pi * g.radius ** 2 * h + 4.0 / 3.0 * math.pi * g.radius ** 3
+    elif t == "box":
+        # btBoxShape(half extents) under the geom's own transform; touches the floor plane only
+        if "fromto" in a:
+            raise NotImplementedError("box geom with fromto (model %s)" % g.name)
+        g.type = RS_GEOM_BOX
+        g.radius = 0.0
+        g.half = np.array([float(size[0]), float(size[1]), float(size[2])])
+        g.p0 = pos.copy()
+        g.p1 = pos.copy()
+        g.volume = 8.0 * float(np.prod(g.half))
     elif t == "plane":
         return None
     else:
@@ -229,6 +239,11 @@ def _geom_aabb(g, com):
     if g.type == RS_GEOM_SPHERE:
         c = g.p0 - com
         return c - g.radius, c + g.radius
+    if g.type == RS_GEOM_BOX:
+        # btBoxShape::getAabb: |R| (half extents without margin + margin)
+        ext = np.abs(g.rot) @ g.half
+        c = g.center - com
+        return c - ext, c + ext
     if g.fromto:
         # btMultiSphereShape: cached local AABB is exact, getAabb adds one more margin
         lo = np.minimum(g.p0, g.p1) - com - g.radius - CONVEX_DISTANCE_MARGIN
@@ -415,7 +430,8 @@ def compile_mjcf(xml_path, honour_density=False, honour_damping=False, has_floor
         m.g_link[gi] = li
         m.g_type[gi] = g.type
         m.arr("g_p0")[gi] = g.p0 - com
-        m.arr("g_p1")[gi] = g.p1 - com
+        m.arr("g_p1")[gi] = g.half if g.type == RS_GEOM_BOX else g.p1 - com
+        m.arr("g_quat")[gi] = mat_to_quat_xyzw(g.rot) if g.type == RS_GEOM_BOX else [0.0, 0.0, 0.0, 1.0]
         m.g_radius[gi] = g.radius
         m.g_friction[gi] = g.friction
         m.g_floor[gi] = int(has_floor and bool((g.contype & floor_conaff) or (floor_contype & g.conaffinity)))
@@ -440,6 +456,8 @@ def compile_mjcf(xml_path, honour_density=False, honour_damping=False, has_floor
                 continue
             if not ((ga.contype & gb.conaffinity) or (gb.contype & ga.conaffinity)):
                 continue
+            if ga.type == RS_GEOM_BOX or gb.type == RS_GEOM_BOX:
+                continue               # box-vs-convex needs GJK/EPA: only box-vs-plane is built
             pairs.append((a, b2))
     if len(pairs) > RS_MAX_PAIRS:
         raise ValueError("too many self-collision pairs (%d)" % len(pairs))
