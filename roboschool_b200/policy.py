@@ -13,7 +13,10 @@ def load_zoo_weights(env_id, version="v1"):
     """Weights of the reference's pretrained policy for `env_id` (converted by tools/convert_zoo_weights.py).
     version "v1": agent_zoo/*_v1_2017jul.weights; "v0": the independently trained agent_zoo/*_v0_2017may.py."""
     name = env_id.replace("-v1", "")
-    z = np.load(os.path.join(ZOO_DIR, name + "_" + version + ".npz"))
+    path = os.path.join(ZOO_DIR, name + "_" + version + ".npz")
+    if version == "v1" and not os.path.exists(path):      # the pendulums and the reacher only have a May-2017 policy
+        path = os.path.join(ZOO_DIR, name + "_v0.npz")
+    z = np.load(path)
     return [z[k] for k in ("dense1_w", "dense1_b", "dense2_w", "dense2_b", "final_w", "final_b")]
 
 
