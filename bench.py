@@ -187,8 +187,10 @@ def main():
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    pev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev0.record()
     for t in range(args.steps):
+        pev[t].record()
         pol.forward(obs_p, act_p, n, stream)
         kev[t][0].record()
         _lib.check(W.L.rs_world_step_stats(W.h, act_p, obs_p, rew_p, done_p, 1, stats.data_ptr(), stream))
@@ -198,6 +200,7 @@ def main():
     clocks = sampler.summary() if rank == 0 else None
     ms_total = ev0.elapsed_time(ev1)
     ms_kernel = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    ms_policy = float(np.mean([p.elapsed_time(k[0]) for p, k in zip(pev, kev)]))
     t_ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.barrier()
@@ -249,7 +252,7 @@ def main():
     achieved = abytes * n / (ms_kernel * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "k_step_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and args.env == ENV_ID and n == 32768:     # the capture is of the default workload
         try:
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
@@ -263,6 +266,15 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d envs x %d env-steps of the same workload, %d threads, %.1f s (CPU restatement of the Bullet path, not Bullet itself)" % (n_cpu, ns, cores, dt)}
 
+    # the policy forward is the one contraction of the path: reported against the tensor peak
+    wshape = [w.shape for w in load_zoo_weights(args.env)]
+    flop_env = 2 * (wshape[0][0] * wshape[0][1] + wshape[2][0] * wshape[2][1] + wshape[4][0] * wshape[4][1])
+    tpeak = float(peaks.get("bf16_tflops", 1660.3))        # the kernel is timed alone between two events: burst figure
+    tachieved = flop_env * n / (ms_policy * 1e-3) / 1e12
+    # launches: policy + step per timed step; the host entry point cuts the envs into stream slices (2 launches per slice)
+    chunks = 1
+    if W.L.rs_world_kernel_variant(W.h) > 0 and n >= 8192:
+        chunks = max(1, min(8, int(os.environ.get("RS_E2E_CHUNKS", "4"))))
     st = stats.cpu().numpy()
     line = {
         "metric": METRIC.replace(ENV_ID, args.env), "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -276,7 +288,10 @@ def main():
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "rs_world_policy_step_host (pinned host obs in -> policy -> step -> pinned host obs/reward/done out), %d steps, wall clock" % e2e_steps},
-        "gpu_launches": 2 * args.steps + 2 * (e2e_steps + 4),
+        "roofline_policy": {"bound": "tensor", "achieved": tachieved, "peak": tpeak, "unit": "TFLOP/s", "frac": tachieved / tpeak,
+                            "kernel": "k_mlp_tc5", "flop_per_env": flop_env, "kernel_ms": ms_policy,
+                            "peak_source": "measured (MEASURED_PEAKS.json, dense bf16 burst)" if "bf16_tflops" in peaks else "fallback"},
+        "gpu_launches": 2 * args.steps + 2 * chunks * (e2e_steps + 4),
         "clocks": clocks,
         "rollout_stats": {"mean_reward": st[0] / max(st[6], 1), "episodes": st[1], "mean_episode_len": st[2] / max(st[1], 1),
                           "nonfinite": st[3], "mean_rows": st[4] / max(st[6], 1), "mean_contacts": st[5] / max(st[6], 1), "env_steps": st[6]},
