@@ -671,10 +671,24 @@ static int policy_step_host_pipelined(rs_world* w, rs_policy* p, const float* ob
     }
     const size_t O = (size_t)w->desc.obs_dim, A = (size_t)w->desc.n_act;
     CK(cudaEventRecord(w->chunk_ev, w->stream));            // everything queued on the world's stream so far comes first
-    const int cta_per_chunk = (ncta + n_chunks - 1) / n_chunks;
+    // slice boundaries in CTAs.  Only the first slice's H2D and the last slice's D2H are exposed, so with 4 or more slices
+    // the two outer ones are half as large as the inner ones (RS_E2E_EVEN=1: equal slices).
+    int bound[RS_MAX_CHUNKS + 1];
+    {
+        const char* ev = getenv("RS_E2E_EVEN");
+        const bool even = n_chunks < 4 || (ev && atoi(ev) != 0);
+        const double units = even ? (double)n_chunks : (double)(n_chunks - 1);     // outer slices weigh 1/2
+        double acc = 0.0;
+        bound[0] = 0;
+        for (int c = 0; c < n_chunks; c++) {
+            acc += (even || (c > 0 && c < n_chunks - 1)) ? 1.0 : 0.5;
+            bound[c + 1] = (int)(acc / units * ncta + 0.5);
+        }
+        bound[n_chunks] = ncta;
+    }
     for (int c = 0; c < n_chunks; c++) {
-        const int c0 = c * cta_per_chunk, c1 = (c0 + cta_per_chunk < ncta) ? c0 + cta_per_chunk : ncta;
-        if (c0 >= c1) break;
+        const int c0 = bound[c], c1 = bound[c + 1];
+        if (c0 >= c1) continue;
         const size_t e0 = (size_t)c0 * per, e1 = ((size_t)c1 * per < (size_t)w->n) ? (size_t)c1 * per : (size_t)w->n, ne = e1 - e0;
         cudaStream_t st = w->chunk_stream[c];
         CK(cudaStreamWaitEvent(st, w->chunk_ev, 0));
@@ -696,7 +710,7 @@ extern "C" int rs_world_policy_step_host(rs_world* w, rs_policy* p, const float*
     size_t N = (size_t)w->n, O = (size_t)w->desc.obs_dim;
     const bool direct = host_is_pinned(obs_out_host) && host_is_pinned(reward_host) && host_is_pinned(done_host);
     {
-        int n_chunks = 4;                                   // RS_E2E_CHUNKS=1 selects the single-stream form (A/B measurements)
+        int n_chunks = 6;                                   // RS_E2E_CHUNKS=1 selects the single-stream form (A/B measurements)
         if (const char* e = getenv("RS_E2E_CHUNKS")) n_chunks = atoi(e);
         if (n_chunks > RS_MAX_CHUNKS) n_chunks = RS_MAX_CHUNKS;
         if (n_chunks > 1 && w->topo && !w->B.motor && direct && w->n >= 8192 && (!obs_in_host || host_is_pinned(obs_in_host)))
