@@ -339,7 +339,7 @@ def test_policy_step_host_pipelined_matches_single_stream(env_id, n, monkeypatch
     ref = run(1, True)
     if env_id == "RoboschoolHopper-v1":        # its zoo policy falls within ~30 steps on the restated physics: auto-resets are covered
         assert sum(int(d.sum()) for _, _, d in ref) > 0
-    for chunks, pinned in [(4, True), (3, True), (4, False)]:
+    for chunks, pinned in [(6, True), (4, True), (3, True), (4, False)]:
         got = run(chunks, pinned)
         for (o, r, d), (o2, r2, d2) in zip(ref, got):
             assert np.array_equal(o, o2) and np.array_equal(r, r2) and np.array_equal(d, d2), (chunks, pinned)
