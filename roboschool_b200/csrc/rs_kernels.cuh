@@ -194,11 +194,34 @@ static int launch_static(const StaticLaunch& a) {
     const size_t smem = sizeof(float) * per * lc_size<T>();
     // the opt-in to > 48 KB of dynamic shared memory is per device: remember which devices have it
     static unsigned attr_devices = 0;
+    static int regs_per_thread = 0, n_sm = 0, last_carveout = -2;
     int dev = 0;
     cudaGetDevice(&dev);
     if (!((attr_devices >> (dev & 31)) & 1u)) {
         cudaFuncSetAttribute(k_step_static<T, MC, PROF, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, k_step_static<T, MC, PROF, WPC>) == cudaSuccess) regs_per_thread = fa.numRegs;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         attr_devices |= 1u << (dev & 31);
+        last_carveout = -2;
+    }
+    {
+        // Shared-memory carve-out: just enough for the CTAs that can be resident (registers) and that this grid needs per SM.
+        // The default heuristic sizes it for ONE small CTA (1 warp, 10-26 KB of link cache) although registers allow eight, so
+        // a multi-wave grid of small CTAs runs at 1/8 of the occupancy; asking for the maximum instead shrinks the L1 that
+        // holds the spilled per-env scratch.  RS_CARVEOUT=<percent> overrides, RS_CARVEOUT=-1 keeps the driver's default.
+        const int grid_all = (a.n + per - 1) / per;       // the whole world: slices of one step run concurrently
+        int by_regs = regs_per_thread > 0 ? 65536 / (((regs_per_thread + 7) / 8 * 8) * per) : 1;
+        if (by_regs < 1) by_regs = 1;
+        int need = n_sm > 0 ? (grid_all + n_sm - 1) / n_sm : 1;
+        if (need > by_regs) need = by_regs;
+        int pct = (int)(((size_t)need * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+        if (pct > 100) pct = 100;
+        if (const char* ev = getenv("RS_CARVEOUT")) pct = atoi(ev);
+        if (pct != last_carveout && pct >= 0) {
+            cudaFuncSetAttribute(k_step_static<T, MC, PROF, WPC>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            last_carveout = pct;
+        }
     }
     const int grid = a.ncta > 0 ? a.ncta : (a.n + per - 1) / per;
     k_step_static<T, MC, PROF, WPC><<<grid, per, smem, a.st>>>(*a.M, *a.B, a.actions, a.obs, a.rew, a.done, a.auto_reset, a.seed, a.env_id0, a.stats, a.cyc, a.cta0);
