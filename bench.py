@@ -273,8 +273,8 @@ def main():
     tachieved = flop_env * n / (ms_policy * 1e-3) / 1e12
     # launches: policy + step per timed step; the host entry point cuts the envs into stream slices (2 launches per slice)
     chunks = 1
-    if W.L.rs_world_kernel_variant(W.h) > 0 and n >= 8192:
-        chunks = max(1, min(8, int(os.environ.get("RS_E2E_CHUNKS", "6"))))
+    if W.L.rs_world_kernel_variant(W.h) > 0 and n >= 1024:
+        chunks = max(1, min(8, int(os.environ.get("RS_E2E_CHUNKS", "6" if n >= 24576 else "1"))))
     st = stats.cpu().numpy()
     line = {
         "metric": METRIC.replace(ENV_ID, args.env), "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -86,7 +86,7 @@ int rs_world_step_host(rs_world* w, const float* actions_host, float* obs_host, 
  * tensor cores -> env step with auto-reset -> D2H obs_out/reward/done; one stream synchronisation.
  * obs_in_host == NULL continues from the observations already on the device.  Page-locked host buffers (cudaHostAlloc /
  * cudaHostRegister, e.g. pinned torch tensors) are the source / target of the async copies directly; pageable ones go
- * through the world's pinned staging buffers.  With page-locked buffers and a static-topology kernel (>= 8192 envs) the envs are
+ * through the world's pinned staging buffers.  With page-locked buffers and a static-topology kernel (>= 24576 envs) the envs are
  * processed as 6 CTA-aligned slices (the two outer ones half-size) on separate streams, so the copies of one slice overlap the kernels of the others; results are
  * bit-identical to the single-stream form (RS_E2E_CHUNKS=1..8 overrides the slice count). */
 int rs_world_policy_step_host(rs_world* w, rs_policy* p, const float* obs_in_host, float* obs_out_host, float* reward_host,
