@@ -445,3 +445,29 @@ def test_free_flight_momentum_converges_on_gpu(variant, monkeypatch):
         drift.append(np.median(np.abs(p1 - p0).max(axis=1)))
         w.close()
     assert drift[1] < drift[0] / 2.5 and drift[2] < drift[1] / 2.0, drift
+
+
+def test_throughput_floor_on_b200():
+    """Guards the measured operating point against silent regressions (a wrong shared-memory carve-out, a fall back to the
+    runtime-topology kernel, a lost phase barrier each cost 20-70 %): 32768 Humanoid envs under the zoo policy, device-resident
+    rollout, CUDA events.  Measured 38-42 M env-steps/s on the pool's B200s; the floor leaves a wide margin for box-to-box spread."""
+    import torch
+    from roboschool_b200.world import BatchedWorld
+    from roboschool_b200.policy import ZooPolicy, load_zoo_weights
+    if "B200" not in torch.cuda.get_device_name(0):
+        pytest.skip("throughput floor is stated for B200")
+    env_id, n = "RoboschoolHumanoid-v1", 32768
+    W = BatchedWorld(load_env_model(env_id), n, 0)
+    assert W.L.rs_world_kernel_variant(W.h) > 0, "static-topology kernel not selected"
+    pol = ZooPolicy(load_zoo_weights(env_id), 0)
+    st = torch.cuda.current_stream().cuda_stream
+    W.rollout_reset(seed=1, stream=st)
+    W.rollout(pol, 200, seed=1, stream=st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    W.rollout(pol, 100, seed=1, stream=st)
+    e1.record()
+    torch.cuda.synchronize()
+    rate = n * 100 / (e0.elapsed_time(e1) * 1e-3)
+    assert rate > 2.5e7, "%.1f M env-steps/s" % (rate / 1e6)
