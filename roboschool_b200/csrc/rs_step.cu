@@ -225,8 +225,9 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
     // warps per CTA (measured on B200): 7-warp CTAs that re-align at the phase barriers once the batch
     // gives every SM several warps (Humanoid 32768: +13 %, Ant 65536: +16 %, HalfCheetah 65536: +67 %); single-warp CTAs for
     // small batches, which would otherwise occupy only a few SMs
-    // measured crossover of 7-warp aligned CTAs over 1-warp CTAs: 16384 envs (Humanoid, Ant, planar models), 8192 for the Flagrun tasks
-    w->wpc = n_envs >= (model->flag_task ? 8192 : 16384) ? 7 : 1;
+    // measured crossover of 7-warp aligned CTAs over 1-warp CTAs (a 7-warp CTA occupies a whole SM: below ~148 CTAs part of the GPU
+    // idles): 24576 envs for Humanoid, Ant and the planar models (16384-20480: 1-warp CTAs +5..25 %), 8192 for the Flagrun tasks
+    w->wpc = n_envs >= (model->flag_task ? 8192 : 24576) ? 7 : 1;
     DevBuf& B = w->B;
     B.N = n_envs; B.S = (model->fixed_base ? 0 : 13) + 2 * model->n_dof; B.MCcap = MC;
     B.rec = 2 * (6 + model->n_dof) + 1; B.maxr = NL + 3 * MC;   // +1: pooled rows keep their denominator in the record

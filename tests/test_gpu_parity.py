@@ -262,7 +262,8 @@ def test_rollout_record_matches_stepping():
 def test_ragged_batch_sizes(env_id):
     """Ragged batches: N = 1, N not a multiple of the warp (32) or of the CTA (7 / 4 warps), tail lanes that own no
     env but still help build the warp's constraint rows.  Each small world must reproduce, bit for bit, the matching
-    slice of one big world (RNG and physics are keyed by the global env id, never by the position in the batch)."""
+    slice of one big world (RNG and physics are keyed by the global env id, never by the position in the batch).
+    (7-warp CTAs against 1-warp CTAs: test_baseline_config_sizes_properties and the pipelined host-path test.)"""
     import torch
     from roboschool_b200.vec_env import VecEnv
     big_n = 1200
@@ -306,7 +307,7 @@ def test_behavioural_fixture_on_gpu_humanoid_walks():
     assert s[1] >= 0.97 * n and s[2] / s[1] > 990, (s[1], s[2] / max(s[1], 1))
 
 
-@pytest.mark.parametrize("env_id,n", [("RoboschoolHumanoid-v1", 17000), ("RoboschoolHopper-v1", 9000), ("RoboschoolAnt-v1", 33152)])
+@pytest.mark.parametrize("env_id,n", [("RoboschoolHumanoid-v1", 25000), ("RoboschoolHopper-v1", 9000), ("RoboschoolAnt-v1", 33152)])
 def test_policy_step_host_pipelined_matches_single_stream(env_id, n, monkeypatch):
     """rs_world_policy_step_host with page-locked buffers cuts the envs into CTA-aligned slices on separate streams (copies of
     one slice overlap the kernels of the others).  Bit-identical to the single-stream form (RS_E2E_CHUNKS=1) and to pageable
