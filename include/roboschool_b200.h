@@ -15,6 +15,11 @@
  * data_ptr()), `*_host` pointers are host memory; `stream` is a cudaStream_t (NULL = default
  * stream).  There is NO CPU fallback: without a CUDA device every compute call fails loudly.
  *
+ * Stream ordering: entry points that take a `stream` enqueue on it and return without waiting.  The `*_host` entry points,
+ * rs_world_substeps, rs_world_link_poses and the host getters / setters run on a private stream of the world and wait for
+ * everything the world has enqueued on caller streams before (an event is recorded behind every enqueue), so
+ * `rs_world_reset(stream); rs_world_step_host(...)` is ordered without a synchronisation by the caller.
+ *
  * Layouts: actions [n_envs][A] float32 row-major, obs [n_envs][O] float32, reward [n_envs] float32,
  * done [n_envs] uint8.  Generalised state [n_envs][S] float32 with
  * S = (floating base: pos3 quat4(xyzw) omega3 vel3) + q[ndof] + qd[ndof]   (SURVEY.md 8(d)).
@@ -128,6 +133,9 @@ int rs_world_link_poses(rs_world* w, float* out_host);
  * solver order.  keys_host[max_pts]: manifold id (floor: geom index; self pair: n_geoms + pair
  * index); data_host[max_pts][10]: localA3 localB3 normal3 distance; *count: number of points. */
 int rs_world_get_contacts(rs_world* w, int env, int* keys_host, float* data_host, int max_pts, int* count);
+/* Overwrite the persistent contact manifolds of every env (test / checkpoint hook; the inverse of rs_world_get_contacts):
+ * counts_host[n_envs], keys_host[n_envs][max_pts], data_host[n_envs][max_pts][10], points in solver order. */
+int rs_world_set_contacts(rs_world* w, const int* counts_host, const int* keys_host, const float* data_host, int max_pts);
 /* rows / contact points of the last solved sub-step, int32[n_envs] each (host) */
 int rs_world_get_counts(rs_world* w, int* rows_host, int* contacts_host);
 /* last step's reward terms [n_envs][5] (alive, progress, electricity, joints_at_limit, feet_collision) */
@@ -148,8 +156,9 @@ int rs_policy_forward(rs_policy* p, const float* obs_dev, float* act_dev, int n,
 /* Fused rollout: n_steps x { act = policy(obs) ; step(auto_reset) } with no host round trip; the
  * rollout statistics (sum reward, episodes finished, sum episode length, non-finite count, contact
  * rows) are accumulated on the device into stats_dev[8] (float64).  policy may be NULL when
- * actions are uniform random (counter-based RNG, seed). */
-int rs_world_rollout(rs_world* w, rs_policy* p, int n_steps, uint32_t seed, uint32_t env_id0, double* stats_dev, void* stream);
+ * actions are uniform random (counter-based RNG).  Auto-resets and random actions use the seed / env_id0 given to the
+ * last rs_world_reset / rs_world_rollout_reset, like every other stepping entry point. */
+int rs_world_rollout(rs_world* w, rs_policy* p, int n_steps, double* stats_dev, void* stream);
 /* reset every env and write the first observations into the world-owned rollout obs buffer */
 int rs_world_rollout_reset(rs_world* w, uint32_t seed, uint32_t env_id0, void* stream);
 /* device pointers of the world-owned rollout buffers: obs [n][O], act [n][A], reward [n], done [n] (uint8) */

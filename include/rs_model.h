@@ -156,6 +156,15 @@ typedef struct rs_model_desc {
     int    task_link2;                   /* Reacher: link "target"                                                */
     int    pad2;
     double g_quat[RS_MAX_GEOMS][4];      /* box geoms: orientation in the link COM frame, quaternion x,y,z,w (identity otherwise) */
+    /* contact rows (btMultiBodyConstraintSolver::setupMultiBodyContactConstraint): positional term -pen*erp/dt with
+       erp = c_erp above c_split_thresh, c_erp2 below it where the term is dropped (split impulse is not solved for
+       multibodies); c_split_thresh = -1e30 keeps the term for every penetration.  erp / erp2 / split_thresh above
+       govern the joint-limit rows (btMultiBodyJointLimitConstraint::createConstraintRows). */
+    double c_erp;
+    double c_erp2;
+    double c_split_thresh;
+    double armature[RS_MAX_LINKS];       /* added to the joint-space inertia D = S^T I^A S of the link's joint (0: not honoured) */
+    double stiffness[RS_MAX_LINKS];      /* joint spring torque -k q, applied like jdamping (0: not honoured)                   */
 } rs_model_desc;
 
 #ifdef __cplusplus

@@ -53,6 +53,10 @@ def lib():
         L.oracle_get_contacts.argtypes = [P, I, dp, I]
         L.oracle_get_contacts.restype = I
         L.oracle_counts.argtypes = [P, I, ip, ip]
+        L.oracle_get_contact_cache.argtypes = [P, I, ip, dp, I]
+        L.oracle_get_contact_cache.restype = I
+        L.oracle_set_knob.argtypes = [ctypes.c_char_p, D]
+        L.oracle_accel_deltas.argtypes = [P, I, dp, dp]
         L.oracle_energy.argtypes = [P, I]
         L.oracle_energy.restype = D
         L.oracle_foot_flags.argtypes = [P, I, ip, ip]
@@ -176,6 +180,22 @@ class OracleWorld:
         out = np.zeros((max_pts, 12))
         c = self.L.oracle_get_contacts(self.h, env, _dp(out), max_pts)
         return out[:c]
+
+    def contact_cache(self, max_pts=16):
+        """Persistent manifolds of every env as the CUDA path stores them: counts [n], keys [n,P], data [n,P,10]."""
+        cnt = np.zeros(self.n, dtype=np.int32)
+        keys = np.zeros((self.n, max_pts), dtype=np.int32)
+        data = np.zeros((self.n, max_pts, 10))
+        for i in range(self.n):
+            cnt[i] = self.L.oracle_get_contact_cache(self.h, i, _ip(keys[i]), _dp(data[i]), max_pts)
+        return cnt, keys, data
+
+    def accel_deltas(self, env, force):
+        """M^-1 force of the env's current configuration (btMultiBody::calcAccelerationDeltasMultiDof)."""
+        f = np.ascontiguousarray(force, dtype=np.float64)
+        out = np.zeros_like(f)
+        self.L.oracle_accel_deltas(self.h, env, _dp(f), _dp(out))
+        return out
 
     def counts(self, env):
         a, b = ctypes.c_int(), ctypes.c_int()

@@ -43,6 +43,26 @@
 #define MANIFOLD_CACHE_SIZE 4
 #define WARMSTART 0 /* "disable warmstarting for btMultiBody, it has issues gaining energy" (btMultiBodyConstraintSolver.cpp, 2.87) */
 
+/* Convention knobs for tools/convention_sweep.py: alternatives of recalled Bullet behaviour that are not
+ * (yet) descriptor data.  The defaults are the conventions the CUDA path implements; a knob that wins the sweep is promoted
+ * to a descriptor field and implemented on the CUDA side. */
+static struct {
+    int limit_always;        /* 0: limit rows only when violated ; 1: a row per limited joint side, gap handled through -gap/dt */
+    int friction_dirs;       /* 2 (SOLVER_USE_2_FRICTION_DIRECTIONS) or 1 */
+    int torque_first_only;   /* 1: joint torques act in the first sub-step only (forces cleared inside the sub-step loop) */
+    double warmstart;        /* applied-impulse warm starting factor for contact rows (0: off) */
+    int damping_mode;        /* joint damping: 0 explicit torque once per env step (applyJointDamping), 1 explicit per sub-step,
+                                2 implicit per sub-step (D += dt*d) */
+} K = {0, 2, 0, 0.0, 0};
+void oracle_set_knob(const char *name, double v) {
+    if (!strcmp(name, "limit_always")) K.limit_always = (int)v;
+    else if (!strcmp(name, "friction_dirs")) K.friction_dirs = (int)v;
+    else if (!strcmp(name, "torque_first_only")) K.torque_first_only = (int)v;
+    else if (!strcmp(name, "warmstart")) K.warmstart = v;
+    else if (!strcmp(name, "damping_mode")) K.damping_mode = (int)v;
+    else fprintf(stderr, "oracle_set_knob: unknown knob %s\n", name);
+}
+
 typedef struct { double w[3], v[3]; } sv6;   /* motion: w=angular v=linear ; force: w=torque v=force */
 
 typedef struct {
@@ -376,8 +396,10 @@ static void aba(const rs_model_desc *m, oenv *e, double dt) {
         if (m->dof_idx[i] >= 0) {
             int d = m->dof_idx[i];
             m6mulv(&e->h[i], IA[i + 1], &e->S[i]);
-            double D = sv_dot(&e->S[i], &e->h[i]);
+            double D = sv_dot(&e->S[i], &e->h[i]) + m->armature[i];
             Y[i] = e->tau[d] - sv_dot(&e->S[i], &Z[i + 1]) - sv_dot(&c[i], &e->h[i]);
+            if (K.damping_mode >= 1) Y[i] -= m->jdamping[i] * e->qd[d] + m->stiffness[i] * e->q[d];
+            if (K.damping_mode == 2) D += dt * m->jdamping[i] + dt * dt * m->stiffness[i];
             e->invD[i] = 1.0 / D;
             double Ia[36], hh[6] = {e->h[i].w[0], e->h[i].w[1], e->h[i].w[2], e->h[i].v[0], e->h[i].v[1], e->h[i].v[2]};
             for (int a = 0; a < 6; a++) for (int b2 = 0; b2 < 6; b2++) Ia[a * 6 + b2] = IA[i + 1][a * 6 + b2] - hh[a] * hh[b2] * e->invD[i];
@@ -698,7 +720,7 @@ static int setup_rows(const rs_model_desc *m, oenv *e, double dt, crow *nc, int 
         int d = m->dof_idx[i];
         for (int row = 0; row < 2; row++) {
             double pen = row == 0 ? e->q[d] - m->lim_lo[i] : m->lim_hi[i] - e->q[d];
-            if (pen > 0) continue;
+            if (pen > 0 && !K.limit_always) continue;
             double jA[MAXDOF]; memset(jA, 0, sizeof jA);
             jA[6 + d] = row == 0 ? 1.0 : -1.0;
             crow *r = &nc[(*n_nc)++];
@@ -706,6 +728,7 @@ static int setup_rows(const rs_model_desc *m, oenv *e, double dt, crow *nc, int 
             double erp = m->erp2;
             if (pen > m->split_thresh) erp = m->erp;   /* m_splitImpulse is on by default */
             double posErr = -pen * erp / dt, velErr = -relvel;
+            if (pen > 0) { posErr = 0; velErr = -pen / dt; }   /* (only reached with limit_always) "velocityError = -penetration / timeStep" */
             if (pen > m->split_thresh) r->rhs = (posErr + velErr) * r->inv_denom;
             else r->rhs = velErr * r->inv_denom;        /* m_rhsPenetration is never used for multibodies */
             r->lo = 0; r->hi = m->max_limit_impulse; r->cp = NULL; r->friction_index = -1;
@@ -740,7 +763,7 @@ static int setup_rows(const rs_model_desc *m, oenv *e, double dt, crow *nc, int 
             v3cpy(dirs[0], cp->normal);
             plane_space(cp->normal, dirs[1], dirs[2]);
             int normal_index = *n_cn;
-            for (int w = 0; w < 3; w++) {
+            for (int w = 0; w < 1 + K.friction_dirs; w++) {
                 double jA[MAXDOF], jB[MAXDOF], nneg[3] = {-dirs[w][0], -dirs[w][1], -dirs[w][2]};
                 contact_jacobian(m, e, bA, cp->posA, dirs[w], jA);
                 if (bB >= 0) contact_jacobian(m, e, bB, cp->posB, nneg, jB);
@@ -749,11 +772,11 @@ static int setup_rows(const rs_model_desc *m, oenv *e, double dt, crow *nc, int 
                 r->cp = cp; r->which = w; r->friction = cp->friction;
                 if (w == 0) {
                     double pen = cp->dist;     /* + m_linearSlop (0) */
-                    double erp = m->erp2;
-                    if (pen > m->split_thresh) erp = m->erp;
+                    double erp = m->c_erp2;
+                    if (pen > m->c_split_thresh) erp = m->c_erp;
                     double posErr = 0, velErr = -relvel;   /* restitution 0 */
                     if (pen > 0) velErr -= pen / dt; else posErr = -pen * erp / dt;
-                    if (pen > m->split_thresh) r->rhs = (posErr + velErr) * r->inv_denom;
+                    if (pen > m->c_split_thresh) r->rhs = (posErr + velErr) * r->inv_denom;
                     else r->rhs = velErr * r->inv_denom;
                     r->lo = 0; r->hi = 1e10; r->friction_index = -1;
                 } else {
@@ -785,6 +808,13 @@ static void solve(const rs_model_desc *m, oenv *e, double dt) {
     e->n_rows_last = total; e->n_contacts_last = n_cn;
     if (!total) return;
     double dv[MAXDOF]; memset(dv, 0, sizeof dv);
+    if (K.warmstart > 0) {   /* sweep knob: applied impulses of the previous sub-step, scaled (m_warmstartingFactor) */
+        for (int j = 0; j < n_cn; j++) { cn[j].applied = K.warmstart * cn[j].cp->imp_n; for (int k = 0; k < nd; k++) dv[k] += cn[j].unit[k] * cn[j].applied; }
+        for (int j = 0; j < n_cf; j++) {
+            cf[j].applied = K.warmstart * (cf[j].which == 1 ? cf[j].cp->imp_f1 : cf[j].cp->imp_f2);
+            for (int k = 0; k < nd; k++) dv[k] += cf[j].unit[k] * cf[j].applied;
+        }
+    }
     /* btMultiBodyConstraintSolver::solveSingleIteration */
     for (int it = 0; it < m->n_iter; it++) {
         for (int j = 0; j < n_nc; j++) { int idx = (it & 1) ? j : n_nc - 1 - j; resolve_row(&nc[idx], dv, nd); }
@@ -1259,8 +1289,14 @@ static void step_one(oracle_world *w, int i, const double *actions, int auto_res
         e->tau[m->act_dof[k]] = (double)(float)(m->act_gain[k] * c);   /* set_motor_torque(float) */
     }
     /* applyJointDamping: once per stepSimulation, from the velocities at its start */
-    for (int l = 0; l < m->n_links; l++) if (m->dof_idx[l] >= 0 && m->jdamping[l] != 0) e->tau[m->dof_idx[l]] += -m->jdamping[l] * e->qd[m->dof_idx[l]];
-    for (int s = 0; s < m->frame_skip; s++) substep(m, e);
+    if (K.damping_mode == 0) {
+        for (int l = 0; l < m->n_links; l++) if (m->dof_idx[l] >= 0 && m->jdamping[l] != 0) e->tau[m->dof_idx[l]] += -m->jdamping[l] * e->qd[m->dof_idx[l]];
+        for (int l = 0; l < m->n_links; l++) if (m->dof_idx[l] >= 0 && m->stiffness[l] != 0) e->tau[m->dof_idx[l]] += -m->stiffness[l] * e->q[m->dof_idx[l]];
+    }
+    for (int s = 0; s < m->frame_skip; s++) {
+        substep(m, e);
+        if (K.torque_first_only) for (int d = 0; d < m->n_dof; d++) e->tau[d] = 0;
+    }
     epilogue(m, e, a, seed, env_id0 + (uint32_t)i);
     if (auto_reset && (e->done || e->frame >= m->max_episode_steps)) {
         /* obs returned for a finished env is the first obs of the next episode (vector-env convention) */
@@ -1310,6 +1346,26 @@ int oracle_get_contacts(const oracle_world *w, int env, double *out, int max_pts
             c++;
         }
     return c;
+}
+/* persistent manifolds in solver order as the CUDA path stores them: keys[c] = manifold id, data[c][10] = localA3 localB3 normal3 dist */
+int oracle_get_contact_cache(const oracle_world *w, int env, int *keys, double *data, int max_pts) {
+    const oenv *e = &w->env[env]; int c = 0;
+    for (int k = 0; k < w->nman; k++)
+        for (int p = 0; p < e->man[k].n && c < max_pts; p++) {
+            const cpoint *cp = &e->man[k].p[p]; double *o = data + c * 10;
+            keys[c] = k; v3cpy(o, cp->localA); v3cpy(o + 3, cp->localB); v3cpy(o + 6, cp->normal); o[9] = cp->dist;
+            c++;
+        }
+    return c;
+}
+/* btMultiBody::calcAccelerationDeltasMultiDof of the env's current configuration (after an ABA pass): out = M^-1 force,
+ * both [base torque3 (world) base force3 (world) joint forces(ndof)] -- exported for the mechanics-identity tests */
+void oracle_accel_deltas(oracle_world *w, int env, const double *force, double *out) {
+    oenv *e = &w->env[env];
+    oenv tmp = *e;                     /* the ABA pass fills the response cache (h, 1/D, base inverse); keep the state */
+    kinematics(&w->m, &tmp);
+    aba(&w->m, &tmp, 0.0);
+    accel_deltas(&w->m, &tmp, force, out);
 }
 void oracle_counts(const oracle_world *w, int env, int *n_rows, int *n_contacts) { *n_rows = w->env[env].n_rows_last; *n_contacts = w->env[env].n_contacts_last; }
 /* mechanical energy (kinetic + potential), for conservation tests */

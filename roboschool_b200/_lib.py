@@ -51,12 +51,13 @@ def lib():
     L.rs_world_link_poses.argtypes = [P, P]
     L.rs_world_get_contacts.argtypes = [P, I, P, P, I, P]
     L.rs_world_get_counts.argtypes = [P, P, P]
+    L.rs_world_set_contacts.argtypes = [P, P, P, P, I]
     L.rs_world_get_rewards5.argtypes = [P, P]
     L.rs_world_state_dev.argtypes = [P, PP]
     L.rs_policy_create.argtypes = [I, I, I, I, P, P, P, P, P, P, I, PP]
     L.rs_policy_destroy.argtypes = [P]
     L.rs_policy_forward.argtypes = [P, P, P, I, P]
-    L.rs_world_rollout.argtypes = [P, P, I, U, U, P, P]
+    L.rs_world_rollout.argtypes = [P, P, I, P, P]
     L.rs_world_rollout_reset.argtypes = [P, U, U, P]
     L.rs_world_rollout_buffers.argtypes = [P, PP, PP, PP, PP]
     L.rs_world_rollout_record.argtypes = [P, P, I, P, P, P, P, P, P, P]
@@ -73,7 +74,7 @@ EXPORTED_SYMBOLS = [
     "rs_last_error", "rs_device_count", "rs_world_create", "rs_world_destroy", "rs_world_n_envs", "rs_world_kernel_variant",
     "rs_world_state_dim", "rs_world_obs_dim", "rs_world_act_dim", "rs_world_reset", "rs_world_step",
     "rs_world_step_stats", "rs_world_step_profile", "rs_world_step_host", "rs_world_policy_step_host", "rs_world_substeps", "rs_world_set_joint_motor", "rs_world_set_state", "rs_world_get_state",
-    "rs_world_set_episode", "rs_world_get_episode", "rs_world_set_flags", "rs_world_get_flags", "rs_world_set_task_state", "rs_world_get_task_state", "rs_world_link_poses", "rs_world_get_contacts",
+    "rs_world_set_episode", "rs_world_get_episode", "rs_world_set_flags", "rs_world_get_flags", "rs_world_set_task_state", "rs_world_get_task_state", "rs_world_link_poses", "rs_world_get_contacts", "rs_world_set_contacts",
     "rs_world_get_counts", "rs_world_get_rewards5", "rs_world_state_dev", "rs_policy_create",
     "rs_policy_destroy", "rs_policy_forward", "rs_world_rollout", "rs_world_rollout_reset",
     "rs_world_rollout_buffers", "rs_world_rollout_record",

@@ -10,8 +10,9 @@ Robot.joints/parts/root_part/set_pose/set_pose_and_speed/query_position; Joint.n
 set_motor_torque/current_position/current_relative_position/reset_current_position/limits;
 Thingy.pose/speed/name/contact_list/__hash__/__eq__; Pose math.  Rendering (Camera, test_window*,
 load_thingy meshes) are inert stubs: the renderer is out of scope.
-Bullet's PD/velocity motor modes (set_servo_target/set_target_speed, used by Pong/Atlas only) raise
-NotImplementedError.  No exceptions on load failure: message on stderr + empty list, like the reference
+Bullet's PD/velocity motor modes (Joint.set_servo_target / set_target_speed, physics-bullet.cpp:510-537) are
+btMultiBodyJointMotor rows of the solver (rs_world_set_joint_motor), with the reference's first_torque_call state
+machine.  No exceptions on load failure: message on stderr + empty list, like the reference
 (physics-bullet.cpp:105-108).
 """
 import math

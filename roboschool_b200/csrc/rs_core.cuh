@@ -46,7 +46,7 @@ struct DevModel {
     float R0[ML][9];                  // parent coords -> link coords at q=0
     float axis[ML][3], e_vec[ML][3], d_vec[ML][3];
     float mass[ML], inertia[ML][3];
-    float lim_lo[ML], lim_hi[ML], jdamping[ML], max_vel[ML];
+    float lim_lo[ML], lim_hi[ML], jdamping[ML], max_vel[ML], armature[ML], stiffness[ML];
     float break_thresh[ML + 1];
     int g_link[MG], g_type[MG], g_floor[MG];
     float g_p0[MG][3], g_p1[MG][3], g_radius[MG], g_fric_floor[MG];
@@ -55,6 +55,7 @@ struct DevModel {
     unsigned char pair_a[MP], pair_b[MP], pair_ss[MP];
     float pair_thresh[MP], pair_friction[MP];
     float gravity, timestep, lin_damping, ang_damping, max_coord_vel, erp, erp2, split_thresh, max_limit_impulse, use_gyro;
+    float c_erp, c_erp2, c_split_thresh;   // contact rows (erp / erp2 / split_thresh: joint-limit rows)
     int act_dof[MA];
     float act_gain[MA];
     int foot_link[MF], part_link[MPT];
@@ -413,7 +414,7 @@ RS_HD void aba(const DevModel& M, Work<NL, MC, SL>& W, float dt) {
             float S[6] = {M.Sw[i][0], M.Sw[i][1], M.Sw[i][2], M.Sv[i][0], M.Sv[i][1], M.Sv[i][2]};
             float h[6];
             inertia_mul(h, IA[i + 1], S);
-            float D = dot6(S, h);
+            float D = dot6(S, h) + M.armature[i];
             float y = W.tau[d] - dot6(S, Z[i + 1]) - dot6(c[i], h);
             float invD = 1.0f / D;
             Y[i] = y; W.invD[i] = invD;
@@ -943,10 +944,10 @@ RS_HD void solve_with(const DevModel& M, Work<NL, MC, SL>& W, float dt, const Ro
             float rhs;
             if (w == 0) {
                 float pen = cd[9];
-                float erp = pen > M.split_thresh ? M.erp : M.erp2;
+                float erp = pen > M.c_split_thresh ? M.c_erp : M.c_erp2;
                 float posErr = 0.f, velErr = -relvel;
                 if (pen > 0.f) velErr -= pen * inv_dt; else posErr = -pen * erp * inv_dt;
-                rhs = pen > M.split_thresh ? (posErr + velErr) * invd : velErr * invd;
+                rhs = pen > M.c_split_thresh ? (posErr + velErr) * invd : velErr * invd;
             } else rhs = -relvel * invd;
             r_rhs[row] = rhs; r_invd[row] = invd; r_applied[row] = 0.f;
         }
@@ -1437,6 +1438,7 @@ RS_HD void apply_action(const DevModel& M, Work<NL, MC, SL>& W, const float* act
     for (int l = 0; l < M.n_links; l++) {
         int d = M.dof_idx[l];
         if (d >= 0 && M.jdamping[l] != 0.f) W.tau[d] += -M.jdamping[l] * W.qd[d];
+        if (d >= 0 && M.stiffness[l] != 0.f) W.tau[d] += -M.stiffness[l] * W.q[d];
     }
 }
 

@@ -17,7 +17,36 @@ inline void quat_to_mat_d(double* R, const double* q) {
 inline int build_dev_model(const rs_model_desc* m, DevModel* D, const char** err) {
     memset(D, 0, sizeof *D);
     if (m->n_links < 0 || m->n_links > ML) { *err = "n_links out of range"; return 1; }
-    if (m->n_geoms > MG || m->n_pairs > MP || m->n_act > MA || m->n_feet > MF || m->n_parts > MPT) { *err = "model exceeds capacity"; return 1; }
+    if (m->n_geoms < 0 || m->n_pairs < 0 || m->n_act < 0 || m->n_feet < 0 || m->n_parts < 0 || m->n_dof < 0 || m->n_reset < 0 ||
+        m->n_geoms > MG || m->n_pairs > MP || m->n_act > MA || m->n_feet > MF || m->n_parts > MPT) { *err = "model exceeds capacity"; return 1; }
+    // a descriptor arrives through the C ABI from any caller: every index it carries is checked against its table
+    if (m->n_dof > m->n_links) { *err = "n_dof exceeds n_links"; return 1; }
+    if (m->n_reset > MA) { *err = "n_reset exceeds capacity"; return 1; }
+    if (m->obs_dim < 0 || m->obs_dim > 8 + 2 * MA + MF) { *err = "obs_dim out of range"; return 1; }
+    if (m->body_link < -1 || m->body_link >= m->n_links) { *err = "body_link out of range"; return 1; }
+    if (m->task_link < -1 || m->task_link >= m->n_links || m->task_link2 < -1 || m->task_link2 >= m->n_links) { *err = "task link out of range"; return 1; }
+    {
+        int seen = 0;
+        for (int i = 0; i < m->n_links; i++) {
+            if (m->parent[i] < -1 || m->parent[i] >= i) { *err = "parent index out of order"; return 1; }
+            if (m->jtype[i] == RS_JOINT_FIXED) { if (m->dof_idx[i] != -1) { *err = "fixed joint with a dof"; return 1; } }
+            else { if (m->dof_idx[i] != seen) { *err = "dof_idx not consecutive"; return 1; } seen++; }
+        }
+        if (seen != m->n_dof) { *err = "n_dof does not match the joint types"; return 1; }
+    }
+    for (int k = 0; k < m->n_act; k++) if (m->act_dof[k] < 0 || m->act_dof[k] >= m->n_dof) { *err = "act_dof out of range"; return 1; }
+    for (int k = 0; k < m->n_reset; k++) if (m->reset_dof[k] < 0 || m->reset_dof[k] >= m->n_dof) { *err = "reset_dof out of range"; return 1; }
+    for (int k = 0; k < m->n_feet; k++) if (m->foot_link[k] < -1 || m->foot_link[k] >= m->n_links) { *err = "foot_link out of range"; return 1; }
+    for (int k = 0; k < m->n_parts; k++) if (m->part_link[k] < -1 || m->part_link[k] >= m->n_links) { *err = "part_link out of range"; return 1; }
+    for (int g = 0; g < m->n_geoms; g++) if (m->g_link[g] < -1 || m->g_link[g] >= m->n_links) { *err = "g_link out of range"; return 1; }
+    for (int k = 0; k < m->n_pairs; k++) if (m->pair_a[k] < 0 || m->pair_a[k] >= m->n_geoms || m->pair_b[k] < 0 || m->pair_b[k] >= m->n_geoms) { *err = "pair geom out of range"; return 1; }
+    if (m->task_kind != RS_TASK_WALKER) {
+        const int nt = m->task_kind == RS_TASK_PENDULUM ? 2 : (m->task_kind == RS_TASK_DOUBLE_PENDULUM ? 3 : 4);
+        for (int k = 0; k < nt; k++) if (m->task_dof[k] < 0 || m->task_dof[k] >= m->n_dof) { *err = "task_dof out of range"; return 1; }
+        if ((m->task_kind == RS_TASK_DOUBLE_PENDULUM || m->task_kind == RS_TASK_REACHER) && m->task_link < 0) { *err = "task_link missing"; return 1; }
+        if (m->task_kind == RS_TASK_REACHER && m->task_link2 < 0) { *err = "task_link2 missing"; return 1; }
+    }
+    if (m->max_contacts < 0) { *err = "max_contacts negative"; return 1; }
     D->n_links = m->n_links; D->n_dof = m->n_dof; D->fixed_base = m->fixed_base; D->n_geoms = m->n_geoms;
     D->n_pairs = m->n_pairs; D->n_act = m->n_act; D->n_feet = m->n_feet; D->n_parts = m->n_parts;
     D->obs_dim = m->obs_dim; D->has_floor = m->has_floor; D->n_iter = m->n_iter; D->frame_skip = m->frame_skip;
@@ -46,6 +75,7 @@ inline int build_dev_model(const rs_model_desc* m, DevModel* D, const char** err
         D->mass[i] = (float)m->mass[i];
         D->lim_lo[i] = (float)m->lim_lo[i]; D->lim_hi[i] = (float)m->lim_hi[i];
         D->jdamping[i] = (float)m->jdamping[i]; D->max_vel[i] = (float)m->max_vel[i];
+        D->armature[i] = (float)m->armature[i]; D->stiffness[i] = (float)m->stiffness[i];
     }
     for (int b = 0; b <= m->n_links; b++) D->break_thresh[b] = (float)m->break_thresh[b];
     for (int g = 0; g < m->n_geoms; g++) {
@@ -80,6 +110,7 @@ inline int build_dev_model(const rs_model_desc* m, DevModel* D, const char** err
     D->gravity = (float)m->gravity; D->timestep = (float)m->timestep;
     D->lin_damping = (float)m->lin_damping; D->ang_damping = (float)m->ang_damping;
     D->max_coord_vel = (float)m->max_coord_vel; D->erp = (float)m->erp; D->erp2 = (float)m->erp2;
+    D->c_erp = (float)m->c_erp; D->c_erp2 = (float)m->c_erp2; D->c_split_thresh = (float)(m->c_split_thresh < -1e30 ? -1e30 : m->c_split_thresh);
     D->split_thresh = (float)m->split_thresh; D->max_limit_impulse = (float)m->max_limit_impulse; D->use_gyro = (float)m->use_gyro;
     for (int k = 0; k < m->n_act; k++) { D->act_dof[k] = m->act_dof[k]; D->act_gain[k] = (float)m->act_gain[k]; }
     for (int k = 0; k < m->n_feet; k++) D->foot_link[k] = m->foot_link[k];

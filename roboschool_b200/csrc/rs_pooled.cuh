@@ -408,10 +408,10 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
             const float invd = denom > RS_FLT_EPS ? 1.0f / denom : 0.f;
             float rhs;
             if (w == 0) {
-                const float erp = pen > M.split_thresh ? M.erp : M.erp2;
+                const float erp = pen > M.c_split_thresh ? M.c_erp : M.c_erp2;
                 float posErr = 0.f, velErr = -relvel;
                 if (pen > 0.f) velErr -= pen * inv_dt; else posErr = -pen * erp * inv_dt;
-                rhs = pen > M.split_thresh ? (posErr + velErr) * invd : velErr * invd;
+                rhs = pen > M.c_split_thresh ? (posErr + velErr) * invd : velErr * invd;
             } else rhs = -relvel * invd;
             r_rhs[row] = rhs; r_invd[row] = invd; r_applied[row] = 0.f;
         }

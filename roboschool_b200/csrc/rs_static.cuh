@@ -470,7 +470,7 @@ RS_HD void static_aba(const DevModel& M, Work<NL, MC, SL>& W, const LinkCache<ST
         if constexpr (dI >= 0) {
             float h[6];
             inertia_mul_S<T, i>(h, IA[i + 1]);
-            float D = sdot<T, i>(h);
+            float D = sdot<T, i>(h) + M.armature[i];
             float y = W.tau[dI] - sdot<T, i>(Z[i + 1]) - dot6(c[i], h);
             float invD = 1.0f / D;
             Y[i] = y;

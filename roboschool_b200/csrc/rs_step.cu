@@ -50,6 +50,7 @@ struct rs_world {
     cudaStream_t stream;
     cudaStream_t chunk_stream[RS_MAX_CHUNKS];   // pipelined host entry point: one stream per env slice (created on first use)
     cudaEvent_t chunk_ev;
+    cudaEvent_t caller_ev;   // recorded behind everything the world enqueues on a caller's stream
     int n_chunk_streams;
     // pinned staging + device staging for the host-buffer entry point
     float *h_act, *h_obs, *h_rew; uint8_t* h_done;
@@ -273,6 +274,7 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
         CK(cudaMemcpy(B.initial_z, iz.data(), sizeof(float) * N, cudaMemcpyHostToDevice));
     }
     CK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&w->caller_ev, cudaEventDisableTiming));
     int A = model->n_act > 0 ? model->n_act : 1, O = model->obs_dim > 0 ? model->obs_dim : 1;
     CK(cudaMallocHost(&w->h_act, sizeof(float) * N * A));
     CK(cudaMallocHost(&w->h_obs, sizeof(float) * N * O));
@@ -297,6 +299,7 @@ extern "C" int rs_world_destroy(rs_world* w) {
     cudaFreeHost(w->h_act); cudaFreeHost(w->h_obs); cudaFreeHost(w->h_rew); cudaFreeHost(w->h_done);
     cudaFree(w->d_act); cudaFree(w->d_obs); cudaFree(w->d_rew); cudaFree(w->d_done); cudaFree(w->d_stats);
     cudaStreamDestroy(w->stream);
+    cudaEventDestroy(w->caller_ev);
     for (int k = 0; k < w->n_chunk_streams; k++) cudaStreamDestroy(w->chunk_stream[k]);
     if (w->n_chunk_streams) cudaEventDestroy(w->chunk_ev);
     delete w;
@@ -312,11 +315,24 @@ extern "C" int rs_world_state_dev(rs_world* w, float** p) { *p = w->B.state; ret
 
 static inline int nblocks(int n) { return (n + 63) / 64; }
 
+// Ordering between caller streams and the world's private stream: every entry point that enqueues on a caller's
+// stream records caller_ev behind its work; every entry point that works on the private stream first makes that stream wait
+// for the event.  (The private stream is synchronised before those entry points return, so the other direction is ordered.)
+static inline cudaError_t mark_caller(rs_world* w, cudaStream_t st) { return cudaEventRecord(w->caller_ev, st); }
+static inline cudaError_t wait_caller(rs_world* w) { return cudaStreamWaitEvent(w->stream, w->caller_ev, 0); }
+// host getters / setters: everything enqueued so far (caller streams through the event, then the private stream) has finished
+static inline cudaError_t quiesce(rs_world* w) {
+    cudaError_t e = wait_caller(w);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(w->stream);
+}
+
 extern "C" int rs_world_reset(rs_world* w, uint32_t seed, uint32_t env_id0, const uint8_t* mask_dev, float* obs_dev, void* stream) {
     CK(cudaSetDevice(w->device));
     cudaStream_t st = (cudaStream_t)stream;
     FAMILY_DISPATCH(w, (k_reset<NL, MC><<<nblocks(w->n), 64, 0, st>>>(w->M, w->B, mask_dev, obs_dev, seed, env_id0)));
     CK(cudaGetLastError());
+    CK(mark_caller(w, st));
     w->rollout_seed = seed; w->env_id0 = env_id0;
     return 0;
 }
@@ -341,14 +357,18 @@ extern "C" int rs_world_step(rs_world* w, const float* actions_dev, float* obs_d
                              int auto_reset, void* stream) {
     if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail("rs_world_step: null buffer");
     CK(cudaSetDevice(w->device));
-    return launch_step(w, actions_dev, obs_dev, reward_dev, done_dev, auto_reset, w->rollout_seed, w->env_id0, nullptr, (cudaStream_t)stream);
+    if (launch_step(w, actions_dev, obs_dev, reward_dev, done_dev, auto_reset, w->rollout_seed, w->env_id0, nullptr, (cudaStream_t)stream)) return 1;
+    CK(mark_caller(w, (cudaStream_t)stream));
+    return 0;
 }
 
 extern "C" int rs_world_step_stats(rs_world* w, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
                                    int auto_reset, double* stats_dev, void* stream) {
     if (!actions_dev || !obs_dev || !reward_dev || !done_dev) return fail("rs_world_step_stats: null buffer");
     CK(cudaSetDevice(w->device));
-    return launch_step(w, actions_dev, obs_dev, reward_dev, done_dev, auto_reset, w->rollout_seed, w->env_id0, stats_dev, (cudaStream_t)stream);
+    if (launch_step(w, actions_dev, obs_dev, reward_dev, done_dev, auto_reset, w->rollout_seed, w->env_id0, stats_dev, (cudaStream_t)stream)) return 1;
+    CK(mark_caller(w, (cudaStream_t)stream));
+    return 0;
 }
 
 // profiling: one step with per-phase warp-cycle totals -> cycles_host[8]
@@ -384,6 +404,7 @@ extern "C" int rs_world_step_host(rs_world* w, const float* actions_host, float*
     CK(cudaSetDevice(w->device));
     size_t N = (size_t)w->n, A = (size_t)w->desc.n_act, O = (size_t)w->desc.obs_dim;
     memcpy(w->h_act, actions_host, sizeof(float) * N * A);
+    CK(wait_caller(w));
     CK(cudaMemcpyAsync(w->d_act, w->h_act, sizeof(float) * N * A, cudaMemcpyHostToDevice, w->stream));
     if (launch_step(w, w->d_act, w->d_obs, w->d_rew, w->d_done, auto_reset, w->rollout_seed, w->env_id0, nullptr, w->stream)) return 1;
     CK(cudaMemcpyAsync(w->h_obs, w->d_obs, sizeof(float) * N * O, cudaMemcpyDeviceToHost, w->stream));
@@ -403,7 +424,7 @@ extern "C" int rs_world_set_joint_motor(rs_world* w, int env, int dof, float kp,
     if (dof < 0 || dof >= nd || env >= N) return fail("rs_world_set_joint_motor: dof or env out of range");
     CK(cudaSetDevice(w->device));
     DevBuf& B = w->B;
-    CK(cudaStreamSynchronize(w->stream));
+    CK(quiesce(w));
     if (!B.motor) {
         if (!(max_impulse > 0.f)) return 0;                  // switching off a motor of a world that never had one
         // first motor of this world: motor table (all off) and a row workspace with room for one motor row per dof
@@ -431,6 +452,7 @@ extern "C" int rs_world_set_joint_motor(rs_world* w, int env, int dof, float kp,
 extern "C" int rs_world_substeps(rs_world* w, int n_substeps, const float* tau_host) {
     CK(cudaSetDevice(w->device));
     size_t N = (size_t)w->n; int nd = w->desc.n_dof;
+    CK(quiesce(w));
     if (tau_host && nd > 0) {
         std::vector<float> t(N * nd);
         for (size_t e = 0; e < N; e++) for (int d = 0; d < nd; d++) t[(size_t)d * N + e] = tau_host[e * nd + d];
@@ -558,6 +580,7 @@ extern "C" int rs_world_link_poses(rs_world* w, float* out_host) {
     size_t cnt = (size_t)w->n * (w->desc.n_links + 1) * 10;
     float* d = nullptr;
     CK(cudaMalloc(&d, sizeof(float) * cnt));
+    CK(wait_caller(w));
     FAMILY_DISPATCH(w, (k_link_poses<NL, MC><<<nblocks(w->n), 64, 0, w->stream>>>(w->M, w->B, d)));
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
@@ -584,6 +607,30 @@ extern "C" int rs_world_get_contacts(rs_world* w, int env, int* keys_host, float
     return 0;
 }
 
+extern "C" int rs_world_set_contacts(rs_world* w, const int* counts_host, const int* keys_host, const float* data_host, int max_pts) {
+    CK(cudaSetDevice(w->device));
+    if (!counts_host || max_pts < 0) return fail("rs_world_set_contacts: bad arguments");
+    const size_t N = (size_t)w->n; const int MC = w->B.MCcap;
+    std::vector<int> cnt(N), key(N * MC, 0);
+    std::vector<float> dat(N * MC * CDAT, 0.f);
+    for (size_t e = 0; e < N; e++) {
+        int c = counts_host[e];
+        if (c < 0 || c > max_pts) return fail("rs_world_set_contacts: count out of range");
+        if (c > MC) c = MC;
+        if (c > w->desc.max_contacts) c = w->desc.max_contacts;
+        cnt[e] = c;
+        for (int i = 0; i < c; i++) {
+            key[(size_t)i * N + e] = keys_host[e * max_pts + i];
+            for (int k = 0; k < CDAT; k++) dat[((size_t)i * CDAT + k) * N + e] = data_host[(e * max_pts + i) * CDAT + k];
+        }
+    }
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(w->B.ccount, cnt.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(w->B.ckey, key.data(), sizeof(int) * N * MC, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(w->B.cdat, dat.data(), sizeof(float) * N * MC * CDAT, cudaMemcpyHostToDevice));
+    return 0;
+}
+
 extern "C" int rs_world_get_counts(rs_world* w, int* rows_host, int* contacts_host) {
     CK(cudaSetDevice(w->device));
     CK(cudaDeviceSynchronize());
@@ -602,7 +649,8 @@ extern "C" int rs_world_get_rewards5(rs_world* w, float* out_host) {
 // implemented in rs_mlp.cu
 extern "C" int rs_policy_forward(rs_policy* p, const float* obs_dev, float* act_dev, int n, void* stream);
 
-extern "C" int rs_world_rollout(rs_world* w, rs_policy* p, int n_steps, uint32_t seed, uint32_t env_id0, double* stats_dev, void* stream) {
+extern "C" int rs_world_rollout(rs_world* w, rs_policy* p, int n_steps, double* stats_dev, void* stream) {
+    const uint32_t seed = w->rollout_seed, env_id0 = w->env_id0;   // as stored by the last reset
     CK(cudaSetDevice(w->device));
     cudaStream_t st = (cudaStream_t)stream;
     for (int t = 0; t < n_steps; t++) {
@@ -614,6 +662,7 @@ extern "C" int rs_world_rollout(rs_world* w, rs_policy* p, int n_steps, uint32_t
         }
         if (launch_step(w, act, w->d_obs, w->d_rew, w->d_done, 1, seed, env_id0, stats_dev, st)) return 1;
     }
+    CK(mark_caller(w, st));
     return 0;
 }
 
@@ -637,6 +686,7 @@ extern "C" int rs_world_rollout_record(rs_world* w, rs_policy* p, int n_steps, c
     }
     // keep the world's own observation buffer current so that rollouts can be chained
     CK(cudaMemcpyAsync(w->d_obs, obs_T + (size_t)n_steps * N * O, sizeof(float) * N * O, cudaMemcpyDeviceToDevice, st));
+    CK(mark_caller(w, st));
     return 0;
 }
 
@@ -672,7 +722,8 @@ static int policy_step_host_pipelined(rs_world* w, rs_policy* p, const float* ob
         w->n_chunk_streams++;
     }
     const size_t O = (size_t)w->desc.obs_dim, A = (size_t)w->desc.n_act;
-    CK(cudaEventRecord(w->chunk_ev, w->stream));            // everything queued on the world's stream so far comes first
+    CK(wait_caller(w));
+    CK(cudaEventRecord(w->chunk_ev, w->stream));            // everything queued on the world's / the callers' streams so far comes first
     // slice boundaries in CTAs.  Only the first slice's H2D and the last slice's D2H are exposed, so with 4 or more slices
     // the two outer ones are half as large as the inner ones (RS_E2E_EVEN=1: equal slices).
     int bound[RS_MAX_CHUNKS + 1];
@@ -720,6 +771,7 @@ extern "C" int rs_world_policy_step_host(rs_world* w, rs_policy* p, const float*
         if (n_chunks > 1 && w->topo && !w->B.motor && direct && w->n >= 1024 && (!obs_in_host || host_is_pinned(obs_in_host)))
             return policy_step_host_pipelined(w, p, obs_in_host, obs_out_host, reward_host, done_host, n_chunks);
     }
+    CK(wait_caller(w));
     if (obs_in_host) {   // NULL: continue from the observations already on the device (after rs_world_rollout_reset / rollout)
         const float* src = obs_in_host;
         if (!host_is_pinned(obs_in_host)) { memcpy(w->h_obs, obs_in_host, sizeof(float) * N * O); src = w->h_obs; }

@@ -59,7 +59,13 @@ class RoboschoolB200Env(gym_shim.Env):
         d = bool(done[0])
         self.done += d
         self.reward += float(rew[0])
-        return obs[0], float(rew[0]), d, {}
+        # gym's TimeLimit wrapper from the registration (roboschool/__init__.py: max_episode_steps=1000, Reacher 150):
+        # done at the limit, flagged as a truncation the way later gym versions do
+        info = {}
+        if self.frame >= self.spec.max_episode_steps:
+            info["TimeLimit.truncated"] = not d
+            d = True
+        return obs[0], float(rew[0]), d, info
 
     def render(self, mode="human"):
         return None   # renderer out of scope

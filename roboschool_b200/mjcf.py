@@ -113,7 +113,7 @@ class _Geom:
 
 
 class _Joint:
-    __slots__ = ("name", "type", "axis", "pos", "lo", "hi", "limited", "damping")
+    __slots__ = ("name", "type", "axis", "pos", "lo", "hi", "limited", "damping", "armature", "stiffness")
 
 
 class _Body:
@@ -126,7 +126,7 @@ def _merged(defaults, tag, elem):
     return d
 
 
-def _parse_geom(elem, defaults, degrees):
+def _parse_geom(elem, defaults, degrees, honour_axisangle=True):
     a = _merged(defaults, "geom", elem)
     g = _Geom()
     g.name = a.get("name", "")
@@ -136,7 +136,7 @@ def _parse_geom(elem, defaults, degrees):
     rot = np.eye(3)
     if "quat" in a:
         rot = quat_wxyz_to_mat(_vec(a["quat"], 4))
-    elif "axisangle" in a:
+    elif "axisangle" in a and honour_axisangle:
         rot = axisangle_to_mat(_vec(a["axisangle"], 4), degrees)
     g.contype = int(a.get("contype", 1))
     g.conaffinity = int(a.get("conaffinity", 1))
@@ -208,10 +208,12 @@ def _parse_joint(elem, defaults, degrees):
         lo, hi = 0.0, -1.0
     j.lo, j.hi = lo, hi
     j.damping = float(a.get("damping", 0.0))
+    j.armature = float(a.get("armature", 0.0))
+    j.stiffness = float(a.get("stiffness", 0.0))
     return j
 
 
-def _parse_body(elem, defaults, degrees, parent=None):
+def _parse_body(elem, defaults, degrees, parent=None, honour_axisangle=True):
     b = _Body()
     b.name = elem.attrib.get("name", "")
     b.pos = _vec(elem.attrib.get("pos"), 3, [0, 0, 0])
@@ -223,18 +225,18 @@ def _parse_body(elem, defaults, degrees, parent=None):
         if ch.tag == "joint":
             b.joints.append(_parse_joint(ch, defaults, degrees))
         elif ch.tag == "geom":
-            g = _parse_geom(ch, defaults, degrees)
+            g = _parse_geom(ch, defaults, degrees, honour_axisangle)
             if g is not None:
                 b.geoms.append(g)
         elif ch.tag == "inertial":
             if "mass" in ch.attrib:
                 b.mass_override = float(ch.attrib["mass"])
         elif ch.tag == "body":
-            b.children.append(_parse_body(ch, defaults, degrees, b))
+            b.children.append(_parse_body(ch, defaults, degrees, b, honour_axisangle))
     return b
 
 
-def _geom_aabb(g, com):
+def _geom_aabb(g, com, margin=CONVEX_DISTANCE_MARGIN):
     """AABB of one child shape in the link COM frame, as Bullet's getAabb reports it."""
     if g.type == RS_GEOM_SPHERE:
         c = g.p0 - com
@@ -246,8 +248,8 @@ def _geom_aabb(g, com):
         return c - ext, c + ext
     if g.fromto:
         # btMultiSphereShape: cached local AABB is exact, getAabb adds one more margin
-        lo = np.minimum(g.p0, g.p1) - com - g.radius - CONVEX_DISTANCE_MARGIN
-        hi = np.maximum(g.p0, g.p1) - com + g.radius + CONVEX_DISTANCE_MARGIN
+        lo = np.minimum(g.p0, g.p1) - com - g.radius - margin
+        hi = np.maximum(g.p0, g.p1) - com + g.radius + margin
         return lo, hi
     # btCapsuleShapeZ under a rotated child transform: OBB -> AABB via |R|
     he = np.array([g.radius, g.radius, g.radius + g.halflen])
@@ -256,11 +258,15 @@ def _geom_aabb(g, com):
     return c - ext, c + ext
 
 
-def _body_inertial(b, honour_density):
+def _body_inertial(b, honour_density, com_rule="last_fromto", aabb_margin=CONVEX_DISTANCE_MARGIN):
     """(mass, com_in_body_frame, diag_inertia, break_thresh) for a real (non-dummy) link."""
-    if b.geoms:
+    if b.geoms and com_rule == "last_fromto":
         last = b.geoms[-1]
         com = last.center.copy() if (last.type == RS_GEOM_CAPSULE and last.fromto) else np.zeros(3)
+    elif b.geoms and com_rule == "centroid":
+        com = sum(g.volume * g.center for g in b.geoms) / sum(g.volume for g in b.geoms)
+    elif b.geoms and com_rule == "first":
+        com = b.geoms[0].center.copy()
     else:
         com = np.zeros(3)
     if b.mass_override is not None:
@@ -272,7 +278,7 @@ def _body_inertial(b, honour_density):
     lo = np.full(3, np.inf)
     hi = np.full(3, -np.inf)
     for g in b.geoms:
-        l, h = _geom_aabb(g, com)
+        l, h = _geom_aabb(g, com, aabb_margin)
         lo, hi = np.minimum(lo, l), np.maximum(hi, h)
     ext = hi - lo
     lx, ly, lz = ext
@@ -284,7 +290,9 @@ def _body_inertial(b, honour_density):
 
 
 def compile_mjcf(xml_path, honour_density=False, honour_damping=False, has_floor=True,
-                 gravity=9.8, timestep=0.0165 / 4, frame_skip=4):
+                 gravity=9.8, timestep=0.0165 / 4, frame_skip=4, honour_axisangle=True, com_rule="last_fromto",
+                 aabb_margin=CONVEX_DISTANCE_MARGIN, honour_armature=False, honour_stiffness=False,
+                 honour_settotalmass=False, contact_erp="split", damping_scale=1.0):
     """Compile one robot MJCF into a :class:`ModelDesc` (physics part only).
 
     ``gravity``/``timestep`` are squeezed through float32 exactly as the reference's
@@ -305,7 +313,7 @@ def compile_mjcf(xml_path, honour_density=False, honour_damping=False, has_floor
     bodies = [ch for ch in wb if ch.tag == "body"]
     if len(bodies) == 0:
         raise NotImplementedError("no top-level body")
-    tops = [_parse_body(b, defaults, degrees) for b in bodies]
+    tops = [_parse_body(b, defaults, degrees, None, honour_axisangle) for b in bodies]
     if len(tops) > 1 and not all(t.joints for t in tops):
         raise NotImplementedError("several top-level bodies are supported only when each hangs from the world by joints")
     top = tops[0]
@@ -332,7 +340,7 @@ def compile_mjcf(xml_path, honour_density=False, honour_damping=False, has_floor
         base_rot = np.eye(3)
     else:
         m.fixed_base = 0
-        mass, com, inertia, thr = _body_inertial(top, honour_density)
+        mass, com, inertia, thr = _body_inertial(top, honour_density, com_rule, aabb_margin)
         m.base_mass = mass
         m.arr("base_inertia")[:] = inertia
         base_name = top.name
@@ -347,7 +355,7 @@ def compile_mjcf(xml_path, honour_density=False, honour_damping=False, has_floor
     def emit(b, parent_link, parent_com, is_top):
         """Create the link chain of body ``b`` whose parent body's real link is
         ``parent_link`` with COM ``parent_com`` (parent body frame)."""
-        mass, com, inertia, thr = _body_inertial(b, honour_density)
+        mass, com, inertia, thr = _body_inertial(b, honour_density, com_rule, aabb_margin)
         pB = b.pos
         R_B = b.rot
         chain = b.joints if b.joints else [None]
@@ -361,13 +369,16 @@ def compile_mjcf(xml_path, honour_density=False, honour_damping=False, has_floor
                 L["axis"] = np.array([0.0, 0.0, 1.0])
                 pj = np.zeros(3)
                 L["lo"], L["hi"], L["limited"], L["damping"] = 0.0, -1.0, 0, 0.0
+                L["armature"], L["stiffness"] = 0.0, 0.0
                 jname = None
             else:
                 L["jtype"] = j.type
                 L["axis"] = j.axis
                 pj = j.pos
                 L["lo"], L["hi"], L["limited"] = j.lo, j.hi, int(j.limited)
-                L["damping"] = j.damping if honour_damping else 0.0
+                L["damping"] = j.damping * damping_scale if honour_damping else 0.0
+                L["armature"] = j.armature if honour_armature else 0.0
+                L["stiffness"] = j.stiffness if honour_stiffness else 0.0
                 jname = j.name
             if k == 0:
                 # parent frame = parent body frame; pivot = pB + R_B pj
@@ -417,9 +428,19 @@ def compile_mjcf(xml_path, honour_density=False, honour_damping=False, has_floor
         m.arr("inertia")[i] = L["inertia"]
         m.lim_lo[i], m.lim_hi[i] = L["lo"], L["hi"]
         m.jdamping[i] = L["damping"]
+        m.armature[i] = L["armature"]
+        m.stiffness[i] = L["stiffness"]
         m.max_vel[i] = 0.0
         m.arr("break_thresh")[i + 1] = L["thresh"]
     m.n_dof = ndof
+    if honour_settotalmass and comp is not None and "settotalmass" in comp.attrib:
+        tot = m.base_mass + sum(m.mass[i] for i in range(m.n_links))
+        k = float(comp.attrib["settotalmass"]) / tot
+        m.base_mass *= k
+        m.arr("base_inertia")[:] *= k
+        for i in range(m.n_links):
+            m.mass[i] *= k
+            m.arr("inertia")[i] *= k
 
     # ---- geoms ----
     if len(geoms) > RS_MAX_GEOMS:
@@ -473,6 +494,14 @@ def compile_mjcf(xml_path, honour_density=False, honour_damping=False, has_floor
     m.erp2 = 0.9                     # physics-bullet.cpp:371 (contactERP)
     m.erp = 0.2                      # btContactSolverInfo default m_erp
     m.split_thresh = -0.04           # m_splitImpulsePenetrationThreshold
+    # contact rows: "split" = m_erp above the split-impulse threshold, positional term dropped below it;
+    # "erp2" = contactERP for every penetration, always combined into the rhs
+    if contact_erp == "split":
+        m.c_erp, m.c_erp2, m.c_split_thresh = m.erp, m.erp2, m.split_thresh
+    elif contact_erp == "erp2":
+        m.c_erp, m.c_erp2, m.c_split_thresh = m.erp2, m.erp2, -1e30
+    else:
+        m.c_erp, m.c_erp2, m.c_split_thresh = float(contact_erp), float(contact_erp), -1e30
     m.lin_damping = 0.04             # btMultiBody ctor
     m.ang_damping = 0.04
     m.max_coord_vel = 100.0

@@ -148,6 +148,13 @@ class BatchedWorld:
         _lib.check(self.L.rs_world_get_contacts(self.h, env, keys.ctypes.data, data.ctypes.data, max_pts, ctypes.addressof(cnt)))
         return keys[:cnt.value], data[:cnt.value]
 
+    def set_contacts(self, counts, keys, data):
+        """Overwrite every env's persistent contact manifolds: counts [n], keys [n,P], data [n,P,10] (solver order)."""
+        c = np.ascontiguousarray(counts, dtype=np.int32).reshape(self.n)
+        k = np.ascontiguousarray(keys, dtype=np.int32).reshape(self.n, -1)
+        d = np.ascontiguousarray(data, dtype=np.float32).reshape(self.n, k.shape[1], 10)
+        _lib.check(self.L.rs_world_set_contacts(self.h, c.ctypes.data, k.ctypes.data, d.ctypes.data, int(k.shape[1])))
+
     def counts(self):
         r = np.empty(self.n, dtype=np.int32)
         c = np.empty(self.n, dtype=np.int32)
@@ -163,9 +170,11 @@ class BatchedWorld:
     def rollout_reset(self, seed=0, env_id0=0, stream=None):
         _lib.check(self.L.rs_world_rollout_reset(self.h, seed, env_id0, stream))
 
-    def rollout(self, policy, n_steps, seed=0, env_id0=0, stats=None, stream=None):
+    def rollout(self, policy, n_steps, seed=None, env_id0=None, stats=None, stream=None):
+        """n_steps fused policy + env steps.  Auto-resets / random actions use the seed and env_id0 of the last
+        reset / rollout_reset (the `seed` / `env_id0` arguments are accepted for source compatibility and ignored)."""
         ph = policy.h if policy is not None else None
-        _lib.check(self.L.rs_world_rollout(self.h, ph, int(n_steps), seed, env_id0, _ptr(stats), stream))
+        _lib.check(self.L.rs_world_rollout(self.h, ph, int(n_steps), _ptr(stats), stream))
 
     def rollout_record(self, policy, n_steps, obs_T, act_T, rew_T, done_T, obs0=None, stats=None, stream=None):
         """T steps into time-major device tensors (raw pointers or torch tensors); see rs_world_rollout_record."""

@@ -251,3 +251,119 @@ def test_joint_motor_rows_closed_forms(oracle_lib):
     w.set_joint_motor(0, 1, 0.1, 0.5, 0.3, 0.0, 0.0)           # off again
     w.substeps(0, 1)
     assert np.array_equal(w.get_state(0), free.get_state(0))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Mechanics identities: the oracle's articulated-body algorithm and its unit-impulse response are
+# checked against the equations of motion built INDEPENDENTLY of any recursive algorithm -- the mass matrix and the
+# gravity force are assembled in numpy from finite differences of the oracle's forward kinematics (link COM poses)
+# alone:  M(x) = sum_i m_i Jv_i^T Jv_i + Jw_i^T (R_i I_i R_i^T) Jw_i ,  G = dV/dx ,  and at zero velocity
+#   M a = tau - G        (ABA: computeAccelerationsArticulatedBodyAlgorithmMultiDof)
+#   M u = f              (calcAccelerationDeltasMultiDof)
+# with x = [base rotation vector (world), base position, q] and a / u / f in [w_base, v_base, qd] order.
+# ---------------------------------------------------------------------------------------------------------------------
+def _quat_mat(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def _perturbed_state(m, s, k, eps):
+    """state with generalized coordinate k moved by eps: k<3 base rotation about world axis k, 3..5 base position, 6.. joints."""
+    s = s.copy()
+    if m.fixed_base:
+        s[k - 6] += eps
+        return s
+    if k < 3:
+        ax = np.zeros(3); ax[k] = 1.0
+        dq = np.concatenate([ax * np.sin(0.5 * eps), [np.cos(0.5 * eps)]])
+        x1, y1, z1, w1 = dq
+        x2, y2, z2, w2 = s[3:7]
+        s[3:7] = [w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2,
+                  w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2, w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2]
+    elif k < 6:
+        s[k - 3] += eps
+    else:
+        s[13 + (k - 6)] += eps
+    return s
+
+
+def _mass_matrix_fd(oracle_lib, m, s, eps=1e-6):
+    w = oracle_lib.OracleWorld(m, 1)
+    nb = m.n_links + 1
+    nd = 6 + m.n_dof
+    k0 = 6 if m.fixed_base else 0
+
+    def poses(state):
+        w.set_state(0, state)
+        P = w.link_poses(0)
+        return P[:, 0:3].copy(), [_quat_mat(P[b, 3:7]) for b in range(nb)]
+    p0, R0 = poses(s)
+    Jv = np.zeros((nb, 3, nd)); Jw = np.zeros((nb, 3, nd))
+    for k in range(k0, nd):
+        pp, Rp = poses(_perturbed_state(m, s, k, eps))
+        pm, Rm = poses(_perturbed_state(m, s, k, -eps))
+        for b in range(nb):
+            Jv[b, :, k] = (pp[b] - pm[b]) / (2 * eps)
+            dR = (Rp[b] - Rm[b]) @ R0[b].T / (2 * eps)       # skew(omega) for a unit rate of coordinate k
+            Jw[b, :, k] = [dR[2, 1], dR[0, 2], dR[1, 0]]
+    masses = [m.base_mass] + [m.mass[i] for i in range(m.n_links)]
+    inert = [np.array(m.arr("base_inertia"))] + [np.array(m.arr("inertia")[i]) for i in range(m.n_links)]
+    M = np.zeros((nd, nd)); G = np.zeros(nd)
+    for b in range(nb):
+        if b == 0 and m.fixed_base:
+            continue
+        Iw = R0[b] @ np.diag(inert[b]) @ R0[b].T
+        M += masses[b] * Jv[b].T @ Jv[b] + Jw[b].T @ Iw @ Jw[b]
+        G += masses[b] * m.gravity * Jv[b][2]
+    return M, G
+
+
+@pytest.mark.parametrize("env_id", ["RoboschoolHopper-v1", "RoboschoolWalker2d-v1", "RoboschoolHalfCheetah-v1", "RoboschoolAnt-v1",
+                                    "RoboschoolHumanoid-v1", "RoboschoolInvertedDoublePendulum-v1"])
+def test_aba_and_response_satisfy_equations_of_motion(env_id, oracle_lib):
+    m = envspec.load_env_model(env_id)
+    rng = np.random.RandomState(5)
+    nd = 6 + m.n_dof
+    k0 = 6 if m.fixed_base else 0
+    for trial in range(3):
+        s = np.zeros(m.state_dim)
+        q = rng.uniform(-0.6, 0.6, m.n_dof)
+        for i in range(m.n_links):                # inside the joint ranges: no limit rows in this test
+            if m.dof_idx[i] >= 0 and m.has_limit[i]:
+                q[m.dof_idx[i]] = m.lim_lo[i] + rng.uniform(0.15, 0.85) * (m.lim_hi[i] - m.lim_lo[i])
+        if m.fixed_base:
+            s[:m.n_dof] = q
+            names = m.meta["joint_names"]
+            for i, nme in enumerate(names):       # lift the planar robots off the floor: no contact rows in this test
+                if nme in ("ignorez", "ignore2"):
+                    s[m.dof_idx[i]] = 1.0
+        else:
+            ax = rng.normal(size=3); ax /= np.linalg.norm(ax); ang = rng.uniform(-1, 1)
+            s[0:3] = [0.1, -0.2, 3.0]
+            s[3:7] = np.concatenate([ax * np.sin(0.5 * ang), [np.cos(0.5 * ang)]])
+            s[13:13 + m.n_dof] = q
+        M, G = _mass_matrix_fd(oracle_lib, m, s)
+        tau = rng.uniform(-20, 20, m.n_dof)
+        w = oracle_lib.OracleWorld(m, 1)
+        w.set_state(0, s)
+        w.set_tau(0, tau)
+        w.substeps(0, 1)
+        s1 = w.get_state(0)
+        dt = m.timestep
+        a = np.zeros(nd)
+        if m.fixed_base:
+            a[6:] = s1[m.n_dof:] / dt
+        else:
+            a[0:3] = s1[7:10] / dt; a[3:6] = s1[10:13] / dt; a[6:] = s1[13 + m.n_dof:] / dt
+        rhs = -G.copy(); rhs[6:] += tau
+        res = (M @ a - rhs)[k0:]
+        scale = max(1.0, np.abs(rhs[k0:]).max())
+        assert np.abs(res).max() / scale < 1e-6, (env_id, trial, np.abs(res).max(), scale)
+        # unit-impulse response: M u = f for random generalized forces (the solver's M^-1 J^T)
+        w.set_state(0, s)
+        for r in range(3):
+            f = np.zeros(nd); f[k0:] = rng.normal(size=nd - k0)
+            u = w.accel_deltas(0, f)
+            assert np.abs((M @ u - f)[k0:]).max() < 1e-6 * max(1.0, np.abs(u).max() * np.abs(M).max()), (env_id, trial, r)
