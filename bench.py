@@ -32,24 +32,39 @@ def algorithmic_bytes(m):
     return 4 * (2 * S + m.n_act + m.obs_dim + 2)
 
 
+_CLOCK_Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+
+def clock_query(index):
+    """One synchronous nvidia-smi query (the line's `clocks` block is never empty, whatever the length of the timed region)."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=" + _CLOCK_Q, "--format=csv,noheader,nounits"],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=20).stdout.strip().splitlines()
+        return [x.strip() for x in out[0].split(",")] if out else None
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
+    """nvidia-smi sampler (50 ms period) running from the warm-up steps to the end of the end-to-end region."""
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.rows = []      # (wall time, fields)
         self.stop_flag = False
+        self.p = None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + _CLOCK_Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                  stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             return
         self.p = p
         for line in p.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
             if self.stop_flag:
                 break
         try:
@@ -57,15 +72,20 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
-    def summary(self):
+    def summary(self, t0=None, t1=None, extra=None):
+        """Median SM clock / throttle reasons over the samples taken inside [t0, t1] (the timed regions), plus `extra`
+        (a synchronous query made while the timed steps were in flight)."""
         self.stop_flag = True
         try:
             self.p.kill()
         except Exception:
             pass
+        rows = [r for (t, r) in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1)]
+        if extra:
+            rows.append(extra)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for k, nm in enumerate(names):
@@ -75,31 +95,63 @@ class ClockSampler(threading.Thread):
                 pass
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "window": "device-timed + end-to-end regions"}
 
 
-def cpu_baseline_run(n_envs, n_steps, threads, warmup=1, min_seconds=0.0):
-    """The CPU restatement (oracle, 'port') on the host cores: same model, same policy (numpy), auto-reset.
-    Runs n_steps env steps, then keeps going until min_seconds of wall time have elapsed."""
-    from roboschool_b200.envspec import load_env_model
-    from roboschool_b200.policy import load_zoo_weights
-    from oracle.oracle import OracleWorld, mlp_forward
-    m = load_env_model(ENV_ID)
-    wts = load_zoo_weights(ENV_ID)
-    o = OracleWorld(m, n_envs)
-    o.reset(seed=0)
-    obs, _, _ = o.obs()
-    for _ in range(warmup):
-        a = mlp_forward(wts, obs)
-        obs, _, _ = o.step(a, auto_reset=True, seed=0, threads=threads)
-    t0 = time.perf_counter()
-    done_steps = 0
-    while done_steps < n_steps or time.perf_counter() - t0 < min_seconds:
-        a = mlp_forward(wts, obs)
-        obs, _, _ = o.step(a, auto_reset=True, seed=0, threads=threads)
-        done_steps += 1
-    dt = time.perf_counter() - t0
-    return n_envs * done_steps / dt, dt, done_steps
+class CpuStepper:
+    """The CPU restatement (oracle, 'port') on the host cores: ONE world kept at steady state (persistent worker threads,
+    >= 64 envs per thread, zoo policy in numpy, auto-reset) -- the world is settled once and then only stepped."""
+
+    def __init__(self, env_id, threads, envs_per_thread=64, settle_steps=60, settle_seconds=3.0):
+        from roboschool_b200.envspec import load_env_model
+        from roboschool_b200.policy import load_zoo_weights
+        from oracle.oracle import OracleWorld
+        try:    # BLAS worker threads spin after every matmul and steal the cores from the stepper's own thread pool (measured: 2.4x)
+            from threadpoolctl import threadpool_limits
+            self._blas = threadpool_limits(limits=1)
+        except Exception:
+            self._blas = None
+        self.m = load_env_model(env_id)
+        self.wts = [np.asarray(w, dtype=np.float32) for w in load_zoo_weights(env_id)]   # fp32 like the reference's TF policy
+        self.threads = threads
+        self.n = max(64, threads * envs_per_thread)
+        self.o = OracleWorld(self.m, self.n)
+        self.o.reset(seed=0)
+        self.obs = self.o.obs()[0]
+        # settle: episodes under way, contacts in steady state, worker threads (and the VM's vCPUs) spun up
+        t0 = time.perf_counter()
+        k = 0
+        while k < settle_steps or time.perf_counter() - t0 < settle_seconds:
+            self.step(); k += 1
+
+    def step(self):
+        w = self.wts
+        x = np.maximum(self.obs.astype(np.float32) @ w[0] + w[1], 0)
+        x = np.maximum(x @ w[2] + w[3], 0)
+        a = (x @ w[4] + w[5]).astype(np.float64)
+        self.obs, _, _ = self.o.step(a, auto_reset=True, seed=0, threads=self.threads)
+
+    def measure(self, seconds, min_steps=4):
+        t0 = time.perf_counter()
+        k = 0
+        while k < min_steps or time.perf_counter() - t0 < seconds:
+            self.step(); k += 1
+        dt = time.perf_counter() - t0
+        return self.n * k / dt, dt, k
+
+
+def cpu_baseline(env_id, cores, seconds_all=12.0, seconds_one=5.0):
+    """All-cores figure (median of 3 equal slices of one settled world) + the single-core figure."""
+    allc = CpuStepper(env_id, cores)
+    runs = [allc.measure(seconds_all / 3.0) for _ in range(3)]
+    v = float(np.median([r[0] for r in runs]))
+    one = CpuStepper(env_id, 1, settle_steps=40, settle_seconds=1.5)
+    v1, dt1, k1 = one.measure(seconds_one)
+    return {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            "runs": [r[0] for r in runs], "single_core": {"value": v1, "cores": 1, "sample": "%d envs x %d env-steps, %.1f s" % (one.n, k1, dt1)},
+            "sample": "%d envs (64 per thread) x %d env-steps of the same workload on one settled world, %d persistent threads, median of 3 x %.1f s "
+                      "(CPU restatement of the Bullet path, not Bullet itself)" % (allc.n, sum(r[2] for r in runs), cores, seconds_all / 3.0)}
 
 
 def reference_arm(args):
@@ -107,28 +159,62 @@ def reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_envs = max(cores * 16, 64)
-    per_step_value = []
-    # bounded: the whole --steps K --warmup W run ends within a few minutes whatever K is
-    k_steps = min(args.steps, 40)
-    for _ in range(min(args.warmup, 3)):
-        cpu_baseline_run(n_envs, 1, cores, warmup=0)
-    t_total = 0.0
-    for _ in range(k_steps):
-        v, dt, _n = cpu_baseline_run(n_envs, 4, cores, warmup=0)
-        per_step_value.append(v); t_total += dt
-    value = float(np.mean(per_step_value))
+    cpu = CpuStepper(args.env, cores)
+    for _ in range(min(max(args.warmup, 3), 50)):
+        cpu.step()
+    # a bench step = one env.step of every env of the settled CPU world; bounded so that the run ends within ~1.5 minutes
+    budget_s = 60.0
+    t0 = time.perf_counter()
+    k = 0
+    while k < args.steps and (k < 4 or time.perf_counter() - t0 < budget_s):
+        cpu.step(); k += 1
+    dt = time.perf_counter() - t0
+    value = cpu.n * k / dt
+    one = CpuStepper(args.env, 1, settle_steps=40, settle_seconds=1.5)
+    v1, dt1, k1 = one.measure(5.0)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(k_steps, 1), "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC.replace(ENV_ID, args.env), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(k, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "RoboschoolHumanoid-v1 CPU stepper, %d envs x 4 env-steps per bench step, zoo v1 MLP in numpy, auto-reset" % n_envs},
+        "config": {"workload": "%s CPU stepper, one settled world of %d envs, %d of the %d bench steps timed (%.0f s budget), zoo v1 MLP in numpy, auto-reset"
+                               % (args.env, cpu.n, k, args.steps, budget_s)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d envs x 4 env-steps per step, %d threads (CPU restatement of the Bullet path; the reference's Bullet fork cannot be built here)" % (n_envs, cores)},
+                         "single_core": {"value": v1, "cores": 1, "sample": "%d envs x %d env-steps, %.1f s" % (one.n, k1, dt1)},
+                         "sample": "%d envs x %d env-steps, %d persistent threads, steady state (CPU restatement of the Bullet path; the reference's Bullet fork cannot be built here)" % (cpu.n, k, cores)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def short_run(env_id, n, device, stream, settle=200, steps=50):
+    """Device-resident env-steps/s of another BASELINE config: settle, stagger the episode clocks, time `steps` steps."""
+    import torch
+    from roboschool_b200.envspec import load_env_model
+    from roboschool_b200.world import BatchedWorld
+    from roboschool_b200.policy import ZooPolicy, load_zoo_weights
+    m = load_env_model(env_id)
+    W = BatchedWorld(m, n, device)
+    pol = ZooPolicy(load_zoo_weights(env_id), device)
+    stats = torch.zeros(8, dtype=torch.float64, device="cuda:%d" % device)
+    W.rollout_reset(seed=0, env_id0=0, stream=stream)
+    W.rollout(pol, settle, stats=stats, stream=stream)
+    torch.cuda.synchronize()
+    W.set_episode(frame=np.random.RandomState(7).randint(0, max(m.max_episode_steps - 1, 1), size=n).astype(np.int32))
+    W.rollout(pol, 10, stats=stats, stream=stream)
+    torch.cuda.synchronize()
+    stats.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    W.rollout(pol, steps, stats=stats, stream=stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    st = stats.cpu().numpy()
+    W.close(); pol.close()
+    return {"env": env_id, "envs": n, "value": n * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+            "settle_steps": settle, "mean_rows": st[4] / max(st[6], 1), "mean_contacts": st[5] / max(st[6], 1),
+            "algorithmic_bytes_per_env_step": algorithmic_bytes(m)}
 
 
 def main():
@@ -140,6 +226,7 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=32768)
     ap.add_argument("--env", default=ENV_ID)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short sub-results of the other BASELINE configs")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -172,8 +259,20 @@ def main():
     W.rollout_reset(seed=0, env_id0=env_id0, stream=stream)
 
     def one_step():
-        W.rollout(pol, 1, seed=0, env_id0=env_id0, stats=stats, stream=stream)
+        W.rollout(pol, 1, stats=stats, stream=stream)
 
+    # --- set-up, untimed: settle the batch into its steady state whatever --warmup is.  SETTLE policy steps after the
+    # synchronised reset (contacts and gait established), then the episode clocks are staggered uniformly over the time
+    # limit so that time-limit resets arrive at their steady rate (n / max_episode_steps per step), not all at once ---
+    SETTLE = 300
+    W.rollout(pol, SETTLE, stats=stats, stream=stream)
+    torch.cuda.synchronize()
+    _p, _z, _f, frame = W.get_episode()
+    rng = np.random.RandomState(1234 + rank)
+    W.set_episode(frame=rng.randint(0, max(m.max_episode_steps - 1, 1), size=n).astype(np.int32))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         one_step()
     torch.cuda.synchronize()
@@ -182,12 +281,10 @@ def main():
     if world_size > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     pev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    t_region0 = time.time()
     ev0.record()
     for t in range(args.steps):
         pev[t].record()
@@ -196,8 +293,8 @@ def main():
         _lib.check(W.L.rs_world_step_stats(W.h, act_p, obs_p, rew_p, done_p, 1, stats.data_ptr(), stream))
         kev[t][1].record()
     ev1.record()
+    clock_now = clock_query(local_rank) if rank == 0 else None     # one query while the timed steps are still in flight
     torch.cuda.synchronize()
-    clocks = sampler.summary() if rank == 0 else None
     ms_total = ev0.elapsed_time(ev1)
     ms_kernel = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     ms_policy = float(np.mean([p.elapsed_time(k[0]) for p, k in zip(pev, kev)]))
@@ -215,7 +312,7 @@ def main():
 
     # --- end-to-end through the host-buffer C-ABI call: every step copies the observations H2D from (pinned-staged)
     # host memory, runs policy + step, and copies obs/reward/done back D2H ---
-    e2e_steps = max(10, args.steps // 4)
+    e2e_steps = max(200, args.steps)          # >= 200 steps (>= ~0.2 s of wall clock at the default workload)
     torch.cuda.synchronize()
     bufs = [W.pinned_host_buffers(), W.pinned_host_buffers()]   # page-locked ping-pong: this step's output is the next step's input
     o_np, r_np, d_np = W.policy_step_host(pol, None, out=bufs[0])   # continue from the device-resident rollout: same steady-state workload
@@ -229,6 +326,8 @@ def main():
         o_np, r_np, d_np = W.policy_step_host(pol, o_np, out=bufs[k & 1])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    t_region1 = time.time()
+    clocks = sampler.summary(t_region0, t_region1, clock_now) if rank == 0 else None
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
@@ -261,10 +360,15 @@ def main():
     cpu = None
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_cpu = max(cores * 16, 64)
-        v, dt, ns = cpu_baseline_run(n_cpu, 8, cores, warmup=2, min_seconds=12.0)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d envs x %d env-steps of the same workload, %d threads, %.1f s (CPU restatement of the Bullet path, not Bullet itself)" % (n_cpu, ns, cores, dt)}
+        cpu = cpu_baseline(args.env, cores)
+
+    # short device-timed sub-results for the other BASELINE.json configs (2: Hopper 4096, 3: Ant 65536, 5: FlagrunHarder)
+    extra = None
+    if world_size == 1 and not args.no_extra and args.env == ENV_ID:
+        extra = {}
+        for cfg, eid, ne in (("configs[1]", "RoboschoolHopper-v1", 4096), ("configs[2]", "RoboschoolAnt-v1", 65536),
+                             ("configs[4]", "RoboschoolHumanoidFlagrunHarder-v1", 32768)):
+            extra[cfg] = short_run(eid, ne, local_rank, stream)
 
     # the policy forward is the one contraction of the path: reported against the tensor peak
     wshape = [w.shape for w in load_zoo_weights(args.env)]
@@ -279,8 +383,10 @@ def main():
     line = {
         "metric": METRIC.replace(ENV_ID, args.env), "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s, %d envs/GPU (%d total), agent_zoo v1 MLP policy on tensor cores, frame_skip 4, on-device auto-reset" % (args.env, n, total_envs),
+        "dtype": "f32", "dtype_policy": "f16xf16->f32 (tcgen05 kind::f16, fp32 accumulate; tolerance 5e-3 of the action scale, tests/test_gpu_parity.py)",
+        "data": "synthetic",
+        "config": {"workload": "%s, %d envs/GPU (%d total), agent_zoo v1 MLP policy on tensor cores, frame_skip 4, on-device auto-reset; steady state: "
+                               "%d untimed settle steps after reset + episode clocks staggered over the time limit, then --warmup" % (args.env, n, total_envs, SETTLE),
                    "l2": "per-step working set (state+contacts+row workspace, >400 MB/GPU) exceeds the 126 MB L2",
                    "parallelism": "env-sharded, %d process(es), no step-path collective" % world_size},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -293,6 +399,7 @@ def main():
                             "peak_source": "measured (MEASURED_PEAKS.json, dense bf16 burst)" if "bf16_tflops" in peaks else "fallback"},
         "gpu_launches": 2 * args.steps + 2 * chunks * (e2e_steps + 4),
         "clocks": clocks,
+        "extra": extra,
         "rollout_stats": {"mean_reward": st[0] / max(st[6], 1), "episodes": st[1], "mean_episode_len": st[2] / max(st[1], 1),
                           "nonfinite": st[3], "mean_rows": st[4] / max(st[6], 1), "mean_contacts": st[5] / max(st[6], 1), "env_steps": st[6]},
     }

@@ -126,11 +126,13 @@ typedef struct {
     sv6 vel[ML + 1];     /* spatial velocity, link coords                   */
 } oenv;
 
+struct step_pool;
 typedef struct oracle_world {
     rs_model_desc m;
     int n_envs;
     int nman;
     oenv *env;
+    struct step_pool *pool;   /* persistent worker threads of oracle_step (created on first multi-threaded call) */
 } oracle_world;
 
 /* ---------------- small vector helpers ---------------- */
@@ -1200,6 +1202,7 @@ static void env_reset(const rs_model_desc *m, oenv *e, int nman, uint32_t seed, 
 }
 
 /* =========================== exported API =========================== */
+static void pool_destroy(struct step_pool *p);
 oracle_world *oracle_create(const rs_model_desc *m, int n_envs) {
     oracle_world *w = (oracle_world *)calloc(1, sizeof *w);
     w->m = *m; w->n_envs = n_envs; w->nman = m->n_geoms + m->n_pairs;
@@ -1213,6 +1216,7 @@ oracle_world *oracle_create(const rs_model_desc *m, int n_envs) {
     return w;
 }
 void oracle_destroy(oracle_world *w) {
+    pool_destroy(w->pool);
     for (int i = 0; i < w->n_envs; i++) free(w->env[i].man);
     free(w->env); free(w);
 }
@@ -1305,23 +1309,77 @@ static void step_one(oracle_world *w, int i, const double *actions, int auto_res
         e->done = 1; e->reward = rew;
     }
 }
-typedef struct { oracle_world *w; const double *actions; int auto_reset; uint32_t seed, env_id0; int lo, hi; } step_job;
-static void *step_worker(void *arg) {
-    step_job *j = (step_job *)arg;
-    for (int i = j->lo; i < j->hi; i++) step_one(j->w, i, j->actions, j->auto_reset, j->seed, j->env_id0);
+/* Persistent worker pool: the threads are created once per world and parked on a condition variable between steps
+ * (spawning and joining pthreads every step made the CPU baseline vary 5x between runs).  Envs are handed out in chunks
+ * from an atomic counter, so a thread that drew cheap envs takes more of them; the calling thread works too. */
+typedef struct step_pool {
+    pthread_t th[256];
+    int n_workers;
+    pthread_mutex_t mu;
+    pthread_cond_t cv_start, cv_done;
+    unsigned long generation;
+    int running, quit;
+    oracle_world *w; const double *actions; int auto_reset; uint32_t seed, env_id0;
+    int next, chunk;
+} step_pool;
+static void pool_drain(step_pool *p) {
+    const int n = p->w->n_envs;
+    for (;;) {
+        int lo = __atomic_fetch_add(&p->next, p->chunk, __ATOMIC_RELAXED);
+        if (lo >= n) break;
+        int hi = lo + p->chunk < n ? lo + p->chunk : n;
+        for (int i = lo; i < hi; i++) step_one(p->w, i, p->actions, p->auto_reset, p->seed, p->env_id0);
+    }
+}
+static void *pool_worker(void *arg) {
+    step_pool *p = (step_pool *)arg;
+    unsigned long seen = 0;
+    pthread_mutex_lock(&p->mu);
+    for (;;) {
+        while (!p->quit && p->generation == seen) pthread_cond_wait(&p->cv_start, &p->mu);
+        if (p->quit) break;
+        seen = p->generation;
+        pthread_mutex_unlock(&p->mu);
+        pool_drain(p);
+        pthread_mutex_lock(&p->mu);
+        if (--p->running == 0) pthread_cond_signal(&p->cv_done);
+    }
+    pthread_mutex_unlock(&p->mu);
     return NULL;
+}
+static void pool_destroy(step_pool *p) {
+    if (!p) return;
+    pthread_mutex_lock(&p->mu); p->quit = 1; pthread_cond_broadcast(&p->cv_start); pthread_mutex_unlock(&p->mu);
+    for (int t = 0; t < p->n_workers; t++) pthread_join(p->th[t], NULL);
+    pthread_mutex_destroy(&p->mu); pthread_cond_destroy(&p->cv_start); pthread_cond_destroy(&p->cv_done);
+    free(p);
+}
+static step_pool *pool_create(oracle_world *w, int n_workers) {
+    step_pool *p = (step_pool *)calloc(1, sizeof *p);
+    p->w = w; p->n_workers = n_workers;
+    pthread_mutex_init(&p->mu, NULL); pthread_cond_init(&p->cv_start, NULL); pthread_cond_init(&p->cv_done, NULL);
+    for (int t = 0; t < n_workers; t++) pthread_create(&p->th[t], NULL, pool_worker, p);
+    return p;
 }
 void oracle_step(oracle_world *w, const double *actions, int auto_reset, uint32_t seed, uint32_t env_id0, int n_threads) {
     if (n_threads < 1) n_threads = 1;
     if (n_threads > w->n_envs) n_threads = w->n_envs;
     if (n_threads > 256) n_threads = 256;
     if (n_threads == 1) { for (int i = 0; i < w->n_envs; i++) step_one(w, i, actions, auto_reset, seed, env_id0); return; }
-    pthread_t th[256]; step_job jobs[256];
-    for (int t = 0; t < n_threads; t++) {
-        jobs[t] = (step_job){w, actions, auto_reset, seed, env_id0, (int)((long)w->n_envs * t / n_threads), (int)((long)w->n_envs * (t + 1) / n_threads)};
-        pthread_create(&th[t], NULL, step_worker, &jobs[t]);
-    }
-    for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+    if (w->pool && w->pool->n_workers != n_threads - 1) { pool_destroy(w->pool); w->pool = NULL; }
+    if (!w->pool) w->pool = pool_create(w, n_threads - 1);
+    step_pool *p = w->pool;
+    pthread_mutex_lock(&p->mu);
+    p->actions = actions; p->auto_reset = auto_reset; p->seed = seed; p->env_id0 = env_id0;
+    p->next = 0;
+    p->chunk = w->n_envs / (n_threads * 8); if (p->chunk < 1) p->chunk = 1;
+    p->running = p->n_workers; p->generation++;
+    pthread_cond_broadcast(&p->cv_start);
+    pthread_mutex_unlock(&p->mu);
+    pool_drain(p);
+    pthread_mutex_lock(&p->mu);
+    while (p->running > 0) pthread_cond_wait(&p->cv_done, &p->mu);
+    pthread_mutex_unlock(&p->mu);
 }
 void oracle_get_obs(const oracle_world *w, double *obs, double *rew, int *done) {
     for (int i = 0; i < w->n_envs; i++) {

@@ -35,7 +35,7 @@ struct RowPool {
     RS_HD float& at(int slot, int k) const { return p[k * CAP + slot]; }
 };
 // slots a warp of WIDTH envs can need: every env at its row capacity
-template <class T, int MC, int WIDTH> constexpr int pool_cap() { return WIDTH * (T::NL + 3 * MC); }
+template <class T, int MC, int WIDTH> constexpr int pool_cap() { return WIDTH * (2 * T::NL + 3 * MC); }   // limit + motor row per joint, 3 per contact
 // words of a row record: [0,nd) J ; [nd,2nd) M^-1 J^T ; [2nd] denominator.  A task descriptor lives in
 // words [0,25) of the task's first row slot until the task is executed (needs 2*nd+1 >= 25).
 constexpr int POOL_DESC_WORDS = 25;
@@ -252,9 +252,13 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
     constexpr int nd = 6 + T::ND, n = T::NL;
     const int lane = warp.lane();
     // ---- owner: enumerate rows ----
+    // non-contact rows: joint limits, then joint motors (the motors join the world after the limit constraints)
+    constexpr int NNC = n > 0 ? 2 * n : 1;
     int n_nc = 0, nc = 0;
-    int lim_code[n > 0 ? n : 1];
-    float lim_pen[n > 0 ? n : 1];
+    int lim_code[NNC];
+    float lim_pen[NNC];     // limit rows: penetration ; motor rows: desired joint velocity
+    float mot_imp[NNC];     // motor rows: impulse bound
+    const float inv_dt = 1.0f / dt;
     if (valid) {
         static_for<n>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
@@ -269,6 +273,25 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
                 }
             }
         });
+        if (W.motor) {
+            // btMultiBodyJointMotor::createConstraintRows: velocity target kp (q* - q) / dt + qd + kd (qd* - qd), impulse within
+            // -+ bound, no positional term (physics-bullet.cpp:510-537 -> rs_world_set_joint_motor)
+            static_for<n>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
+                constexpr int d = T::dof[i];
+                if constexpr (d >= 0) {
+                    const float* mp = W.motor + (size_t)d * W.motor_stride;
+                    const size_t fs = (size_t)T::ND * W.motor_stride;
+                    const float imp = mp[4 * fs];
+                    if (imp > 0.f) {
+                        const float kp = mp[0], kd = mp[fs], tp = mp[2 * fs], tv = mp[3 * fs];
+                        lim_code[n_nc] = lane | ((i + 1) << 8) | (1 << 17);
+                        lim_pen[n_nc] = kp * (tp - W.q[d]) * inv_dt + W.qd[d] + kd * (tv - W.qd[d]);
+                        mot_imp[n_nc] = imp; n_nc++;
+                    }
+                }
+            });
+        }
         nc = W.ccount[W.cur];
     }
     int LT, CT;
@@ -322,7 +345,7 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
         if (t < LT) {
             const int code = f2i(pool.at(t, 0));
             const int o = code & 255, body = (code >> 8) & 255;
-            const float dir = (code >> 16) ? -1.f : 1.f;
+            const float dir = ((code >> 16) & 1) ? -1.f : 1.f;
             LinkCache<STRIDE> lco{lc_lane0 + o};
             float dn[1];
             pooled_response<T, 1, false, true>(lco, body, (const float (*)[6]) nullptr, dir, pool, t, dn);
@@ -380,8 +403,7 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
     }
 #pragma unroll
     for (int d = 0; d < T::ND; d++) vel[6 + d] = W.qd[d];
-    const float inv_dt = 1.0f / dt;
-    float r_rhs[n + 3 * MC], r_invd[n + 3 * MC], r_applied[n + 3 * MC];
+    float r_rhs[NNC + 3 * MC], r_invd[NNC + 3 * MC], r_applied[NNC + 3 * MC];
     auto row_relvel = [&](int slot) {
         float j[nd], s = 0.f;
 #pragma unroll
@@ -396,7 +418,8 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
         const float relvel = row_relvel(slot), denom = pool.at(slot, 2 * nd), pen = lim_pen[j];
         const float invd = denom > RS_FLT_EPS ? 1.0f / denom : 0.f;
         const float erp = pen > M.split_thresh ? M.erp : M.erp2;
-        r_rhs[j] = pen > M.split_thresh ? (-pen * erp * inv_dt - relvel) * invd : (-relvel) * invd;
+        if (lim_code[j] & (1 << 17)) r_rhs[j] = (pen - relvel) * invd;      // motor row: pen holds the desired velocity
+        else { r_rhs[j] = pen > M.split_thresh ? (-pen * erp * inv_dt - relvel) * invd : (-relvel) * invd; mot_imp[j] = -1.f; }
         r_invd[j] = invd; r_applied[j] = 0.f;
     }
     for (int ci = 0; ci < nc; ci++) {
@@ -423,7 +446,8 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
     for (int it = 0; it < M.n_iter; it++) {
         for (int j = 0; j < n_nc; j++) {
             const int row = (it & 1) ? j : n_nc - 1 - j;
-            resolve_pooled<nd>(pool, lbase + row, dv, r_rhs[row], r_invd[row], 0.f, lim_hi_imp, r_applied[row]);
+            const float mi = mot_imp[row];      // < 0: limit row (unilateral) ; > 0: motor row (+- impulse bound)
+            resolve_pooled<nd>(pool, lbase + row, dv, r_rhs[row], r_invd[row], mi > 0.f ? -mi : 0.f, mi > 0.f ? mi : lim_hi_imp, r_applied[row]);
         }
         for (int ci = 0; ci < nc; ci++) {
             const int row = n_nc + 3 * ci;

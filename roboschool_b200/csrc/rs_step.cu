@@ -231,7 +231,7 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
     w->wpc = n_envs >= (model->flag_task ? 8192 : 24576) ? 7 : 1;
     DevBuf& B = w->B;
     B.N = n_envs; B.S = (model->fixed_base ? 0 : 13) + 2 * model->n_dof; B.MCcap = MC;
-    B.rec = 2 * (6 + model->n_dof) + 1; B.maxr = NL + 3 * MC;   // +1: pooled rows keep their denominator in the record
+    B.rec = 2 * (6 + model->n_dof) + 1; B.maxr = 2 * NL + 3 * MC;   // +1: pooled rows keep their denominator in the record; a limit and a motor row per joint
     size_t N = (size_t)n_envs;
     CK(cudaMalloc(&B.state, sizeof(float) * N * (B.S > 0 ? B.S : 1)));
     CK(cudaMalloc(&B.ccount, sizeof(int) * N));
@@ -339,7 +339,7 @@ extern "C" int rs_world_reset(rs_world* w, uint32_t seed, uint32_t env_id0, cons
 
 static int launch_step(rs_world* w, const float* actions, float* obs, float* rew, uint8_t* done, int auto_reset, uint32_t seed,
                        uint32_t env_id0, double* stats, cudaStream_t st, int cta0 = 0, int ncta = 0) {
-    if (w->topo && !w->B.motor) {      // worlds with joint motors step on the runtime-topology kernel (motor rows live there)
+    if (w->topo) {
         StaticLaunch a{&w->M, &w->B, w->n, actions, obs, rew, done, auto_reset, seed, env_id0, stats, nullptr, st};
         a.cta0 = cta0; a.ncta = ncta;
         StaticLaunchFn fn = pick_static(w->topo, 0, w->wpc);
@@ -427,15 +427,7 @@ extern "C" int rs_world_set_joint_motor(rs_world* w, int env, int dof, float kp,
     CK(quiesce(w));
     if (!B.motor) {
         if (!(max_impulse > 0.f)) return 0;                  // switching off a motor of a world that never had one
-        // first motor of this world: motor table (all off) and a row workspace with room for one motor row per dof
-        int NLc = 0, MCc = 0;
-        family_of(&w->desc, &NLc, &MCc);
-        const int maxr = 2 * NLc + 3 * MCc;
-        float* rows = nullptr;
-        CK(cudaMalloc(&rows, sizeof(float) * (size_t)((N + 255) / 256 * 256 + 256) * B.rec * maxr));
-        CK(cudaDeviceSynchronize());
-        cudaFree(B.rows);
-        B.rows = rows; B.maxr = maxr;
+        // first motor of this world: motor table (all off); the row workspace already has room for one motor row per dof
         CK(cudaMalloc(&B.motor, sizeof(float) * 5 * (size_t)nd * N));
         CK(cudaMemset(B.motor, 0, sizeof(float) * 5 * (size_t)nd * N));
     }
@@ -768,7 +760,7 @@ extern "C" int rs_world_policy_step_host(rs_world* w, rs_policy* p, const float*
         int n_chunks = w->n >= 24576 ? 6 : 1;
         if (const char* e = getenv("RS_E2E_CHUNKS")) n_chunks = atoi(e);
         if (n_chunks > RS_MAX_CHUNKS) n_chunks = RS_MAX_CHUNKS;
-        if (n_chunks > 1 && w->topo && !w->B.motor && direct && w->n >= 1024 && (!obs_in_host || host_is_pinned(obs_in_host)))
+        if (n_chunks > 1 && w->topo && direct && w->n >= 1024 && (!obs_in_host || host_is_pinned(obs_in_host)))
             return policy_step_host_pipelined(w, p, obs_in_host, obs_out_host, reward_host, done_host, n_chunks);
     }
     CK(wait_caller(w));

@@ -53,7 +53,7 @@ void* emul_create(const rs_model_desc* m, int n) {
     if (build_dev_model(m, &e->M, &err)) { delete e; return nullptr; }
     e->n = n; e->w.resize(n); e->ep.resize(n); e->out.resize(n);
     for (int i = 0; i < n; i++) { memset(&e->w[i], 0, sizeof(W_t)); e->w[i].bquat[3] = 1; memset(&e->ep[i], 0, sizeof(Episode)); e->ep[i].initial_z = e->M.initial_z; e->ep[i].target_x = e->M.walk_target_x; e->ep[i].target_y = e->M.walk_target_y; }
-    e->rec = 2 * (6 + e->M.n_dof) + 1; e->maxr = NL + 3 * MC;
+    e->rec = 2 * (6 + e->M.n_dof) + 1; e->maxr = 2 * NL + 3 * MC;
     e->ws.resize((size_t)e->rec * e->maxr);
     e->obs.resize((size_t)n * e->M.obs_dim); e->rew.resize(n); e->done.resize(n);
     e->topo = 0; e->lcsize = 9 * RS_MAX_LINKS + 30; e->lcbuf.assign((size_t)n * e->lcsize, 0.f);
@@ -86,7 +86,7 @@ void emul_get_state(void* h, int env, double* s) {
     for (int d = 0; d < e->M.n_dof; d++) { s[d] = W.q[d]; s[e->M.n_dof + d] = W.qd[d]; }
 }
 void emul_set_tau(void* h, int env, const double* tau) { Emul* e = (Emul*)h; for (int d = 0; d < e->M.n_dof; d++) e->w[env].tau[d] = (float)tau[d]; }
-// btMultiBodyJointMotor of one dof (rs_world_set_joint_motor); envs with motors run the runtime-topology sweeps, like the library
+// btMultiBodyJointMotor of one dof (rs_world_set_joint_motor); envs with motors stay on the static-topology sweeps, like the library
 void emul_set_joint_motor(void* h, int env, int dof, double kp, double kd, double pos, double vel, double imp) {
     Emul* e = (Emul*)h; const int nd = e->M.n_dof;
     if (e->motor.empty()) {
@@ -100,7 +100,7 @@ void emul_set_joint_motor(void* h, int env, int dof, double kp, double kd, doubl
 }
 void emul_substeps(void* h, int env, int n) {
     Emul* e = (Emul*)h; RowWS ws{e->ws.data(), 1};
-    switch (e->w[env].motor ? 0 : e->topo) {
+    switch (e->topo) {
         case 1: substeps_static<TopoHumanoid>(e, env, n); return;
         case 2: substeps_static<TopoAnt>(e, env, n); return;
         case 3: substeps_static<TopoHopper>(e, env, n); return;
