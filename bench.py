@@ -269,7 +269,8 @@ def main():
     torch.cuda.synchronize()
     _p, _z, _f, frame = W.get_episode()
     rng = np.random.RandomState(1234 + rank)
-    W.set_episode(frame=rng.randint(0, max(m.max_episode_steps - 1, 1), size=n).astype(np.int32))
+    if not os.environ.get("RS_BENCH_NO_STAGGER"):       # diagnosis only: synchronised episodes (no resets inside the timed region)
+        W.set_episode(frame=rng.randint(0, max(m.max_episode_steps - 1, 1), size=n).astype(np.int32))
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()

@@ -165,6 +165,17 @@ typedef struct rs_model_desc {
     double c_split_thresh;
     double armature[RS_MAX_LINKS];       /* added to the joint-space inertia D = S^T I^A S of the link's joint (0: not honoured) */
     double stiffness[RS_MAX_LINKS];      /* joint spring torque -k q, applied like jdamping (0: not honoured)                   */
+    /* FlagrunHarder's thrown cube (gym_humanoid_flagrun.py:81-118, models_household/cube.urdf): a second free body per env,
+       btMultiBody with no links, loaded next to the robot; state = 13 more floats appended to the env state (pos3, quat4
+       x,y,z,w cube->world, omega3, vel3, world frame); contact manifolds cube-floor and cube-vs-every robot geom */
+    int    has_cube;
+    int    pad3;
+    double cube_half[3];                 /* btBoxShape half extents (URDF box size / 2)                                          */
+    double cube_mass;                    /* cube.urdf:22                                                                         */
+    double cube_inertia[3];              /* diagonal; recomputed from the collision shape's AABB (no URDF_USE_INERTIA_FROM_FILE) */
+    double cube_friction;                /* lateral friction of the link (UrdfContactInfo default 0.5: cube.urdf has no <contact>) */
+    double cube_break_thresh;            /* contact breaking threshold: 0.02 x bounding-sphere disc of the cube's compound shape */
+    double cube_start[3];                /* pose at load (gym_humanoid_flagrun.py:84-85)                                         */
 } rs_model_desc;
 
 #ifdef __cplusplus

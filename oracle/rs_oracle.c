@@ -39,7 +39,7 @@
 
 #define ML RS_MAX_LINKS
 #define MAXROWS 256
-#define MAXDOF (6 + RS_MAX_LINKS)
+#define MAXDOF (6 + RS_MAX_LINKS + 6)   /* base + joints + the free cube of FlagrunHarder */
 #define MANIFOLD_CACHE_SIZE 4
 #define WARMSTART 0 /* "disable warmstarting for btMultiBody, it has issues gaining energy" (btMultiBodyConstraintSolver.cpp, 2.87) */
 
@@ -86,6 +86,9 @@ typedef struct {
     double base_w[3], base_v[3];      /* world frame */
     double q[ML], qd[ML];
     double tau[ML];                   /* joint torques, persist over the sub-steps of one env step */
+    /* FlagrunHarder's cube: free body, world-frame velocities like the base (rs_model_desc.has_cube) */
+    double cube_pos[3], cube_quat[4], cube_w[3], cube_v[3];
+    double body_xyz[3], body_vel[3];  /* calc_state's body_xyz and robot_body.speed(), read by the cube throw */
     /* btMultiBodyJointMotor per dof (Joint::set_servo_target / set_target_speed, physics-bullet.cpp:510-537):
      * kp, kd, position / velocity targets and the impulse bound per sub-step; bound 0 = motor off (torque control) */
     double mot_kp[ML], mot_kd[ML], mot_pos[ML], mot_vel[ML], mot_imp[ML];
@@ -134,6 +137,11 @@ typedef struct oracle_world {
     oenv *env;
     struct step_pool *pool;   /* persistent worker threads of oracle_step (created on first multi-threaded call) */
 } oracle_world;
+
+/* manifolds: [n_geoms geom-floor][n_pairs self pairs] and, with the cube, [cube-floor][cube-vs-geom g for every geom] */
+static inline int nman_of(const rs_model_desc *m) { return m->n_geoms + m->n_pairs + (m->has_cube ? 1 + m->n_geoms : 0); }
+static inline int nd_of(const rs_model_desc *m) { return 6 + m->n_dof + (m->has_cube ? 6 : 0); }
+#define CUBE_BODY(m) ((m)->n_links + 1)   /* body index of the cube: transform cached in Rwl / pos like a link's */
 
 /* ---------------- small vector helpers ---------------- */
 static inline void v3set(double *a, double x, double y, double z) { a[0] = x; a[1] = y; a[2] = z; }
@@ -316,6 +324,12 @@ static void kinematics(const rs_model_desc *m, oenv *e) {
         m3tmulv(rw, e->Rwl[i + 1], e->rvec[i]);
         v3add(e->pos[i + 1], e->pos[p + 1], rw);
     }
+    if (m->has_cube) {
+        double Rcw[9];
+        quat_to_mat(Rcw, e->cube_quat);
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) e->Rwl[CUBE_BODY(m)][i * 3 + j] = Rcw[j * 3 + i];
+        v3cpy(e->pos[CUBE_BODY(m)], e->cube_pos);
+    }
 }
 
 /* spatial velocities of all links in link coords (first sweep of the ABA) */
@@ -346,6 +360,11 @@ static void clamp_vel(const rs_model_desc *m, oenv *e) {
             if (e->base_v[k] > c) e->base_v[k] = c; if (e->base_v[k] < -c) e->base_v[k] = -c;
         }
     for (int d = 0; d < m->n_dof; d++) { if (e->qd[d] > c) e->qd[d] = c; if (e->qd[d] < -c) e->qd[d] = -c; }
+    if (m->has_cube)
+        for (int k = 0; k < 3; k++) {
+            if (e->cube_w[k] > c) e->cube_w[k] = c; if (e->cube_w[k] < -c) e->cube_w[k] = -c;
+            if (e->cube_v[k] > c) e->cube_v[k] = c; if (e->cube_v[k] < -c) e->cube_v[k] = -c;
+        }
 }
 
 static void aba(const rs_model_desc *m, oenv *e, double dt) {
@@ -486,12 +505,26 @@ static void accel_deltas(const rs_model_desc *m, const oenv *e, const double *fo
     }
     if (m->fixed_base) { for (int k = 0; k < 6; k++) out[k] = 0; }
     else { m3tmulv(out, e->Rwl[0], acc[0].w); m3tmulv(out + 3, e->Rwl[0], acc[0].v); }
+    if (m->has_cube) {   /* a btMultiBody without links: M^-1 = (R^T I^-1 R, 1/m) on the world-frame base velocities */
+        const double *f = force + 6 + m->n_dof, *R = e->Rwl[CUBE_BODY(m)];
+        double *o = out + 6 + m->n_dof, tl[3];
+        m3mulv(tl, R, f);
+        for (int k = 0; k < 3; k++) tl[k] /= m->cube_inertia[k];
+        m3tmulv(o, R, tl);
+        for (int k = 0; k < 3; k++) o[3 + k] = f[3 + k] / m->cube_mass;
+    }
 }
 
 /* ---------------- btMultiBody::fillContactJacobianMultiDof ----------------
  * jac . [w_base v_base qd] = n . (velocity of world point p rigidly attached to body b)  (b: 0=base, i+1=link i) */
 static void contact_jacobian(const rs_model_desc *m, const oenv *e, int b, const double *p, const double *n, double *jac) {
-    memset(jac, 0, sizeof(double) * (6 + m->n_dof));
+    memset(jac, 0, sizeof(double) * nd_of(m));
+    if (m->has_cube && b == CUBE_BODY(m)) {
+        double r[3]; v3sub(r, p, e->pos[b]);
+        v3cross(jac + 6 + m->n_dof, r, n);
+        v3cpy(jac + 6 + m->n_dof + 3, n);
+        return;
+    }
     if (!m->fixed_base) {
         double r[3]; v3sub(r, p, e->pos[0]);
         v3cross(jac, r, n);
@@ -615,6 +648,84 @@ static void seg_seg_closest(const double *p1, const double *q1, const double *p2
     for (int k = 0; k < 3; k++) { c1[k] = p1[k] + d1[k] * s; c2[k] = p2[k] + d2[k] * t; }
 }
 
+/* Closest points between a solid box (half extents h, axis aligned in its own frame) and the segment [a,b] (box coords):
+ * the analytic answer of GJK (separated) / of the minimum-translation search EPA performs (core inside the box) for
+ * btBoxShape against the sphere-swept cores of sphere / capsule / btMultiSphereShape geoms.
+ * Returns the signed distance box <-> segment core; n: unit vector from the box towards the segment, pb: point on the box,
+ * ps: point on the segment.
+ * Separated: dist^2(p(t), box) is convex and piecewise quadratic in t; its derivative G(t) = sum_i excess_i(t) d_i is
+ * piecewise linear and non-decreasing with kinks where a coordinate crosses a face, so the root lies between the two
+ * bracketing candidates {0, 1, kinks} and follows by linear interpolation.
+ * Touching / penetrating: separating-axis search over the 3 face normals and the 3 edge directions d x e_i; the axis of
+ * least overlap gives normal and depth, the witness point on the segment is its deeper end (its midpoint for an edge axis). */
+static double box_seg_G(const double *h, const double *a, const double *d, double t) {
+    double g = 0;
+    for (int i = 0; i < 3; i++) {
+        double p = a[i] + t * d[i];
+        double ex = p > h[i] ? p - h[i] : (p < -h[i] ? p + h[i] : 0.0);
+        g += ex * d[i];
+    }
+    return g;
+}
+static double box_seg_closest(const double *h, const double *a, const double *b, double *n, double *pb, double *ps) {
+    double d[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+    double cand[8]; int nc = 0;
+    cand[nc++] = 0.0; cand[nc++] = 1.0;
+    for (int i = 0; i < 3; i++) {
+        if (fabs(d[i]) > 1e-12) {
+            double t0 = (h[i] - a[i]) / d[i], t1 = (-h[i] - a[i]) / d[i];
+            cand[nc++] = t0 > 0 && t0 < 1 ? t0 : 0.0;
+            cand[nc++] = t1 > 0 && t1 < 1 ? t1 : 0.0;
+        } else { cand[nc++] = 0.0; cand[nc++] = 0.0; }
+    }
+    double t;
+    double G0 = box_seg_G(h, a, d, 0.0), G1 = box_seg_G(h, a, d, 1.0);
+    if (G0 >= 0) t = 0.0;
+    else if (G1 <= 0) t = 1.0;
+    else {
+        double tl = 0.0, gl = G0, th = 1.0, gh = G1;
+        for (int k = 2; k < 8; k++) {
+            double tc = cand[k], gc = box_seg_G(h, a, d, tc);
+            if (gc <= 0) { if (tc > tl) { tl = tc; gl = gc; } }
+            else if (tc < th) { th = tc; gh = gc; }
+        }
+        t = gh - gl > 0 ? tl + (th - tl) * (-gl) / (gh - gl) : tl;
+    }
+    double df[3], dist2 = 0;
+    for (int i = 0; i < 3; i++) {
+        ps[i] = a[i] + t * d[i];
+        pb[i] = ps[i] > h[i] ? h[i] : (ps[i] < -h[i] ? -h[i] : ps[i]);
+        df[i] = ps[i] - pb[i]; dist2 += df[i] * df[i];
+    }
+    if (dist2 > 1e-18) {
+        double dist = sqrt(dist2);
+        for (int i = 0; i < 3; i++) n[i] = df[i] / dist;
+        return dist;
+    }
+    /* core touches or intersects the box: minimum-translation axis */
+    double c[3] = {0.5 * (a[0] + b[0]), 0.5 * (a[1] + b[1]), 0.5 * (a[2] + b[2])}, hd[3] = {0.5 * d[0], 0.5 * d[1], 0.5 * d[2]};
+    double best = 1e300, bn[3] = {0, 0, 1}; int best_edge = 0;
+    for (int i = 0; i < 3; i++) {
+        double ov = h[i] + fabs(hd[i]) - fabs(c[i]);
+        if (ov < best) { best = ov; bn[0] = bn[1] = bn[2] = 0; bn[i] = c[i] >= 0 ? 1.0 : -1.0; best_edge = 0; }
+    }
+    for (int i = 0; i < 3; i++) {
+        double u[3] = {0, 0, 0}, ei[3] = {0, 0, 0}; ei[i] = 1;
+        v3cross(u, d, ei);
+        double l2 = v3dot(u, u);
+        if (l2 < 1e-18) continue;
+        double il = 1.0 / sqrt(l2); u[0] *= il; u[1] *= il; u[2] *= il;
+        double cu = v3dot(c, u);
+        double ov = h[0] * fabs(u[0]) + h[1] * fabs(u[1]) + h[2] * fabs(u[2]) - fabs(cu);
+        if (ov < best) { best = ov; double sg = cu >= 0 ? 1.0 : -1.0; bn[0] = sg * u[0]; bn[1] = sg * u[1]; bn[2] = sg * u[2]; best_edge = 1; }
+    }
+    v3cpy(n, bn);
+    if (best_edge) v3cpy(ps, c);
+    else { double da = v3dot(a, bn), db = v3dot(b, bn); if (db < da) v3cpy(ps, b); else v3cpy(ps, a); }
+    for (int i = 0; i < 3; i++) pb[i] = ps[i] + bn[i] * best;
+    return -best;
+}
+
 static void collide(const rs_model_desc *m, oenv *e) {
     /* floor: btConvexPlaneCollisionAlgorithm::collideSingleContact -- one support vertex per geom per
      * sub-step into that (geom, plane) manifold, then refreshContactPoints */
@@ -675,9 +786,52 @@ static void collide(const rs_model_desc *m, oenv *e) {
         }
         if (mf->n) manifold_refresh(mf, e, bA, bB, thr);
     }
+    if (m->has_cube) {
+        /* the cube (btBoxShape): against the floor plane like any convex (one support vertex per sub-step), against every
+         * robot geom through the closest points of box and sphere-swept segment.  Threshold: min of the two bodies' = the cube's */
+        const int cb = CUBE_BODY(m), k0 = m->n_geoms + m->n_pairs;
+        const double thr = m->cube_break_thresh;
+        {
+            manifold *mf = &e->man[k0];
+            const double down[3] = {0, 0, -1};
+            double dl[3], sv[3], vtx[3];
+            m3mulv(dl, e->Rwl[cb], down);
+            for (int k = 0; k < 3; k++) sv[k] = dl[k] >= 0 ? m->cube_half[k] : -m->cube_half[k];
+            link_to_world(e, cb, sv, vtx);
+            double dist = vtx[2];
+            if (dist < thr) {
+                double pOnB[3] = {vtx[0], vtx[1], 0.0};
+                manifold_add(mf, e, cb, -1, nz, pOnB, dist, thr, m->cube_friction * m->floor_friction);
+            }
+            if (mf->n) manifold_refresh(mf, e, cb, -1, thr);
+        }
+        for (int g = 0; g < m->n_geoms; g++) {
+            manifold *mf = &e->man[k0 + 1 + g];
+            int bA = m->g_link[g] + 1;
+            if (m->g_type[g] == RS_GEOM_BOX) { mf->n = 0; continue; }   /* box-box needs a polytope narrowphase: no shipped model has it */
+            double a0[3], a1[3], al[3], bl[3], n[3], pb[3], ps[3];
+            link_to_world(e, bA, m->g_p0[g], a0); link_to_world(e, bA, m->g_p1[g], a1);
+            world_to_link(e, cb, a0, al); world_to_link(e, cb, a1, bl);
+            double rA = m->g_radius[g];
+            /* broadphase: bounding spheres */
+            double mid[3] = {0.5 * (al[0] + bl[0]), 0.5 * (al[1] + bl[1]), 0.5 * (al[2] + bl[2])}, hl[3];
+            v3sub(hl, bl, al);
+            double reach = 0.5 * v3len(hl) + rA + v3len(m->cube_half) + thr;
+            if (v3dot(mid, mid) <= reach * reach) {
+                double dist = box_seg_closest(m->cube_half, al, bl, n, pb, ps) - rA;
+                if (dist < thr) {
+                    double nw[3], pOnB[3];
+                    m3tmulv(nw, e->Rwl[cb], n);
+                    link_to_world(e, cb, pb, pOnB);
+                    manifold_add(mf, e, bA, cb, nw, pOnB, dist, thr, m->g_friction[g] * m->cube_friction);
+                }
+            }
+            if (mf->n) manifold_refresh(mf, e, bA, cb, thr);
+        }
+    }
     /* bounded live-point pool shared with the CUDA path: points beyond max_contacts are dropped in manifold order */
     int total = 0;
-    for (int k = 0; k < m->n_geoms + m->n_pairs; k++) {
+    for (int k = 0; k < nman_of(m); k++) {
         manifold *mf = &e->man[k];
         if (total + mf->n > m->max_contacts) mf->n = m->max_contacts - total;
         total += mf->n;
@@ -700,6 +854,7 @@ static double row_finish(const rs_model_desc *m, const oenv *e, crow *r, const d
     double vel[MAXDOF];
     for (int k = 0; k < 3; k++) { vel[k] = e->base_w[k]; vel[3 + k] = e->base_v[k]; }
     for (int d = 0; d < m->n_dof; d++) vel[6 + d] = e->qd[d];
+    if (m->has_cube) for (int k = 0; k < 3; k++) { vel[6 + m->n_dof + k] = e->cube_w[k]; vel[6 + m->n_dof + 3 + k] = e->cube_v[k]; }
     accel_deltas(m, e, jA, uA);
     for (int k = 0; k < nd; k++) { denom += jA[k] * uA[k]; relvel += jA[k] * vel[k]; r->jac[k] = jA[k]; r->unit[k] = uA[k]; }
     if (jB) {
@@ -714,7 +869,7 @@ static double row_finish(const rs_model_desc *m, const oenv *e, crow *r, const d
 }
 
 static int setup_rows(const rs_model_desc *m, oenv *e, double dt, crow *nc, int *n_nc, crow *cn, int *n_cn, crow *cf, int *n_cf) {
-    int nd = 6 + m->n_dof;
+    int nd = nd_of(m);
     *n_nc = *n_cn = *n_cf = 0;
     /* btMultiBodyJointLimitConstraint::createConstraintRows: row 0 lower, row 1 upper, only when violated */
     for (int i = 0; i < m->n_links; i++) {
@@ -752,12 +907,14 @@ static int setup_rows(const rs_model_desc *m, oenv *e, double dt, crow *nc, int 
         r->lo = -e->mot_imp[d]; r->hi = e->mot_imp[d]; r->cp = NULL; r->friction_index = -1;
     }
     /* contacts: btMultiBodyConstraintSolver::convertMultiBodyContact, manifold order, point order */
-    int nman = m->n_geoms + m->n_pairs;
+    int nman = nman_of(m), ngp = m->n_geoms + m->n_pairs;
     for (int k = 0; k < nman; k++) {
         manifold *mf = &e->man[k];
         int bA, bB;
         if (k < m->n_geoms) { bA = m->g_link[k] + 1; bB = -1; }
-        else { bA = m->g_link[m->pair_a[k - m->n_geoms]] + 1; bB = m->g_link[m->pair_b[k - m->n_geoms]] + 1; }
+        else if (k < ngp) { bA = m->g_link[m->pair_a[k - m->n_geoms]] + 1; bB = m->g_link[m->pair_b[k - m->n_geoms]] + 1; }
+        else if (k == ngp) { bA = CUBE_BODY(m); bB = -1; }
+        else { bA = m->g_link[k - ngp - 1] + 1; bB = CUBE_BODY(m); }
         for (int pi = 0; pi < mf->n; pi++) {
             cpoint *cp = &mf->p[pi];
             if (*n_cn >= MAXROWS / 4) continue;
@@ -805,7 +962,7 @@ static inline void resolve_row(crow *c, double *dv, int nd) {
 
 static void solve(const rs_model_desc *m, oenv *e, double dt) {
     static __thread crow nc[3 * ML], cn[MAXROWS / 4], cf[MAXROWS / 2];
-    int n_nc, n_cn, n_cf, nd = 6 + m->n_dof;
+    int n_nc, n_cn, n_cf, nd = nd_of(m);
     int total = setup_rows(m, e, dt, nc, &n_nc, cn, &n_cn, cf, &n_cf);
     e->n_rows_last = total; e->n_contacts_last = n_cn;
     if (!total) return;
@@ -829,6 +986,7 @@ static void solve(const rs_model_desc *m, oenv *e, double dt) {
     /* write back: velocities += deltaV ; applied impulses -> manifold points */
     if (!m->fixed_base) for (int k = 0; k < 3; k++) { e->base_w[k] += dv[k]; e->base_v[k] += dv[3 + k]; }
     for (int d = 0; d < m->n_dof; d++) e->qd[d] += dv[6 + d];
+    if (m->has_cube) for (int k = 0; k < 3; k++) { e->cube_w[k] += dv[6 + m->n_dof + k]; e->cube_v[k] += dv[6 + m->n_dof + 3 + k]; }
     clamp_vel(m, e);
     for (int j = 0; j < n_cn; j++) cn[j].cp->imp_n = cn[j].applied;
     for (int j = 0; j < n_cf; j++) { if (cf[j].which == 1) cf[j].cp->imp_f1 = cf[j].applied; else cf[j].cp->imp_f2 = cf[j].applied; }
@@ -853,13 +1011,44 @@ static void integrate(const rs_model_desc *m, oenv *e, double dt) {
     for (int d = 0; d < m->n_dof; d++) e->q[d] += dt * e->qd[d];
 }
 
+/* the cube is a btMultiBody without links: computeAccelerationsArticulatedBodyAlgorithmMultiDof reduces to the base terms --
+ * gravity, velocity damping k v (1 + |v|) and the gyroscopic torque in body coordinates -- applied with applyDeltaVee(dt) */
+static void cube_dynamics(const rs_model_desc *m, oenv *e, double dt) {
+    const double *R = e->Rwl[CUBE_BODY(m)];
+    double wl[3], Iw[3], g1[3], al[3], aw[3];
+    m3mulv(wl, R, e->cube_w);
+    double wn = v3len(wl), vn = v3len(e->cube_v);
+    double ka = m->ang_damping * (1 + wn), kl = m->lin_damping * (1 + vn);
+    for (int k = 0; k < 3; k++) Iw[k] = m->cube_inertia[k] * wl[k];
+    v3cross(g1, wl, Iw);
+    for (int k = 0; k < 3; k++) al[k] = -(Iw[k] * ka + m->use_gyro * g1[k]) / m->cube_inertia[k];
+    m3tmulv(aw, R, al);
+    for (int k = 0; k < 3; k++) { e->cube_w[k] += dt * aw[k]; e->cube_v[k] += dt * (-kl * e->cube_v[k]); }
+    e->cube_v[2] += dt * -m->gravity;
+}
+static void cube_integrate(const rs_model_desc *m, oenv *e, double dt) {
+    v3axpy(e->cube_pos, dt, e->cube_v);
+    double ang = v3len(e->cube_w), axis[3];
+    if (ang * dt > 0.7853981633974483) ang = 0.5 * 1.5707963267948966 / dt;
+    double k;
+    if (ang < 0.001) k = 0.5 * dt - dt * dt * dt * 0.020833333333 * ang * ang;
+    else k = sin(0.5 * ang * dt) / ang;
+    for (int i = 0; i < 3; i++) axis[i] = e->cube_w[i] * k;
+    double dq[4] = {axis[0], axis[1], axis[2], cos(ang * dt * 0.5)}, nq[4];
+    quat_mul(nq, dq, e->cube_quat);
+    double nn = sqrt(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2] + nq[3] * nq[3]);
+    for (int i = 0; i < 4; i++) e->cube_quat[i] = nq[i] / nn;
+}
+
 static void substep(const rs_model_desc *m, oenv *e) {
     double dt = m->timestep;
     kinematics(m, e);
     collide(m, e);      /* performDiscreteCollisionDetection */
     aba(m, e, dt);      /* solveConstraints: forward dynamics ... */
+    if (m->has_cube) { cube_dynamics(m, e, dt); clamp_vel(m, e); }
     solve(m, e, dt);    /* ... then the multibody constraint solver */
     integrate(m, e, dt);
+    if (m->has_cube) cube_integrate(m, e, dt);
 }
 
 /* ---------------- state readback: query_body_position (physics-bullet.cpp:440-495) ---------------- */
@@ -898,6 +1087,8 @@ static void foot_contacts(const rs_model_desc *m, const oenv *e, int foot, int *
         int bA = m->g_link[m->pair_a[k]] + 1, bB = m->g_link[m->pair_b[k]] + 1;
         if ((bA == fb || bB == fb) && e->man[m->n_geoms + k].n > 0) *other = 1;
     }
+    if (m->has_cube)   /* the cube is an object other than the floor (gym_forward_walker.py:110-113) */
+        for (int g = 0; g < m->n_geoms; g++) if (m->g_link[g] + 1 == fb && e->man[m->n_geoms + m->n_pairs + 1 + g].n > 0) *other = 1;
 }
 
 /* calc_state (gym_forward_walker.py:45-76), float32 squeezes where the reference has them */
@@ -960,6 +1151,7 @@ static void calc_state(const rs_model_desc *m, oenv *e, double *body_xy_dist) {
     mx /= m->n_parts; my /= m->n_parts;
     double z = bp[2], r, p, yaw;
     quat_rpy(bq, &r, &p, &yaw);
+    e->body_xyz[0] = mx; e->body_xyz[1] = my; e->body_xyz[2] = z; v3cpy(e->body_vel, bv);
     if (e->initial_z < 0) e->initial_z = z;
     double theta = atan2(e->target_y - my, e->target_x - mx);
     double dy = e->target_y - my, dx = e->target_x - mx;
@@ -1024,10 +1216,31 @@ static double task_potential(const rs_model_desc *m, oenv *e, double dist) {
     if (m->flag_task == 2) return harder_potential(m, e, dist);
     return -dist / m->dt_env;
 }
-/* FlagrunHarder.alive_bonus (gym_humanoid_flagrun.py:101-139).  The flying cube itself is not simulated;
- * its five np_random draws are still consumed so that the flag positions drawn later stay on the reference's stream. */
-static double harder_alive(const rs_model_desc *m, oenv *e, double z) {
-    if (e->frame % 30 == 0 && e->frame > 100 && e->on_ground == 0) e->flag_draws += 5;
+/* FlagrunHarder.alive_bonus (gym_humanoid_flagrun.py:101-139).  Every 30 frames (after frame 100, robot not on the ground)
+ * the cube is thrown at the position the robot will have reached when it arrives: five np_random draws (angle, speed,
+ * 3 x velocity noise) from the flag stream, then Robot::set_pose_and_speed (python-binding.cpp:289 -> robot_move,
+ * physics-bullet.cpp:579-591: pose in doubles, velocity through float, orientation identity, angular velocity zeroed
+ * by the pose command).  Worlds without the cube (has_cube 0) still consume the draws. */
+static double harder_alive(const rs_model_desc *m, oenv *e, double z, uint32_t seed, uint32_t env_id) {
+    if (e->frame % 30 == 0 && e->frame > 100 && e->on_ground == 0) {
+        double u[5];
+        for (int k = 0; k < 5; k++) u[k] = rs_uniform(seed, env_id, e->episode, 2000u + e->flag_draws++);
+        if (m->has_cube) {
+            double target[3], cp[3], v[3];
+            v3cpy(target, e->body_xyz);
+            double angle = -3.14 + (3.14 - -3.14) * u[0], from_dist = 4.0;
+            double attack_speed = 20.0 + (30.0 - 20.0) * u[1];
+            double ttt = from_dist / attack_speed;
+            v3axpy(target, ttt, e->body_vel);
+            cp[0] = target[0] + from_dist * cos(angle); cp[1] = target[1] + from_dist * sin(angle); cp[2] = target[2] + 1.0;
+            v3sub(v, target, cp);
+            double sc = attack_speed / v3len(v);
+            for (int k = 0; k < 3; k++) v[k] = v[k] * sc + (-1.0 + (1.0 - -1.0) * u[2 + k]);
+            v3cpy(e->cube_pos, cp);
+            e->cube_quat[0] = e->cube_quat[1] = e->cube_quat[2] = 0; e->cube_quat[3] = 1;
+            for (int k = 0; k < 3; k++) { e->cube_v[k] = (double)(float)v[k]; e->cube_w[k] = 0; }
+        }
+    }
     if (z < 0.8) {
         if (e->task == 0) e->on_ground = 10000;      /* TASK_WALK: ends the episode immediately */
         e->on_ground += 1;
@@ -1110,7 +1323,7 @@ static void epilogue(const rs_model_desc *m, oenv *e, const double *a, uint32_t 
     double z = e->obs[0] + e->initial_z;   /* state[0]+initial_z, state already float32 & clipped */
     double alive;
     if (m->alive_rule == RS_ALIVE_Z_AND_PITCH) alive = (z > m->alive_z && fabs(pitch) < 1.0) ? m->alive_bonus : -1;
-    else if (m->flag_task == 2) alive = harder_alive(m, e, z);
+    else if (m->flag_task == 2) alive = harder_alive(m, e, z, seed, env_id);
     else if (m->alive_rule == RS_ALIVE_Z) alive = (z > m->alive_z) ? m->alive_bonus : -1;
     else if (m->alive_rule == RS_ALIVE_CHEETAH)   /* gym_mujoco_walkers.py:50-52: stale feet_contact of shins and thighs */
         alive = (fabs(pitch) < 1.0 && !e->feet_contact[1] && !e->feet_contact[2] && !e->feet_contact[4] && !e->feet_contact[5]) ? m->alive_bonus : -1;
@@ -1188,6 +1401,11 @@ static void env_reset(const rs_model_desc *m, oenv *e, int nman, uint32_t seed, 
         e->base_quat[2] = t1 * t2 * t4 - t0 * t3 * t5;
     }
     v3set(e->base_w, 0, 0, 0); v3set(e->base_v, 0, 0, 0);
+    if (m->has_cube) {   /* load_urdf(cube.urdf, cpose) of robot_specific_reset (gym_humanoid_flagrun.py:83-86): a fresh body at rest */
+        v3cpy(e->cube_pos, m->cube_start);
+        e->cube_quat[0] = e->cube_quat[1] = e->cube_quat[2] = 0; e->cube_quat[3] = 1;
+        v3set(e->cube_w, 0, 0, 0); v3set(e->cube_v, 0, 0, 0);
+    }
     for (int k = 0; k < nman; k++) e->man[k].n = 0;
     memset(e->feet_contact, 0, sizeof e->feet_contact);
     e->initial_z = m->initial_z;
@@ -1205,11 +1423,11 @@ static void env_reset(const rs_model_desc *m, oenv *e, int nman, uint32_t seed, 
 static void pool_destroy(struct step_pool *p);
 oracle_world *oracle_create(const rs_model_desc *m, int n_envs) {
     oracle_world *w = (oracle_world *)calloc(1, sizeof *w);
-    w->m = *m; w->n_envs = n_envs; w->nman = m->n_geoms + m->n_pairs;
+    w->m = *m; w->n_envs = n_envs; w->nman = nman_of(m);
     w->env = (oenv *)calloc((size_t)n_envs, sizeof(oenv));
     for (int i = 0; i < n_envs; i++) {
         w->env[i].man = (manifold *)calloc((size_t)(w->nman > 0 ? w->nman : 1), sizeof(manifold));
-        w->env[i].base_quat[3] = 1;
+        w->env[i].base_quat[3] = 1; w->env[i].cube_quat[3] = 1;
         w->env[i].initial_z = m->initial_z;
         w->env[i].target_x = m->walk_target_x; w->env[i].target_y = m->walk_target_y;
     }
@@ -1220,12 +1438,13 @@ void oracle_destroy(oracle_world *w) {
     for (int i = 0; i < w->n_envs; i++) free(w->env[i].man);
     free(w->env); free(w);
 }
-int oracle_state_dim(const oracle_world *w) { return (w->m.fixed_base ? 0 : 13) + 2 * w->m.n_dof; }
+int oracle_state_dim(const oracle_world *w) { return (w->m.fixed_base ? 0 : 13) + 2 * w->m.n_dof + (w->m.has_cube ? 13 : 0); }
 /* state layout: [pos3 quat4(xyzw) omega3 vel3] (floating base only) q[ndof] qd[ndof] */
 void oracle_set_state(oracle_world *w, int env, const double *s, int clear_contacts) {
     oenv *e = &w->env[env]; const rs_model_desc *m = &w->m;
     if (!m->fixed_base) { v3cpy(e->base_pos, s); memcpy(e->base_quat, s + 3, 4 * sizeof(double)); v3cpy(e->base_w, s + 7); v3cpy(e->base_v, s + 10); s += 13; }
     for (int d = 0; d < m->n_dof; d++) { e->q[d] = s[d]; e->qd[d] = s[m->n_dof + d]; }
+    if (m->has_cube) { const double *c = s + 2 * m->n_dof; v3cpy(e->cube_pos, c); memcpy(e->cube_quat, c + 3, 4 * sizeof(double)); v3cpy(e->cube_w, c + 7); v3cpy(e->cube_v, c + 10); }
     if (clear_contacts) for (int k = 0; k < w->nman; k++) e->man[k].n = 0;
     kinematics(m, e); velocities(m, e);
 }
@@ -1233,6 +1452,7 @@ void oracle_get_state(const oracle_world *w, int env, double *s) {
     const oenv *e = &w->env[env]; const rs_model_desc *m = &w->m;
     if (!m->fixed_base) { v3cpy(s, e->base_pos); memcpy(s + 3, e->base_quat, 4 * sizeof(double)); v3cpy(s + 7, e->base_w); v3cpy(s + 10, e->base_v); s += 13; }
     for (int d = 0; d < m->n_dof; d++) { s[d] = e->q[d]; s[m->n_dof + d] = e->qd[d]; }
+    if (m->has_cube) { double *c = s + 2 * m->n_dof; v3cpy(c, e->cube_pos); memcpy(c + 3, e->cube_quat, 4 * sizeof(double)); v3cpy(c + 7, e->cube_w); v3cpy(c + 10, e->cube_v); }
 }
 void oracle_set_episode(oracle_world *w, int env, double potential, double initial_z, const double *feet_contact, int frame) {
     oenv *e = &w->env[env];

@@ -68,6 +68,10 @@ struct DevModel {
     int task_kind, task_swingup, task_link, task_link2, n_reset;
     int reset_dof[MA], task_dof[4];
     float reset_center[MA], reset_spread[MA];
+    // FlagrunHarder's thrown cube (rs_model_desc.has_cube): a free box next to the robot, body index n_links + 1
+    int has_cube;
+    float cube_half[3], cube_mass, cube_inertia[3], cube_thresh, cube_bound, cube_fric_floor, cube_start[3];
+    float cube_fric_geom[MG];         // combined friction cube x robot geom
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -277,6 +281,11 @@ struct Work {
     // motor[(f * n_dof + d) * motor_stride], fields kp, kd, target position, target velocity, impulse bound per sub-step
     const float* motor = nullptr;
     int motor_stride = 0;
+    // FlagrunHarder's cube (only touched by kernels instantiated for a cube topology): world-frame state like the base,
+    // cR = world -> cube coords (valid after the kinematics of the sub-step); body_xyz / body_vel: calc_state's body_xyz and
+    // robot_body.speed(), read by the throw in the epilogue
+    float cpos[3], cquat[4], cw[3], cv[3], cR[9];
+    float body_xyz[3], body_vel[3];
 };
 
 // row workspace: one record per constraint row, strided so that lane-adjacent envs are address-adjacent
@@ -356,6 +365,59 @@ RS_HD void clamp_vel(const DevModel& M, Work<NL, MC, SL>& W) {
         for (int k = 0; k < 3; k++) { W.bw[k] = fminf(fmaxf(W.bw[k], -c), c); W.bv[k] = fminf(fmaxf(W.bv[k], -c), c); }
     }
     for (int d = 0; d < M.n_dof; d++) W.qd[d] = fminf(fmaxf(W.qd[d], -c), c);
+}
+
+// ---- FlagrunHarder's cube: a btMultiBody without links (oracle/rs_oracle.c cube_dynamics / cube_integrate) ----
+template <int NL, int MC, bool SL>
+RS_HD void cube_kinematics(Work<NL, MC, SL>& W) {
+    float Rcw[9];
+    quat_to_mat(Rcw, W.cquat[0], W.cquat[1], W.cquat[2], W.cquat[3]);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) W.cR[i * 3 + j] = Rcw[j * 3 + i];
+}
+template <int NL, int MC, bool SL>
+RS_HD void cube_clamp(const DevModel& M, Work<NL, MC, SL>& W) {
+    const float c = M.max_coord_vel;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { W.cw[k] = fminf(fmaxf(W.cw[k], -c), c); W.cv[k] = fminf(fmaxf(W.cv[k], -c), c); }
+}
+// gravity, velocity damping k v (1 + |v|) and the gyroscopic torque (body coordinates), applied with applyDeltaVee(dt)
+template <int NL, int MC, bool SL>
+RS_HD void cube_dynamics(const DevModel& M, Work<NL, MC, SL>& W, float dt) {
+    float wl[3], Iw[3], g1[3], al[3], aw[3];
+    mulv(wl, W.cR, W.cw);
+    const float wn = sqrtf(dot3(wl, wl)), vn = sqrtf(dot3(W.cv, W.cv));
+    const float ka = M.ang_damping * (1.0f + wn), kl = M.lin_damping * (1.0f + vn);
+#pragma unroll
+    for (int k = 0; k < 3; k++) Iw[k] = M.cube_inertia[k] * wl[k];
+    cross3(g1, wl, Iw);
+#pragma unroll
+    for (int k = 0; k < 3; k++) al[k] = -(Iw[k] * ka + M.use_gyro * g1[k]) / M.cube_inertia[k];
+    tmulv(aw, W.cR, al);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { W.cw[k] += dt * aw[k]; W.cv[k] += dt * (-kl * W.cv[k]); }
+    W.cv[2] += dt * -M.gravity;
+    cube_clamp(M, W);
+}
+template <int NL, int MC, bool SL>
+RS_HD void cube_integrate(Work<NL, MC, SL>& W, float dt) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) W.cpos[k] += dt * W.cv[k];
+    float ang = sqrtf(dot3(W.cw, W.cw));
+    if (ang * dt > 0.78539816f) ang = 0.5f * 1.57079633f / dt;
+    float kk;
+    if (ang < 0.001f) kk = 0.5f * dt - dt * dt * dt * 0.020833333333f * ang * ang;
+    else kk = sinf(0.5f * ang * dt) / ang;
+    float ax = W.cw[0] * kk, ay = W.cw[1] * kk, az = W.cw[2] * kk, aw = cosf(ang * dt * 0.5f);
+    float bx = W.cquat[0], by = W.cquat[1], bz = W.cquat[2], bwq = W.cquat[3];
+    float x = aw * bx + ax * bwq + ay * bz - az * by;
+    float y = aw * by - ax * bz + ay * bwq + az * bx;
+    float z = aw * bz + ax * by - ay * bx + az * bwq;
+    float w = aw * bwq - ax * bx - ay * by - az * bz;
+    float inv = 1.0f / sqrtf(x * x + y * y + z * z + w * w);
+    W.cquat[0] = x * inv; W.cquat[1] = y * inv; W.cquat[2] = z * inv; W.cquat[3] = w * inv;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -604,6 +666,85 @@ RS_HD void seg_seg_closest(const float* p1, const float* q1, const float* p2, co
     for (int k = 0; k < 3; k++) { c1[k] = p1[k] + d1[k] * s; c2[k] = p2[k] + d2[k] * t; }
 }
 
+// Closest points between a solid box (half extents h, axis aligned in its own frame) and the segment [a,b] (box coords);
+// same algorithm as oracle/rs_oracle.c box_seg_closest (GJK / EPA answer for btBoxShape against a sphere-swept segment).
+// Returns the signed distance box <-> segment core; n: unit vector box -> segment, pb: point on the box, ps: on the segment.
+RS_HD float box_seg_G(const float* h, const float* a, const float* d, float t) {
+    float g = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float p = a[i] + t * d[i];
+        const float ex = p > h[i] ? p - h[i] : (p < -h[i] ? p + h[i] : 0.f);
+        g += ex * d[i];
+    }
+    return g;
+}
+RS_HD float box_seg_closest(const float* h, const float* a, const float* b, float* n, float* pb, float* ps) {
+    const float d[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+    float t;
+    const float G0 = box_seg_G(h, a, d, 0.f), G1 = box_seg_G(h, a, d, 1.f);
+    if (G0 >= 0.f) t = 0.f;
+    else if (G1 <= 0.f) t = 1.f;
+    else {
+        float tl = 0.f, gl = G0, th = 1.f, gh = G1;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+#pragma unroll
+            for (int sgn = 0; sgn < 2; sgn++) {
+                float tc = 0.f;
+                if (fabsf(d[i]) > 1e-12f) { const float tt = ((sgn ? -h[i] : h[i]) - a[i]) / d[i]; if (tt > 0.f && tt < 1.f) tc = tt; }
+                const float gc = box_seg_G(h, a, d, tc);
+                if (gc <= 0.f) { if (tc > tl) { tl = tc; gl = gc; } }
+                else if (tc < th) { th = tc; gh = gc; }
+            }
+        }
+        t = gh - gl > 0.f ? tl + (th - tl) * (-gl) / (gh - gl) : tl;
+    }
+    float df[3], dist2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        ps[i] = a[i] + t * d[i];
+        pb[i] = ps[i] > h[i] ? h[i] : (ps[i] < -h[i] ? -h[i] : ps[i]);
+        df[i] = ps[i] - pb[i]; dist2 += df[i] * df[i];
+    }
+    if (dist2 > 1e-18f) {
+        const float dist = sqrtf(dist2), il = 1.0f / dist;
+        n[0] = df[0] * il; n[1] = df[1] * il; n[2] = df[2] * il;
+        return dist;
+    }
+    // core touches or intersects the box: minimum-translation axis over the face normals and the edge directions d x e_i
+    const float c[3] = {0.5f * (a[0] + b[0]), 0.5f * (a[1] + b[1]), 0.5f * (a[2] + b[2])}, hd[3] = {0.5f * d[0], 0.5f * d[1], 0.5f * d[2]};
+    float best = 1e30f, bn[3] = {0.f, 0.f, 1.f};
+    bool best_edge = false;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float ov = h[i] + fabsf(hd[i]) - fabsf(c[i]);
+        if (ov < best) { best = ov; bn[0] = bn[1] = bn[2] = 0.f; bn[i] = c[i] >= 0.f ? 1.f : -1.f; best_edge = false; }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        float ei[3] = {0.f, 0.f, 0.f}, u[3];
+        ei[i] = 1.f;
+        cross3(u, d, ei);
+        const float l2 = dot3(u, u);
+        if (l2 < 1e-18f) continue;
+        const float il = 1.0f / sqrtf(l2);
+        u[0] *= il; u[1] *= il; u[2] *= il;
+        const float cu = dot3(c, u);
+        const float ov = h[0] * fabsf(u[0]) + h[1] * fabsf(u[1]) + h[2] * fabsf(u[2]) - fabsf(cu);
+        if (ov < best) { best = ov; const float sg = cu >= 0.f ? 1.f : -1.f; bn[0] = sg * u[0]; bn[1] = sg * u[1]; bn[2] = sg * u[2]; best_edge = true; }
+    }
+    n[0] = bn[0]; n[1] = bn[1]; n[2] = bn[2];
+    if (best_edge) { ps[0] = c[0]; ps[1] = c[1]; ps[2] = c[2]; }
+    else {
+        const bool useb = dot3(b, bn) < dot3(a, bn);
+        ps[0] = useb ? b[0] : a[0]; ps[1] = useb ? b[1] : a[1]; ps[2] = useb ? b[2] : a[2];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) pb[i] = ps[i] + bn[i] * best;
+    return -best;
+}
+
 // one manifold (<=4 points) worth of cached points, processed in registers/scratch
 struct Manifold4 {
     int n;
@@ -642,6 +783,12 @@ RS_HD void load_xf(const Work<NL, MC, SL>& W, int b, BodyXf& X) {
 #pragma unroll
     for (int k = 0; k < 9; k++) X.R[k] = W.Rwl[b][k];
     X.p[0] = W.pos[b][0]; X.p[1] = W.pos[b][1]; X.p[2] = W.pos[b][2];
+}
+template <int NL, int MC, bool SL>
+RS_HD void load_xf_cube(const Work<NL, MC, SL>& W, BodyXf& X) {
+#pragma unroll
+    for (int k = 0; k < 9; k++) X.R[k] = W.cR[k];
+    X.p[0] = W.cpos[0]; X.p[1] = W.cpos[1]; X.p[2] = W.cpos[2];
 }
 RS_HD void xf_to_world(const BodyXf& X, const float* l, float* w) {
     float t[3]; tmulv(t, X.R, l);
@@ -722,7 +869,8 @@ RS_HD void geom_ends(const DevModel& M, int g, const BodyXf& X, float* e) {
 // refresh, append to the new list.  The geom end points are rebuilt from the body transform, which is fetched once
 // (a manifold reaches this function only if the broadphase flagged it or it still holds points: a handful per env).
 // oi / no: cursors into the old / new list.
-template <int NL, int MC, bool SL>
+// CUBE: manifolds n_geoms + n_pairs (cube-floor) and n_geoms + n_pairs + 1 + g (cube vs robot geom g) exist as well.
+template <bool CUBE = false, int NL, int MC, bool SL>
 RS_HD void collide_manifold(const DevModel& M, Work<NL, MC, SL>& W, int k, int old, int nw, int nold, int& oi, int& no) {
     Manifold4 mf; mf.n = 0;
     while (oi < nold && W.ckey[old][oi] == k) {
@@ -763,6 +911,45 @@ RS_HD void collide_manifold(const DevModel& M, Work<NL, MC, SL>& W, int k, int o
             manifold_add(mf, XA, XA, -1, nz, pOnB, dist, thr);
         }
         if (mf.n) manifold_refresh(mf, XA, XA, -1, thr);
+    } else if (CUBE && k >= M.n_geoms + M.n_pairs) {
+        const float thr = M.cube_thresh;
+        BodyXf XC;
+        load_xf_cube(W, XC);
+        if (k == M.n_geoms + M.n_pairs) {
+            // cube vs floor: btConvexPlaneCollisionAlgorithm, one support vertex of the btBoxShape per sub-step
+            const float down[3] = {0.f, 0.f, -1.f};
+            float dl[3], sv[3], vtx[3];
+            mulv(dl, XC.R, down);
+#pragma unroll
+            for (int a = 0; a < 3; a++) sv[a] = dl[a] >= 0.f ? M.cube_half[a] : -M.cube_half[a];
+            xf_to_world(XC, sv, vtx);
+            const float dist = vtx[2];
+            if (dist < thr) {
+                const float nz[3] = {0.f, 0.f, 1.f};
+                float pOnB[3] = {vtx[0], vtx[1], 0.f};
+                manifold_add(mf, XC, XC, -1, nz, pOnB, dist, thr);
+            }
+            if (mf.n) manifold_refresh(mf, XC, XC, -1, thr);
+        } else {
+            // robot geom g (body A) vs cube (body B): closest points of the box and the geom's sphere-swept segment
+            const int g = k - M.n_geoms - M.n_pairs - 1;
+            const int bA = M.g_link[g] + 1;
+            BodyXf XA;
+            load_xf(W, bA, XA);
+            if (M.g_type[g] != RS_GEOM_BOX) {
+                float ge[6], al[3], bl[3], n[3], pb[3], ps[3];
+                geom_ends(M, g, XA, ge);
+                xf_to_local(XC, ge, al); xf_to_local(XC, ge + 3, bl);
+                const float dist = box_seg_closest(M.cube_half, al, bl, n, pb, ps) - M.g_radius[g];
+                if (dist < thr) {
+                    float nw3[3], pOnB[3];
+                    tmulv(nw3, XC.R, n);
+                    xf_to_world(XC, pb, pOnB);
+                    manifold_add(mf, XA, XC, 1, nw3, pOnB, dist, thr);
+                }
+            }
+            if (mf.n) manifold_refresh(mf, XA, XC, 1, thr);
+        }
     } else {
         int pk = k - M.n_geoms;
         int ga = M.pair_a[pk], gb = M.pair_b[pk];
@@ -1152,6 +1339,8 @@ RS_HD void calc_state_core(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, c
     float mx = 0.f, my = 0.f;
     for (int k = 0; k < M.n_parts; k++) { mx += W.pos[M.part_link[k] + 1][0]; my += W.pos[M.part_link[k] + 1][1]; }
     mx /= (float)M.n_parts; my /= (float)M.n_parts;
+    W.body_xyz[0] = mx; W.body_xyz[1] = my; W.body_xyz[2] = bp[2];
+    W.body_vel[0] = bv[0]; W.body_vel[1] = bv[1]; W.body_vel[2] = bv[2];
     // Pose::rpy (python-binding.cpp:60-73)
     float qx = bq[0], qy = bq[1], qz = bq[2], qw = bq[3];
     float sqw = qw * qw, sqx = qx * qx, sqy = qy * qy, sqz = qz * qz;
@@ -1181,6 +1370,60 @@ RS_HD void calc_state(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, float*
     kinematics(M, W); velocities(M, W);
     float bp[3], bq[4], bv[3];
     body_pose(W, M.body_link + 1, bp, bq, bv);
+    calc_state_core(M, W, E, bp, bq, bv, obs, ostride, dist, pitch, at_limit);
+}
+
+// First observation of a new episode for the static-topology kernels.  A reset happens once per ~1000 env steps, in one lane
+// of one warp, after the other warps of the CTA have finished: whatever it executes is COLD code fetched by a lone warp
+// (measured: the fully unrolled static_calc_state made every step of a staggered batch 0.14 ms longer).  So the world
+// transforms come from this compact loop over the runtime topology tables instead (a few hundred instructions), and the
+// link velocities are not swept at all: a freshly reset env is at rest (env_reset_with zeroes qd, base and joint speeds).
+template <int NL, int MC, bool SL>
+RS_HD void reset_calc_state(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, float* obs, int ostride, double* dist, float* pitch, int* at_limit) {
+    float Rbw[9];
+    quat_to_mat(Rbw, W.bquat[0], W.bquat[1], W.bquat[2], W.bquat[3]);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) W.Rwl[0][i * 3 + j] = Rbw[j * 3 + i];
+    W.pos[0][0] = W.bpos[0]; W.pos[0][1] = W.bpos[1]; W.pos[0][2] = W.bpos[2];
+#pragma unroll 1
+    for (int i = 0; i < M.n_links; i++) {
+        const int p = M.parent[i];
+        float R[9];
+        if (M.jtype[i] == RS_JOINT_REVOLUTE) {
+            const float half = -0.5f * W.q[M.dof_idx[i]];
+            const float s = sinf(half), c = cosf(half);
+            float Ra[9];
+            quat_to_mat(Ra, M.axis[i][0] * s, M.axis[i][1] * s, M.axis[i][2] * s, c);
+            mul33(R, Ra, M.R0[i]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; k++) R[k] = M.R0[i][k];
+        }
+        float rv[3], rw[3];
+        mulv(rv, R, M.e_vec[i]);
+        rv[0] += M.d_vec[i][0]; rv[1] += M.d_vec[i][1]; rv[2] += M.d_vec[i][2];
+        if (M.jtype[i] == RS_JOINT_PRISMATIC) {
+            const float qq = W.q[M.dof_idx[i]];
+            rv[0] += qq * M.axis[i][0]; rv[1] += qq * M.axis[i][1]; rv[2] += qq * M.axis[i][2];
+        }
+        mul33(W.Rwl[i + 1], R, W.Rwl[p + 1]);
+        tmulv(rw, W.Rwl[i + 1], rv);
+        W.pos[i + 1][0] = W.pos[p + 1][0] + rw[0]; W.pos[i + 1][1] = W.pos[p + 1][1] + rw[1]; W.pos[i + 1][2] = W.pos[p + 1][2] + rw[2];
+    }
+    const int body = M.body_link + 1;
+    float bp[3] = {W.pos[body][0], W.pos[body][1], W.pos[body][2]}, bq[4];
+    const float bv[3] = {0.f, 0.f, 0.f};
+    if (body == 0) { bq[0] = W.bquat[0]; bq[1] = W.bquat[1]; bq[2] = W.bquat[2]; bq[3] = W.bquat[3]; }
+    else {
+        float Rlw[9];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) Rlw[i * 3 + j] = W.Rwl[body][j * 3 + i];
+        mat_to_quat(Rlw, bq);
+    }
     calc_state_core(M, W, E, bp, bq, bv, obs, ostride, dist, pitch, at_limit);
 }
 
@@ -1221,9 +1464,36 @@ RS_HD double harder_potential(const DevModel& M, Episode& E, double dist, float 
     }
     return frp + harder_leak(z1, z2) * 100.0;
 }
-// alive_bonus (:101-139).  The flying cube is not simulated; its five np_random draws are still consumed.
-RS_HD float harder_alive(Episode& E, float z, float z1, float z2) {
-    if (E.frame % 30 == 0 && E.frame > 100 && E.on_ground == 0) E.flag_draws += 5;
+// alive_bonus (:101-139).  Every 30 frames the cube is thrown at the position the robot will have reached when it arrives:
+// five np_random draws from the flag stream (angle, speed, 3 x velocity noise), then Robot::set_pose_and_speed
+// (python-binding.cpp:289: pose in doubles, velocity through float, identity orientation, angular velocity zeroed).
+// Worlds without the cube still consume the draws.
+template <int NL, int MC, bool SL>
+RS_HD float harder_alive(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, float z, float z1, float z2, uint32_t seed, uint32_t env_id) {
+    if (E.frame % 30 == 0 && E.frame > 100 && E.on_ground == 0) {
+        double u[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) u[k] = (double)rs_uniform(seed, env_id, E.episode, 2000u + E.flag_draws++);
+        if (M.has_cube) {
+            double target[3] = {(double)W.body_xyz[0], (double)W.body_xyz[1], (double)W.body_xyz[2]}, cp[3], v[3];
+            const double angle = -3.14 + (3.14 - -3.14) * u[0], from_dist = 4.0;
+            const double attack_speed = 20.0 + (30.0 - 20.0) * u[1];
+            const double ttt = from_dist / attack_speed;
+#pragma unroll
+            for (int k = 0; k < 3; k++) target[k] += (double)W.body_vel[k] * ttt;
+            cp[0] = target[0] + from_dist * cos(angle); cp[1] = target[1] + from_dist * sin(angle); cp[2] = target[2] + 1.0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) v[k] = target[k] - cp[k];
+            const double sc = attack_speed / sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                W.cpos[k] = (float)cp[k];
+                W.cv[k] = (float)(v[k] * sc + (-1.0 + (1.0 - -1.0) * u[2 + k]));
+                W.cw[k] = 0.f;
+            }
+            W.cquat[0] = W.cquat[1] = W.cquat[2] = 0.f; W.cquat[3] = 1.f;
+        }
+    }
     if (z < 0.8f) {
         if (E.task == 0) E.on_ground = 10000;
         E.on_ground += 1;
@@ -1331,7 +1601,7 @@ RS_HD void epilogue_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, con
     float z = obs[0] + E.initial_z;
     const float z_body = W.pos[M.body_link + 1][2], z_aux = W.pos[(M.task_link >= 0 ? M.task_link : M.body_link) + 1][2];
     float alive;
-    if (M.flag_task == 2) alive = harder_alive(E, z, z_body, z_aux);
+    if (M.flag_task == 2) alive = harder_alive(M, W, E, z, z_body, z_aux, seed, env_id);
     else if (M.alive_rule == RS_ALIVE_Z_AND_PITCH) alive = (z > M.alive_z && fabsf(pitch) < 1.0f) ? M.alive_bonus : -1.f;
     else if (M.alive_rule == RS_ALIVE_Z) alive = (z > M.alive_z) ? M.alive_bonus : -1.f;
     else if (M.alive_rule == RS_ALIVE_CHEETAH)   // feet_contact still holds the previous step's flags here
@@ -1350,7 +1620,8 @@ RS_HD void epilogue_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, con
         for (int ci = 0; ci < nc; ci++) {
             int key = W.ckey[cur][ci];
             if (key < M.n_geoms) { if (M.g_link[key] + 1 == fb) g = 1; }
-            else { int pk = key - M.n_geoms; if (M.g_link[M.pair_a[pk]] + 1 == fb || M.g_link[M.pair_b[pk]] + 1 == fb) o = 1; }
+            else if (key < M.n_geoms + M.n_pairs) { int pk = key - M.n_geoms; if (M.g_link[M.pair_a[pk]] + 1 == fb || M.g_link[M.pair_b[pk]] + 1 == fb) o = 1; }
+            else if (key > M.n_geoms + M.n_pairs) { if (M.g_link[key - M.n_geoms - M.n_pairs - 1] + 1 == fb) o = 1; }   // the cube is not the floor
         }
         E.feet_contact[f] = g ? 1.f : 0.f;
         if (o) feet_cost += M.foot_collision_cost;
@@ -1407,6 +1678,11 @@ RS_HD void env_reset_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, ui
         else if (E.task == 2) { pitch = 3.141592653589793 * 3 / 2 - 0.15; W.bpos[2] = M.reset_base_pos[2] - 1.4f + 0.22f; }
         const double t0 = cos(yaw * 0.5), t1 = sin(yaw * 0.5), t4 = cos(pitch * 0.5), t5 = sin(pitch * 0.5);
         W.bquat[3] = (float)(t0 * t4); W.bquat[0] = (float)(-t1 * t5); W.bquat[1] = (float)(t0 * t5); W.bquat[2] = (float)(t1 * t4);
+    }
+    if (M.has_cube) {   // load_urdf(cube.urdf, cpose) of robot_specific_reset: a fresh body at rest (gym_humanoid_flagrun.py:83-86)
+#pragma unroll
+        for (int k = 0; k < 3; k++) { W.cpos[k] = M.cube_start[k]; W.cw[k] = 0.f; W.cv[k] = 0.f; W.cquat[k] = 0.f; }
+        W.cquat[3] = 1.f;
     }
     W.ccount[0] = W.ccount[1] = 0; W.cur = 0;
     for (int k = 0; k < M.n_feet; k++) E.feet_contact[k] = 0.f;

@@ -129,6 +129,21 @@ inline int build_dev_model(const rs_model_desc* m, DevModel* D, const char** err
     for (int k = 0; k < 4; k++) D->task_dof[k] = m->task_dof[k];
     D->flag_task = m->flag_task; D->flag_timeout_steps = m->flag_timeout_steps;
     D->flag_halflen = m->flag_halflen; D->flag_halfwidth = m->flag_halfwidth;
+    D->has_cube = m->has_cube ? 1 : 0;
+    if (m->has_cube) {
+        if (!(m->cube_mass > 0) || !(m->cube_inertia[0] > 0) || !(m->cube_inertia[1] > 0) || !(m->cube_inertia[2] > 0) ||
+            !(m->cube_half[0] > 0) || !(m->cube_half[1] > 0) || !(m->cube_half[2] > 0)) { *err = "cube mass / inertia / half extents must be positive"; return 1; }
+        if (m->n_links + 1 > 254) { *err = "cube body index out of range"; return 1; }
+        double b2 = 0;
+        for (int k = 0; k < 3; k++) {
+            D->cube_half[k] = (float)m->cube_half[k]; D->cube_inertia[k] = (float)m->cube_inertia[k]; D->cube_start[k] = (float)m->cube_start[k];
+            b2 += m->cube_half[k] * m->cube_half[k];
+        }
+        D->cube_mass = (float)m->cube_mass; D->cube_thresh = (float)m->cube_break_thresh;
+        D->cube_bound = (float)sqrt(b2) * 1.0001f + 1e-6f;
+        D->cube_fric_floor = (float)(m->cube_friction * m->floor_friction);
+        for (int g = 0; g < m->n_geoms; g++) D->cube_fric_geom[g] = (float)(m->g_friction[g] * m->cube_friction);
+    }
     return 0;
 }
 

@@ -41,6 +41,13 @@ __device__ __forceinline__ void load_env(const DevModel& M, const DevBuf& B, int
     }
     for (int d = 0; d < M.n_dof; d++) W.q[d] = s[(size_t)(f + d) * N];
     for (int d = 0; d < M.n_dof; d++) W.qd[d] = s[(size_t)(f + M.n_dof + d) * N];
+    if (M.has_cube) {   // 13 more state rows: pos3 quat4 omega3 vel3 of the cube
+        const int c0 = f + 2 * M.n_dof;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { W.cpos[k] = s[(size_t)(c0 + k) * N]; W.cw[k] = s[(size_t)(c0 + 7 + k) * N]; W.cv[k] = s[(size_t)(c0 + 10 + k) * N]; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) W.cquat[k] = s[(size_t)(c0 + 3 + k) * N];
+    }
     int nc = B.ccount[e];
     W.cur = 0; W.ccount[0] = nc; W.ccount[1] = 0;
     for (int i = 0; i < nc; i++) {
@@ -82,6 +89,13 @@ __device__ __forceinline__ void store_env(const DevModel& M, const DevBuf& B, in
     }
     for (int d = 0; d < M.n_dof; d++) s[(size_t)(f + d) * N] = W.q[d];
     for (int d = 0; d < M.n_dof; d++) s[(size_t)(f + M.n_dof + d) * N] = W.qd[d];
+    if (M.has_cube) {
+        const int c0 = f + 2 * M.n_dof;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { s[(size_t)(c0 + k) * N] = W.cpos[k]; s[(size_t)(c0 + 7 + k) * N] = W.cw[k]; s[(size_t)(c0 + 10 + k) * N] = W.cv[k]; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) s[(size_t)(c0 + 3 + k) * N] = W.cquat[k];
+    }
     const int cur = W.cur, nc = W.ccount[cur];
     B.ccount[e] = nc;
     for (int i = 0; i < nc; i++) {
@@ -153,7 +167,11 @@ __global__ void __launch_bounds__(32 * WPC) k_step_static(const __grid_constant_
         int finished = dn || E.frame >= M.max_episode_steps;
         st_rew = out.reward; st_rows = W.n_rows; st_con = W.n_contacts; st_steps = 1; st_nf = finite ? 0 : 1;
         if (finished) { st_ep = 1; st_len = E.frame; }
-        if (auto_reset && finished) { env_reset_with(M, W, E, seed, env_id0 + e, o, 1, cs); dn = 1; }
+        if (auto_reset && finished) {
+            auto cs_reset = [&](float* oo, int os, double* dist, float* pitch, int* al) { reset_calc_state(M, W, E, oo, os, dist, pitch, al); };
+            env_reset_with(M, W, E, seed, env_id0 + e, o, 1, cs_reset);
+            dn = 1;
+        }
         rew[e] = out.reward; done[e] = (uint8_t)dn;
         if (B.rewards5) {
 #pragma unroll

@@ -39,7 +39,9 @@ template <class T, int MC, int WIDTH> constexpr int pool_cap() { return WIDTH * 
 // words of a row record: [0,nd) J ; [nd,2nd) M^-1 J^T ; [2nd] denominator.  A task descriptor lives in
 // words [0,25) of the task's first row slot until the task is executed (needs 2*nd+1 >= 25).
 constexpr int POOL_DESC_WORDS = 25;
-template <class T> constexpr int pool_rec() { return 2 * (6 + T::ND) + 1; }
+// solver dofs of a topology: base 6 + joints, + the 6 world-frame dofs of FlagrunHarder's cube (T::CUBE) at the end
+template <class T> constexpr int nd_of() { return 6 + T::ND + (T::CUBE ? 6 : 0); }
+template <class T> constexpr int pool_rec() { return 2 * nd_of<T>() + 1; }
 
 struct WarpHost {
     static constexpr int WIDTH = 1;
@@ -99,7 +101,7 @@ RS_HD int f2i(float v) { union { int i; float f; } u; u.f = v; return u.i; }
 template <class T, int NR, bool HASW, bool first, int STRIDE, class Pool>
 RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*wr)[6], float jdir,
                            const Pool& pool, int slot0, float* denom) {
-    constexpr int n = T::NL, nd = 6 + T::ND;
+    constexpr int n = T::NL, nd = nd_of<T>();
     float F[HASW ? NR : 1][6], Z[NR][6], Y[NR][n];
 #pragma unroll
     for (int rr = 0; rr < NR; rr++) {
@@ -249,7 +251,8 @@ RS_HD void resolve_pooled(const Pool& pool, int slot, float* dv, float rhs, floa
 template <class T, class Warp, int NL, int MC, bool SL, int STRIDE, class Pool>
 RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL, MC, SL>& W, float dt, const Pool& pool, float* lc_lane0) {
     static_assert(pool_rec<T>() >= POOL_DESC_WORDS, "row record too small to hold a task descriptor");
-    constexpr int nd = 6 + T::ND, n = T::NL;
+    constexpr int nd = nd_of<T>(), n = T::NL, ndr = 6 + T::ND;   // ndr: the robot's dofs; [ndr, nd): the cube's
+    constexpr int CB = n + 1;                                     // body index of the cube
     const int lane = warp.lane();
     // ---- owner: enumerate rows ----
     // non-contact rows: joint limits, then joint motors (the motors join the world after the limit constraints)
@@ -306,11 +309,65 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
         const float* cd = W.cdat[cur][ci];
         int bA, bB;
         if (key < M.n_geoms) { bA = M.g_link[key] + 1; bB = -1; }
-        else { int pk = key - M.n_geoms; bA = M.g_link[M.pair_a[pk]] + 1; bB = M.g_link[M.pair_b[pk]] + 1; }
+        else if (!T::CUBE || key < M.n_geoms + M.n_pairs) { int pk = key - M.n_geoms; bA = M.g_link[M.pair_a[pk]] + 1; bB = M.g_link[M.pair_b[pk]] + 1; }
+        else if (key == M.n_geoms + M.n_pairs) { bA = CB; bB = -1; }
+        else { bA = M.g_link[key - M.n_geoms - M.n_pairs - 1] + 1; bB = CB; }
         float dirs[3][3];
         dirs[0][0] = cd[6]; dirs[0][1] = cd[7]; dirs[0][2] = cd[8];
         plane_space(dirs[0], dirs[1], dirs[2]);
         const int slot = LT + 3 * (cbase + ci);
+        if constexpr (T::CUBE != 0) {
+            if (bA == CB || bB == CB) {
+                // The cube's side of the three rows is written by the owner lane itself (its transform is not in the shared link
+                // cache): J = (r x n, n) and M^-1 J^T = (R^T I^-1 R (r x n), n / m) on the cube's world-frame dofs, plus this side's
+                // J.M^-1 J^T.  A cube-floor point has no robot side: the owner zero-fills the robot words and marks the task done.
+                const float* lp = bA == CB ? cd : cd + 3;           // contact point in cube coords
+                const float sgn = bA == CB ? 1.f : -1.f;
+                float rw[3], cden[3];
+                tmulv(rw, W.cR, lp);
+#pragma unroll
+                for (int w = 0; w < 3; w++) {
+                    const float nn[3] = {sgn * dirs[w][0], sgn * dirs[w][1], sgn * dirs[w][2]};
+                    float jw[3], tl[3], uw[3];
+                    cross3(jw, rw, nn);
+                    mulv(tl, W.cR, jw);
+#pragma unroll
+                    for (int k = 0; k < 3; k++) tl[k] /= M.cube_inertia[k];
+                    tmulv(uw, W.cR, tl);
+                    const float im = 1.0f / M.cube_mass;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        pool.at(slot + w, ndr + k) = jw[k]; pool.at(slot + w, ndr + 3 + k) = nn[k];
+                        pool.at(slot + w, nd + ndr + k) = uw[k]; pool.at(slot + w, nd + ndr + 3 + k) = nn[k] * im;
+                    }
+                    cden[w] = dot3(jw, uw) + dot3(nn, nn) * im;
+                }
+                if (bA == CB) {
+#pragma unroll
+                    for (int w = 0; w < 3; w++) {
+                        for (int k = 0; k < ndr; k++) { pool.at(slot + w, k) = 0.f; pool.at(slot + w, nd + k) = 0.f; }
+                        pool.at(slot + w, 2 * nd) = cden[w];
+                    }
+                    pool.at(slot, 0) = i2f(lane | (255 << 8));       // body 255: nothing left to do for the helpers
+                    continue;
+                }
+                // robot geom vs cube: the helpers build the robot side like a floor contact and add the cube's denominators
+                pool.at(slot, 0) = i2f(lane | (bA << 8) | (1 << 24));
+#pragma unroll
+                for (int k = 0; k < 3; k++) { pool.at(slot, 1 + k) = cd[k]; pool.at(slot, 13 + k) = cden[k]; }
+                float Rb[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) Rb[k] = W.Rwl[bA][k];
+#pragma unroll
+                for (int w = 0; w < 3; w++) {
+                    float dl[3];
+                    mulv(dl, Rb, dirs[w]);
+#pragma unroll
+                    for (int k = 0; k < 3; k++) pool.at(slot, 4 + 3 * w + k) = dl[k];
+                }
+                continue;
+            }
+        }
         pool.at(slot, 0) = i2f(lane | (bA << 8) | ((bB + 1) << 16));
 #pragma unroll
         for (int k = 0; k < 3; k++) pool.at(slot, 1 + k) = cd[k];
@@ -349,6 +406,10 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
             LinkCache<STRIDE> lco{lc_lane0 + o};
             float dn[1];
             pooled_response<T, 1, false, true>(lco, body, (const float (*)[6]) nullptr, dir, pool, t, dn);
+            if constexpr (T::CUBE != 0) {
+#pragma unroll
+                for (int k = ndr; k < nd; k++) { pool.at(t, k) = 0.f; pool.at(t, nd + k) = 0.f; }
+            }
             pool.at(t, 2 * nd) = dn[0];
         }
     }
@@ -360,8 +421,14 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
             float desc[POOL_DESC_WORDS];
             const int code = f2i(pool.at(slot, 0));
             const int o = code & 255, bA = (code >> 8) & 255, bB = ((code >> 16) & 255) - 1;
+            const bool cube_side = T::CUBE != 0 && ((code >> 24) & 1);
+            if (T::CUBE != 0 && bA == 255) continue;       // cube-floor point: rows already complete
 #pragma unroll
             for (int k = 1; k < 13; k++) desc[k] = pool.at(slot, k);
+            if (cube_side) {
+#pragma unroll
+                for (int k = 13; k < 16; k++) desc[k] = pool.at(slot, k);
+            }
             if (bB >= 0) {
 #pragma unroll
                 for (int k = 13; k < POOL_DESC_WORDS; k++) desc[k] = pool.at(slot, k);
@@ -387,6 +454,15 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
                 pooled_response_second<T>(lco, bB, (const float (*)[6]) wr, pool, slot, dn);
                 dsum[0] += dn[0]; dsum[1] += dn[1]; dsum[2] += dn[2];
             }
+            if (cube_side) { dsum[0] += desc[13]; dsum[1] += desc[14]; dsum[2] += desc[15]; }
+            if constexpr (T::CUBE != 0) {
+                if (!cube_side) {     // no cube in this contact: its dofs take no part in the rows
+#pragma unroll
+                    for (int w = 0; w < 3; w++)
+#pragma unroll
+                        for (int k = ndr; k < nd; k++) { pool.at(slot + w, k) = 0.f; pool.at(slot + w, nd + k) = 0.f; }
+                }
+            }
 #pragma unroll
             for (int w = 0; w < 3; w++) pool.at(slot + w, 2 * nd) = dsum[w];
         }
@@ -403,6 +479,10 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
     }
 #pragma unroll
     for (int d = 0; d < T::ND; d++) vel[6 + d] = W.qd[d];
+    if constexpr (T::CUBE != 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { vel[ndr + k] = W.cw[k]; vel[ndr + 3 + k] = W.cv[k]; }
+    }
     float r_rhs[NNC + 3 * MC], r_invd[NNC + 3 * MC], r_applied[NNC + 3 * MC];
     auto row_relvel = [&](int slot) {
         float j[nd], s = 0.f;
@@ -457,7 +537,10 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
             const float tot = r_applied[n_nc + 3 * ci];
             if (tot > 0.f) {
                 const int key = W.ckey[cur][ci];
-                const float fr = key < M.n_geoms ? M.g_fric_floor[key] : M.pair_friction[key - M.n_geoms];
+                float fr;
+                if (key < M.n_geoms) fr = M.g_fric_floor[key];
+                else if (!T::CUBE || key < M.n_geoms + M.n_pairs) fr = M.pair_friction[key - M.n_geoms];
+                else fr = key == M.n_geoms + M.n_pairs ? M.cube_fric_floor : M.cube_fric_geom[key - M.n_geoms - M.n_pairs - 1];
 #pragma unroll
                 for (int w = 1; w < 3; w++) {
                     const int row = n_nc + 3 * ci + w;
@@ -473,6 +556,11 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
 #pragma unroll
     for (int d = 0; d < T::ND; d++) W.qd[d] += dv[6 + d];
     clamp_vel(M, W);
+    if constexpr (T::CUBE != 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { W.cw[k] += dv[ndr + k]; W.cv[k] += dv[ndr + 3 + k]; }
+        cube_clamp(M, W);
+    }
 }
 
 // one sub-step with the pooled solver; every lane of the warp must call it (valid == false: helper only)
@@ -491,14 +579,20 @@ RS_HD void substep_pooled(const Warp& warp, bool valid, const DevModel& M, Work<
     }
     if (pc) { c1 = RS_CLOCK(); pc->t[1] += c1 - c0; c0 = c1; }
     warp.cta_sync();
-    if (valid) static_aba<T>(M, W, lc, dt);
+    if (valid) {
+        static_aba<T>(M, W, lc, dt);
+        if constexpr (T::CUBE != 0) cube_dynamics(M, W, dt);
+    }
     if (pc) { c1 = RS_CLOCK(); pc->t[2] += c1 - c0; c0 = c1; }
     warp.cta_sync();
     warp.sync();   // link caches complete before other lanes read them
     solve_pooled<T, Warp, NL, MC, SL, STRIDE, Pool>(warp, valid, M, W, dt, pool, lc_lane0);
     warp.sync();   // all helpers done with this sub-step's caches before kinematics overwrites them
     if (pc) { c1 = RS_CLOCK(); pc->t[3] += c1 - c0; c0 = c1; }
-    if (valid) integrate(M, W, dt);
+    if (valid) {
+        integrate(M, W, dt);
+        if constexpr (T::CUBE != 0) cube_integrate(W, dt);
+    }
     if (pc) { c1 = RS_CLOCK(); pc->t[4] += c1 - c0; }
 }
 

@@ -315,6 +315,7 @@ RS_HD void static_kinematics(Work<NL, MC, SL>& W, const LinkCache<STRIDE>& lc, f
 #pragma unroll
     for (int k = 0; k < 9; k++) lc.at(lc_rb<T>() + k) = W.Rwl[0][k];
     if constexpr (GEOMS) static_body_geoms<T, 0>(W, gwr);
+    if constexpr (T::CUBE != 0) cube_kinematics(W);
     static_for<T::NL>([&](auto ic) {
         constexpr int i = decltype(ic)::value;
         constexpr int p = T::parent[i], jt = T::jtype[i], dI = T::dof[i];
@@ -342,7 +343,7 @@ RS_HD void static_kinematics(Work<NL, MC, SL>& W, const LinkCache<STRIDE>& lc, f
 // ---------------------------------------------------------------------------------------------
 template <class T, int NL, int MC, bool SL>
 RS_HD void static_collide(const DevModel& M, Work<NL, MC, SL>& W, const float (*gwr)[6]) {
-    constexpr int NG = T::NG, NP = T::NP, NMAN = NG + NP, NW = (NMAN + 31) / 32;
+    constexpr int NG = T::NG, NP = T::NP, NMAN = NG + NP + (T::CUBE ? 1 + NG : 0), NW = (NMAN + 31) / 32;
     uint32_t cand[NW];
 #pragma unroll
     for (int w = 0; w < NW; w++) cand[w] = 0u;
@@ -368,6 +369,20 @@ RS_HD void static_collide(const DevModel& M, Work<NL, MC, SL>& W, const float (*
             if (!(dx * dx + dy * dy + dz * dz > reach * reach)) cand[k >> 5] |= 1u << (k & 31);
         });
     }
+    if constexpr (T::CUBE != 0) {
+        // the cube: against the floor when its bounding sphere reaches the threshold, against a geom when the bounding spheres do
+        constexpr int kf = NG + NP;
+        if (W.cpos[2] - M.cube_bound < M.cube_thresh) cand[kf >> 5] |= 1u << (kf & 31);
+        static_for<NG>([&](auto gc) {
+            constexpr int g = decltype(gc)::value;
+            constexpr int k = NG + NP + 1 + g;
+            constexpr float hl0 = 0.5f * (T::g_p1[3 * g] - T::g_p0[3 * g]), hl1 = 0.5f * (T::g_p1[3 * g + 1] - T::g_p0[3 * g + 1]), hl2 = 0.5f * (T::g_p1[3 * g + 2] - T::g_p0[3 * g + 2]);
+            const float bound = sqrtf(hl0 * hl0 + hl1 * hl1 + hl2 * hl2) + T::g_radius[g];
+            const float dx = 0.5f * (gwr[g][0] + gwr[g][3]) - W.cpos[0], dy = 0.5f * (gwr[g][1] + gwr[g][4]) - W.cpos[1], dz = 0.5f * (gwr[g][2] + gwr[g][5]) - W.cpos[2];
+            const float reach = bound * 1.0001f + 1e-6f + M.cube_bound + M.cube_thresh;
+            if (!(dx * dx + dy * dy + dz * dz > reach * reach)) cand[k >> 5] |= 1u << (k & 31);
+        });
+    }
     const int old = W.cur, nw = 1 - W.cur;
     const int nold = W.ccount[old];
     for (int i = 0; i < nold; i++) {
@@ -382,7 +397,7 @@ RS_HD void static_collide(const DevModel& M, Work<NL, MC, SL>& W, const float (*
         while (m) {
             const int k = w * 32 + rs_ctz(m);
             m &= m - 1u;
-            collide_manifold(M, W, k, old, nw, nold, oi, no);
+            collide_manifold<T::CUBE != 0>(M, W, k, old, nw, nold, oi, no);
         }
     }
     W.ccount[nw] = no;
@@ -590,7 +605,7 @@ RS_HD void static_calc_state(const DevModel& M, Work<NL, MC, SL>& W, const LinkC
 // true iff the run-time descriptor is exactly the model this topology was generated from
 template <class T>
 inline bool topo_matches(const DevModel& D) {
-    if (D.n_links != T::NL || D.n_dof != T::ND || D.fixed_base != T::FIXED_BASE) return false;
+    if (D.n_links != T::NL || D.n_dof != T::ND || D.fixed_base != T::FIXED_BASE || (D.has_cube != 0) != (T::CUBE != 0)) return false;
     auto eq = [](float a, float b) { return fabsf(a - b) <= 1e-6f * fmaxf(1.0f, fabsf(b)); };
     for (int i = 0; i < T::NL; i++) {
         if (D.parent[i] != T::parent[i] || D.jtype[i] != T::jtype[i] || D.dof_idx[i] != T::dof[i]) return false;

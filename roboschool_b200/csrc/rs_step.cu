@@ -216,12 +216,14 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
     if (w->family < 0) { delete w; return fail("rs_world_create: model exceeds kernel capacity (links<=20, contacts<=16)"); }
     w->topo = 0;
     if (!getenv("RS_FORCE_GENERIC")) {
-        if (topo_matches<TopoHumanoid>(w->M) && model->max_contacts <= 16) w->topo = 1;
+        if (topo_matches<TopoHumanoidCube>(w->M) && model->max_contacts <= 16) w->topo = 6;
+        else if (topo_matches<TopoHumanoid>(w->M) && model->max_contacts <= 16) w->topo = 1;
         else if (topo_matches<TopoAnt>(w->M) && model->max_contacts <= 16) w->topo = 2;
         else if (topo_matches<TopoHopper>(w->M) && model->max_contacts <= 8) w->topo = 3;
         else if (topo_matches<TopoWalker2d>(w->M) && model->max_contacts <= 16) w->topo = 4;
         else if (topo_matches<TopoHalfCheetah>(w->M) && model->max_contacts <= 16) w->topo = 5;
     }
+    if (model->has_cube && !w->topo) { delete w; return fail("rs_world_create: a world with the cube needs its static-topology kernel (model does not match TopoHumanoidCube)"); }
     w->device = device; w->n = n_envs;
     // warps per CTA (measured on B200): 7-warp CTAs that re-align at the phase barriers once the batch
     // gives every SM several warps (Humanoid 32768: +13 %, Ant 65536: +16 %, HalfCheetah 65536: +67 %); single-warp CTAs for
@@ -230,8 +232,8 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
     // idles): 24576 envs for Humanoid, Ant and the planar models (16384-20480: 1-warp CTAs +5..25 %), 8192 for the Flagrun tasks
     w->wpc = n_envs >= (model->flag_task ? 8192 : 24576) ? 7 : 1;
     DevBuf& B = w->B;
-    B.N = n_envs; B.S = (model->fixed_base ? 0 : 13) + 2 * model->n_dof; B.MCcap = MC;
-    B.rec = 2 * (6 + model->n_dof) + 1; B.maxr = 2 * NL + 3 * MC;   // +1: pooled rows keep their denominator in the record; a limit and a motor row per joint
+    B.N = n_envs; B.S = (model->fixed_base ? 0 : 13) + 2 * model->n_dof + (model->has_cube ? 13 : 0); B.MCcap = MC;
+    B.rec = 2 * (6 + model->n_dof + (model->has_cube ? 6 : 0)) + 1; B.maxr = 2 * NL + 3 * MC;   // +1: pooled rows keep their denominator in the record; a limit and a motor row per joint
     size_t N = (size_t)n_envs;
     CK(cudaMalloc(&B.state, sizeof(float) * N * (B.S > 0 ? B.S : 1)));
     CK(cudaMalloc(&B.ccount, sizeof(int) * N));
@@ -270,6 +272,7 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
     {   // identity base quaternion, initial_z from the model
         std::vector<float> s((size_t)N * (B.S > 0 ? B.S : 1), 0.f), iz(N, (float)model->initial_z);
         if (!model->fixed_base) for (size_t e = 0; e < N; e++) s[6 * N + e] = 1.f;
+        if (model->has_cube) for (size_t e = 0; e < N; e++) s[(size_t)(B.S - 13 + 6) * N + e] = 1.f;
         CK(cudaMemcpy(B.state, s.data(), sizeof(float) * s.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(B.initial_z, iz.data(), sizeof(float) * N, cudaMemcpyHostToDevice));
     }
@@ -442,6 +445,7 @@ extern "C" int rs_world_set_joint_motor(rs_world* w, int env, int dof, float kp,
 }
 
 extern "C" int rs_world_substeps(rs_world* w, int n_substeps, const float* tau_host) {
+    if (w->desc.has_cube) return fail("rs_world_substeps: not available for worlds with the cube (physics-only sub-steps run on the runtime-topology kernel, which does not step the cube); use rs_world_step");
     CK(cudaSetDevice(w->device));
     size_t N = (size_t)w->n; int nd = w->desc.n_dof;
     CK(quiesce(w));

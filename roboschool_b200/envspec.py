@@ -72,8 +72,8 @@ ENV_SPECS = {
         reset_base=dict(z=1.4, yaw_spread=math.pi / 16), reward_threshold=2000.0,
         flag=dict(halflen=105 * 0.25, halfwidth=50 * 0.25, timeout=600)),
     # Flagrun + stand-up / roll-over starts chosen by a per-env curriculum, potential "leak" alive bonus, crawl-proof potential
-    # (gym_humanoid_flagrun.py:73-169).  The flying cube that pelts the robot is NOT simulated (box narrowphase + a second
-    # free body per env: DESIGN.md section 7); its RNG draws are consumed so the flag stream matches the reference.
+    # (gym_humanoid_flagrun.py:73-169), and the flying cube that pelts the robot every 30 frames (:81-118,
+    # models_household/cube.urdf: 0.1 m box, 1.2 kg): a second free body per env with box-floor and box-vs-geom contacts.
     "RoboschoolHumanoidFlagrunHarder-v1": dict(
         xml="humanoid_symmetric.xml", robot="torso", A=17, O=44, power=0.41,
         feet=["right_foot", "left_foot"],
@@ -85,7 +85,11 @@ ENV_SPECS = {
               "right_shoulder1": 75, "right_shoulder2": 75, "right_elbow": 75,
               "left_shoulder1": 75, "left_shoulder2": 75, "left_elbow": 75},
         reset_base=dict(z=1.4, yaw_spread=math.pi / 16), reward_threshold=None,
-        flag=dict(halflen=105 * 0.25, halfwidth=50 * 0.25, timeout=600, harder=True, pelvis="pelvis")),
+        flag=dict(halflen=105 * 0.25, halfwidth=50 * 0.25, timeout=600, harder=True, pelvis="pelvis"),
+        # cube.urdf:8,16,22 -- inertia is NOT the file's (0.001): load_urdf passes no URDF_USE_INERTIA_FROM_FILE flag
+        # (physics-bullet.cpp:70-93), so Bullet recomputes it from the collision shape's AABB box; lateral friction is the
+        # URDF importer's default (no <contact> element)
+        cube=dict(half=(0.05, 0.05, 0.05), mass=1.2, start=(-1.5, 0.0, 0.05), friction=0.5)),
     # BASELINE.json configs[0] and its siblings (gym_pendulums.py): empty scene, dt 0.0165, frame_skip 1, no contacts
     "RoboschoolInvertedPendulum-v1": dict(
         xml="inverted_pendulum.xml", robot="cart", A=1, O=5, power=1.0, feet=[],
@@ -192,6 +196,17 @@ def apply_task(m: ModelDesc, spec: dict) -> ModelDesc:
             m.task_link = ln.index(fl["pelvis"])
         m.flag_timeout_steps = int(fl["timeout"] // m.frame_skip)   # 600/frame_skip (gym_humanoid_flagrun.py:35)
         m.flag_halflen, m.flag_halfwidth = fl["halflen"], fl["halfwidth"]
+    cb = spec.get("cube")
+    if cb:
+        m.has_cube = 1
+        hx, hy, hz = cb["half"]
+        m.arr("cube_half")[:] = [hx, hy, hz]
+        m.cube_mass = cb["mass"]
+        lx, ly, lz = 2 * hx, 2 * hy, 2 * hz     # btCompoundShape::calculateLocalInertia: box of the AABB
+        m.arr("cube_inertia")[:] = [cb["mass"] / 12.0 * (ly * ly + lz * lz), cb["mass"] / 12.0 * (lx * lx + lz * lz), cb["mass"] / 12.0 * (lx * lx + ly * ly)]
+        m.cube_friction = cb["friction"]
+        m.cube_break_thresh = 0.02 * math.sqrt(hx * hx + hy * hy + hz * hz)   # gContactBreakingThreshold x getAngularMotionDisc()
+        m.arr("cube_start")[:] = list(cb["start"])
     m.max_episode_steps = spec.get("max_episode_steps", 1000)
     m.max_contacts = spec.get("max_contacts", 16)
     m.meta["env_id"] = spec.get("env_id", "")

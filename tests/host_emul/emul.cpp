@@ -36,7 +36,10 @@ static void step_env_static(Emul* e, int i, const float* a, int auto_reset, uint
     auto cs = [&](float* o, int os, double* dist, float* pitch, int* al) { static_calc_state<T>(M, W, lc, e->ep[i], o, os, dist, pitch, al); };
     epilogue_with(M, W, e->ep[i], a, 1, obs, 1, e->out[i], cs, seed, env0 + i);
     int done = e->out[i].done;
-    if (auto_reset && (done || e->ep[i].frame >= M.max_episode_steps)) { env_reset_with(M, W, e->ep[i], seed, env0 + i, obs, 1, cs); done = 1; }
+    if (auto_reset && (done || e->ep[i].frame >= M.max_episode_steps)) {   // compact reset observation, like k_step_static
+        auto cs_reset = [&](float* o, int os, double* dist, float* pitch, int* al) { reset_calc_state(M, W, e->ep[i], o, os, dist, pitch, al); };
+        env_reset_with(M, W, e->ep[i], seed, env0 + i, obs, 1, cs_reset); done = 1;
+    }
     e->rew[i] = e->out[i].reward; e->done[i] = done;
 }
 template <class T>
@@ -52,8 +55,8 @@ void* emul_create(const rs_model_desc* m, int n) {
     const char* err = nullptr;
     if (build_dev_model(m, &e->M, &err)) { delete e; return nullptr; }
     e->n = n; e->w.resize(n); e->ep.resize(n); e->out.resize(n);
-    for (int i = 0; i < n; i++) { memset(&e->w[i], 0, sizeof(W_t)); e->w[i].bquat[3] = 1; memset(&e->ep[i], 0, sizeof(Episode)); e->ep[i].initial_z = e->M.initial_z; e->ep[i].target_x = e->M.walk_target_x; e->ep[i].target_y = e->M.walk_target_y; }
-    e->rec = 2 * (6 + e->M.n_dof) + 1; e->maxr = 2 * NL + 3 * MC;
+    for (int i = 0; i < n; i++) { memset(&e->w[i], 0, sizeof(W_t)); e->w[i].bquat[3] = 1; e->w[i].cquat[3] = 1; memset(&e->ep[i], 0, sizeof(Episode)); e->ep[i].initial_z = e->M.initial_z; e->ep[i].target_x = e->M.walk_target_x; e->ep[i].target_y = e->M.walk_target_y; }
+    e->rec = 2 * (6 + e->M.n_dof + (e->M.has_cube ? 6 : 0)) + 1; e->maxr = 2 * NL + 3 * MC;
     e->ws.resize((size_t)e->rec * e->maxr);
     e->obs.resize((size_t)n * e->M.obs_dim); e->rew.resize(n); e->done.resize(n);
     e->topo = 0; e->lcsize = 9 * RS_MAX_LINKS + 30; e->lcbuf.assign((size_t)n * e->lcsize, 0.f);
@@ -64,7 +67,8 @@ int emul_use_static(void* h, int on) {
     Emul* e = (Emul*)h;
     e->topo = 0;
     if (on) {
-        if (topo_matches<TopoHumanoid>(e->M)) e->topo = 1;
+        if (topo_matches<TopoHumanoidCube>(e->M)) e->topo = 6;
+        else if (topo_matches<TopoHumanoid>(e->M)) e->topo = 1;
         else if (topo_matches<TopoAnt>(e->M)) e->topo = 2;
         else if (topo_matches<TopoHopper>(e->M)) e->topo = 3;
         else if (topo_matches<TopoWalker2d>(e->M)) e->topo = 4;
@@ -73,17 +77,19 @@ int emul_use_static(void* h, int on) {
     return e->topo;
 }
 void emul_destroy(void* h) { delete (Emul*)h; }
-int emul_state_dim(void* h) { Emul* e = (Emul*)h; return (e->M.fixed_base ? 0 : 13) + 2 * e->M.n_dof; }
+int emul_state_dim(void* h) { Emul* e = (Emul*)h; return (e->M.fixed_base ? 0 : 13) + 2 * e->M.n_dof + (e->M.has_cube ? 13 : 0); }
 void emul_set_state(void* h, int env, const double* s, int clear) {
     Emul* e = (Emul*)h; W_t& W = e->w[env];
     if (!e->M.fixed_base) { for (int k = 0; k < 3; k++) { W.bpos[k] = (float)s[k]; W.bw[k] = (float)s[7 + k]; W.bv[k] = (float)s[10 + k]; } for (int k = 0; k < 4; k++) W.bquat[k] = (float)s[3 + k]; s += 13; }
     for (int d = 0; d < e->M.n_dof; d++) { W.q[d] = (float)s[d]; W.qd[d] = (float)s[e->M.n_dof + d]; }
+    if (e->M.has_cube) { const double* c = s + 2 * e->M.n_dof; for (int k = 0; k < 3; k++) { W.cpos[k] = (float)c[k]; W.cw[k] = (float)c[7 + k]; W.cv[k] = (float)c[10 + k]; } for (int k = 0; k < 4; k++) W.cquat[k] = (float)c[3 + k]; }
     if (clear) { W.ccount[0] = W.ccount[1] = 0; W.cur = 0; }
 }
 void emul_get_state(void* h, int env, double* s) {
     Emul* e = (Emul*)h; W_t& W = e->w[env];
     if (!e->M.fixed_base) { for (int k = 0; k < 3; k++) { s[k] = W.bpos[k]; s[7 + k] = W.bw[k]; s[10 + k] = W.bv[k]; } for (int k = 0; k < 4; k++) s[3 + k] = W.bquat[k]; s += 13; }
     for (int d = 0; d < e->M.n_dof; d++) { s[d] = W.q[d]; s[e->M.n_dof + d] = W.qd[d]; }
+    if (e->M.has_cube) { double* c = s + 2 * e->M.n_dof; for (int k = 0; k < 3; k++) { c[k] = W.cpos[k]; c[7 + k] = W.cw[k]; c[10 + k] = W.cv[k]; } for (int k = 0; k < 4; k++) c[3 + k] = W.cquat[k]; }
 }
 void emul_set_tau(void* h, int env, const double* tau) { Emul* e = (Emul*)h; for (int d = 0; d < e->M.n_dof; d++) e->w[env].tau[d] = (float)tau[d]; }
 // btMultiBodyJointMotor of one dof (rs_world_set_joint_motor); envs with motors stay on the static-topology sweeps, like the library
@@ -106,6 +112,7 @@ void emul_substeps(void* h, int env, int n) {
         case 3: substeps_static<TopoHopper>(e, env, n); return;
         case 4: substeps_static<TopoWalker2d>(e, env, n); return;
         case 5: substeps_static<TopoHalfCheetah>(e, env, n); return;
+        case 6: substeps_static<TopoHumanoidCube>(e, env, n); return;
     }
     for (int s = 0; s < n; s++) substep(e->M, e->w[env], ws);
 }
@@ -147,6 +154,7 @@ void emul_step(void* h, const double* actions, int auto_reset, uint32_t seed, ui
                 case 2: step_env_static<TopoAnt>(e, i, a, auto_reset, seed, env0); break;
                 case 3: step_env_static<TopoHopper>(e, i, a, auto_reset, seed, env0); break;
                 case 4: step_env_static<TopoWalker2d>(e, i, a, auto_reset, seed, env0); break;
+                case 6: step_env_static<TopoHumanoidCube>(e, i, a, auto_reset, seed, env0); break;
                 default: step_env_static<TopoHalfCheetah>(e, i, a, auto_reset, seed, env0); break;
             }
             continue;
@@ -173,11 +181,20 @@ int emul_get_contacts(void* h, int env, double* out, int max_pts) {
         slot = key == last ? slot + 1 : 0; last = key;
         double* o = out + c * 12; const float* d = W.cdat[W.cur][i];
         o[0] = key; o[1] = slot; o[2] = d[9]; o[3] = d[6]; o[4] = d[7]; o[5] = d[8];
-        float pA[3]; to_world(W, key < e->M.n_geoms ? e->M.g_link[key] + 1 : e->M.g_link[e->M.pair_a[key - e->M.n_geoms]] + 1, d, pA);
+        const int ngp = e->M.n_geoms + e->M.n_pairs;
+        float pA[3] = {0.f, 0.f, 0.f};
+        if (key < ngp) to_world(W, key < e->M.n_geoms ? e->M.g_link[key] + 1 : e->M.g_link[e->M.pair_a[key - e->M.n_geoms]] + 1, d, pA);
+        else if (key > ngp) to_world(W, e->M.g_link[key - ngp - 1] + 1, d, pA);
         o[6] = pA[0]; o[7] = pA[1]; o[8] = pA[2]; o[9] = 0; o[10] = 0; o[11] = 0;
         c++;
     }
     return c;
+}
+// overwrite one env's persistent contact manifolds (solver order), like rs_world_set_contacts
+void emul_set_contacts(void* h, int env, int count, const int* keys, const double* data) {
+    Emul* e = (Emul*)h; W_t& W = e->w[env];
+    W.cur = 0; W.ccount[0] = count > MC ? MC : count; W.ccount[1] = 0;
+    for (int i = 0; i < W.ccount[0]; i++) { W.ckey[0][i] = keys[i]; for (int k = 0; k < CDAT; k++) W.cdat[0][i][k] = (float)data[i * CDAT + k]; }
 }
 void emul_counts(void* h, int env, int* rows, int* contacts) { Emul* e = (Emul*)h; *rows = e->w[env].n_rows; *contacts = e->w[env].n_contacts; }
 void emul_link_poses(void* h, int env, double* out) {

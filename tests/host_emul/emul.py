@@ -44,6 +44,7 @@ def lib():
         L.emul_get_rewards5.argtypes = [P, I, dp]
         L.emul_get_contacts.argtypes = [P, I, dp, I]; L.emul_get_contacts.restype = I
         L.emul_counts.argtypes = [P, I, ip, ip]
+        L.emul_set_contacts.argtypes = [P, I, I, ip, dp]
         L.emul_link_poses.argtypes = [P, I, dp]
         L.emul_set_flag.argtypes = [P, I, D, D, I, U]
         L.emul_get_flag.argtypes = [P, I, dp]
@@ -125,6 +126,10 @@ class EmulWorld:
 
     def contacts(self, env, max_pts=128):
         out = np.zeros((max_pts, 12)); c = self.L.emul_get_contacts(self.h, env, _dp(out), max_pts); return out[:c]
+
+    def set_contacts(self, env, count, keys, data):
+        k = np.ascontiguousarray(keys, dtype=np.int32); d = np.ascontiguousarray(data, dtype=np.float64)
+        self.L.emul_set_contacts(self.h, env, int(count), k.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _dp(d))
 
     def counts(self, env):
         a, b = ctypes.c_int(), ctypes.c_int(); self.L.emul_counts(self.h, env, ctypes.byref(a), ctypes.byref(b)); return a.value, b.value

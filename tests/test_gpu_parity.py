@@ -133,6 +133,62 @@ def test_step_teacher_forced(env_id, oracle_lib):
     assert n_done_ok / max(n_done, 1) >= 0.998, n_done_ok / max(n_done, 1)
 
 
+def test_cube_throw_flight_and_hits(oracle_lib):
+    """FlagrunHarder's cube on the GPU (gym_humanoid_flagrun.py:81-118, BASELINE config 5): episodes advanced to frame 110 under
+    the zoo policy on the oracle, then 45 teacher-forced steps covering the throw at frame 120 (five RNG draws ->
+    set_pose_and_speed), the flight (drag, gravity), the hit on the robot (box vs capsule / sphere, two-body contact rows)
+    and the cube coming to rest on the floor (box-plane manifold).  State compared includes the cube's 13 floats."""
+    from roboschool_b200.policy import load_zoo_weights
+    env_id = "RoboschoolHumanoidFlagrunHarder-v1"
+    n = 128
+    m, w, o = _worlds(env_id, n, 2)
+    assert m.has_cube == 1 and w.S == m.state_dim == 13 + 2 * m.n_dof + 13
+    wts = load_zoo_weights(env_id)
+    obs = o.obs()[0]
+    for t in range(110):
+        obs, _, _ = o.step(oracle_lib.mlp_forward(wts, obs), auto_reset=True, seed=2, threads=8)
+    S, nman = m.state_dim, m.n_geoms + m.n_pairs
+    errs, thrown, cube_floor, cube_hits, n_match, n_samples = [], 0, 0, 0, 0, 0
+    for t in range(45):
+        a = oracle_lib.mlp_forward(wts, obs).astype(np.float32)
+        so = o.get_state()
+        w.set_state(so.astype(np.float32), clear_contacts=False)
+        w.set_contacts(*o.contact_cache(max_pts=16))
+        ep = [o.get_episode(i) for i in range(n)]
+        w.set_episode(potential=[e[0] for e in ep], initial_z=[e[1] for e in ep],
+                      feet_contact=np.array([e[2] for e in ep]).reshape(n, m.n_feet), frame=[e[3] for e in ep])
+        fl = [o.get_flag(i) for i in range(n)]
+        w.set_flags(target_xy=[[f[0], f[1]] for f in fl], timeout=[f[2] for f in fl], draws=[f[3] for f in fl])
+        w.set_task_state(np.stack([o.get_task_state(i) for i in range(n)]))
+        for i in range(n):
+            o.set_state(i, so[i].astype(np.float32).astype(np.float64), clear_contacts=False)
+        obs_g, rew_g, done_g = w.step_host(a)
+        obs, rew_o, done_o = o.step(a.astype(np.float64), threads=8)
+        sg, so2 = w.get_state(), o.get_state()
+        thrown += int((np.abs(so2[:, S - 13:S - 10] - so[:, S - 13:S - 10]).max(axis=1) > 2.0).sum())
+        cnt_o, keys_o, _ = o.contact_cache(max_pts=16)
+        for i in range(n):
+            kg, _ = w.contacts(i)
+            n_samples += 1
+            if not (len(kg) == cnt_o[i] and np.array_equal(kg, keys_o[i, :cnt_o[i]])):
+                continue
+            n_match += 1
+            cube_floor += int((kg == nman).sum()); cube_hits += int((kg > nman).sum())
+            r = np.abs(sg[i] - so2[i]).max() / max(1.0, np.abs(so2[i]).max())
+            errs.append(r)
+            if r < STEP_RTOL:
+                assert np.abs(obs_g[i] - obs[i]).max() < 2e-3 and bool(done_g[i]) == bool(done_o[i])
+    errs = np.array(errs)
+    print("\n[cube] throws %d, cube-floor points %d, cube-robot points %d, manifolds identical %.4f, state err median %.2e p95 %.2e max %.2e"
+          % (thrown, cube_floor, cube_hits, n_match / n_samples, np.median(errs), np.percentile(errs, 95), errs.max()))
+    PARITY_REPORT["cube"] = dict(throws=thrown, cube_floor_points=cube_floor, cube_robot_points=cube_hits, manifold_exact_match=n_match / n_samples,
+                                 state_err_median=float(np.median(errs)), state_err_p95=float(np.percentile(errs, 95)), state_err_max=float(errs.max()))
+    _write_parity_report()
+    assert thrown >= n // 2 and cube_floor > 0 and cube_hits > 0, (thrown, cube_floor, cube_hits)
+    assert n_match / n_samples >= 0.99
+    assert np.median(errs) <= 1e-5 and (errs <= STEP_RTOL).mean() >= 0.95 and errs.max() < 0.5, (np.median(errs), (errs <= STEP_RTOL).mean(), errs.max())
+
+
 @pytest.mark.parametrize("env_id", STEP_ENVS)
 def test_free_running_bounded_divergence(env_id, oracle_lib):
     """No teacher forcing: fp32 GPU vs fp64 oracle over a short horizon; divergence stays bounded and

@@ -28,6 +28,8 @@ def test_emul_teacher_forced(env_id, static, emul, oracle_lib):
         if m.task_kind != 0:
             pytest.skip("pendulums run on the runtime-topology kernel")
         assert e.use_static(True) > 0
+    elif m.has_cube:
+        pytest.skip("the cube is stepped by its static-topology kernel only")
     o.reset(seed=5); e.reset(seed=5)
     assert np.abs(np.stack([e.get_state(i) for i in range(n)]) - o.get_state()).max() < 1e-6
     rng = np.random.RandomState(1)
@@ -67,6 +69,62 @@ def test_emul_teacher_forced(env_id, static, emul, oracle_lib):
     errs = np.array(errs)
     assert alive.mean() >= 0.9
     assert np.median(errs) <= 1e-5 and (errs <= 1e-4).mean() >= 0.95 and errs.max() < 0.2
+
+
+def test_emul_cube_throw_flight_and_hits(emul, oracle_lib):
+    """FlagrunHarder's cube (gym_humanoid_flagrun.py:81-118): episodes advanced to frame 110 under the zoo policy (free running
+    on the oracle), then 45 teacher-forced steps that cover the throw at frame 120, the flight (drag, gravity), the hit on the
+    robot (box-vs-capsule/sphere contact rows between two bodies) and the cube coming to rest on the floor (box-plane manifold)."""
+    from roboschool_b200.policy import load_zoo_weights
+    m = envspec.load_env_model("RoboschoolHumanoidFlagrunHarder-v1")
+    assert m.has_cube == 1
+    n = 24
+    o = oracle_lib.OracleWorld(m, n)
+    e = emul.EmulWorld(m, n)
+    assert e.use_static(True) == 6
+    o.reset(seed=2); e.reset(seed=2)
+    wts = load_zoo_weights("RoboschoolHumanoidFlagrunHarder-v1")
+    obs = o.obs()[0]
+    for t in range(110):
+        obs, _, _ = o.step(oracle_lib.mlp_forward(wts, obs), auto_reset=True, seed=2)
+    errs, alive, thrown, cube_rows, hit = [], np.ones(n, bool), 0, 0, 0
+    S = m.state_dim
+    for t in range(45):
+        a = oracle_lib.mlp_forward(wts, obs).astype(np.float32).astype(np.float64)
+        so = o.get_state()
+        for i in range(n):
+            s32 = so[i].astype(np.float32).astype(np.float64)
+            o.set_state(i, s32, clear_contacts=False); e.set_state(i, s32, clear_contacts=False)
+            ep = o.get_episode(i); e.set_episode(i, ep[0], ep[1], ep[2], ep[3])
+            e.set_flag(i, *o.get_flag(i)); e.set_task_state(i, o.get_task_state(i))
+        if t == 0:     # the emulator has not followed the free-running prefix: adopt the oracle's contact cache
+            cnt, keys, data = o.contact_cache()
+            for i in range(n):
+                e.set_contacts(i, cnt[i], keys[i], data[i])
+        cube_before = so[:, S - 13:S - 10].copy()
+        obs, orw, od = o.step(a)
+        eo, erw, ed = e.step(a)
+        s_o = o.get_state()
+        thrown += int((np.abs(s_o[:, S - 13:S - 10] - cube_before).max(axis=1) > 2.0).sum())      # teleported to the throw position
+        for i in range(n):
+            if not alive[i]:
+                continue
+            co, ce = o.contacts(i), e.contacts(i)
+            if len(co) != len(ce) or not np.array_equal(co[:, :2], ce[:, :2]):
+                alive[i] = False
+                continue
+            if len(co):
+                nman = m.n_geoms + m.n_pairs
+                cube_rows += int((co[:, 0] == nman).sum()); hit += int((co[:, 0] > nman).sum())
+            s1, s2 = s_o[i], e.get_state(i)
+            errs.append(np.abs(s1 - s2).max() / max(1.0, np.abs(s1).max()))
+            if errs[-1] < 1e-4:
+                assert abs(orw[i] - erw[i]) < 5e-2 and od[i] == ed[i]
+    errs = np.array(errs)
+    assert thrown >= n // 2, thrown                    # robots lying on the ground are not pelted
+    assert cube_rows > 0 and hit > 0, (cube_rows, hit)
+    assert alive.mean() >= 0.8, alive.mean()
+    assert np.median(errs) <= 1e-5 and (errs <= 1e-4).mean() >= 0.9 and errs.max() < 0.5, (np.median(errs), (errs <= 1e-4).mean(), errs.max())
 
 
 def test_emul_auto_reset_matches_oracle(emul, oracle_lib):

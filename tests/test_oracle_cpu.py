@@ -87,11 +87,16 @@ def test_determinism_and_thread_independence(oracle_lib):
 @pytest.mark.parametrize("env_id", ["RoboschoolInvertedPendulum-v1", "RoboschoolInvertedPendulumSwingup-v1",
                                     "RoboschoolInvertedDoublePendulum-v1", "RoboschoolReacher-v1", "RoboschoolHopper-v1", "RoboschoolWalker2d-v1",
                                     "RoboschoolHalfCheetah-v1", "RoboschoolAnt-v1", "RoboschoolHumanoid-v1", "RoboschoolHumanoidFlagrun-v1",
-                                    "RoboschoolHumanoidFlagrunHarder-v1"])
+                                    "RoboschoolHumanoidFlagrunHarder-v1", "RoboschoolHumanoidFlagrunHarder-v1_cube"])
 def test_epilogue_matches_reference_python(env_id, oracle_lib):
-    """Golden vectors made by the reference's own gym_forward_walker.py (tools/gen_golden_epilogue.py)."""
+    """Golden vectors made by the reference's own gym_forward_walker.py (tools/gen_golden_epilogue.py).  `_cube`: FlagrunHarder
+    under its zoo policy -- the reference class throws the cube (gym_humanoid_flagrun.py:101-118) and every
+    set_pose_and_speed it issued is in the fixture."""
     g = np.load(os.path.join(GOLDEN, "epilogue_%s.npz" % env_id))
+    env_id = env_id.replace("_cube", "")
     m = envspec.load_env_model(env_id)
+    throws = {int(r[0]): r[1:] for r in g["ref_throws"]} if "ref_throws" in g else {}
+    n_throws = 0
     w = oracle_lib.OracleWorld(m, 1)
     w.reset(seed=int(g["seed"]))
     assert np.abs(w.obs()[0][0] - g["ref_obs0"]).max() < 1e-6
@@ -101,6 +106,12 @@ def test_epilogue_matches_reference_python(env_id, oracle_lib):
         obs, rew, done = w.step(g["actions"][t:t + 1])
         s = w.get_state(0)
         row += 1
+        if m.has_cube:
+            cube, s = s[-13:], s[:-13]
+            if row in throws:     # the reference class called aggressive_cube.set_pose_and_speed(...) in this step
+                assert np.abs(cube[:3] - throws[row][:3]).max() < 1e-9 and np.abs(cube[10:] - throws[row][3:]).max() < 1e-12
+                assert np.abs(cube[3:7] - [0, 0, 0, 1]).max() == 0 and np.abs(cube[7:10]).max() == 0
+                n_throws += 1
         # the replayed trajectory must be the one the fixture was recorded from
         assert np.abs(s[-2 * nd:-nd] - g["q"][row]).max() < 1e-9, "fixture stale: rerun tools/gen_golden_epilogue.py"
         assert np.abs(obs[0] - g["ref_obs"][t]).max() < 1e-6
@@ -120,6 +131,7 @@ def test_epilogue_matches_reference_python(env_id, oracle_lib):
             row += 1
     if m.flag_task:
         assert len(np.unique(g["ref_flags"][:, 0])) >= 2, "fixture must contain a flag reposition"
+    assert n_throws == len(throws)
 
 
 def test_behavioural_fixture_flagrun_chases_flags(oracle_lib):

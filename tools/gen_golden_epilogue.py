@@ -143,9 +143,15 @@ class Robot(object):
     def __init__(self, root, parts, joints):
         self.root_part, self.parts, self.joints = root, parts, joints
 
+    throws = None      # list that receives (frame index, x, y, z, vx, vy, vz) of every set_pose_and_speed on the cube
+    replay = None
+
     def query_position(self): pass
     def set_pose(self, p): pass
-    def set_pose_and_speed(self, p, vx, vy, vz): pass
+
+    def set_pose_and_speed(self, p, vx, vy, vz):
+        if self.throws is not None:
+            self.throws.append((self.replay.t,) + tuple(p.xyz()) + (float(np.float32(vx)), float(np.float32(vy)), float(np.float32(vz))))
 
 
 def make_cpp_household(model, replay, foot_names):
@@ -170,7 +176,10 @@ def make_cpp_household(model, replay, foot_names):
         def load_thingy(self, *a): return Thingy("stadium", -1, replay)
         def new_camera_free_float(self, *a): return None
         def debug_sphere(self, *a): return None
-        def load_urdf(self, *a): return Robot(Thingy("cube", -1, replay), [], [])
+        def load_urdf(self, *a):
+            r = Robot(Thingy("cube", -1, replay), [], [])
+            r.throws, r.replay = replay.throws, replay
+            return r
 
         def load_mjcf(self, fn):
             if fn.endswith("ground_plane.xml"):
@@ -223,7 +232,7 @@ class CounterRNG(object):
         return 0 if self._u() < 0.5 else 1
 
 
-def generate(env_id, cls_name, n_steps=60, seed=3, counter_rng=False, multi_episode=False):
+def generate(env_id, cls_name, n_steps=60, seed=3, counter_rng=False, multi_episode=False, zoo_policy=False, tag=""):
     from roboschool_b200 import envspec
     from oracle.oracle import OracleWorld
     m = envspec.compile_env(env_id, os.path.join(REF, "roboschool", "mujoco_assets"))
@@ -234,11 +243,20 @@ def generate(env_id, cls_name, n_steps=60, seed=3, counter_rng=False, multi_epis
     acts = rng.uniform(-1.3, 1.3, (n_steps, m.n_act))      # some outside [-1,1]: clip vs electricity cost
     R = Replay()
     R.poses, R.q, R.qd, R.foot_flags = [], [], [], []
+    R.throws = []
+    oracle_cube = []      # cube pos3 + vel3 after every step (FlagrunHarder)
+    if zoo_policy:        # actions of the reference's own pretrained policy (+ noise): the robot has to stay on its feet
+        from roboschool_b200.policy import load_zoo_weights    # beyond frame 100 for the cube to be thrown at it
+        from oracle.oracle import mlp_forward
+        wts = load_zoo_weights(env_id)
     oracle_obs, oracle_rew, oracle_done, oracle_r5 = [], [], [], []
 
     def record():
         s = o.get_state(0)
         nd = m.n_dof
+        if m.has_cube:
+            oracle_cube.append(np.concatenate([s[-13:-10], s[-3:]]))
+            s = s[:-13]
         R.poses.append(o.link_poses(0).copy())
         R.q.append(s[-2 * nd:-nd].copy())
         R.qd.append(s[-nd:].copy())
@@ -249,8 +267,12 @@ def generate(env_id, cls_name, n_steps=60, seed=3, counter_rng=False, multi_epis
     obs0 = o.obs()[0][0].copy()
     reset_after = []          # steps after which the env was reset (multi_episode): the next frame is the reset state
     oracle_reset_obs = {}
+    cur_obs = o.obs()[0]
     for t in range(n_steps):
+        if zoo_policy:
+            acts[t] = mlp_forward(wts, cur_obs)[0] + 0.05 * rng.standard_normal(m.n_act)
         ob, rw, dn = o.step(acts[t:t + 1])
+        cur_obs = ob
         record()
         oracle_obs.append(ob[0].copy()); oracle_rew.append(rw[0]); oracle_done.append(dn[0]); oracle_r5.append(o.rewards5(0))
         if multi_episode and dn[0]:
@@ -258,6 +280,7 @@ def generate(env_id, cls_name, n_steps=60, seed=3, counter_rng=False, multi_epis
             record()
             reset_after.append(t)
             oracle_reset_obs[t] = o.obs()[0][0].copy()
+            cur_obs = o.obs()[0]
 
     # ---- run the reference's Python over the recorded trajectory
     install_stub_gym()
@@ -301,13 +324,21 @@ def generate(env_id, cls_name, n_steps=60, seed=3, counter_rng=False, multi_epis
         np.random.choice = np_choice
         for t in reset_after:
             assert np.abs(ref_reset_obs[t] - oracle_reset_obs[t]).max() < 1e-6, ("reset obs", t)
-    out = os.path.join(ROOT, "tests", "golden", "epilogue_%s.npz" % env_id)
+    throws = np.array(R.throws, dtype=np.float64).reshape(len(R.throws), 7)
+    if m.has_cube:        # every throw of the reference class lands on the oracle's cube: same pose, same (float) velocity
+        assert len(throws) >= 3 or not zoo_policy, "fixture without throws"
+        oc = np.array(oracle_cube)
+        for row in throws:
+            fi = int(row[0])
+            assert np.abs(oc[fi][:3] - row[1:4]).max() < 1e-9 and np.abs(oc[fi][3:] - row[4:7]).max() < 1e-12, ("throw", fi, oc[fi], row)
+    out = os.path.join(ROOT, "tests", "golden", "epilogue_%s%s.npz" % (env_id, tag))
     os.makedirs(os.path.dirname(out), exist_ok=True)
     np.savez_compressed(out, seed=seed, actions=acts, poses=np.array(R.poses), q=np.array(R.q), qd=np.array(R.qd),
                         foot_flags=np.array(R.foot_flags, dtype=np.int32).reshape(len(R.foot_flags), -1, 2),
                         ref_obs0=np.asarray(ref_obs0, dtype=np.float64), ref_obs=np.array(ref_obs), ref_rew=np.array(ref_rew),
                         ref_done=np.array(ref_done), ref_rewards5=np.array(ref_r5), ref_flags=np.array(ref_flags, dtype=np.float64),
                         ref_task=np.array(ref_task, dtype=np.int32), reset_after=np.array(reset_after, dtype=np.int32),
+                        ref_throws=throws,
                         ref_reset_obs=np.array([ref_reset_obs[t] for t in reset_after]).reshape(len(reset_after), m.obs_dim))
     d_obs = np.abs(np.array(ref_obs) - np.array(oracle_obs)).max()
     d_rew = np.abs(np.array(ref_rew) - np.array(oracle_rew)).max()
@@ -329,3 +360,7 @@ if __name__ == "__main__":
     generate("RoboschoolHumanoidFlagrun-v1", "RoboschoolHumanoidFlagrun", n_steps=170, counter_rng=True)
     # FlagrunHarder: several episodes (the task curriculum and the stand-up / roll-over starts are part of the fixture)
     generate("RoboschoolHumanoidFlagrunHarder-v1", "RoboschoolHumanoidFlagrunHarder", n_steps=420, counter_rng=True, multi_episode=True)
+    # FlagrunHarder driven by the zoo policy, so that the robot walks past frame 100 and is pelted by the cube (throws, hits on
+    # the robot, feet touching the cube) -- every set_pose_and_speed of the reference class is checked against the oracle's cube
+    generate("RoboschoolHumanoidFlagrunHarder-v1", "RoboschoolHumanoidFlagrunHarder", n_steps=700, counter_rng=True, multi_episode=True,
+             zoo_policy=True, tag="_cube")

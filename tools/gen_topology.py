@@ -50,6 +50,7 @@ def emit(env_id, cname):
     n = m.n_links
     s = "// %s (%s)\nstruct %s {\n" % (env_id, m.meta["xml"], cname)
     s += "    static constexpr int NL = %d, ND = %d, FIXED_BASE = %d;\n" % (n, m.n_dof, m.fixed_base)
+    s += "    static constexpr int CUBE = 0;   // 1: a free cube (rs_model_desc.has_cube) steps next to the robot\n"
     I = lambda v: str(int(v))
     s += arr("parent", [m.parent[i] for i in range(n)], "int", I)
     s += arr("jtype", [m.jtype[i] for i in range(n)], "int", I)
@@ -114,6 +115,8 @@ if __name__ == "__main__":
     for env_id, cname in MODELS:
         s, sig = emit(env_id, cname)
         out += s
+    out += ("// RoboschoolHumanoidFlagrunHarder-v1: the Humanoid plus the thrown cube (gym_humanoid_flagrun.py:81-118)\n"
+            "struct TopoHumanoidCube : TopoHumanoid {\n    static constexpr int CUBE = 1;\n};\n\n")
     out += "}  // namespace rs\n"
     open(OUT, "w").write(out)
     print("wrote", OUT, len(out), "bytes")
