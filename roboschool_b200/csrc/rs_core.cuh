@@ -1468,9 +1468,13 @@ RS_HD double harder_potential(const DevModel& M, Episode& E, double dist, float 
 // five np_random draws from the flag stream (angle, speed, 3 x velocity noise), then Robot::set_pose_and_speed
 // (python-binding.cpp:289: pose in doubles, velocity through float, identity orientation, angular velocity zeroed).
 // Worlds without the cube still consume the draws.
-template <int NL, int MC, bool SL>
+// CUBE: compile-time, true only in the kernels instantiated for a cube topology (the throw is double-precision trigonometry:
+// ~1.5 k instructions that every other step kernel would otherwise carry in its epilogue).
+template <bool CUBE, int NL, int MC, bool SL>
 RS_HD float harder_alive(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, float z, float z1, float z2, uint32_t seed, uint32_t env_id) {
     if (E.frame % 30 == 0 && E.frame > 100 && E.on_ground == 0) {
+        if constexpr (!CUBE) E.flag_draws += 5;
+        else {
         double u[5];
 #pragma unroll
         for (int k = 0; k < 5; k++) u[k] = (double)rs_uniform(seed, env_id, E.episode, 2000u + E.flag_draws++);
@@ -1492,6 +1496,7 @@ RS_HD float harder_alive(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, flo
                 W.cw[k] = 0.f;
             }
             W.cquat[0] = W.cquat[1] = W.cquat[2] = 0.f; W.cquat[3] = 1.f;
+        }
         }
     }
     if (z < 0.8f) {
@@ -1559,7 +1564,7 @@ RS_HD bool calc_state_flag(const DevModel& M, const Work<NL, MC, SL>& W, Episode
 }
 
 // `cs(obs, ostride, &dist, &pitch, &at_limit)` computes the observation (generic or static kinematics)
-template <int NL, int MC, bool SL, class CS>
+template <bool CUBE = false, int NL, int MC, bool SL, class CS>
 RS_HD void epilogue_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, const float* act, int astride, float* obs, int ostride, StepOut& out, CS&& cs,
                          uint32_t seed = 0, uint32_t env_id = 0) {
     double dist; float pitch; int at_limit;
@@ -1601,7 +1606,7 @@ RS_HD void epilogue_with(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, con
     float z = obs[0] + E.initial_z;
     const float z_body = W.pos[M.body_link + 1][2], z_aux = W.pos[(M.task_link >= 0 ? M.task_link : M.body_link) + 1][2];
     float alive;
-    if (M.flag_task == 2) alive = harder_alive(M, W, E, z, z_body, z_aux, seed, env_id);
+    if (M.flag_task == 2) alive = harder_alive<CUBE>(M, W, E, z, z_body, z_aux, seed, env_id);
     else if (M.alive_rule == RS_ALIVE_Z_AND_PITCH) alive = (z > M.alive_z && fabsf(pitch) < 1.0f) ? M.alive_bonus : -1.f;
     else if (M.alive_rule == RS_ALIVE_Z) alive = (z > M.alive_z) ? M.alive_bonus : -1.f;
     else if (M.alive_rule == RS_ALIVE_CHEETAH)   // feet_contact still holds the previous step's flags here

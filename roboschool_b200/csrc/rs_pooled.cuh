@@ -49,6 +49,7 @@ struct WarpHost {
     RS_HD int excl_scan(int v, int& total) const { total = v; return 0; }
     RS_HD void sync() const {}
     RS_HD void cta_sync() const {}
+    RS_HD void extra_sync() const {}
 };
 #ifdef __CUDACC__
 // WPC: warps per CTA.  With WPC > 1 the warps of a CTA are re-aligned at the phase boundaries of the sub-step
@@ -56,9 +57,17 @@ struct WarpHost {
 template <int WPC>
 struct WarpDev {
     static constexpr int WIDTH = 32;
+    bool cluster = false;      // launched as a thread-block cluster: the phase barriers span the CTAs of the cluster
+    bool extra = false;        // two more re-alignment points inside the solve phase (before the row tasks, before the PGS): pays
+                               // when the envs of a batch differ a lot in row count (FlagrunHarder: 6.0 -> 5.0 ms per step), costs ~5 %
+                               // on homogeneous batches
+    RS_HD void extra_sync() const { if (extra) cta_sync(); }
     RS_HD void cta_sync() const {
 #ifdef __CUDA_ARCH__
         if (WPC > 1) __syncthreads();
+        // Cluster-wide re-alignment: the CTAs of a cluster sit on SMs of one GPC and walk the same (instruction-fetch bound)
+        // stream; keeping them on the same lines lets the GPC-level instruction cache serve all of them with one L2 fetch.
+        if (cluster) asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
 #endif
     }
     RS_HD int lane() const {
@@ -225,22 +234,40 @@ RS_HDN void pooled_response_second(const LinkCache<STRIDE>& lc, int body, const 
     pooled_response<T, 3, true, false>(lc, body, wr, 0.f, pool, slot0, denom);
 }
 
-// resolveSingleConstraintRowGeneric on a pooled row record
-template <int ND, class Pool>
+// resolveSingleConstraintRowGeneric on a pooled row record, over the dofs [K0, K1) the row acts on: a row between the robot
+// and the floor (or itself) has exact zeros on the cube's dofs and vice versa, so leaving those words out changes nothing
+// (0 * dv adds an exact zero to the dot product, u = 0 leaves dv alone) -- and they are then never written either.
+template <int K0, int K1, int ND, class Pool>
 RS_HD void resolve_pooled(const Pool& pool, int slot, float* dv, float rhs, float invd, float lo, float hi, float& applied) {
-    float j[ND], u[ND];
+    float j[K1 - K0], u[K1 - K0];
 #pragma unroll
-    for (int k = 0; k < ND; k++) { j[k] = pool.at(slot, k); u[k] = pool.at(slot, ND + k); }
+    for (int k = K0; k < K1; k++) { j[k - K0] = pool.at(slot, k); u[k - K0] = pool.at(slot, ND + k); }
     float dot = 0.f;
 #pragma unroll
-    for (int k = 0; k < ND; k++) dot += j[k] * dv[k];
+    for (int k = K0; k < K1; k++) dot += j[k - K0] * dv[k];
     float dimp = rhs - dot * invd;
     float sum = applied + dimp;
     if (sum < lo) { dimp = lo - applied; applied = lo; }
     else if (sum > hi) { dimp = hi - applied; applied = hi; }
     else applied = sum;
 #pragma unroll
-    for (int k = 0; k < ND; k++) dv[k] += u[k] * dimp;
+    for (int k = K0; k < K1; k++) dv[k] += u[k - K0] * dimp;
+}
+// dofs of a contact row by manifold id: 0 robot only, 1 cube only (cube-floor), 2 both (robot geom vs cube)
+template <class T>
+RS_HD int row_span(const DevModel& M, int key) {
+    if (T::CUBE == 0) return 0;
+    const int ngp = M.n_geoms + M.n_pairs;
+    return key < ngp ? 0 : (key == ngp ? 1 : 2);
+}
+template <class T, class Pool>
+RS_HD void resolve_span(int span, const Pool& pool, int slot, float* dv, float rhs, float invd, float lo, float hi, float& applied) {
+    constexpr int nd = nd_of<T>(), ndr = 6 + T::ND;
+    if constexpr (T::CUBE != 0) {
+        if (span == 1) { resolve_pooled<ndr, nd, nd>(pool, slot, dv, rhs, invd, lo, hi, applied); return; }
+        if (span == 2) { resolve_pooled<0, nd, nd>(pool, slot, dv, rhs, invd, lo, hi, applied); return; }
+    }
+    resolve_pooled<0, ndr, nd>(pool, slot, dv, rhs, invd, lo, hi, applied);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -301,7 +328,7 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
     const int lbase = warp.excl_scan(n_nc, LT);
     const int cbase = warp.excl_scan(nc, CT);
     W.n_rows = n_nc + 3 * nc; W.n_contacts = nc;
-    if (LT + CT == 0) return;   // warp-uniform
+    if (LT + CT == 0) { warp.extra_sync(); warp.extra_sync(); return; }   // warp-uniform (the CTA-wide syncs below must still be matched)
     const int cur = W.cur;
     for (int j = 0; j < n_nc; j++) pool.at(lbase + j, 0) = i2f(lim_code[j]);
     for (int ci = 0; ci < nc; ci++) {
@@ -320,7 +347,7 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
             if (bA == CB || bB == CB) {
                 // The cube's side of the three rows is written by the owner lane itself (its transform is not in the shared link
                 // cache): J = (r x n, n) and M^-1 J^T = (R^T I^-1 R (r x n), n / m) on the cube's world-frame dofs, plus this side's
-                // J.M^-1 J^T.  A cube-floor point has no robot side: the owner zero-fills the robot words and marks the task done.
+                // J.M^-1 J^T.  A cube-floor point has no robot side: the task is marked done.
                 const float* lp = bA == CB ? cd : cd + 3;           // contact point in cube coords
                 const float sgn = bA == CB ? 1.f : -1.f;
                 float rw[3], cden[3];
@@ -342,12 +369,9 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
                     }
                     cden[w] = dot3(jw, uw) + dot3(nn, nn) * im;
                 }
-                if (bA == CB) {
+                if (bA == CB) {     // (the robot words of these rows are never read: row_span)
 #pragma unroll
-                    for (int w = 0; w < 3; w++) {
-                        for (int k = 0; k < ndr; k++) { pool.at(slot + w, k) = 0.f; pool.at(slot + w, nd + k) = 0.f; }
-                        pool.at(slot + w, 2 * nd) = cden[w];
-                    }
+                    for (int w = 0; w < 3; w++) pool.at(slot + w, 2 * nd) = cden[w];
                     pool.at(slot, 0) = i2f(lane | (255 << 8));       // body 255: nothing left to do for the helpers
                     continue;
                 }
@@ -396,6 +420,7 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
         }
     }
     warp.sync();
+    warp.extra_sync();
     // ---- all lanes: limit-row tasks ----
     for (int t0 = 0; t0 < LT; t0 += Warp::WIDTH) {
         const int t = t0 + lane;
@@ -406,10 +431,6 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
             LinkCache<STRIDE> lco{lc_lane0 + o};
             float dn[1];
             pooled_response<T, 1, false, true>(lco, body, (const float (*)[6]) nullptr, dir, pool, t, dn);
-            if constexpr (T::CUBE != 0) {
-#pragma unroll
-                for (int k = ndr; k < nd; k++) { pool.at(t, k) = 0.f; pool.at(t, nd + k) = 0.f; }
-            }
             pool.at(t, 2 * nd) = dn[0];
         }
     }
@@ -455,19 +476,12 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
                 dsum[0] += dn[0]; dsum[1] += dn[1]; dsum[2] += dn[2];
             }
             if (cube_side) { dsum[0] += desc[13]; dsum[1] += desc[14]; dsum[2] += desc[15]; }
-            if constexpr (T::CUBE != 0) {
-                if (!cube_side) {     // no cube in this contact: its dofs take no part in the rows
-#pragma unroll
-                    for (int w = 0; w < 3; w++)
-#pragma unroll
-                        for (int k = ndr; k < nd; k++) { pool.at(slot + w, k) = 0.f; pool.at(slot + w, nd + k) = 0.f; }
-                }
-            }
 #pragma unroll
             for (int w = 0; w < 3; w++) pool.at(slot + w, 2 * nd) = dsum[w];
         }
     }
     warp.sync();
+    warp.extra_sync();
     if (!valid || W.n_rows == 0) return;
     // ---- owner: right-hand sides, then PGS in Bullet's order ----
     float vel[nd];
@@ -484,18 +498,27 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
         for (int k = 0; k < 3; k++) { vel[ndr + k] = W.cw[k]; vel[ndr + 3 + k] = W.cv[k]; }
     }
     float r_rhs[NNC + 3 * MC], r_invd[NNC + 3 * MC], r_applied[NNC + 3 * MC];
-    auto row_relvel = [&](int slot) {
-        float j[nd], s = 0.f;
+    auto row_relvel = [&](int slot, int span) {     // J . v over the dofs the row acts on (row_span)
+        float s = 0.f;
+        if (span != 1) {
+            float j[ndr];
 #pragma unroll
-        for (int k = 0; k < nd; k++) j[k] = pool.at(slot, k);
+            for (int k = 0; k < ndr; k++) j[k] = pool.at(slot, k);
 #pragma unroll
-        for (int k = 0; k < nd; k++) s += j[k] * vel[k];
+            for (int k = 0; k < ndr; k++) s += j[k] * vel[k];
+        }
+        if constexpr (T::CUBE != 0) {
+            if (span != 0) {
+#pragma unroll
+                for (int k = ndr; k < nd; k++) s += pool.at(slot, k) * vel[k];
+            }
+        }
         return s;
     };
     // local row index: [0,n_nc) limits ; n_nc + 3*ci + w  contact ci, direction w
     for (int j = 0; j < n_nc; j++) {
         const int slot = lbase + j;
-        const float relvel = row_relvel(slot), denom = pool.at(slot, 2 * nd), pen = lim_pen[j];
+        const float relvel = row_relvel(slot, 0), denom = pool.at(slot, 2 * nd), pen = lim_pen[j];
         const float invd = denom > RS_FLT_EPS ? 1.0f / denom : 0.f;
         const float erp = pen > M.split_thresh ? M.erp : M.erp2;
         if (lim_code[j] & (1 << 17)) r_rhs[j] = (pen - relvel) * invd;      // motor row: pen holds the desired velocity
@@ -504,10 +527,11 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
     }
     for (int ci = 0; ci < nc; ci++) {
         const float pen = W.cdat[cur][ci][9];
+        const int span = row_span<T>(M, W.ckey[cur][ci]);
 #pragma unroll
         for (int w = 0; w < 3; w++) {
             const int slot = LT + 3 * (cbase + ci) + w, row = n_nc + 3 * ci + w;
-            const float relvel = row_relvel(slot), denom = pool.at(slot, 2 * nd);
+            const float relvel = row_relvel(slot, span), denom = pool.at(slot, 2 * nd);
             const float invd = denom > RS_FLT_EPS ? 1.0f / denom : 0.f;
             float rhs;
             if (w == 0) {
@@ -527,11 +551,11 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
         for (int j = 0; j < n_nc; j++) {
             const int row = (it & 1) ? j : n_nc - 1 - j;
             const float mi = mot_imp[row];      // < 0: limit row (unilateral) ; > 0: motor row (+- impulse bound)
-            resolve_pooled<nd>(pool, lbase + row, dv, r_rhs[row], r_invd[row], mi > 0.f ? -mi : 0.f, mi > 0.f ? mi : lim_hi_imp, r_applied[row]);
+            resolve_span<T>(0, pool, lbase + row, dv, r_rhs[row], r_invd[row], mi > 0.f ? -mi : 0.f, mi > 0.f ? mi : lim_hi_imp, r_applied[row]);
         }
         for (int ci = 0; ci < nc; ci++) {
             const int row = n_nc + 3 * ci;
-            resolve_pooled<nd>(pool, LT + 3 * (cbase + ci), dv, r_rhs[row], r_invd[row], 0.f, 1e10f, r_applied[row]);
+            resolve_span<T>(row_span<T>(M, W.ckey[cur][ci]), pool, LT + 3 * (cbase + ci), dv, r_rhs[row], r_invd[row], 0.f, 1e10f, r_applied[row]);
         }
         for (int ci = 0; ci < nc; ci++) {
             const float tot = r_applied[n_nc + 3 * ci];
@@ -544,7 +568,7 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
 #pragma unroll
                 for (int w = 1; w < 3; w++) {
                     const int row = n_nc + 3 * ci + w;
-                    resolve_pooled<nd>(pool, LT + 3 * (cbase + ci) + w, dv, r_rhs[row], r_invd[row], -fr * tot, fr * tot, r_applied[row]);
+                    resolve_span<T>(row_span<T>(M, key), pool, LT + 3 * (cbase + ci) + w, dv, r_rhs[row], r_invd[row], -fr * tot, fr * tot, r_applied[row]);
                 }
             }
         }

@@ -34,12 +34,9 @@ static void step_env_static(Emul* e, int i, const float* a, int auto_reset, uint
     for (int s = 0; s < M.frame_skip; s++) substep_pooled<T>(WarpHost(), true, M, W, pool, lc, lc.p);
     float* obs = &e->obs[(size_t)i * M.obs_dim];
     auto cs = [&](float* o, int os, double* dist, float* pitch, int* al) { static_calc_state<T>(M, W, lc, e->ep[i], o, os, dist, pitch, al); };
-    epilogue_with(M, W, e->ep[i], a, 1, obs, 1, e->out[i], cs, seed, env0 + i);
+    epilogue_with<T::CUBE != 0>(M, W, e->ep[i], a, 1, obs, 1, e->out[i], cs, seed, env0 + i);
     int done = e->out[i].done;
-    if (auto_reset && (done || e->ep[i].frame >= M.max_episode_steps)) {   // compact reset observation, like k_step_static
-        auto cs_reset = [&](float* o, int os, double* dist, float* pitch, int* al) { reset_calc_state(M, W, e->ep[i], o, os, dist, pitch, al); };
-        env_reset_with(M, W, e->ep[i], seed, env0 + i, obs, 1, cs_reset); done = 1;
-    }
+    if (auto_reset && (done || e->ep[i].frame >= M.max_episode_steps)) { env_reset(M, W, e->ep[i], seed, env0 + i, obs, 1); done = 1; }   // k_reset_deferred
     e->rew[i] = e->out[i].reward; e->done[i] = done;
 }
 template <class T>

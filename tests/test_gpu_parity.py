@@ -293,7 +293,7 @@ def test_policy_known_answers():
         assert np.abs(got - ref).max() <= 5e-3 * max(1.0, np.abs(ref).max()), env_id
 
 
-def test_vec_env_full_size_properties():
+def test_vec_env_full_size_properties(monkeypatch):
     """BASELINE-size run (32768 Humanoid envs): finite, deterministic, independent of batch position."""
     import torch
     from roboschool_b200.vec_env import VecEnv
@@ -314,7 +314,9 @@ def test_vec_env_full_size_properties():
     for a, (o, r, d) in zip(acts, outs):
         o2, r2, d2 = env2.step(a)
         assert torch.equal(o, o2) and torch.equal(r, r2) and torch.equal(d, d2)
-    # sharding invariance: envs [1000, 1256) stepped in a small world with env_id0=1000 give the same results
+    # sharding invariance: envs [1000, 1256) stepped in a small world with env_id0=1000 give the same results (same compiled
+    # kernel on both sides -- 7-warp CTAs -- since bit-identity cannot be asked of two different instantiations)
+    monkeypatch.setenv("RS_WPC", "7")
     env3 = VecEnv("RoboschoolHumanoid-v1", 256, 0, env_id0=1000)
     o3 = env3.reset(seed=1)
     assert torch.equal(o3, obs[1000:1256])
@@ -471,7 +473,7 @@ def test_behavioural_fixture_on_gpu_v0_policies(env_id, min_return, min_len):
 
 
 @pytest.mark.parametrize("env_id,n", [("RoboschoolHopper-v1", 4096), ("RoboschoolAnt-v1", 65536)])
-def test_baseline_config_sizes_properties(env_id, n):
+def test_baseline_config_sizes_properties(env_id, n, monkeypatch):
     """BASELINE.json configs[1] (Hopper, 4096 envs) and configs[2] (Ant, 65536 envs) at full size, through the
     size-independent properties: finite outputs, bit-identical reruns, independence of the position in the batch
     (a slice stepped in its own small world with the matching env_id0), contact pools consistent with feet flags."""
@@ -492,6 +494,11 @@ def test_baseline_config_sizes_properties(env_id, n):
         o2, r2, d2 = env2.step(a)
         assert torch.equal(o, o2) and torch.equal(r, r2) and torch.equal(d, d2)
     off = n - 300
+    # bit-identity is a property of ONE compiled kernel: a 300-env world would pick 1-warp CTAs, the full-size one 7-warp
+    # CTAs from 24576 envs up, and ptxas contracts multiply-adds differently in the two instantiations (measured on the Ant:
+    # observations differ by 1-7 ulp, 1e-7 .. 9e-7, between them; identical with the same CTA shape)
+    if n >= 24576:
+        monkeypatch.setenv("RS_WPC", "7")
     env3 = VecEnv(env_id, 300, 0, env_id0=off)
     assert torch.equal(env3.reset(seed=2), obs0[off:])
     for a, (o, r, d) in zip(acts, outs):
@@ -510,8 +517,6 @@ def test_free_flight_momentum_converges_on_gpu(variant, monkeypatch):
     dynamics, so its drift under the semi-implicit integrator must shrink ~linearly with dt -- a check of the ABA
     sweeps, Coriolis and bias terms of the step kernel (the compile-time-topology one and the runtime-topology twin)."""
     from roboschool_b200.world import BatchedWorld
-    if variant == "generic":
-        monkeypatch.setenv("RS_FORCE_GENERIC", "1")
     drift = []
     n = 64
     for div in (1, 4, 16):
@@ -522,6 +527,8 @@ def test_free_flight_momentum_converges_on_gpu(variant, monkeypatch):
             m.has_limit[i] = 0
         for k in range(m.n_act):
             m.act_gain[k] = 0.0          # actions produce no torque: free motion
+        if variant == "generic":         # any model that is not one of the generated topologies runs on the runtime-topology
+            m.mass[2] *= 1.01            # kernel (e.g. everything loaded through load_mjcf): 1 % more mass on one link is enough
         w = BatchedWorld(m, n, 0)
         assert (w.L.rs_world_kernel_variant(w.h) > 0) == (variant == "static-pooled")
         w.reset(seed=2)

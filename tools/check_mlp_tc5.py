@@ -1,6 +1,5 @@
 """Development check of the tcgen05 policy kernel against numpy float64 (run on the GPU box, under `timeout`)."""
 import os, sys, time
-os.environ["RS_MLP_TC5"] = sys.argv[1] if len(sys.argv) > 1 else "1"
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np, torch
 from roboschool_b200.policy import ZooPolicy, load_zoo_weights

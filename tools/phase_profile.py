@@ -19,6 +19,10 @@ st = torch.cuda.current_stream().cuda_stream
 W.rollout_reset(seed=0, stream=st)
 W.rollout(pol, warm, stream=st)
 torch.cuda.synchronize()
+if len(sys.argv) > 4 and sys.argv[4] == "stagger":
+    W.set_episode(frame=np.random.RandomState(7).randint(0, m.max_episode_steps - 1, size=n).astype(np.int32))
+    W.rollout(pol, 100, stream=st)
+    torch.cuda.synchronize()
 names = ["kinematics", "collide", "aba", "solve", "integrate", "epilogue+store", "load+action", "total"]
 acc = np.zeros(8)
 for _ in range(5):
