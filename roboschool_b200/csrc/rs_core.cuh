@@ -1373,60 +1373,6 @@ RS_HD void calc_state(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, float*
     calc_state_core(M, W, E, bp, bq, bv, obs, ostride, dist, pitch, at_limit);
 }
 
-// First observation of a new episode for the static-topology kernels.  A reset happens once per ~1000 env steps, in one lane
-// of one warp, after the other warps of the CTA have finished: whatever it executes is COLD code fetched by a lone warp
-// (measured: the fully unrolled static_calc_state made every step of a staggered batch 0.14 ms longer).  So the world
-// transforms come from this compact loop over the runtime topology tables instead (a few hundred instructions), and the
-// link velocities are not swept at all: a freshly reset env is at rest (env_reset_with zeroes qd, base and joint speeds).
-template <int NL, int MC, bool SL>
-RS_HD void reset_calc_state(const DevModel& M, Work<NL, MC, SL>& W, Episode& E, float* obs, int ostride, double* dist, float* pitch, int* at_limit) {
-    float Rbw[9];
-    quat_to_mat(Rbw, W.bquat[0], W.bquat[1], W.bquat[2], W.bquat[3]);
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) W.Rwl[0][i * 3 + j] = Rbw[j * 3 + i];
-    W.pos[0][0] = W.bpos[0]; W.pos[0][1] = W.bpos[1]; W.pos[0][2] = W.bpos[2];
-#pragma unroll 1
-    for (int i = 0; i < M.n_links; i++) {
-        const int p = M.parent[i];
-        float R[9];
-        if (M.jtype[i] == RS_JOINT_REVOLUTE) {
-            const float half = -0.5f * W.q[M.dof_idx[i]];
-            const float s = sinf(half), c = cosf(half);
-            float Ra[9];
-            quat_to_mat(Ra, M.axis[i][0] * s, M.axis[i][1] * s, M.axis[i][2] * s, c);
-            mul33(R, Ra, M.R0[i]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 9; k++) R[k] = M.R0[i][k];
-        }
-        float rv[3], rw[3];
-        mulv(rv, R, M.e_vec[i]);
-        rv[0] += M.d_vec[i][0]; rv[1] += M.d_vec[i][1]; rv[2] += M.d_vec[i][2];
-        if (M.jtype[i] == RS_JOINT_PRISMATIC) {
-            const float qq = W.q[M.dof_idx[i]];
-            rv[0] += qq * M.axis[i][0]; rv[1] += qq * M.axis[i][1]; rv[2] += qq * M.axis[i][2];
-        }
-        mul33(W.Rwl[i + 1], R, W.Rwl[p + 1]);
-        tmulv(rw, W.Rwl[i + 1], rv);
-        W.pos[i + 1][0] = W.pos[p + 1][0] + rw[0]; W.pos[i + 1][1] = W.pos[p + 1][1] + rw[1]; W.pos[i + 1][2] = W.pos[p + 1][2] + rw[2];
-    }
-    const int body = M.body_link + 1;
-    float bp[3] = {W.pos[body][0], W.pos[body][1], W.pos[body][2]}, bq[4];
-    const float bv[3] = {0.f, 0.f, 0.f};
-    if (body == 0) { bq[0] = W.bquat[0]; bq[1] = W.bquat[1]; bq[2] = W.bquat[2]; bq[3] = W.bquat[3]; }
-    else {
-        float Rlw[9];
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int j = 0; j < 3; j++) Rlw[i * 3 + j] = W.Rwl[body][j * 3 + i];
-        mat_to_quat(Rlw, bq);
-    }
-    calc_state_core(M, W, E, bp, bq, bv, obs, ostride, dist, pitch, at_limit);
-}
-
 // RoboschoolHumanoidFlagrun.flag_reposition (gym_humanoid_flagrun.py:21-35); draws come from the counter-based RNG
 // in the reference's order: [randint(2) if first,] uniform x [, uniform y]
 RS_HD void flag_reposition(const DevModel& M, Episode& E, uint32_t seed, uint32_t env_id, bool first) {

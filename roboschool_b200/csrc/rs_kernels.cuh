@@ -16,7 +16,6 @@ struct DevBuf {
     double* target; int* flag_timeout; uint32_t* flag_draws;   // Flagrun: target [2][N], steps left, RNG draws used
     int* hx_i; double* hx_d;   // FlagrunHarder: [7][N] task, on_ground, crawl_valid, done_latch, hist[3] ; [2][N] crawl_start, crawl_ignored
     float* rows; float* tau; float* rewards5; int* nrows; int* ncontacts;
-    uint8_t* reset_mask;       // [N] envs whose reset was deferred by the step kernel (auto_reset 2), cleared by k_reset_deferred
     float* motor;              // joint motors [5][n_dof][N] (kp, kd, target pos, target vel, impulse bound), nullptr until one is set
     int N, S, MCcap, rec, maxr;
 };
@@ -171,12 +170,9 @@ __global__ void __launch_bounds__(32 * WPC) k_step_static(const __grid_constant_
         st_rew = out.reward; st_rows = W.n_rows; st_con = W.n_contacts; st_steps = 1; st_nf = finite ? 0 : 1;
         if (finished) { st_ep = 1; st_len = E.frame; }
         if (auto_reset && finished) {
-            // auto_reset 2: the reset is DEFERRED to k_reset_deferred, launched right behind this kernel (rs_step.cu launch_step).
-            // A reset runs in one lane of one warp after the rest of its CTA has finished, i.e. as cold code fetched by a lone
-            // warp: in-kernel it made every step of a steady-state batch (n / 1000 resets per step) ~0.19 ms longer; the small
-            // runtime-topology reset kernel does the same work for all finished envs of the step in ~10 us.
-            if (auto_reset == 2) B.reset_mask[e] = 1;
-            else env_reset_with(M, W, E, seed, env_id0 + e, o, 1, cs);
+            // (a reset runs in one lane after the rest of its CTA has finished: measured, moving it into a separate small kernel
+            // does not pay -- what a steady-state batch costs over a synchronised one is the spread of per-CTA times, not this code)
+            env_reset_with(M, W, E, seed, env_id0 + e, o, 1, cs);
             dn = 1;
         }
         rew[e] = out.reward; done[e] = (uint8_t)dn;

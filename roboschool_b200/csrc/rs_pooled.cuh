@@ -35,7 +35,8 @@ struct RowPool {
     RS_HD float& at(int slot, int k) const { return p[k * CAP + slot]; }
 };
 // slots a warp of WIDTH envs can need: every env at its row capacity
-template <class T, int MC, int WIDTH> constexpr int pool_cap() { return WIDTH * (2 * T::NL + 3 * MC); }   // limit + motor row per joint, 3 per contact
+// limit + motor row per joint, 3 per contact; cube topologies: + one task-directory slot per contact (see solve_pooled)
+template <class T, int MC, int WIDTH> constexpr int pool_cap() { return WIDTH * (2 * T::NL + 3 * MC + (T::CUBE ? MC : 0)); }
 // words of a row record: [0,nd) J ; [nd,2nd) M^-1 J^T ; [2nd] denominator.  A task descriptor lives in
 // words [0,25) of the task's first row slot until the task is executed (needs 2*nd+1 >= 25).
 constexpr int POOL_DESC_WORDS = 25;
@@ -328,6 +329,16 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
     const int lbase = warp.excl_scan(n_nc, LT);
     const int cbase = warp.excl_scan(nc, CT);
     W.n_rows = n_nc + 3 * nc; W.n_contacts = nc;
+    // Cube topologies: a cube-floor point needs no helper (the owner writes its rows), and a resting cube has four of them in
+    // every env -- so the helpers' task list is the compacted list of contacts WITH a robot side: a directory of row slots
+    // behind the rows of the warp (slots [LT + 3 CT, LT + 3 CT + TT)), filled by the owners.
+    int TT = CT, tbase = 0, n_rt = 0;
+    if constexpr (T::CUBE != 0) {
+        if (valid) for (int ci = 0; ci < nc; ci++) n_rt += W.ckey[W.cur][ci] != M.n_geoms + M.n_pairs;
+        tbase = warp.excl_scan(n_rt, TT);
+    }
+    const int DIR0 = LT + 3 * CT;
+    int rt_k = 0;
     if (LT + CT == 0) { warp.extra_sync(); warp.extra_sync(); return; }   // warp-uniform (the CTA-wide syncs below must still be matched)
     const int cur = W.cur;
     for (int j = 0; j < n_nc; j++) pool.at(lbase + j, 0) = i2f(lim_code[j]);
@@ -372,10 +383,10 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
                 if (bA == CB) {     // (the robot words of these rows are never read: row_span)
 #pragma unroll
                     for (int w = 0; w < 3; w++) pool.at(slot + w, 2 * nd) = cden[w];
-                    pool.at(slot, 0) = i2f(lane | (255 << 8));       // body 255: nothing left to do for the helpers
-                    continue;
+                    continue;                                        // no helper task (not in the directory)
                 }
                 // robot geom vs cube: the helpers build the robot side like a floor contact and add the cube's denominators
+                pool.at(DIR0 + tbase + rt_k, 0) = i2f(slot); rt_k++;
                 pool.at(slot, 0) = i2f(lane | (bA << 8) | (1 << 24));
 #pragma unroll
                 for (int k = 0; k < 3; k++) { pool.at(slot, 1 + k) = cd[k]; pool.at(slot, 13 + k) = cden[k]; }
@@ -392,6 +403,7 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
                 continue;
             }
         }
+        if constexpr (T::CUBE != 0) { pool.at(DIR0 + tbase + rt_k, 0) = i2f(slot); rt_k++; }
         pool.at(slot, 0) = i2f(lane | (bA << 8) | ((bB + 1) << 16));
 #pragma unroll
         for (int k = 0; k < 3; k++) pool.at(slot, 1 + k) = cd[k];
@@ -435,15 +447,14 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
         }
     }
     // ---- all lanes: contact-point tasks (normal + 2 friction rows each) ----
-    for (int t0 = 0; t0 < CT; t0 += Warp::WIDTH) {
+    for (int t0 = 0; t0 < TT; t0 += Warp::WIDTH) {
         const int t = t0 + lane;
-        if (t < CT) {
-            const int slot = LT + 3 * t;
+        if (t < TT) {
+            const int slot = T::CUBE != 0 ? f2i(pool.at(DIR0 + t, 0)) : LT + 3 * t;
             float desc[POOL_DESC_WORDS];
             const int code = f2i(pool.at(slot, 0));
             const int o = code & 255, bA = (code >> 8) & 255, bB = ((code >> 16) & 255) - 1;
             const bool cube_side = T::CUBE != 0 && ((code >> 24) & 1);
-            if (T::CUBE != 0 && bA == 255) continue;       // cube-floor point: rows already complete
 #pragma unroll
             for (int k = 1; k < 13; k++) desc[k] = pool.at(slot, k);
             if (cube_side) {

@@ -155,23 +155,6 @@ __global__ void __launch_bounds__(64) k_reset(const __grid_constant__ DevModel M
     store_env(M, B, e, W, E);
 }
 
-// Resets deferred by the static-topology step kernel (auto_reset 2): envs [e0, e1) whose flag is set get the reference's reset
-// distribution and the first observation of the new episode (same counter-based RNG stream, same code as rs_world_reset).
-template <int NL, int MC>
-__global__ void __launch_bounds__(64) k_reset_deferred(const __grid_constant__ DevModel M, const DevBuf B, float* __restrict__ obs,
-                                                       uint32_t seed, uint32_t env_id0, int e0, int e1) {
-    const int e = e0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= e1 || !B.reset_mask[e]) return;
-    B.reset_mask[e] = 0;
-    Work<NL, MC> W;
-    Episode E;
-    load_env(M, B, e, W, E);
-    float tmp[8 + 2 * MA + MF];
-    env_reset(M, W, E, seed, env_id0 + e, tmp, 1);
-    for (int k = 0; k < M.obs_dim; k++) obs[(size_t)e * M.obs_dim + k] = tmp[k];
-    store_env(M, B, e, W, E);
-}
-
 template <int NL, int MC>
 __global__ void __launch_bounds__(64) k_substeps(const __grid_constant__ DevModel M, const DevBuf B, int nsub) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -257,7 +240,7 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
     if (const char* e = getenv("RS_EXTRA_SYNC")) w->extra_sync = atoi(e) != 0;
     DevBuf& B = w->B;
     B.N = n_envs; B.S = (model->fixed_base ? 0 : 13) + 2 * model->n_dof + (model->has_cube ? 13 : 0); B.MCcap = MC;
-    B.rec = 2 * (6 + model->n_dof + (model->has_cube ? 6 : 0)) + 1; B.maxr = 2 * NL + 3 * MC;   // +1: pooled rows keep their denominator in the record; a limit and a motor row per joint
+    B.rec = 2 * (6 + model->n_dof + (model->has_cube ? 6 : 0)) + 1; B.maxr = 2 * NL + 3 * MC + (model->has_cube ? MC : 0);   // +1: pooled rows keep their denominator in the record; a limit and a motor row per joint
     size_t N = (size_t)n_envs;
     CK(cudaMalloc(&B.state, sizeof(float) * N * (B.S > 0 ? B.S : 1)));
     CK(cudaMalloc(&B.ccount, sizeof(int) * N));
@@ -281,8 +264,6 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
     CK(cudaMalloc(&B.rows, sizeof(float) * (size_t)((n_envs + 255) / 256 * 256 + 256) * B.rec * B.maxr));   // one pool per warp of 32 envs, incl. the spare warps of the last CTA (up to 8 warps per CTA)
     CK(cudaMalloc(&B.tau, sizeof(float) * N * (model->n_dof > 0 ? model->n_dof : 1)));
     CK(cudaMalloc(&B.rewards5, sizeof(float) * N * 5));
-    CK(cudaMalloc(&B.reset_mask, N));
-    CK(cudaMemset(B.reset_mask, 0, N));
     CK(cudaMalloc(&B.nrows, sizeof(int) * N));
     CK(cudaMalloc(&B.ncontacts, sizeof(int) * N));
     CK(cudaMemset(B.state, 0, sizeof(float) * N * (B.S > 0 ? B.S : 1)));
@@ -324,7 +305,7 @@ extern "C" int rs_world_destroy(rs_world* w) {
     DevBuf& B = w->B;
     cudaFree(B.state); cudaFree(B.ccount); cudaFree(B.ckey); cudaFree(B.cdat); cudaFree(B.potential); cudaFree(B.initial_z);
     cudaFree(B.feet); cudaFree(B.frame); cudaFree(B.episode); cudaFree(B.rows); cudaFree(B.tau); cudaFree(B.rewards5);
-    cudaFree(B.nrows); cudaFree(B.ncontacts); cudaFree(B.target); cudaFree(B.flag_timeout); cudaFree(B.flag_draws); cudaFree(B.hx_i); cudaFree(B.hx_d); cudaFree(B.motor); cudaFree(B.reset_mask);
+    cudaFree(B.nrows); cudaFree(B.ncontacts); cudaFree(B.target); cudaFree(B.flag_timeout); cudaFree(B.flag_draws); cudaFree(B.hx_i); cudaFree(B.hx_d); cudaFree(B.motor);
     cudaFreeHost(w->h_act); cudaFreeHost(w->h_obs); cudaFreeHost(w->h_rew); cudaFreeHost(w->h_done);
     cudaFree(w->d_act); cudaFree(w->d_obs); cudaFree(w->d_rew); cudaFree(w->d_done); cudaFree(w->d_stats);
     cudaStreamDestroy(w->stream);
@@ -369,23 +350,12 @@ extern "C" int rs_world_reset(rs_world* w, uint32_t seed, uint32_t env_id0, cons
 static int launch_step(rs_world* w, const float* actions, float* obs, float* rew, uint8_t* done, int auto_reset, uint32_t seed,
                        uint32_t env_id0, double* stats, cudaStream_t st, int cta0 = 0, int ncta = 0) {
     if (w->topo) {
-        // auto-reset is deferred to a second, small kernel over the same envs (see k_step_static); RS_INKERNEL_RESET=1 keeps it
-        // inside the step kernel (one launch per step)
-        static const bool inkernel = getenv("RS_INKERNEL_RESET") && atoi(getenv("RS_INKERNEL_RESET")) != 0;
-        const int ar = auto_reset ? (inkernel ? 1 : 2) : 0;
-        StaticLaunch a{&w->M, &w->B, w->n, actions, obs, rew, done, ar, seed, env_id0, stats, nullptr, st};
+        StaticLaunch a{&w->M, &w->B, w->n, actions, obs, rew, done, auto_reset, seed, env_id0, stats, nullptr, st};
         a.cta0 = cta0; a.ncta = ncta; a.cluster = w->cluster; a.extra_sync = w->extra_sync;
         StaticLaunchFn fn = pick_static(w->topo, 0, w->wpc);
         if (!fn) return fail("static-topology kernel not linked");
         fn(a);
         CK(cudaGetLastError());
-        if (ar == 2) {
-            int per = 0;
-            StaticLaunch q = a; q.per_out = &per; fn(q);
-            const int e0 = cta0 * per, e1 = ncta > 0 ? ((cta0 + ncta) * per < w->n ? (cta0 + ncta) * per : w->n) : w->n;
-            FAMILY_DISPATCH(w, (k_reset_deferred<NL, MC><<<nblocks(e1 - e0), 64, 0, st>>>(w->M, w->B, obs, seed, env_id0, e0, e1)));
-            CK(cudaGetLastError());
-        }
         return 0;
     }
     FAMILY_DISPATCH(w, (k_step<NL, MC><<<nblocks(w->n), 64, 0, st>>>(w->M, w->B, actions, obs, rew, done, auto_reset, seed, env_id0, stats)));

@@ -36,7 +36,7 @@ static void step_env_static(Emul* e, int i, const float* a, int auto_reset, uint
     auto cs = [&](float* o, int os, double* dist, float* pitch, int* al) { static_calc_state<T>(M, W, lc, e->ep[i], o, os, dist, pitch, al); };
     epilogue_with<T::CUBE != 0>(M, W, e->ep[i], a, 1, obs, 1, e->out[i], cs, seed, env0 + i);
     int done = e->out[i].done;
-    if (auto_reset && (done || e->ep[i].frame >= M.max_episode_steps)) { env_reset(M, W, e->ep[i], seed, env0 + i, obs, 1); done = 1; }   // k_reset_deferred
+    if (auto_reset && (done || e->ep[i].frame >= M.max_episode_steps)) { env_reset_with(M, W, e->ep[i], seed, env0 + i, obs, 1, cs); done = 1; }
     e->rew[i] = e->out[i].reward; e->done[i] = done;
 }
 template <class T>
@@ -53,7 +53,7 @@ void* emul_create(const rs_model_desc* m, int n) {
     if (build_dev_model(m, &e->M, &err)) { delete e; return nullptr; }
     e->n = n; e->w.resize(n); e->ep.resize(n); e->out.resize(n);
     for (int i = 0; i < n; i++) { memset(&e->w[i], 0, sizeof(W_t)); e->w[i].bquat[3] = 1; e->w[i].cquat[3] = 1; memset(&e->ep[i], 0, sizeof(Episode)); e->ep[i].initial_z = e->M.initial_z; e->ep[i].target_x = e->M.walk_target_x; e->ep[i].target_y = e->M.walk_target_y; }
-    e->rec = 2 * (6 + e->M.n_dof + (e->M.has_cube ? 6 : 0)) + 1; e->maxr = 2 * NL + 3 * MC;
+    e->rec = 2 * (6 + e->M.n_dof + (e->M.has_cube ? 6 : 0)) + 1; e->maxr = 2 * NL + 4 * MC;
     e->ws.resize((size_t)e->rec * e->maxr);
     e->obs.resize((size_t)n * e->M.obs_dim); e->rew.resize(n); e->done.resize(n);
     e->topo = 0; e->lcsize = 9 * RS_MAX_LINKS + 30; e->lcbuf.assign((size_t)n * e->lcsize, 0.f);
