@@ -42,6 +42,27 @@ const char* rs_last_error(void);
 /* Number of CUDA devices visible (0 => every compute call fails). */
 int rs_device_count(void);
 
+/* Names that travel with a compiled model (b3GetBodyInfo / b3GetJointInfo strings, physics-bullet.cpp:133-251):
+ * what the reference's env classes look parts and joints up by (gym_mujoco_xml_env.py:47-76). */
+#define RS_NAME_LEN 48
+typedef struct rs_model_names {
+    char base_name[RS_NAME_LEN];                    /* root part ("world" for a jointed root)      */
+    char link_names[RS_MAX_LINKS][RS_NAME_LEN];     /* body name; "dummy_<joint>" for importer-made links */
+    char joint_names[RS_MAX_LINKS][RS_NAME_LEN];    /* "" for fixed joints                          */
+    char geom_names[RS_MAX_GEOMS][RS_NAME_LEN];
+} rs_model_names;
+
+/* World::load_mjcf: MJCF file -> compiled model        physics-bullet.cpp:95-131 (b3LoadMJCFCommandInit with
+ * URDF_USE_SELF_COLLISION | URDF_USE_SELF_COLLISION_EXCLUDE_ALL_PARENTS) + b3GetJointInfo :206-251.
+ * Host-only (no CUDA device needed).  Fills the physics part of *out: topology, joint frames, mass / inertia / COM frames,
+ * collision geoms, self-collision pairs, solver constants (physics-bullet.cpp:368-376); gravity and timestep are squeezed
+ * through float32 like World(float gravity, float timestep) (python-binding.cpp:297).  The task constants (action gains,
+ * feet, alive rule, costs: class attributes of gym_mujoco_walkers.py, not part of the MJCF) are left zero for the caller to
+ * set; max_contacts = 16.  `names` may be NULL.  Same conventions and results as
+ * roboschool_b200/mjcf.py with its default arguments. */
+int rs_model_compile(const char* mjcf_path, double gravity, double timestep, int frame_skip, int has_floor,
+                     rs_model_desc* out, rs_model_names* names);
+
 /* World(gravity, timestep) + load_mjcf()            python-binding.cpp:297-301, 332-343;
  * physics-bullet.cpp:12-21, 95-131.  gravity/timestep/frame_skip come from the compiled model. */
 int rs_world_create(const rs_model_desc* model, int n_envs, int device, rs_world** out);
@@ -78,7 +99,9 @@ int rs_world_step_stats(rs_world* w, const float* actions_dev, float* obs_dev, f
                         int auto_reset, double* stats_dev, void* stream);
 
 /* Profiling twin of rs_world_step (auto_reset on): also returns clock64() warp-cycle totals per phase in
- * cycles_host[8] = {kinematics, collide, aba, solve, integrate, epilogue+store, load+apply_action, total}. */
+ * cycles_host[16] = {kinematics, collide, aba, solve, integrate, epilogue+store, load+apply_action, total,
+ * then inside the solve phase (static-topology kernels): enumerate rows, limit-row tasks, contact tasks, right-hand sides,
+ * PGS iterations, 0, 0, 0}. */
 int rs_world_step_profile(rs_world* w, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
                           unsigned long long* cycles_host, void* stream);
 

@@ -1208,7 +1208,7 @@ RS_HD void integrate(const DevModel& M, Work<NL, MC, SL>& W, float dt) {
 
 // optional per-phase cycle accounting (profiling build of the step kernel only)
 struct PhaseClock {
-    long long t[6];   // kinematics, collide, aba, solve, integrate, (epilogue)
+    long long t[12];  // kinematics, collide, aba, solve, integrate, (epilogue) ; [6..10] inside solve: enumerate, limit tasks, contact tasks, rhs, PGS
 };
 #if defined(__CUDA_ARCH__)
 #define RS_CLOCK() clock64()

@@ -125,7 +125,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Step kernel specialised on a compile-time topology: one warp per CTA (32 envs), link cache in shared memory,
 // constraint rows built by the whole warp (rs_pooled.cuh).  Every lane runs the kernel to the end: the spare lanes of
 // the tail warp own no env (valid == false) but still help with the warp's row tasks.
-// PROF: also accumulate clock64() deltas per phase into cyc[8] (profiling twin).
+// PROF: also accumulate clock64() deltas per phase into cyc[16] (profiling twin).
 template <class T, int MC, bool PROF, int WPC>
 __global__ void __launch_bounds__(32 * WPC) k_step_static(const __grid_constant__ DevModel M, const DevBuf B, const float* __restrict__ actions,
                                                     float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ done,
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(32 * WPC) k_step_static(const __grid_constant_
     WarpDev<WPC> warp;
     warp.cluster = (cluster & 1) != 0; warp.extra = (cluster & 2) != 0;
     PhaseClock pc;
-    if (PROF) { for (int k = 0; k < 6; k++) pc.t[k] = 0; t1 = clock64(); }
+    if (PROF) { for (int k = 0; k < 12; k++) pc.t[k] = 0; t1 = clock64(); }
     for (int s = 0; s < M.frame_skip; s++) substep_pooled<T>(warp, valid, M, W, pool, lc, lc0, PROF ? &pc : nullptr);
     if (PROF) t2 = clock64();
     if (valid) {
@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(32 * WPC) k_step_static(const __grid_constant_
     if (PROF && lane == 0) {
         long long t3 = clock64();
         for (int k = 0; k < 5; k++) atomicAdd(cyc + k, (unsigned long long)pc.t[k]);
+        for (int k = 0; k < 5; k++) atomicAdd(cyc + 8 + k, (unsigned long long)pc.t[6 + k]);   // inside the solve phase
         atomicAdd(cyc + 5, (unsigned long long)(t3 - t2));
         atomicAdd(cyc + 6, (unsigned long long)(t1 - t0));
         atomicAdd(cyc + 7, (unsigned long long)(t3 - t0));

@@ -277,7 +277,9 @@ RS_HD void resolve_span(int span, const Pool& pool, int slot, float* dv, float r
 //   lc_lane0: link cache of lane 0 of this warp; the cache of lane o is lc_lane0 + o (host: o == 0)
 // ---------------------------------------------------------------------------------------------
 template <class T, class Warp, int NL, int MC, bool SL, int STRIDE, class Pool>
-RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL, MC, SL>& W, float dt, const Pool& pool, float* lc_lane0) {
+RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL, MC, SL>& W, float dt, const Pool& pool, float* lc_lane0, PhaseClock* pc = nullptr) {
+    long long q0 = 0, q1 = 0;
+    if (pc) q0 = RS_CLOCK();
     static_assert(pool_rec<T>() >= POOL_DESC_WORDS, "row record too small to hold a task descriptor");
     constexpr int nd = nd_of<T>(), n = T::NL, ndr = 6 + T::ND;   // ndr: the robot's dofs; [ndr, nd): the cube's
     constexpr int CB = n + 1;                                     // body index of the cube
@@ -433,6 +435,7 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
     }
     warp.sync();
     warp.extra_sync();
+    if (pc) { q1 = RS_CLOCK(); pc->t[6] += q1 - q0; q0 = q1; }
     // ---- all lanes: limit-row tasks ----
     for (int t0 = 0; t0 < LT; t0 += Warp::WIDTH) {
         const int t = t0 + lane;
@@ -446,6 +449,7 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
             pool.at(t, 2 * nd) = dn[0];
         }
     }
+    if (pc) { q1 = RS_CLOCK(); pc->t[7] += q1 - q0; q0 = q1; }
     // ---- all lanes: contact-point tasks (normal + 2 friction rows each) ----
     for (int t0 = 0; t0 < TT; t0 += Warp::WIDTH) {
         const int t = t0 + lane;
@@ -493,6 +497,7 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
     }
     warp.sync();
     warp.extra_sync();
+    if (pc) { q1 = RS_CLOCK(); pc->t[8] += q1 - q0; q0 = q1; }
     if (!valid || W.n_rows == 0) return;
     // ---- owner: right-hand sides, then PGS in Bullet's order ----
     float vel[nd];
@@ -554,6 +559,7 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
             r_rhs[row] = rhs; r_invd[row] = invd; r_applied[row] = 0.f;
         }
     }
+    if (pc) { q1 = RS_CLOCK(); pc->t[9] += q1 - q0; q0 = q1; }
     float dv[nd];
 #pragma unroll
     for (int k = 0; k < nd; k++) dv[k] = 0.f;
@@ -584,6 +590,7 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
             }
         }
     }
+    if (pc) { q1 = RS_CLOCK(); pc->t[10] += q1 - q0; }
     if constexpr (!T::FIXED_BASE) {
 #pragma unroll
         for (int k = 0; k < 3; k++) { W.bw[k] += dv[k]; W.bv[k] += dv[3 + k]; }
@@ -621,7 +628,7 @@ RS_HD void substep_pooled(const Warp& warp, bool valid, const DevModel& M, Work<
     if (pc) { c1 = RS_CLOCK(); pc->t[2] += c1 - c0; c0 = c1; }
     warp.cta_sync();
     warp.sync();   // link caches complete before other lanes read them
-    solve_pooled<T, Warp, NL, MC, SL, STRIDE, Pool>(warp, valid, M, W, dt, pool, lc_lane0);
+    solve_pooled<T, Warp, NL, MC, SL, STRIDE, Pool>(warp, valid, M, W, dt, pool, lc_lane0, pc);
     warp.sync();   // all helpers done with this sub-step's caches before kinematics overwrites them
     if (pc) { c1 = RS_CLOCK(); pc->t[3] += c1 - c0; c0 = c1; }
     if (valid) {

@@ -381,18 +381,19 @@ extern "C" int rs_world_step_stats(rs_world* w, const float* actions_dev, float*
     return 0;
 }
 
-// profiling: one step with per-phase warp-cycle totals -> cycles_host[8]
-// [kinematics, collide, aba, solve, integrate, epilogue+store, load+apply_action, total]
+// profiling: one step with per-phase warp-cycle totals -> cycles_host[16]
+// [kinematics, collide, aba, solve, integrate, epilogue+store, load+apply_action, total,
+//  inside solve (static-topology kernels): enumerate rows, limit-row tasks, contact tasks, right-hand sides, PGS, 0, 0, 0]
 extern "C" int rs_world_step_profile(rs_world* w, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
                                      unsigned long long* cycles_host, void* stream) {
     CK(cudaSetDevice(w->device));
     unsigned long long* d = nullptr;
-    CK(cudaMalloc(&d, 8 * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), (cudaStream_t)stream));
+    CK(cudaMalloc(&d, 16 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(d, 0, 16 * sizeof(unsigned long long), (cudaStream_t)stream));
     cudaStream_t st = (cudaStream_t)stream;
     StaticLaunch sl{&w->M, &w->B, w->n, actions_dev, obs_dev, reward_dev, done_dev, 1, w->rollout_seed, w->env_id0, nullptr, d, st};
     switch (w->topo) {
-        case 1: case 2: case 3: case 4: case 5: {
+        case 1: case 2: case 3: case 4: case 5: case 6: {
             StaticLaunchFn fn = pick_static(w->topo, 1, 1);
             if (!fn) { cudaFree(d); return fail("profiling kernel not linked"); }
             fn(sl);
@@ -403,7 +404,7 @@ extern "C" int rs_world_step_profile(rs_world* w, const float* actions_dev, floa
     }
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
-    if (e == cudaSuccess) e = cudaMemcpy(cycles_host, d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(cycles_host, d, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) return fail(std::string("rs_world_step_profile: ") + cudaGetErrorString(e));
     return 0;

@@ -214,10 +214,12 @@ def apply_task(m: ModelDesc, spec: dict) -> ModelDesc:
     return m
 
 
-def compile_env(env_id, assets_dir, **kw):
-    """MJCF (from a roboschool ``mujoco_assets`` dir) -> full descriptor for ``env_id``."""
+def compile_env(env_id, assets_dir, native=False, **kw):
+    """MJCF (from a roboschool ``mujoco_assets`` dir) -> full descriptor for ``env_id``.
+    ``native``: compile through the library's C entry ``rs_model_compile`` instead of the Python compiler (same result)."""
     spec = dict(ENV_SPECS[env_id], env_id=env_id)
-    m = mjcf.compile_mjcf(os.path.join(assets_dir, spec["xml"]),
+    comp = mjcf.compile_mjcf_native if native else mjcf.compile_mjcf
+    m = comp(os.path.join(assets_dir, spec["xml"]),
                           has_floor=not spec.get("no_floor", False),
                           timestep=spec.get("timestep", 0.0165 / 4), gravity=spec.get("gravity", 9.8),
                           frame_skip=spec.get("frame_skip", 4), **kw)

@@ -528,3 +528,31 @@ def compile_mjcf(xml_path, honour_density=False, honour_damping=False, has_floor
         "geom_names": [g.name for (_, g, _) in geoms],
     }
     return m
+
+
+def compile_mjcf_native(xml_path, has_floor=True, gravity=9.8, timestep=0.0165 / 4, frame_skip=4):
+    """Same descriptor through the library's C entry ``rs_model_compile`` (csrc/rs_model_compile.cpp): the compiler a
+    native binding uses.  Default conventions only; the keyword knobs of :func:`compile_mjcf` exist for
+    the convention sweeps and stay in Python."""
+    import ctypes
+    from . import _lib
+    from .model import DEFINES
+
+    n = 48   # RS_NAME_LEN
+
+    class _Names(ctypes.Structure):
+        _fields_ = [("base_name", ctypes.c_char * n), ("link_names", (ctypes.c_char * n) * DEFINES["RS_MAX_LINKS"]),
+                    ("joint_names", (ctypes.c_char * n) * DEFINES["RS_MAX_LINKS"]), ("geom_names", (ctypes.c_char * n) * DEFINES["RS_MAX_GEOMS"])]
+
+    m, names = ModelDesc(), _Names()
+    _lib.check(_lib.lib().rs_model_compile(os.fsencode(xml_path), gravity, timestep, frame_skip, int(bool(has_floor)),
+                                           ctypes.byref(m), ctypes.byref(names)))
+    m.max_contacts = 0     # like compile_mjcf: the task layer sets it (envspec.apply_task)
+    m.meta = {
+        "xml": os.path.basename(xml_path),
+        "base_name": names.base_name.decode(),
+        "link_names": [names.link_names[i].value.decode() for i in range(m.n_links)],
+        "joint_names": [(names.joint_names[i].value.decode() or None) for i in range(m.n_links)],
+        "geom_names": [names.geom_names[g].value.decode() for g in range(m.n_geoms)],
+    }
+    return m

@@ -23,11 +23,12 @@ if len(sys.argv) > 4 and sys.argv[4] == "stagger":
     W.set_episode(frame=np.random.RandomState(7).randint(0, m.max_episode_steps - 1, size=n).astype(np.int32))
     W.rollout(pol, 100, stream=st)
     torch.cuda.synchronize()
-names = ["kinematics", "collide", "aba", "solve", "integrate", "epilogue+store", "load+action", "total"]
-acc = np.zeros(8)
+names = ["kinematics", "collide", "aba", "solve", "integrate", "epilogue+store", "load+action", "total",
+         "solve:enumerate", "solve:limit_tasks", "solve:contact_tasks", "solve:rhs", "solve:pgs"]
+acc = np.zeros(16)
 for _ in range(5):
     pol.forward(obs_p, act_p, n, st)
-    cyc = (ctypes.c_ulonglong * 8)()
+    cyc = (ctypes.c_ulonglong * 16)()
     _lib.check(W.L.rs_world_step_profile(W.h, act_p, obs_p, rew_p, done_p, cyc, st))
     acc += np.array(list(cyc), dtype=np.float64)
 r, c = W.counts()
