@@ -2,17 +2,19 @@
 //
 //   act = relu(relu(obs W1 + b1) W2 + b2) W3 + b3        (agent_zoo/RoboschoolHumanoid_v1_2017jul.py:21-34,63-68)
 //
-// One persistent CTA per SM, 128 threads; a tile is 128 envs (UMMA M = 128, one env per TMEM lane / per thread).
-// The three layers are chained on chip:
+// One persistent CTA per SM, 256 threads = two tile slots of 128 threads; a tile is 128 envs (UMMA M = 128, one env per TMEM
+// lane / per thread of the slot).  The slots share the weight image and the tensor pipe: one slot's epilogue overlaps the other
+// slot's MMAs, and 2 x 148 slots hold all 256 tiles of a 32768-env batch at once.  Per tile, chained on chip:
 //   obs tile -> fp16 -> smem A1 [128 x 64]            (K-major, 128-byte swizzle: the canonical UMMA operand layout)
-//   tcgen05.mma  D1[128 x H1] (TMEM)  = A1 . W1^T     (one elected thread issues K/16 instructions)
-//   tcgen05.ld   D1 -> registers, + b1, relu, -> fp16 -> smem A2 [128 x H1]
-//   tcgen05.mma  D2[128 x H2]         = A2 . W2^T ;  epilogue -> smem A3 [128 x H2]
-//   tcgen05.mma  D3[128 x OUTP]       = A3 . W3^T ;  epilogue + b3 -> global act
+//   for each chunk c of 128 hidden units:
+//     tcgen05.mma  X[128 x 128] (TMEM) = A1 . W1^T[chunk c]       (one elected thread per slot issues K/16 instructions)
+//     tcgen05.ld   X -> registers, + b1, relu, -> fp16 -> smem A2 [128 x 128]
+//     tcgen05.mma  D2[128 x H2] (+)= A2 . W2^T[:, chunk c]        (issued together with chunk c+1's layer-1 MMA)
+//   epilogue D2 -> smem A3 [128 x H2] (in A2's place) ;  tcgen05.mma X[128 x OUTP] = A3 . W3^T ;  + b3 -> global act
 // Hidden activations never leave the SM; the weights are staged once per CTA, already in operand layout
-// (the host packs them swizzled, so staging is one linear TMA bulk copy, cp.async.bulk, overlapped with the first tile's load).  Completion of each MMA group is signalled with
-// tcgen05.commit on an mbarrier; generic-proxy writes of the next A operand are ordered before the async-proxy reads
-// with fence.proxy.async.
+// (the host packs them swizzled, so staging is one linear TMA bulk copy, cp.async.bulk, overlapped with the first tiles' loads).
+// Completion of each MMA group is signalled with tcgen05.commit on the slot's mbarrier; generic-proxy writes of the next A
+// operand are ordered before the async-proxy reads with fence.proxy.async.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -34,23 +36,28 @@ __host__ __device__ inline uint32_t sw128_offset(int rows, int r, int c) {
     return (uint32_t)(atom * rows * 128 + r * 128 + ((cc ^ (r & 7)) << 4) + e * 2);
 }
 
+constexpr int NCHUNK = 128;      // hidden-layer-1 columns per pass (layer 1 is produced and consumed in N-chunks of 128)
+constexpr int TMEM_PER_TILE = 256;   // TMEM columns of one tile slot: X[128] (layer-1 chunk, later the output) | D2[<=128]
+
 template <int H1, int H2, int OUTP>
 struct Layout {
-    // weights first (one contiguous image copied from global), then the activation operands
+    // weights first (one contiguous image copied from global), then the activation operands of the two tile slots
     static constexpr uint32_t b1 = 0;                                   // W1^T : H1 rows x K1P
     static constexpr uint32_t b2 = b1 + H1 * 128 * (K1P / ATOM_K);      // W2^T : H2 rows x H1
     static constexpr uint32_t b3 = b2 + H2 * 128 * (H1 / ATOM_K);       // W3^T : OUTP rows x H2
     static constexpr uint32_t bias = b3 + OUTP * 128 * (H2 / ATOM_K);   // fp32 [H1 + H2 + OUTP]
     static constexpr uint32_t image_bytes = (bias + 4 * (H1 + H2 + OUTP) + 1023) / 1024 * 1024;
-    static constexpr uint32_t a1 = image_bytes;                         // 128 x K1P
-    static constexpr uint32_t a2 = a1 + TILE_M * 128 * (K1P / ATOM_K);  // 128 x H1
-    static constexpr uint32_t a3 = a2 + TILE_M * 128 * (H1 / ATOM_K);   // 128 x H2
-    static constexpr uint32_t bar = a3 + TILE_M * 128 * (H2 / ATOM_K);  // MMA mbarrier (8 B), weight mbarrier (8 B), TMEM base (4 B)
-    static constexpr uint32_t bytes = bar + 32;
-    static constexpr int tmem_cols_used = H1 + H2 + OUTP;
-    static constexpr int tmem_cols = tmem_cols_used <= 32 ? 32 : tmem_cols_used <= 64 ? 64 : tmem_cols_used <= 128 ? 128 : tmem_cols_used <= 256 ? 256 : 512;
-    static_assert(H1 % 64 == 0 && H2 % 64 == 0 && OUTP % 16 == 0 && OUTP <= 32, "layer widths");
-    static_assert(tmem_cols_used <= 512, "TMEM columns");
+    // per tile slot: A1 [128 x K1P] and A2 [128 x NCHUNK] (one chunk of the hidden layer; the layer-3 operand A3 [128 x H2]
+    // reuses it once layer 2 has consumed the last chunk)
+    static constexpr uint32_t a1_bytes = TILE_M * 128 * (K1P / ATOM_K);
+    static constexpr uint32_t a2_bytes = TILE_M * 128 * (NCHUNK / ATOM_K);
+    static constexpr uint32_t slot_bytes = a1_bytes + a2_bytes;
+    static constexpr uint32_t slots = image_bytes;                      // slot s at slots + s * slot_bytes : A1 | A2
+    static constexpr uint32_t bar = slots + 2 * slot_bytes;             // MMA mbarrier per slot (2 x 8 B), two weight mbarriers (2 x 8 B), TMEM base (4 B)
+    static constexpr uint32_t bytes = bar + 48;
+    static constexpr int tmem_cols = 2 * TMEM_PER_TILE;
+    static_assert(H1 % NCHUNK == 0 && H2 % 64 == 0 && H2 <= 128 && OUTP % 16 == 0 && OUTP <= 32, "layer widths");
+    static_assert(bytes <= 227 * 1024, "shared memory");
 };
 
 #if defined(__CUDA_ARCH__)
@@ -127,21 +134,21 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// D[128 x N] (TMEM column tmem_d) = A[128 x K] . B[N x K]^T, both K-major SW128 in shared memory; issued by one thread
+// D[128 x N] (TMEM column tmem_d) (+)= A[128 x K] . B[N x K]^T over K-atoms [atom0, atom0 + K/64) of B (rows_b rows per atom);
+// A's atoms start at 0.  Both K-major SW128 in shared memory; issued by one thread, no commit.
 template <int N, int K>
-__device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, uint32_t bar) {
+__device__ __forceinline__ void issue_mma(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, int rows_b, int b_atom0, bool accumulate) {
     const uint32_t idesc = umma_idesc(TILE_M, N);
 #pragma unroll
     for (int k = 0; k < K / 16; k++) {
         const int atom = (k * 16) / ATOM_K, kin = (k * 16) % ATOM_K;
         const uint64_t ad = umma_desc(a_base + atom * (TILE_M * 128) + kin * 2);
-        const uint64_t bd = umma_desc(b_base + atom * (N * 128) + kin * 2);
-        umma_f16(tmem_d, ad, bd, idesc, k > 0 ? 1u : 0u);
+        const uint64_t bd = umma_desc(b_base + (b_atom0 + atom) * (rows_b * 128) + kin * 2);
+        umma_f16(tmem_d, ad, bd, idesc, (accumulate || k > 0) ? 1u : 0u);
     }
-    umma_commit(bar);
 }
 
-// accumulators of this thread's row -> + bias, relu -> fp16 -> next A operand (row `row`, columns 0..N-1)
+// accumulators of this thread's row (N columns from tmem_row) -> + bias, relu -> fp16 -> next A operand (row `row`, columns 0..N-1)
 template <int N>
 __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, const float* bias, unsigned char* a_next, int row) {
 #pragma unroll 2
@@ -160,28 +167,44 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_row, const float* 
         }
     }
 }
+// barrier over the 128 threads of one tile slot (named barriers 1 and 2; barrier 0 is __syncthreads)
+__device__ __forceinline__ void slot_sync(int slot) { asm volatile("bar.sync %0, 128;\n" :: "r"(slot + 1) : "memory"); }
 #endif  // __CUDA_ARCH__
 
+// Two tile slots per CTA (one per warpgroup of 128 threads) share the weight image and the tensor pipe: while one slot is in
+// an epilogue (tcgen05.ld, bias, relu, fp16, swizzled store) the other slot's MMAs run.  With one CTA per SM that is 296 slots
+// for the 256 tiles of 32768 envs: every tile is in flight from the start (one pass instead of 1.73 waves).  A slot owns 256
+// TMEM columns: X[128] | D2[H2].  Layer 1 is produced in chunks of 128 hidden units into X; each chunk goes through its
+// epilogue into A2 and is consumed at once by a partial layer-2 MMA (K = 128, accumulating into D2) that is issued together
+// with the next chunk's layer-1 MMA; the layer-3 result lands in X again.
 template <int H1, int H2, int OUTP>
-__global__ void __launch_bounds__(TILE_M, 1) k_mlp_tc5(const unsigned char* __restrict__ image, const float* __restrict__ obs,
-                                                       float* __restrict__ act, int n, int in_dim, int out_dim) {
+__global__ void __launch_bounds__(2 * TILE_M, 1) k_mlp_tc5(const unsigned char* __restrict__ image, const float* __restrict__ obs,
+                                                           float* __restrict__ act, int n, int in_dim, int out_dim) {
 #if defined(__CUDA_ARCH__)
     using L = Layout<H1, H2, OUTP>;
+    constexpr int NC = H1 / NCHUNK;
     extern __shared__ __align__(1024) unsigned char smem[];
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t bar = smem_u32(smem + L::bar), wbar = bar + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::bar + 16);
+    const int tid = threadIdx.x, warp = tid >> 5, slot = tid >> 7, row = tid & (TILE_M - 1);
+    const uint32_t bar = smem_u32(smem + L::bar) + 8 * slot, wbar1 = smem_u32(smem + L::bar) + 16, wbar2 = wbar1 + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::bar + 32);
     if (tid == 0) {
-        mbar_init(bar, 1);
-        mbar_init(wbar, 1);
+        mbar_init(smem_u32(smem + L::bar), 1);
+        mbar_init(smem_u32(smem + L::bar) + 8, 1);
+        mbar_init(wbar1, 1);
+        mbar_init(wbar2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        // stage the weight image (already in operand layout) + biases with the TMA bulk engine; it lands while the
-        // first observation tile is being converted
-        mbar_expect_tx(wbar, L::image_bytes);
+        // stage the weight image (already in operand layout) + biases with the TMA bulk engine, in the order the layers need
+        // them: W1 and the biases complete on wbar1 (layer 1 starts as soon as those 34 KB are in), W2 and W3 on wbar2 (they
+        // land while the first observation tiles are converted and layer 1 runs)
         constexpr uint32_t CH = 32768;
-#pragma unroll
-        for (uint32_t off = 0; off < L::image_bytes; off += CH)
-            bulk_g2s(smem_u32(smem) + off, image + off, (L::image_bytes - off) < CH ? (L::image_bytes - off) : CH, wbar);
+        auto stage = [&](uint32_t lo, uint32_t hi, uint32_t wb) {
+            for (uint32_t off = lo; off < hi; off += CH) bulk_g2s(smem_u32(smem) + off, image + off, (hi - off) < CH ? (hi - off) : CH, wb);
+        };
+        mbar_expect_tx(wbar1, (L::b2 - L::b1) + (L::image_bytes - L::bias));
+        mbar_expect_tx(wbar2, L::bias - L::b2);
+        stage(L::b1, L::b2, wbar1);
+        stage(L::bias, L::image_bytes, wbar1);
+        stage(L::b2, L::bias, wbar2);
     }
     if (warp == 0) {
         __syncwarp();
@@ -191,19 +214,20 @@ __global__ void __launch_bounds__(TILE_M, 1) k_mlp_tc5(const unsigned char* __re
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);     // this warp's 32 lanes
+    const uint32_t tmem_base = *tmem_slot + (uint32_t)(slot * TMEM_PER_TILE);  // this slot's columns
+    const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16); // this warp's 32 lanes (a warp reaches lanes 32 (warp % 4) ..)
+    const uint32_t tmX = tmem_base, tmD2 = tmem_base + NCHUNK;
     const float* sbias = reinterpret_cast<const float*>(smem + L::bias);
-    unsigned char* sA1 = smem + L::a1;
-    unsigned char* sA2 = smem + L::a2;
-    unsigned char* sA3 = smem + L::a3;
-    const uint32_t a1 = smem_u32(sA1), a2 = smem_u32(sA2), a3 = smem_u32(sA3);
+    unsigned char* sA1 = smem + L::slots + slot * L::slot_bytes;
+    unsigned char* sA2 = sA1 + L::a1_bytes;
+    const uint32_t a1 = smem_u32(sA1), a2 = smem_u32(sA2);
     const uint32_t b1 = smem_u32(smem + L::b1), b2 = smem_u32(smem + L::b2), b3 = smem_u32(smem + L::b3);
+    const bool issuer = row == 0;
     uint32_t phase = 0;
     bool first_tile = true;
     const int n_tiles = (n + TILE_M - 1) / TILE_M;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int row = tid, env = tile * TILE_M + row;
+    for (int tile = slot * gridDim.x + blockIdx.x; tile < n_tiles; tile += 2 * gridDim.x) {
+        const int env = tile * TILE_M + row;
         // ---- obs row -> fp16 -> A1 (one row per thread; columns >= in_dim are zero).  Rows of a tile are adjacent in
         // global memory, so the 128-bit loads of neighbouring threads share cache lines ----
         {
@@ -232,43 +256,56 @@ __global__ void __launch_bounds__(TILE_M, 1) k_mlp_tc5(const unsigned char* __re
                 *reinterpret_cast<uint4*>(sA1 + sw128_offset(TILE_M, row, ch * 8)) = w;
             }
         }
-        if (first_tile) { mbar_wait(wbar, 0); first_tile = false; }   // weights + biases have landed
+        if (first_tile) mbar_wait(wbar1, 0);   // W1 + biases have landed
         proxy_fence();
         tc_fence_before();
-        __syncthreads();
-        // ---- layer 1 ----
-        if (tid == 0) { tc_fence_after(); issue_layer<H1, K1P>(tmem_base, a1, b1, bar); }
+        slot_sync(slot);
+        // ---- layer 1, chunk 0 -> X ----
+        if (issuer) { tc_fence_after(); issue_mma<NCHUNK, K1P>(tmX, a1, b1, NCHUNK, 0, false); umma_commit(bar); }
         mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
-        epilogue_hidden<H1>(tmem_row, sbias, sA2, row);
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            // chunk c of the hidden layer: X -> + b1, relu, fp16 -> A2 (the partial layer-2 MMA that read A2 before has completed:
+            // the commit waited on above covered it)
+            epilogue_hidden<NCHUNK>(tmem_row, sbias + c * NCHUNK, sA2, row);
+            if (first_tile && c == 0) { mbar_wait(wbar2, 0); first_tile = false; }   // W2 + W3 have landed
+            proxy_fence();
+            tc_fence_before();
+            slot_sync(slot);
+            if (issuer) {
+                tc_fence_after();
+                issue_mma<H2, NCHUNK>(tmD2, a2, b2, H2, c * (NCHUNK / ATOM_K), c > 0);                          // D2 (+)= A2 . W2^T[:, chunk c]
+                if (c + 1 < NC) issue_mma<NCHUNK, K1P>(tmX, a1, b1 + (c + 1) * (NCHUNK * 128), NCHUNK, 0, false); // next chunk of layer 1 -> X
+                umma_commit(bar);
+            }
+            mbar_wait(bar, phase); phase ^= 1;
+            tc_fence_after();
+        }
+        // ---- layer 2 epilogue -> A3 (in A2's place), layer 3 -> X[0, OUTP) ----
+        epilogue_hidden<H2>(tmem_row + NCHUNK, sbias + H1, sA2, row);
         proxy_fence();
         tc_fence_before();
-        __syncthreads();
-        // ---- layer 2 ----
-        if (tid == 0) { tc_fence_after(); issue_layer<H2, H1>(tmem_base + H1, a2, b2, bar); }
-        mbar_wait(bar, phase); phase ^= 1;
-        tc_fence_after();
-        epilogue_hidden<H2>(tmem_row + H1, sbias + H1, sA3, row);
-        proxy_fence();
-        tc_fence_before();
-        __syncthreads();
-        // ---- layer 3 ----
-        if (tid == 0) { tc_fence_after(); issue_layer<OUTP, H2>(tmem_base + H1 + H2, a3, b3, bar); }
+        slot_sync(slot);
+        if (issuer) { tc_fence_after(); issue_mma<OUTP, H2>(tmX, a2, b3, OUTP, 0, false); umma_commit(bar); }
         mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
         {
             float v[32];
-            if (OUTP == 32) tmem_ld32(tmem_row + H1 + H2, v); else tmem_ld16(tmem_row + H1 + H2, v);
+            if (OUTP == 32) tmem_ld32(tmem_row, v); else tmem_ld16(tmem_row, v);
             if (env < n) {
 #pragma unroll
                 for (int c = 0; c < OUTP; c++) if (c < out_dim) act[(size_t)env * out_dim + c] = v[c] + sbias[H1 + H2 + c];
             }
         }
         tc_fence_before();
-        __syncthreads();      // all accumulators consumed before the next tile's MMAs overwrite them
+        slot_sync(slot);      // all accumulators consumed before the slot's next tile overwrites them
     }
+    tc_fence_before();
+    __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_base), "r"((uint32_t)L::tmem_cols) : "memory");
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(*tmem_slot), "r"((uint32_t)L::tmem_cols) : "memory");
     }
 #endif
 }
@@ -326,7 +363,7 @@ int rs_tc5_forward(int variant, const void* image_dev, size_t smem_bytes, const 
     const int tiles = (n + tc5::TILE_M - 1) / tc5::TILE_M;
     const int grid = tiles < n_sm ? tiles : n_sm;
     const unsigned char* img = (const unsigned char*)image_dev;
-    if (variant == 1) tc5::k_mlp_tc5<256, 128, 32><<<grid, tc5::TILE_M, smem_bytes, st>>>(img, obs, act, n, in_dim, out_dim);
-    else tc5::k_mlp_tc5<128, 64, 16><<<grid, tc5::TILE_M, smem_bytes, st>>>(img, obs, act, n, in_dim, out_dim);
+    if (variant == 1) tc5::k_mlp_tc5<256, 128, 32><<<grid, 2 * tc5::TILE_M, smem_bytes, st>>>(img, obs, act, n, in_dim, out_dim);
+    else tc5::k_mlp_tc5<128, 64, 16><<<grid, 2 * tc5::TILE_M, smem_bytes, st>>>(img, obs, act, n, in_dim, out_dim);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
