@@ -252,6 +252,13 @@ RS_HD int rs_ctz(uint32_t x) {   // index of the lowest set bit (x != 0)
     return __builtin_ctz(x);
 #endif
 }
+RS_HD int rs_popc(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
 RS_HD float rs_uniform(uint32_t seed, uint32_t env, uint32_t episode, uint32_t k) {
     return (float)(rs_hash(seed, env, episode, k) >> 8) * (1.0f / 16777216.0f);
 }

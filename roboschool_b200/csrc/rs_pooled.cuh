@@ -29,10 +29,37 @@ namespace rs {
 
 // pool of row records shared by the lanes of a warp: word k of slot s at p[k * cap + s]
 // CAP (slots per pool) is a compile-time constant so that the word index k becomes an immediate offset
+// Pool words are written by one lane and read by another within the same sub-step and are dead after it: on the device they
+// are accessed with the cache-streaming (evict-first) policy so that they do not push the per-thread local frames and the
+// instruction lines out of the L2 (RS_POOL_CS=0 builds the plain accessors for A/B runs).
+#ifndef RS_POOL_CS
+#define RS_POOL_CS 0
+#endif
+struct PoolRef {
+    float* p;
+    RS_HD float get() const {
+#if defined(__CUDA_ARCH__) && RS_POOL_CS
+        return __ldcs(p);
+#else
+        return *p;
+#endif
+    }
+    RS_HD void put(float v) const {
+#if defined(__CUDA_ARCH__) && RS_POOL_CS
+        __stcs(p, v);
+#else
+        *p = v;
+#endif
+    }
+    RS_HD operator float() const { return get(); }
+    RS_HD const PoolRef& operator=(float v) const { put(v); return *this; }
+    RS_HD const PoolRef& operator=(const PoolRef& o) const { put(o.get()); return *this; }
+    RS_HD const PoolRef& operator+=(float v) const { put(get() + v); return *this; }
+};
 template <int CAP>
 struct RowPool {
     float* p;
-    RS_HD float& at(int slot, int k) const { return p[k * CAP + slot]; }
+    RS_HD PoolRef at(int slot, int k) const { return PoolRef{p + (k * CAP + slot)}; }
 };
 // slots a warp of WIDTH envs can need: every env at its row capacity
 // limit + motor row per joint, 3 per contact; cube topologies: + one task-directory slot per contact (see solve_pooled)
@@ -51,6 +78,9 @@ struct WarpHost {
     RS_HD void sync() const {}
     RS_HD void cta_sync() const {}
     RS_HD void extra_sync() const {}
+    RS_HD unsigned ballot(bool p) const { return p ? 1u : 0u; }
+    RS_HD float shfl(float v, int) const { return v; }
+    RS_HD int shfl(int v, int) const { return v; }
 };
 #ifdef __CUDACC__
 // WPC: warps per CTA.  With WPC > 1 the warps of a CTA are re-aligned at the phase boundaries of the sub-step
@@ -93,6 +123,27 @@ struct WarpDev {
     RS_HD void sync() const {
 #ifdef __CUDA_ARCH__
         __syncwarp();
+#endif
+    }
+    RS_HD unsigned ballot(bool p) const {
+#ifdef __CUDA_ARCH__
+        return __ballot_sync(0xffffffffu, p);
+#else
+        return p ? 1u : 0u;
+#endif
+    }
+    RS_HD float shfl(float v, int src) const {
+#ifdef __CUDA_ARCH__
+        return __shfl_sync(0xffffffffu, v, src);
+#else
+        return v;
+#endif
+    }
+    RS_HD int shfl(int v, int src) const {
+#ifdef __CUDA_ARCH__
+        return __shfl_sync(0xffffffffu, v, src);
+#else
+        return v;
 #endif
     }
 };
@@ -145,7 +196,7 @@ RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*
                     const float kk = invD * y;
 #pragma unroll
                     for (int k = 0; k < 6; k++) Z[rr][k] += h[k] * kk;
-                    float& J = pool.at(slot0 + rr, 6 + d);
+                    const PoolRef J = pool.at(slot0 + rr, 6 + d);
                     if constexpr (first) J = j; else J += j;
                 }
             }
@@ -195,8 +246,8 @@ RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*
             tmulv(uw, Rb, acc[rr][0]); tmulv(uv, Rb, acc[rr][0] + 3);
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                float& J0 = pool.at(slot0 + rr, k); float& J1 = pool.at(slot0 + rr, 3 + k);
-                float& U0 = pool.at(slot0 + rr, nd + k); float& U1 = pool.at(slot0 + rr, nd + 3 + k);
+                const PoolRef J0 = pool.at(slot0 + rr, k), J1 = pool.at(slot0 + rr, 3 + k);
+                const PoolRef U0 = pool.at(slot0 + rr, nd + k), U1 = pool.at(slot0 + rr, nd + 3 + k);
                 if constexpr (first) { J0 = jw[k]; J1 = jv[k]; U0 = uw[k]; U1 = uv[k]; }
                 else { J0 += jw[k]; J1 += jv[k]; U0 += uw[k]; U1 += uv[k]; }
             }
@@ -220,7 +271,7 @@ RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*
             if constexpr (d >= 0) {
                 const float a = invD * (Y[rr][i] - dot6(acc[rr][i + 1], h));
                 saxpy<T, i>(acc[rr][i + 1], a);
-                float& U = pool.at(slot0 + rr, nd + 6 + d);
+                const PoolRef U = pool.at(slot0 + rr, nd + 6 + d);
                 if constexpr (first) U = a; else U += a;
                 if constexpr (!HASW) { if (body == i + 1) denom[rr] = a * jdir; }
             }
@@ -451,13 +502,45 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
     }
     if (pc) { q1 = RS_CLOCK(); pc->t[7] += q1 - q0; q0 = q1; }
     // ---- all lanes: contact-point tasks (normal + 2 friction rows each) ----
+    // A contact between two robot bodies needs a second pair of sweeps (the wrench on the second body, accumulated into the same
+    // rows).  Run inside the task it would idle the other lanes of the round for a whole response, in every round that holds one
+    // such contact (measured on FlagrunHarder, whose robots lie on the floor with arms against legs: half of the contact-task
+    // time).  So second bodies are tasks of their own: their descriptors are dealt to the lanes of the warp (one pending task per
+    // lane, handed over with shuffles) and executed together when 32 are pending or the contact tasks are through.  Per row the
+    // arithmetic and its order are unchanged (first body written, second body added).
+    bool have2 = false;
+    int slot2 = 0, own2 = 0, body2 = 0, npend = 0;     // npend: warp-uniform
+    float d2[12];                                       // contact point and the three directions in the second body's coords
+#pragma unroll
+    for (int k = 0; k < 12; k++) d2[k] = 0.f;
+    auto flush_second = [&]() {
+        warp.sync();                                    // the first bodies' rows are complete and visible
+        if (have2) {
+            float wr[3][6], dn[3];
+#pragma unroll
+            for (int w = 0; w < 3; w++) {
+                cross3(wr[w], d2, d2 + 3 + 3 * w);
+                wr[w][3] = d2[3 + 3 * w]; wr[w][4] = d2[4 + 3 * w]; wr[w][5] = d2[5 + 3 * w];
+            }
+            LinkCache<STRIDE> lco{lc_lane0 + own2};
+            pooled_response_second<T>(lco, body2, (const float (*)[6]) wr, pool, slot2, dn);
+#pragma unroll
+            for (int w = 0; w < 3; w++) pool.at(slot2 + w, 2 * nd) += dn[w];
+            have2 = false;
+        }
+        npend = 0;
+    };
     for (int t0 = 0; t0 < TT; t0 += Warp::WIDTH) {
         const int t = t0 + lane;
+        int slot = 0, o = 0, bB = -1;
+        float desc[POOL_DESC_WORDS];
+#pragma unroll
+        for (int k = 13; k < POOL_DESC_WORDS; k++) desc[k] = 0.f;
         if (t < TT) {
-            const int slot = T::CUBE != 0 ? f2i(pool.at(DIR0 + t, 0)) : LT + 3 * t;
-            float desc[POOL_DESC_WORDS];
+            slot = T::CUBE != 0 ? f2i(pool.at(DIR0 + t, 0)) : LT + 3 * t;
             const int code = f2i(pool.at(slot, 0));
-            const int o = code & 255, bA = (code >> 8) & 255, bB = ((code >> 16) & 255) - 1;
+            o = code & 255; bB = ((code >> 16) & 255) - 1;
+            const int bA = (code >> 8) & 255;
             const bool cube_side = T::CUBE != 0 && ((code >> 24) & 1);
 #pragma unroll
             for (int k = 1; k < 13; k++) desc[k] = pool.at(slot, k);
@@ -480,21 +563,31 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
                 }
                 pooled_response<T, 3, true, true>(lco, bA, (const float (*)[6]) wr, 0.f, pool, slot, dsum);
             }
-            if (bB >= 0) {   // second body of a self-collision pair: rare, accumulates into the same rows
-                float wr[3][6], dn[3];
-#pragma unroll
-                for (int w = 0; w < 3; w++) {
-                    cross3(wr[w], desc + 13, desc + 16 + 3 * w);
-                    wr[w][3] = desc[16 + 3 * w]; wr[w][4] = desc[17 + 3 * w]; wr[w][5] = desc[18 + 3 * w];
-                }
-                pooled_response_second<T>(lco, bB, (const float (*)[6]) wr, pool, slot, dn);
-                dsum[0] += dn[0]; dsum[1] += dn[1]; dsum[2] += dn[2];
-            }
             if (cube_side) { dsum[0] += desc[13]; dsum[1] += desc[14]; dsum[2] += desc[15]; }
 #pragma unroll
             for (int w = 0; w < 3; w++) pool.at(slot + w, 2 * nd) = dsum[w];
         }
+        // hand this round's second bodies to the lanes without a pending one
+        unsigned m2 = warp.ballot(bB >= 0);
+        if (m2) {
+            if (npend + rs_popc(m2) > Warp::WIDTH) flush_second();
+            while (m2) {
+                const int src = rs_ctz(m2);
+                m2 &= m2 - 1u;
+                const int dst = npend++;
+                const int s_slot = warp.shfl(slot, src), s_o = warp.shfl(o, src), s_b = warp.shfl(bB, src);
+                float v[12];
+#pragma unroll
+                for (int k = 0; k < 12; k++) v[k] = warp.shfl(desc[13 + k], src);
+                if (lane == dst) {
+                    have2 = true; slot2 = s_slot; own2 = s_o; body2 = s_b;
+#pragma unroll
+                    for (int k = 0; k < 12; k++) d2[k] = v[k];
+                }
+            }
+        }
     }
+    if (npend > 0) flush_second();
     warp.sync();
     warp.extra_sync();
     if (pc) { q1 = RS_CLOCK(); pc->t[8] += q1 - q0; q0 = q1; }

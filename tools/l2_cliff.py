@@ -34,7 +34,7 @@ for ctas in sizes:
     for t in range(T):
         pol.forward(obs_p, act_p, n, st)
         ev[t][0].record()
-        W.step(act_p, obs_p, rew_p, done_p, True, st)
+        _lib.check(W.L.rs_world_step(W.h, act_p, obs_p, rew_p, done_p, 1, st))
         ev[t][1].record()
     torch.cuda.synchronize()
     ms = float(np.median([a.elapsed_time(b) for a, b in ev]))
