@@ -61,9 +61,23 @@ struct RowPool {
     float* p;
     RS_HD PoolRef at(int slot, int k) const { return PoolRef{p + (k * CAP + slot)}; }
 };
-// slots a warp of WIDTH envs can need: every env at its row capacity
-// limit + motor row per joint, 3 per contact; cube topologies: + one task-directory slot per contact (see solve_pooled)
-template <class T, int MC, int WIDTH> constexpr int pool_cap() { return WIDTH * (2 * T::NL + 3 * MC + (T::CUBE ? MC : 0)); }
+// Slot map of a warp's pool (WIDTH = lanes = envs of the warp), two forms chosen per topology (pool_columns<T>):
+//   dense    rows of the warp packed in owner order: non-contact row j of an env at lbase + j, contact ci direction w at
+//            LT + 3 (cbase + ci) + w (lbase / cbase: warp prefix sums).  Touches the fewest cache lines when the envs of a warp
+//            differ in row count (Humanoid family: 0.85 vs 0.96 ms per step against the column form; FlagrunHarder 2.95 vs 3.47).
+//   columns  every env owns a column: non-contact row j of env o at j * WIDTH + o, contact ci direction w at
+//            (NNC + 3 ci + w) * WIDTH + o, so owner lanes that walk their rows in step -- the Gauss-Seidel sweeps -- read adjacent
+//            words.  Pays when every env of a warp has about the same rows (Ant, four feet down: 0.79 -> 0.70 ms per step).
+//   both     directory of limit-row tasks at slots [ROWS * WIDTH, ...), of contact tasks at [(ROWS + NNC) * WIDTH, ...): word 0 =
+//            the task's first row slot      (NNC = 2 NL non-contact rows, ROWS = NNC + 3 MC rows per env)
+#ifdef RS_POOL_COLUMNS
+template <class T> constexpr bool pool_columns() { return RS_POOL_COLUMNS != 0; }      // A/B builds
+#else
+template <class T> constexpr bool pool_columns() { return T::NL <= 12 && !T::CUBE; }
+#endif
+template <class T> constexpr int pool_nnc() { return T::NL > 0 ? 2 * T::NL : 1; }
+template <class T, int MC> constexpr int pool_rows() { return pool_nnc<T>() + 3 * MC; }
+template <class T, int MC, int WIDTH> constexpr int pool_cap() { return WIDTH * (pool_rows<T, MC>() + pool_nnc<T>() + MC); }
 // words of a row record: [0,nd) J ; [nd,2nd) M^-1 J^T ; [2nd] denominator.  A task descriptor lives in
 // words [0,25) of the task's first row slot until the task is executed (needs 2*nd+1 >= 25).
 constexpr int POOL_DESC_WORDS = 25;
@@ -156,12 +170,12 @@ RS_HD int f2i(float v) { union { int i; float f; } u; u.f = v; return u.i; }
 // NR simultaneous unit-impulse responses that share the loaded body.
 //   HASW: the right-hand sides are wrenches wr[rr] (torque;force) on body `body` (0 = base, i+1 = link i), in that
 //         body's coordinates about its COM.  !HASW: one unit generalized force jdir on the joint of link `body-1`.
-//   Rows go to pool slots slot0 .. slot0+NR-1.  first: overwrite; else accumulate (second body of a pair).
+//   Rows go to pool slots slot0, slot0 + rstr, ...  first: overwrite; else accumulate (second body of a pair).
 //   denom[rr] = J . M^-1 J^T of THIS side.
 // ---------------------------------------------------------------------------------------------
 template <class T, int NR, bool HASW, bool first, int STRIDE, class Pool>
 RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*wr)[6], float jdir,
-                           const Pool& pool, int slot0, float* denom) {
+                           const Pool& pool, int slot0, float* denom, int rstr = 1) {   // rstr: slots between the NR rows
     constexpr int n = T::NL, nd = nd_of<T>();
     float F[HASW ? NR : 1][6], Z[NR][6], Y[NR][n];
 #pragma unroll
@@ -196,7 +210,7 @@ RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*
                     const float kk = invD * y;
 #pragma unroll
                     for (int k = 0; k < 6; k++) Z[rr][k] += h[k] * kk;
-                    const PoolRef J = pool.at(slot0 + rr, 6 + d);
+                    const PoolRef J = pool.at(slot0 + rr * rstr, 6 + d);
                     if constexpr (first) J = j; else J += j;
                 }
             }
@@ -216,7 +230,7 @@ RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*
         } else {
             if constexpr (d >= 0) {
 #pragma unroll
-                for (int rr = 0; rr < NR; rr++) { Y[rr][i] = 0.f; if constexpr (first) pool.at(slot0 + rr, 6 + d) = 0.f; }
+                for (int rr = 0; rr < NR; rr++) { Y[rr][i] = 0.f; if constexpr (first) pool.at(slot0 + rr * rstr, 6 + d) = 0.f; }
             }
         }
     });
@@ -227,7 +241,7 @@ RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*
 #pragma unroll
             for (int k = 0; k < 6; k++) {
                 acc[rr][0][k] = 0.f;
-                if constexpr (first) { pool.at(slot0 + rr, k) = 0.f; pool.at(slot0 + rr, nd + k) = 0.f; }
+                if constexpr (first) { pool.at(slot0 + rr * rstr, k) = 0.f; pool.at(slot0 + rr * rstr, nd + k) = 0.f; }
             }
         }
     } else {
@@ -246,8 +260,8 @@ RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*
             tmulv(uw, Rb, acc[rr][0]); tmulv(uv, Rb, acc[rr][0] + 3);
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                const PoolRef J0 = pool.at(slot0 + rr, k), J1 = pool.at(slot0 + rr, 3 + k);
-                const PoolRef U0 = pool.at(slot0 + rr, nd + k), U1 = pool.at(slot0 + rr, nd + 3 + k);
+                const PoolRef J0 = pool.at(slot0 + rr * rstr, k), J1 = pool.at(slot0 + rr * rstr, 3 + k);
+                const PoolRef U0 = pool.at(slot0 + rr * rstr, nd + k), U1 = pool.at(slot0 + rr * rstr, nd + 3 + k);
                 if constexpr (first) { J0 = jw[k]; J1 = jv[k]; U0 = uw[k]; U1 = uv[k]; }
                 else { J0 += jw[k]; J1 += jv[k]; U0 += uw[k]; U1 += uv[k]; }
             }
@@ -271,7 +285,7 @@ RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*
             if constexpr (d >= 0) {
                 const float a = invD * (Y[rr][i] - dot6(acc[rr][i + 1], h));
                 saxpy<T, i>(acc[rr][i + 1], a);
-                const PoolRef U = pool.at(slot0 + rr, nd + 6 + d);
+                const PoolRef U = pool.at(slot0 + rr * rstr, nd + 6 + d);
                 if constexpr (first) U = a; else U += a;
                 if constexpr (!HASW) { if (body == i + 1) denom[rr] = a * jdir; }
             }
@@ -282,8 +296,8 @@ RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*
 
 // second body of a two-body contact: accumulate variant, kept out of line (rare; keeps the hot instruction stream short)
 template <class T, int STRIDE, class Pool>
-RS_HDN void pooled_response_second(const LinkCache<STRIDE>& lc, int body, const float (*wr)[6], const Pool& pool, int slot0, float* denom) {
-    pooled_response<T, 3, true, false>(lc, body, wr, 0.f, pool, slot0, denom);
+RS_HDN void pooled_response_second(const LinkCache<STRIDE>& lc, int body, const float (*wr)[6], const Pool& pool, int slot0, float* denom, int rstr) {
+    pooled_response<T, 3, true, false>(lc, body, wr, 0.f, pool, slot0, denom, rstr);
 }
 
 // resolveSingleConstraintRowGeneric on a pooled row record, over the dofs [K0, K1) the row acts on: a row between the robot
@@ -337,7 +351,10 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
     const int lane = warp.lane();
     // ---- owner: enumerate rows ----
     // non-contact rows: joint limits, then joint motors (the motors join the world after the limit constraints)
-    constexpr int NNC = n > 0 ? 2 * n : 1;
+    constexpr int NNC = pool_nnc<T>(), Wd = Warp::WIDTH;
+    constexpr int LDIR = pool_rows<T, MC>() * Wd, CDIR = LDIR + NNC * Wd;     // task directories behind the rows (slot map above)
+    constexpr bool COL = pool_columns<T>();
+    constexpr int RST = COL ? Wd : 1;                                         // slots between the three rows of a contact
     int n_nc = 0, nc = 0;
     int lim_code[NNC];
     float lim_pen[NNC];     // limit rows: penetration ; motor rows: desired joint velocity
@@ -381,20 +398,22 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
     int LT, CT;
     const int lbase = warp.excl_scan(n_nc, LT);
     const int cbase = warp.excl_scan(nc, CT);
+    auto slot_nc = [&](int j) { return COL ? j * Wd + lane : lbase + j; };                       // this lane's rows
+    auto slot_c = [&](int ci) { return COL ? (NNC + 3 * ci) * Wd + lane : LT + 3 * (cbase + ci); };  // direction w: + w * RST
     W.n_rows = n_nc + 3 * nc; W.n_contacts = nc;
-    // Cube topologies: a cube-floor point needs no helper (the owner writes its rows), and a resting cube has four of them in
-    // every env -- so the helpers' task list is the compacted list of contacts WITH a robot side: a directory of row slots
-    // behind the rows of the warp (slots [LT + 3 CT, LT + 3 CT + TT)), filled by the owners.
-    int TT = CT, tbase = 0, n_rt = 0;
+    // The helpers' task lists are compact directories filled by the owners: one entry per limit / motor row, one per contact
+    // that has a robot side (a cube-floor point needs no helper: the owner writes its rows, and a resting cube has four of them
+    // in every env).
+    int TT = 0, n_rt = nc;
     if constexpr (T::CUBE != 0) {
+        n_rt = 0;
         if (valid) for (int ci = 0; ci < nc; ci++) n_rt += W.ckey[W.cur][ci] != M.n_geoms + M.n_pairs;
-        tbase = warp.excl_scan(n_rt, TT);
     }
-    const int DIR0 = LT + 3 * CT;
+    const int tbase = warp.excl_scan(n_rt, TT);
     int rt_k = 0;
     if (LT + CT == 0) { warp.extra_sync(); warp.extra_sync(); return; }   // warp-uniform (the CTA-wide syncs below must still be matched)
     const int cur = W.cur;
-    for (int j = 0; j < n_nc; j++) pool.at(lbase + j, 0) = i2f(lim_code[j]);
+    for (int j = 0; j < n_nc; j++) { pool.at(slot_nc(j), 0) = i2f(lim_code[j]); pool.at(LDIR + lbase + j, 0) = i2f(slot_nc(j)); }
     for (int ci = 0; ci < nc; ci++) {
         const int key = W.ckey[cur][ci];
         const float* cd = W.cdat[cur][ci];
@@ -406,7 +425,7 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
         float dirs[3][3];
         dirs[0][0] = cd[6]; dirs[0][1] = cd[7]; dirs[0][2] = cd[8];
         plane_space(dirs[0], dirs[1], dirs[2]);
-        const int slot = LT + 3 * (cbase + ci);
+        const int slot = slot_c(ci);
         if constexpr (T::CUBE != 0) {
             if (bA == CB || bB == CB) {
                 // The cube's side of the three rows is written by the owner lane itself (its transform is not in the shared link
@@ -428,18 +447,18 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
                     const float im = 1.0f / M.cube_mass;
 #pragma unroll
                     for (int k = 0; k < 3; k++) {
-                        pool.at(slot + w, ndr + k) = jw[k]; pool.at(slot + w, ndr + 3 + k) = nn[k];
-                        pool.at(slot + w, nd + ndr + k) = uw[k]; pool.at(slot + w, nd + ndr + 3 + k) = nn[k] * im;
+                        pool.at(slot + w * RST, ndr + k) = jw[k]; pool.at(slot + w * RST, ndr + 3 + k) = nn[k];
+                        pool.at(slot + w * RST, nd + ndr + k) = uw[k]; pool.at(slot + w * RST, nd + ndr + 3 + k) = nn[k] * im;
                     }
                     cden[w] = dot3(jw, uw) + dot3(nn, nn) * im;
                 }
                 if (bA == CB) {     // (the robot words of these rows are never read: row_span)
 #pragma unroll
-                    for (int w = 0; w < 3; w++) pool.at(slot + w, 2 * nd) = cden[w];
+                    for (int w = 0; w < 3; w++) pool.at(slot + w * RST, 2 * nd) = cden[w];
                     continue;                                        // no helper task (not in the directory)
                 }
                 // robot geom vs cube: the helpers build the robot side like a floor contact and add the cube's denominators
-                pool.at(DIR0 + tbase + rt_k, 0) = i2f(slot); rt_k++;
+                pool.at(CDIR + tbase + rt_k, 0) = i2f(slot); rt_k++;
                 pool.at(slot, 0) = i2f(lane | (bA << 8) | (1 << 24));
 #pragma unroll
                 for (int k = 0; k < 3; k++) { pool.at(slot, 1 + k) = cd[k]; pool.at(slot, 13 + k) = cden[k]; }
@@ -456,7 +475,7 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
                 continue;
             }
         }
-        if constexpr (T::CUBE != 0) { pool.at(DIR0 + tbase + rt_k, 0) = i2f(slot); rt_k++; }
+        pool.at(CDIR + tbase + rt_k, 0) = i2f(slot); rt_k++;
         pool.at(slot, 0) = i2f(lane | (bA << 8) | ((bB + 1) << 16));
 #pragma unroll
         for (int k = 0; k < 3; k++) pool.at(slot, 1 + k) = cd[k];
@@ -491,13 +510,14 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
     for (int t0 = 0; t0 < LT; t0 += Warp::WIDTH) {
         const int t = t0 + lane;
         if (t < LT) {
-            const int code = f2i(pool.at(t, 0));
+            const int slot = f2i(pool.at(LDIR + t, 0));
+            const int code = f2i(pool.at(slot, 0));
             const int o = code & 255, body = (code >> 8) & 255;
             const float dir = ((code >> 16) & 1) ? -1.f : 1.f;
             LinkCache<STRIDE> lco{lc_lane0 + o};
             float dn[1];
-            pooled_response<T, 1, false, true>(lco, body, (const float (*)[6]) nullptr, dir, pool, t, dn);
-            pool.at(t, 2 * nd) = dn[0];
+            pooled_response<T, 1, false, true>(lco, body, (const float (*)[6]) nullptr, dir, pool, slot, dn);
+            pool.at(slot, 2 * nd) = dn[0];
         }
     }
     if (pc) { q1 = RS_CLOCK(); pc->t[7] += q1 - q0; q0 = q1; }
@@ -523,9 +543,9 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
                 wr[w][3] = d2[3 + 3 * w]; wr[w][4] = d2[4 + 3 * w]; wr[w][5] = d2[5 + 3 * w];
             }
             LinkCache<STRIDE> lco{lc_lane0 + own2};
-            pooled_response_second<T>(lco, body2, (const float (*)[6]) wr, pool, slot2, dn);
+            pooled_response_second<T>(lco, body2, (const float (*)[6]) wr, pool, slot2, dn, RST);
 #pragma unroll
-            for (int w = 0; w < 3; w++) pool.at(slot2 + w, 2 * nd) += dn[w];
+            for (int w = 0; w < 3; w++) pool.at(slot2 + w * RST, 2 * nd) += dn[w];
             have2 = false;
         }
         npend = 0;
@@ -537,7 +557,7 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
 #pragma unroll
         for (int k = 13; k < POOL_DESC_WORDS; k++) desc[k] = 0.f;
         if (t < TT) {
-            slot = T::CUBE != 0 ? f2i(pool.at(DIR0 + t, 0)) : LT + 3 * t;
+            slot = f2i(pool.at(CDIR + t, 0));
             const int code = f2i(pool.at(slot, 0));
             o = code & 255; bB = ((code >> 16) & 255) - 1;
             const int bA = (code >> 8) & 255;
@@ -561,11 +581,11 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
                     cross3(wr[w], desc + 1, desc + 4 + 3 * w);
                     wr[w][3] = desc[4 + 3 * w]; wr[w][4] = desc[5 + 3 * w]; wr[w][5] = desc[6 + 3 * w];
                 }
-                pooled_response<T, 3, true, true>(lco, bA, (const float (*)[6]) wr, 0.f, pool, slot, dsum);
+                pooled_response<T, 3, true, true>(lco, bA, (const float (*)[6]) wr, 0.f, pool, slot, dsum, RST);
             }
             if (cube_side) { dsum[0] += desc[13]; dsum[1] += desc[14]; dsum[2] += desc[15]; }
 #pragma unroll
-            for (int w = 0; w < 3; w++) pool.at(slot + w, 2 * nd) = dsum[w];
+            for (int w = 0; w < 3; w++) pool.at(slot + w * RST, 2 * nd) = dsum[w];
         }
         // hand this round's second bodies to the lanes without a pending one
         unsigned m2 = warp.ballot(bB >= 0);
@@ -626,7 +646,7 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
     };
     // local row index: [0,n_nc) limits ; n_nc + 3*ci + w  contact ci, direction w
     for (int j = 0; j < n_nc; j++) {
-        const int slot = lbase + j;
+        const int slot = slot_nc(j);
         const float relvel = row_relvel(slot, 0), denom = pool.at(slot, 2 * nd), pen = lim_pen[j];
         const float invd = denom > RS_FLT_EPS ? 1.0f / denom : 0.f;
         const float erp = pen > M.split_thresh ? M.erp : M.erp2;
@@ -639,7 +659,7 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
         const int span = row_span<T>(M, W.ckey[cur][ci]);
 #pragma unroll
         for (int w = 0; w < 3; w++) {
-            const int slot = LT + 3 * (cbase + ci) + w, row = n_nc + 3 * ci + w;
+            const int slot = slot_c(ci) + w * RST, row = n_nc + 3 * ci + w;
             const float relvel = row_relvel(slot, span), denom = pool.at(slot, 2 * nd);
             const float invd = denom > RS_FLT_EPS ? 1.0f / denom : 0.f;
             float rhs;
@@ -661,11 +681,11 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
         for (int j = 0; j < n_nc; j++) {
             const int row = (it & 1) ? j : n_nc - 1 - j;
             const float mi = mot_imp[row];      // < 0: limit row (unilateral) ; > 0: motor row (+- impulse bound)
-            resolve_span<T>(0, pool, lbase + row, dv, r_rhs[row], r_invd[row], mi > 0.f ? -mi : 0.f, mi > 0.f ? mi : lim_hi_imp, r_applied[row]);
+            resolve_span<T>(0, pool, slot_nc(row), dv, r_rhs[row], r_invd[row], mi > 0.f ? -mi : 0.f, mi > 0.f ? mi : lim_hi_imp, r_applied[row]);
         }
         for (int ci = 0; ci < nc; ci++) {
             const int row = n_nc + 3 * ci;
-            resolve_span<T>(row_span<T>(M, W.ckey[cur][ci]), pool, LT + 3 * (cbase + ci), dv, r_rhs[row], r_invd[row], 0.f, 1e10f, r_applied[row]);
+            resolve_span<T>(row_span<T>(M, W.ckey[cur][ci]), pool, slot_c(ci), dv, r_rhs[row], r_invd[row], 0.f, 1e10f, r_applied[row]);
         }
         for (int ci = 0; ci < nc; ci++) {
             const float tot = r_applied[n_nc + 3 * ci];
@@ -678,7 +698,7 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
 #pragma unroll
                 for (int w = 1; w < 3; w++) {
                     const int row = n_nc + 3 * ci + w;
-                    resolve_span<T>(row_span<T>(M, key), pool, LT + 3 * (cbase + ci) + w, dv, r_rhs[row], r_invd[row], -fr * tot, fr * tot, r_applied[row]);
+                    resolve_span<T>(row_span<T>(M, key), pool, slot_c(ci) + w * RST, dv, r_rhs[row], r_invd[row], -fr * tot, fr * tot, r_applied[row]);
                 }
             }
         }

@@ -240,7 +240,7 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
     if (const char* e = getenv("RS_EXTRA_SYNC")) w->extra_sync = atoi(e) != 0;
     DevBuf& B = w->B;
     B.N = n_envs; B.S = (model->fixed_base ? 0 : 13) + 2 * model->n_dof + (model->has_cube ? 13 : 0); B.MCcap = MC;
-    B.rec = 2 * (6 + model->n_dof + (model->has_cube ? 6 : 0)) + 1; B.maxr = 2 * NL + 3 * MC + (model->has_cube ? MC : 0);   // +1: pooled rows keep their denominator in the record; a limit and a motor row per joint
+    B.rec = 2 * (6 + model->n_dof + (model->has_cube ? 6 : 0)) + 1; B.maxr = 4 * NL + 4 * MC;   // +1: pooled rows keep their denominator in the record; slots per env: a limit and a motor row per joint, 3 rows per contact, the two task directories (rs_pooled.cuh pool_cap)
     size_t N = (size_t)n_envs;
     CK(cudaMalloc(&B.state, sizeof(float) * N * (B.S > 0 ? B.S : 1)));
     CK(cudaMalloc(&B.ccount, sizeof(int) * N));

@@ -53,7 +53,7 @@ void* emul_create(const rs_model_desc* m, int n) {
     if (build_dev_model(m, &e->M, &err)) { delete e; return nullptr; }
     e->n = n; e->w.resize(n); e->ep.resize(n); e->out.resize(n);
     for (int i = 0; i < n; i++) { memset(&e->w[i], 0, sizeof(W_t)); e->w[i].bquat[3] = 1; e->w[i].cquat[3] = 1; memset(&e->ep[i], 0, sizeof(Episode)); e->ep[i].initial_z = e->M.initial_z; e->ep[i].target_x = e->M.walk_target_x; e->ep[i].target_y = e->M.walk_target_y; }
-    e->rec = 2 * (6 + e->M.n_dof + (e->M.has_cube ? 6 : 0)) + 1; e->maxr = 2 * NL + 4 * MC;
+    e->rec = 2 * (6 + e->M.n_dof + (e->M.has_cube ? 6 : 0)) + 1; e->maxr = 4 * NL + 4 * MC;   // rs_pooled.cuh pool_cap: rows + task directories
     e->ws.resize((size_t)e->rec * e->maxr);
     e->obs.resize((size_t)n * e->M.obs_dim); e->rew.resize(n); e->done.resize(n);
     e->topo = 0; e->lcsize = 9 * RS_MAX_LINKS + 30; e->lcbuf.assign((size_t)n * e->lcsize, 0.f);
@@ -94,7 +94,7 @@ void emul_set_joint_motor(void* h, int env, int dof, double kp, double kd, doubl
     Emul* e = (Emul*)h; const int nd = e->M.n_dof;
     if (e->motor.empty()) {
         e->motor.assign((size_t)e->n * 5 * nd, 0.f);
-        e->ws.resize((size_t)e->rec * (2 * NL + 3 * MC));
+        e->ws.resize((size_t)e->rec * e->maxr);
         for (int i = 0; i < e->n; i++) { e->w[i].motor = e->motor.data() + (size_t)i * 5 * nd; e->w[i].motor_stride = 1; }
     }
     const double v[5] = {kp, kd, pos, vel, imp > 0 ? imp : 0};
