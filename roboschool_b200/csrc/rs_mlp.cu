@@ -21,7 +21,9 @@ struct rs_policy {
     int tc5_variant, n_sm;
     void* tc5_image;
     size_t tc5_smem;
+    uint64_t serial;     // unique per object: keys the step graphs that hold this policy's launch arguments (rs_step.cu)
 };
+uint64_t rs_policy_serial(const rs_policy* p) { return p ? p->serial : 0; }
 
 extern "C" int rs_policy_create(int in_dim, int h1, int h2, int out_dim, const float* w1, const float* b1, const float* w2,
                                 const float* b2, const float* w3, const float* b3, int device, rs_policy** out) {
@@ -48,6 +50,7 @@ extern "C" int rs_policy_create(int in_dim, int h1, int h2, int out_dim, const f
         }
     }
     rs_policy* p = new rs_policy();
+    { static uint64_t next_serial = 0; p->serial = ++next_serial; }
     p->in_dim = in_dim; p->h1 = h1; p->h2 = h2; p->out_dim = out_dim; p->device = device;
     p->tc5_variant = rs_tc5_supported(in_dim, h1, h2, out_dim);
     p->tc5_image = nullptr;

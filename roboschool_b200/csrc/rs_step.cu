@@ -40,6 +40,7 @@ static StaticLaunchFn pick_static(int topo, int prof, int def_wpc) {
 }
 
 #define RS_MAX_CHUNKS 8
+#define RS_MAX_GRAPHS 4
 struct rs_world {
     rs_model_desc desc;
     DevModel M;
@@ -51,8 +52,15 @@ struct rs_world {
     cudaStream_t stream;
     cudaStream_t chunk_stream[RS_MAX_CHUNKS];   // pipelined host entry point: one stream per env slice (created on first use)
     cudaEvent_t chunk_ev;
+    cudaEvent_t chunk_done[RS_MAX_CHUNKS];      // join events of the slices (graph form of the pipelined entry point)
     cudaEvent_t caller_ev;   // recorded behind everything the world enqueues on a caller's stream
     int n_chunk_streams;
+    // The pipelined host entry point enqueues ~40 operations per env step (6 slices x {wait, H2D, policy, step, 3 x D2H});
+    // a caller that alternates between a few sets of page-locked buffers (ping-pong) replays them as ONE CUDA graph launch.
+    // Key = everything the captured nodes hold by value: the caller's pointers, the policy, the slice count, the RNG keys.
+    struct StepGraph { const float* in; float* out; float* rew; uint8_t* done; uint64_t pol; int n_chunks; uint32_t seed, env_id0; cudaGraphExec_t exec; };
+    StepGraph graphs[RS_MAX_GRAPHS];
+    int n_graphs, graph_next, graph_off;        // graph_off: capture failed once (or RS_E2E_GRAPH=0): direct launches from then on
     // pinned staging + device staging for the host-buffer entry point
     float *h_act, *h_obs, *h_rew; uint8_t* h_done;
     float *d_act, *d_obs, *d_rew; uint8_t* d_done;
@@ -299,6 +307,12 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
     return 0;
 }
 
+// the captured step graphs hold DevModel / DevBuf by value: dropped whenever either changes
+static void drop_graphs(rs_world* w) {
+    for (int k = 0; k < w->n_graphs; k++) { if (w->graphs[k].exec) cudaGraphExecDestroy(w->graphs[k].exec); w->graphs[k].exec = nullptr; }
+    w->n_graphs = 0; w->graph_next = 0;
+}
+
 extern "C" int rs_world_destroy(rs_world* w) {
     if (!w) return 0;
     cudaSetDevice(w->device);
@@ -310,7 +324,8 @@ extern "C" int rs_world_destroy(rs_world* w) {
     cudaFree(w->d_act); cudaFree(w->d_obs); cudaFree(w->d_rew); cudaFree(w->d_done); cudaFree(w->d_stats);
     cudaStreamDestroy(w->stream);
     cudaEventDestroy(w->caller_ev);
-    for (int k = 0; k < w->n_chunk_streams; k++) cudaStreamDestroy(w->chunk_stream[k]);
+    drop_graphs(w);
+    for (int k = 0; k < w->n_chunk_streams; k++) { cudaStreamDestroy(w->chunk_stream[k]); cudaEventDestroy(w->chunk_done[k]); }
     if (w->n_chunk_streams) cudaEventDestroy(w->chunk_ev);
     delete w;
     return 0;
@@ -441,6 +456,7 @@ extern "C" int rs_world_set_joint_motor(rs_world* w, int env, int dof, float kp,
         // first motor of this world: motor table (all off); the row workspace already has room for one motor row per dof
         CK(cudaMalloc(&B.motor, sizeof(float) * 5 * (size_t)nd * N));
         CK(cudaMemset(B.motor, 0, sizeof(float) * 5 * (size_t)nd * N));
+        drop_graphs(w);                                      // DevBuf changed
     }
     const float v[5] = {kp, kd, target_pos, target_vel, max_impulse > 0.f ? max_impulse : 0.f};
     const int e0 = env < 0 ? 0 : env, ne = env < 0 ? N : 1;
@@ -708,38 +724,28 @@ static bool host_is_pinned(const void* p) {
 // into slices of whole CTAs, each slice runs H2D -> policy -> step -> D2H on its own stream, so the copies of one slice overlap
 // the kernels of the others (one copy engine per direction keeps the copies themselves in issue order).  Slices touch disjoint
 // envs, constraint-row pools and output rows, so the result is bit-identical to the single-stream form.
-static int policy_step_host_pipelined(rs_world* w, rs_policy* p, const float* obs_in_host, float* obs_out_host, float* reward_host,
-                                      uint8_t* done_host, int n_chunks) {
-    int per = 0;
-    {
-        StaticLaunch q{&w->M, &w->B, w->n, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, nullptr, nullptr, nullptr};
-        q.per_out = &per;
-        StaticLaunchFn fn = pick_static(w->topo, 0, w->wpc);
-        if (!fn) return fail("static-topology kernel not linked");
-        fn(q);
-    }
-    const int ncta = (w->n + per - 1) / per;
-    if (n_chunks > ncta) n_chunks = ncta;
-    while (w->n_chunk_streams < n_chunks) {
-        if (!w->n_chunk_streams) CK(cudaEventCreateWithFlags(&w->chunk_ev, cudaEventDisableTiming));
-        CK(cudaStreamCreateWithFlags(&w->chunk_stream[w->n_chunk_streams], cudaStreamNonBlocking));
-        w->n_chunk_streams++;
-    }
+uint64_t rs_policy_serial(const rs_policy* p);   // rs_mlp.cu: unique per policy object (a freed policy's address may be reused)
+
+// the slices of one env step: H2D -> policy -> step -> D2H per slice, each on its own stream behind chunk_ev
+static int enqueue_slices(rs_world* w, rs_policy* p, const float* obs_in_host, float* obs_out_host, float* reward_host,
+                          uint8_t* done_host, int n_chunks, int per, int ncta, bool join) {
     const size_t O = (size_t)w->desc.obs_dim, A = (size_t)w->desc.n_act;
-    CK(wait_caller(w));
-    CK(cudaEventRecord(w->chunk_ev, w->stream));            // everything queued on the world's / the callers' streams so far comes first
     // slice boundaries in CTAs.  Only the first slice's H2D and the last slice's D2H are exposed, so with 4 or more slices
-    // the two outer ones are half as large as the inner ones (RS_E2E_EVEN=1: equal slices).
+    // the two outer ones are half as large as the inner ones (RS_E2E_EVEN=1: equal slices).  With cluster launches a boundary
+    // is a multiple of the cluster size: a slice with an odd number of CTAs is padded with a CTA that owns no env but occupies
+    // an SM to the end, and six such slices asked for 152 SMs (a second wave) where 148 exist.
     int bound[RS_MAX_CHUNKS + 1];
     {
         const char* ev = getenv("RS_E2E_EVEN");
         const bool even = n_chunks < 4 || (ev && atoi(ev) != 0);
         const double units = even ? (double)n_chunks : (double)(n_chunks - 1);     // outer slices weigh 1/2
+        const int cl = (w->cluster > 1 && w->wpc > 1) ? w->cluster : 1;
         double acc = 0.0;
         bound[0] = 0;
         for (int c = 0; c < n_chunks; c++) {
             acc += (even || (c > 0 && c < n_chunks - 1)) ? 1.0 : 0.5;
-            bound[c + 1] = (int)(acc / units * ncta + 0.5);
+            bound[c + 1] = (int)(acc / units * ncta / cl + 0.5) * cl;
+            if (bound[c + 1] > ncta) bound[c + 1] = ncta;
         }
         bound[n_chunks] = ncta;
     }
@@ -755,7 +761,77 @@ static int policy_step_host_pipelined(rs_world* w, rs_policy* p, const float* ob
         CK(cudaMemcpyAsync(obs_out_host + e0 * O, w->d_obs + e0 * O, sizeof(float) * ne * O, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(reward_host + e0, w->d_rew + e0, sizeof(float) * ne, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(done_host + e0, w->d_done + e0, ne, cudaMemcpyDeviceToHost, st));
+        if (join) {     // graph form: the slices join the origin stream again
+            CK(cudaEventRecord(w->chunk_done[c], st));
+            CK(cudaStreamWaitEvent(w->stream, w->chunk_done[c], 0));
+        }
     }
+    return 0;
+}
+
+static int policy_step_host_pipelined(rs_world* w, rs_policy* p, const float* obs_in_host, float* obs_out_host, float* reward_host,
+                                      uint8_t* done_host, int n_chunks) {
+    int per = 0;
+    {
+        StaticLaunch q{&w->M, &w->B, w->n, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, nullptr, nullptr, nullptr};
+        q.per_out = &per;
+        StaticLaunchFn fn = pick_static(w->topo, 0, w->wpc);
+        if (!fn) return fail("static-topology kernel not linked");
+        fn(q);
+    }
+    const int ncta = (w->n + per - 1) / per;
+    if (n_chunks > ncta) n_chunks = ncta;
+    while (w->n_chunk_streams < n_chunks) {
+        if (!w->n_chunk_streams) CK(cudaEventCreateWithFlags(&w->chunk_ev, cudaEventDisableTiming));
+        CK(cudaStreamCreateWithFlags(&w->chunk_stream[w->n_chunk_streams], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&w->chunk_done[w->n_chunk_streams], cudaEventDisableTiming));
+        w->n_chunk_streams++;
+    }
+    CK(wait_caller(w));
+    if (const char* e = getenv("RS_E2E_GRAPH")) { if (atoi(e) == 0) w->graph_off = 1; }
+    if (!w->graph_off) {
+        // replay the step as one graph launch when this set of buffers has been seen before; capture it on its second use (a
+        // caller that passes fresh buffers every step never pays for a capture)
+        const uint64_t pol = rs_policy_serial(p);
+        rs_world::StepGraph* g = nullptr;
+        for (int k = 0; k < w->n_graphs; k++) {
+            rs_world::StepGraph& q = w->graphs[k];
+            if (q.in == obs_in_host && q.out == obs_out_host && q.rew == reward_host && q.done == done_host && q.pol == pol &&
+                q.n_chunks == n_chunks && q.seed == w->rollout_seed && q.env_id0 == w->env_id0) { g = &q; break; }
+        }
+        if (!g) {
+            // first sight: remember the key (exec == nullptr), run this step with direct launches
+            int k;
+            if (w->n_graphs < RS_MAX_GRAPHS) k = w->n_graphs++;
+            else { k = w->graph_next++ % RS_MAX_GRAPHS; if (w->graphs[k].exec) cudaGraphExecDestroy(w->graphs[k].exec); }
+            w->graphs[k] = rs_world::StepGraph{obs_in_host, obs_out_host, reward_host, done_host, pol, n_chunks, w->rollout_seed, w->env_id0, nullptr};
+        } else {
+            if (!g->exec) {
+                cudaGraph_t graph = nullptr;
+                bool ok = cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+                if (ok) {
+                    ok = cudaEventRecord(w->chunk_ev, w->stream) == cudaSuccess &&
+                         enqueue_slices(w, p, obs_in_host, obs_out_host, reward_host, done_host, n_chunks, per, ncta, true) == 0;
+                    cudaError_t ce = cudaStreamEndCapture(w->stream, &graph);
+                    ok = ok && ce == cudaSuccess && graph != nullptr;
+                }
+                if (ok) ok = cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess;
+                if (graph) cudaGraphDestroy(graph);
+                if (!ok) {
+                    cudaGetLastError();
+                    g->exec = nullptr; w->graph_off = 1;
+                    fprintf(stderr, "roboschool_b200: CUDA graph capture of the pipelined host step failed (%s); using direct launches\n", g_err.c_str());
+                }
+            }
+            if (g->exec) {
+                CK(cudaGraphLaunch(g->exec, w->stream));
+                CK(cudaStreamSynchronize(w->stream));
+                return 0;
+            }
+        }
+    }
+    CK(cudaEventRecord(w->chunk_ev, w->stream));            // everything queued on the world's / the callers' streams so far comes first
+    if (enqueue_slices(w, p, obs_in_host, obs_out_host, reward_host, done_host, n_chunks, per, ncta, false)) return 1;
     for (int c = 0; c < n_chunks; c++) CK(cudaStreamSynchronize(w->chunk_stream[c]));
     return 0;
 }

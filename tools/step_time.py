@@ -10,6 +10,8 @@ from roboschool_b200.policy import ZooPolicy, load_zoo_weights
 from roboschool_b200 import _lib
 
 st = torch.cuda.current_stream().cuda_stream
+# STEP_TIME_STATS=1: step through rs_world_step_stats (the entry point bench.py times) instead of rs_world_step
+stats = torch.zeros(8, dtype=torch.float64, device="cuda") if os.environ.get("STEP_TIME_STATS") else None
 for arg in sys.argv[1:]:
     env_id, n = arg.split(":")
     n = int(n)
@@ -28,11 +30,15 @@ for arg in sys.argv[1:]:
     for t in range(T):
         pol.forward(obs_p, act_p, n, st)
         ev[t][0].record()
-        _lib.check(W.L.rs_world_step(W.h, act_p, obs_p, rew_p, done_p, 1, st))
+        if stats is not None:
+            _lib.check(W.L.rs_world_step_stats(W.h, act_p, obs_p, rew_p, done_p, 1, stats.data_ptr(), st))
+        else:
+            _lib.check(W.L.rs_world_step(W.h, act_p, obs_p, rew_p, done_p, 1, st))
         ev[t][1].record()
     torch.cuda.synchronize()
-    ms = float(np.median([a.elapsed_time(b) for a, b in ev]))
+    ts = [a.elapsed_time(b) for a, b in ev]
+    ms = float(np.median(ts))
     r, c = W.counts()
-    print(json.dumps({"env": env_id, "envs": n, "k_step_ms": ms, "env_steps_per_s": n / ms * 1e3, "mean_rows": float(r.mean()),
+    print(json.dumps({"env": env_id, "envs": n, "k_step_ms": ms, "env_steps_per_s": n / ms * 1e3, "k_step_ms_mean": float(np.mean(ts)), "k_step_ms_max": float(np.max(ts)), "stats": stats is not None, "mean_rows": float(r.mean()),
                       "variant": W.L.rs_world_kernel_variant(W.h)}), flush=True)
     del W
