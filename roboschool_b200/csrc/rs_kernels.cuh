@@ -193,7 +193,24 @@ __global__ void __launch_bounds__(32 * WPC) k_step_static(const __grid_constant_
     if (stats) {
         st_rew = warp_sum(st_rew); st_ep = warp_sum(st_ep); st_len = warp_sum(st_len); st_nf = warp_sum(st_nf);
         st_rows = warp_sum(st_rows); st_con = warp_sum(st_con); st_steps = warp_sum(st_steps);
-        if ((threadIdx.x & 31) == 0) {
+        // one set of atomics per CTA: 1024 warps adding to the same seven doubles serialise in the L2 (measured: 3 % of the step)
+        double* sv = stats;
+        if constexpr (WPC > 1) {
+            __shared__ double s_st[WPC][7];
+            if (lane == 0) {
+                s_st[wic][0] = st_rew; s_st[wic][1] = st_ep; s_st[wic][2] = st_len; s_st[wic][3] = st_nf;
+                s_st[wic][4] = st_rows; s_st[wic][5] = st_con; s_st[wic][6] = st_steps;
+            }
+            __syncthreads();
+            if (threadIdx.x < 7) {
+                double v = 0;
+#pragma unroll
+                for (int k = 0; k < WPC; k++) v += s_st[k][threadIdx.x];
+                atomicAdd(stats + threadIdx.x, v);
+            }
+            sv = nullptr;
+        }
+        if (sv && lane == 0) {
             atomicAdd(stats + 0, st_rew); atomicAdd(stats + 1, st_ep); atomicAdd(stats + 2, st_len); atomicAdd(stats + 3, st_nf);
             atomicAdd(stats + 4, st_rows); atomicAdd(stats + 5, st_con); atomicAdd(stats + 6, st_steps);
         }

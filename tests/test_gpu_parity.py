@@ -406,7 +406,8 @@ def test_behavioural_fixture_on_gpu_humanoid_walks():
 @pytest.mark.parametrize("env_id,n", [("RoboschoolHumanoid-v1", 25000), ("RoboschoolHopper-v1", 9000), ("RoboschoolAnt-v1", 33152)])
 def test_policy_step_host_pipelined_matches_single_stream(env_id, n, monkeypatch):
     """rs_world_policy_step_host with page-locked buffers cuts the envs into CTA-aligned slices on separate streams (copies of
-    one slice overlap the kernels of the others).  Bit-identical to the single-stream form (RS_E2E_CHUNKS=1) and to pageable
+    one slice overlap the kernels of the others; from the second use of a buffer set on, the slices of a step are replayed as one
+    CUDA graph).  Bit-identical to the single-stream form (RS_E2E_CHUNKS=1) and to pageable
     buffers (staged path), over steps that include auto-resets; n is ragged on purpose (partial tail CTA, partial tail slice)."""
     import torch
     from roboschool_b200.world import BatchedWorld
@@ -414,8 +415,9 @@ def test_policy_step_host_pipelined_matches_single_stream(env_id, n, monkeypatch
     m = load_env_model(env_id)
     pol = ZooPolicy(load_zoo_weights(env_id), 0)
     st = torch.cuda.current_stream().cuda_stream
-    def run(chunks, pinned):
+    def run(chunks, pinned, graph=True):
         monkeypatch.setenv("RS_E2E_CHUNKS", str(chunks))
+        monkeypatch.setenv("RS_E2E_GRAPH", "1" if graph else "0")   # slices replayed as one CUDA graph per buffer set / launched directly
         W = BatchedWorld(m, n, 0)
         obs0 = torch.empty((n, m.obs_dim), dtype=torch.float32, device="cuda")
         W.reset(seed=9, obs=obs0, stream=st)
@@ -436,10 +438,10 @@ def test_policy_step_host_pipelined_matches_single_stream(env_id, n, monkeypatch
     ref = run(1, True)
     if env_id == "RoboschoolHopper-v1":        # its zoo policy falls within ~30 steps on the restated physics: auto-resets are covered
         assert sum(int(d.sum()) for _, _, d in ref) > 0
-    for chunks, pinned in [(6, True), (4, True), (3, True), (4, False)]:
-        got = run(chunks, pinned)
+    for chunks, pinned, graph in [(6, True, True), (6, True, False), (4, True, True), (3, True, False), (4, False, True)]:
+        got = run(chunks, pinned, graph)
         for (o, r, d), (o2, r2, d2) in zip(ref, got):
-            assert np.array_equal(o, o2) and np.array_equal(r, r2) and np.array_equal(d, d2), (chunks, pinned)
+            assert np.array_equal(o, o2) and np.array_equal(r, r2) and np.array_equal(d, d2), (chunks, pinned, graph)
 
 
 @pytest.mark.parametrize("env_id,min_return,min_len", [
