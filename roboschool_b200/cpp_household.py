@@ -119,7 +119,8 @@ class Thingy(object):
     def pose(self):
         p = Pose()
         row = self._robot._pose_row(self._b)
-        p.set_xyz(float(row[0]) / SCALE, float(row[1]) / SCALE, float(row[2]) / SCALE)
+        off = self._robot._offset
+        p.set_xyz((float(row[0]) + off[0]) / SCALE, (float(row[1]) + off[1]) / SCALE, (float(row[2]) + off[2]) / SCALE)
         p.set_quaternion(float(row[3]), float(row[4]), float(row[5]), float(row[6]))
         return p
 
@@ -216,6 +217,10 @@ class Robot(object):
         self._queried = False
         self._poses = None
         self._state = None
+        # A fixed-base robot (planar walkers, pendulums) is anchored at the world origin in its own world; the floor is an infinite
+        # plane, so moving its base (the multiplayer stadium puts player n in lane y = n - 1, scene_stadium.py:23-29) is a pure
+        # translation of what the readback reports.  Floating-base robots carry their position in the state instead.
+        self._offset = (0.0, 0.0, 0.0)
         if model is None:      # static body (floor): a root part only
             self.root_part = Thingy(self, 0, static_name)
             self.parts, self.joints = [], []
@@ -305,7 +310,11 @@ class Robot(object):
 
     def set_pose_and_speed(self, p, vx, vy, vz):
         """World::robot_move (physics-bullet.cpp:583-594): base pose and base LINEAR velocity only."""
-        if self._backend is None or self._model.fixed_base:
+        if self._backend is None:
+            return
+        if self._model.fixed_base:
+            raw = self._pose_row(0)
+            self._offset = (p.x - float(raw[0]), p.y - float(raw[1]), p.z - float(raw[2]))
             return
         s = self._backend.get_state()
         s[0, 0:3] = [p.x, p.y, p.z]

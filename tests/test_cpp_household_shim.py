@@ -132,3 +132,58 @@ def test_joint_motor_state_machine_on_shim(ref_roboschool, oracle_lib):
     b2.set_joint_motor(knee._dof, 0.1, 0.4, -1.0, 0.0, 0.0)
     ref.substeps(1, np.zeros(env.cpp_robot._model.n_dof)); b2.substeps(1, np.zeros(env.cpp_robot._model.n_dof))
     assert np.array_equal(ref.get_state(), b2.get_state())
+
+
+@pytest.mark.parametrize("cls,env_id", [("RoboschoolAnt", "RoboschoolAnt-v1"), ("RoboschoolHopper", "RoboschoolHopper-v1")])
+def test_multiplayer_stadium_scene_on_shim(cls, env_id, ref_roboschool, oracle_lib):
+    """SURVEY 8f.4, the reference's own multiplayer loop (multiplayer.py:237-288 without the shared-memory pipes): three robots
+    loaded into ONE cpp_household.World by the reference's MultiplayerStadiumScene (scene_stadium.py:23-29: player n runs in lane
+    y = n - 1), actions applied to all, ONE scene.global_step(), then every env's step() reads its own result.  Each robot
+    reproduces the single-player rollout of the same seed and actions shifted into its lane (the robots are three envs of the
+    batch: no inter-robot contacts -- DESIGN.md section 7)."""
+    from roboschool.scene_stadium import MultiplayerStadiumScene
+    Cls = getattr(ref_roboschool, cls)
+    scene = MultiplayerStadiumScene(gravity=9.8, timestep=0.0165 / 4, frame_skip=4)
+    envs = []
+    for n in range(3):
+        e = Cls()
+        e.spec = _Spec()
+        e.scene = scene
+        e.player_n = n
+        envs.append(e)
+    scene.episode_restart()
+    obs = []
+    for n, e in enumerate(envs):
+        e.seed(5 + n)
+        obs.append(e.reset())
+    assert len(scene.multiplayer_robots) == 3
+    # the same three episodes, single player
+    solo = []
+    for n in range(3):
+        e = Cls()
+        e.spec = _Spec()
+        e.seed(5 + n)
+        o0 = e.reset()
+        solo.append(e)
+        lane = n - 1
+        assert abs(envs[n].cpp_robot.root_part.pose().xyz()[1] - (e.cpp_robot.root_part.pose().xyz()[1] + lane)) < 1e-6
+        if lane == 0:
+            assert np.abs(o0 - obs[n]).max() < 1e-6
+    rng = np.random.RandomState(1)
+    for t in range(20):
+        acts = [rng.uniform(-1, 1, e.action_space.shape[0]).astype(np.float32) for e in envs]
+        for e, a in zip(envs, acts):
+            e.apply_action(a)
+        scene.global_step()
+        for n, (e, a) in enumerate(zip(envs, acts)):
+            ob, rew, done, _ = e.step(a)
+            ob1, rew1, done1, _ = solo[n].step(a)
+            # lanes differ in y only: joint, height, velocity and feet entries agree; the two angle-to-target entries see the
+            # 1 m lane offset against a target 1 km away (< 1e-3 rad)
+            keep = np.ones(ob.shape[0], dtype=bool)
+            keep[1:3] = False
+            assert np.abs(ob[keep] - ob1[keep]).max() < 1e-5, (t, n)
+            assert np.abs(ob[1:3] - ob1[1:3]).max() < 2e-3
+            assert bool(done) == bool(done1)
+            by = e.body_xyz[1] - solo[n].body_xyz[1]
+            assert abs(by - (n - 1)) < 1e-4, (t, n, by)
