@@ -122,7 +122,9 @@ int rs_world_policy_step_host(rs_world* w, rs_policy* p, const float* obs_in_hos
 
 /* Physics only: n sub-steps with explicit joint torques tau_host[n_envs][ndof] (NULL = keep the
  * torques of the last call); no task logic.  Joint::set_motor_torque + World::bullet_step
- * (physics-bullet.cpp:497-508, 358-412). */
+ * (physics-bullet.cpp:497-508, 358-412).  A world with FlagrunHarder's cube (rs_model_desc.has_cube: World::load_urdf of
+ * models_household/cube.urdf, physics-bullet.cpp:70-93) steps the cube too; Robot::set_pose_and_speed on it
+ * (robot_move, :579-591) is rs_world_set_state on the last 13 state words. */
 int rs_world_substeps(rs_world* w, int n_substeps, const float* tau_host);
 
 /* Joint::set_servo_target(pos, kp, kd, maxforce) / Joint::set_target_speed(v, kd, maxforce) (physics-bullet.cpp:510-537;

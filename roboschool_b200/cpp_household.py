@@ -240,6 +240,34 @@ class Robot(object):
         self._state = s
 
     # ---- internal ----
+    def _attach_box(self, half, mass, pose):
+        """Rebuild this robot's world with a free box as second body (load_urdf of a single-box URDF): same descriptor plus the
+        cube block -- inertia of the collision AABB (load_urdf passes no URDF_USE_INERTIA_FROM_FILE), URDF importer default
+        friction 0.5, contact-breaking threshold 0.02 x the half diagonal -- and the current state carried over."""
+        m = self._model.clone()
+        hx, hy, hz = half
+        m.has_cube = 1
+        m.arr("cube_half")[:] = [hx, hy, hz]
+        m.cube_mass = mass
+        lx, ly, lz = 2 * hx, 2 * hy, 2 * hz
+        m.arr("cube_inertia")[:] = [mass / 12.0 * (ly * ly + lz * lz), mass / 12.0 * (lx * lx + lz * lz), mass / 12.0 * (lx * lx + ly * ly)]
+        m.cube_friction = 0.5
+        m.cube_break_thresh = 0.02 * math.sqrt(hx * hx + hy * hy + hz * hz)
+        m.arr("cube_start")[:] = [pose.x, pose.y, pose.z]
+        old = self._backend
+        s_old = np.asarray(old.get_state(), dtype=np.float64)
+        nb = _make_backend(m, 1)
+        s = np.zeros((1, nb.S), dtype=np.float64)
+        s[0, :s_old.shape[1]] = s_old[0]
+        c0 = s_old.shape[1]
+        s[0, c0:c0 + 3] = [pose.x, pose.y, pose.z]
+        s[0, c0 + 3:c0 + 7] = [pose.qx, pose.qy, pose.qz, pose.qw]
+        nb.set_state(s, clear_contacts=True)
+        if hasattr(old, "close"):
+            old.close()
+        self._backend, self._model = nb, m
+        self._state, self._poses = None, None
+
     def _refresh(self):
         if self._backend is None:
             self._poses = np.zeros((1, 10), dtype=np.float32)
@@ -325,6 +353,67 @@ class Robot(object):
         self._poses = None
 
 
+def _parse_single_box_urdf(fn):
+    """A URDF with one link, no joint and one <collision><geometry><box size=...>: (half extents, mass) -- the thrown cube of
+    RoboschoolHumanoidFlagrunHarder (models_household/cube.urdf).  Anything else: None (the general URDF importer is SURVEY 8f.3)."""
+    import xml.etree.ElementTree as ET
+    root = ET.parse(fn).getroot()
+    links, joints = root.findall("link"), root.findall("joint")
+    if root.tag != "robot" or len(links) != 1 or joints:
+        return None
+    col = links[0].findall("collision")
+    if len(col) != 1:
+        return None
+    origin = col[0].find("origin")
+    if origin is not None and any(abs(float(v)) > 0 for k in ("xyz", "rpy") for v in origin.attrib.get(k, "0 0 0").split()):
+        return None
+    box = col[0].find("geometry/box")
+    mass = links[0].find("inertial/mass")
+    if box is None or mass is None:
+        return None
+    size = [float(v) for v in box.attrib["size"].split()]
+    return [0.5 * v * SCALE for v in size], float(mass.attrib["value"]), links[0].attrib.get("name", "cube")
+
+
+class _FreeBoxRobot(Robot):
+    """The robot handle World::load_urdf returns for a free box (python-binding.cpp:278-295 surface).  The box is the second
+    free body of its host robot's world (FlagrunHarder's cube): the last 13 state words of the host's
+    backend -- position, quaternion, angular and linear velocity."""
+
+    def __init__(self, world, host, name):
+        self._world, self._model, self._host = world, None, host
+        self._queried, self._poses, self._state = False, None, None
+        self._offset = (0.0, 0.0, 0.0)
+        self._backend = None                 # stepped with its host
+        self.root_part = Thingy(self, 0, name)
+        self.parts, self.joints = [self.root_part], []
+
+    def _refresh(self):
+        c = np.asarray(self._host._backend.get_state())[0, -13:]
+        row = np.zeros((1, 10), dtype=np.float64)
+        row[0, 0:7] = c[0:7]
+        row[0, 7:10] = c[10:13]
+        self._poses = row
+        self._queried = True
+
+    def _contact_list(self, b):
+        return []
+
+    def set_pose_and_speed(self, p, vx, vy, vz):
+        """World::robot_move (physics-bullet.cpp:579-591): pose in doubles, linear velocity through float, angular velocity
+        zeroed by the pose command; the box's cached contact points go with the old pose."""
+        h = self._host
+        s = np.array(h._backend.get_state(), dtype=np.float64)
+        c0 = s.shape[1] - 13
+        s[0, c0:c0 + 3] = [p.x, p.y, p.z]
+        s[0, c0 + 3:c0 + 7] = [p.qx, p.qy, p.qz, p.qw]
+        s[0, c0 + 7:c0 + 10] = 0.0
+        s[0, c0 + 10:c0 + 13] = [float(np.float32(vx * SCALE)), float(np.float32(vy * SCALE)), float(np.float32(vz * SCALE))]
+        h._backend.set_state(s, clear_contacts=False)
+        h._state = None
+        self._poses = None
+
+
 class Camera(object):
     """Inert stub (renderer out of scope)."""
 
@@ -390,8 +479,23 @@ class World(object):
             return []
 
     def load_urdf(self, fn, pose, fixed_base, self_collision):
-        sys.stderr.write("Cannot load URDF file '%s'.\n" % fn)   # URDF loader is a 'next' row
-        return Robot(self, None, static_name="")
+        """physics-bullet.cpp:70-93.  Supported: a free single-box URDF (FlagrunHarder's cube.urdf) next to a floating-base robot --
+        it becomes the second free body of that robot's world; the host's backend is rebuilt on the cube topology with its state
+        carried over.  Everything else (Atlas) fails the way the reference does: a message on stderr, an empty robot."""
+        try:
+            box = _parse_single_box_urdf(fn)
+            host = next((r for r in reversed(self._robots) if r._backend is not None and not r._model.fixed_base
+                         and not r._model.has_cube), None)
+            if box is None or fixed_base or host is None:
+                raise ValueError("only a free single-box URDF next to a floating-base robot is supported")
+            half, mass, name = box
+            host._attach_box(half, mass, pose)
+            r = _FreeBoxRobot(self, host, name)
+            self._robots.append(r)
+            return r
+        except Exception as e:
+            sys.stderr.write("Cannot load URDF file '%s'. (%s)\n" % (fn, e))
+            return Robot(self, None, static_name="")
 
     def load_sdf(self, fn):
         sys.stderr.write("'%s': cannot load SDF.\n" % fn)

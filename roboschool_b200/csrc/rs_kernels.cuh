@@ -217,6 +217,38 @@ __global__ void __launch_bounds__(32 * WPC) k_step_static(const __grid_constant_
     }
 }
 
+// Physics-only sub-steps on a compile-time topology (World::step(n) of the drop-in shim, where the env's own Python computes
+// observation and reward): the generalized forces come from the world's torque table instead of an action, no epilogue, no reset.
+// One warp per CTA.  Instantiated for the topologies the runtime-topology kernel cannot step (FlagrunHarder's cube).
+template <class T, int MC>
+__global__ void __launch_bounds__(32) k_substeps_static(const __grid_constant__ DevModel M, const DevBuf B, int nsub) {
+    extern __shared__ float s_lc[];
+    const int e = blockIdx.x * 32 + threadIdx.x, lane = threadIdx.x & 31;
+    const bool valid = e < B.N;
+    Work<T::NL, MC, true> W;
+    Episode E;
+    LinkCache<32> lc{s_lc + lane};
+    if (valid) {
+        load_env(M, B, e, W, E);
+        for (int d = 0; d < M.n_dof; d++) W.tau[d] = B.tau[(size_t)d * B.N + e];
+    }
+    constexpr int CAP = pool_cap<T, MC, 32>();
+    const RowPool<CAP> pool{B.rows + (size_t)blockIdx.x * ((size_t)CAP * pool_rec<T>())};
+    WarpDev<1> warp;
+    for (int s = 0; s < nsub; s++) substep_pooled<T>(warp, valid, M, W, pool, lc, s_lc, nullptr);
+    if (valid) store_env(M, B, e, W, E);
+}
+struct SubstepsLaunch { const DevModel* M; const DevBuf* B; int n, nsub; cudaStream_t st; };
+template <class T, int MC>
+static int launch_substeps_static(const SubstepsLaunch& a) {
+    const size_t smem = sizeof(float) * 32 * lc_size<T>();
+    cudaFuncSetAttribute(k_substeps_static<T, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_substeps_static<T, MC><<<(a.n + 31) / 32, 32, smem, a.st>>>(*a.M, *a.B, a.nsub);
+    return 0;
+}
+typedef int (*SubstepsLaunchFn)(const SubstepsLaunch&);
+void rs_register_substeps(int topo, SubstepsLaunchFn fn);
+
 // arguments of one static-topology step launch (plain struct: the instantiations live in other translation units)
 struct StaticLaunch {
     const DevModel* M; const DevBuf* B; int n;

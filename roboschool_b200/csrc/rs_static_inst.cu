@@ -7,3 +7,8 @@
 #endif
 static int launch(const StaticLaunch& a) { return launch_static<RS_TOPO, RS_MC, RS_PROF != 0, RS_WPC>(a); }
 namespace { struct Reg { Reg() { rs_register_static(RS_TOPO_ID, RS_PROF, RS_WPC, launch); } } reg; }
+// physics-only sub-steps for the cube topology (rs_world_substeps of a world with FlagrunHarder's cube), once per topology
+#if RS_TOPO_ID == 6 && RS_PROF == 0 && RS_WPC == 1
+static int launch_sub(const SubstepsLaunch& a) { return launch_substeps_static<RS_TOPO, RS_MC>(a); }
+namespace { struct RegSub { RegSub() { rs_register_substeps(RS_TOPO_ID, launch_sub); } } reg_sub; }
+#endif

@@ -30,6 +30,8 @@ static StaticLaunchFn g_static[8][2][9];   // [topology id][profiling][warps per
 void rs_register_static(int topo, int prof, int wpc, StaticLaunchFn fn) {
     if (topo >= 0 && topo < 8 && wpc >= 0 && wpc < 9) g_static[topo][prof ? 1 : 0][wpc] = fn;
 }
+static SubstepsLaunchFn g_substeps[8];
+void rs_register_substeps(int topo, SubstepsLaunchFn fn) { if (topo >= 0 && topo < 8) g_substeps[topo] = fn; }
 // warps per CTA of the step kernel: RS_WPC (tuning knob) if that instantiation exists, else the per-topology default
 static StaticLaunchFn pick_static(int topo, int prof, int def_wpc) {
     int wpc = def_wpc;
@@ -469,7 +471,7 @@ extern "C" int rs_world_set_joint_motor(rs_world* w, int env, int dof, float kp,
 }
 
 extern "C" int rs_world_substeps(rs_world* w, int n_substeps, const float* tau_host) {
-    if (w->desc.has_cube) return fail("rs_world_substeps: not available for worlds with the cube (physics-only sub-steps run on the runtime-topology kernel, which does not step the cube); use rs_world_step");
+    if (w->desc.has_cube && !(w->topo > 0 && w->topo < 8 && g_substeps[w->topo])) return fail("rs_world_substeps: the physics-only kernel of this cube topology is not linked");
     CK(cudaSetDevice(w->device));
     size_t N = (size_t)w->n; int nd = w->desc.n_dof;
     CK(quiesce(w));
@@ -478,7 +480,13 @@ extern "C" int rs_world_substeps(rs_world* w, int n_substeps, const float* tau_h
         for (size_t e = 0; e < N; e++) for (int d = 0; d < nd; d++) t[(size_t)d * N + e] = tau_host[e * nd + d];
         CK(cudaMemcpy(w->B.tau, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice));
     }
-    FAMILY_DISPATCH(w, (k_substeps<NL, MC><<<nblocks(w->n), 64, 0, w->stream>>>(w->M, w->B, n_substeps)));
+    if (w->desc.has_cube) {
+        // the cube is stepped by the static-topology code only (rs_kernels.cuh k_substeps_static)
+        SubstepsLaunch a{&w->M, &w->B, w->n, n_substeps, w->stream};
+        g_substeps[w->topo](a);
+    } else {
+        FAMILY_DISPATCH(w, (k_substeps<NL, MC><<<nblocks(w->n), 64, 0, w->stream>>>(w->M, w->B, n_substeps)));
+    }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(w->stream));
     return 0;

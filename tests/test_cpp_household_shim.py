@@ -187,3 +187,62 @@ def test_multiplayer_stadium_scene_on_shim(cls, env_id, ref_roboschool, oracle_l
             assert bool(done) == bool(done1)
             by = e.body_xyz[1] - solo[n].body_xyz[1]
             assert abs(by - (n - 1)) < 1e-4, (t, n, by)
+
+
+def test_flagrun_harder_with_thrown_cube_on_shim(ref_roboschool, oracle_lib):
+    """BASELINE config 5 at the drop-in boundary: the reference's own RoboschoolHumanoidFlagrunHarder class
+    (gym_humanoid_flagrun.py:72-169) on the shim.  Its reset loads models_household/cube.urdf through World.load_urdf -- the free
+    box becomes the second body of the humanoid's world -- and its alive_bonus throws it with Robot.set_pose_and_speed every 30
+    frames once the robot has been up for 100.  Driven by the shipped zoo policy so that the robot stays up: throws happen, every
+    throw starts 4 m from the predicted robot position and 1 m above it at 20-31 m/s, the cube then FLIES (gravity + drag only,
+    until it hits something), and the physics the class sees is the oracle's world with the cube (same state words)."""
+    from roboschool_b200.policy import load_zoo_weights
+    from oracle.oracle import mlp_forward
+    env = ref_roboschool.RoboschoolHumanoidFlagrunHarder()
+    env.spec = _Spec()
+    env.seed(0)
+    for k in range(64):            # the class draws its task from the GLOBAL numpy RNG (RepeatUnderlearnedTasks.decide_best_task):
+        np.random.seed(k)          # take the first seed that gives the walking task -- throws need the robot on its feet
+        obs = env.reset()
+        if env.task == env.TASK_WALK:
+            break
+    assert env.task == env.TASK_WALK
+    assert obs.shape == (44,)
+    cube = env.aggressive_cube
+    host = env.cpp_robot
+    assert host._model.has_cube == 1 and host._backend.S == 13 + 2 * 17 + 13
+    cube.query_position()
+    assert np.allclose(cube.root_part.pose().xyz(), (-1.5, 0, 0.05), atol=1e-9)      # where the class loads it
+    wts = load_zoo_weights("RoboschoolHumanoidFlagrunHarder-v1")
+    throws, flights = [], 0
+    calls = []
+    orig = cube.set_pose_and_speed
+    def spy(p, vx, vy, vz):
+        calls.append((np.array(p.xyz()), np.array([vx, vy, vz])))
+        return orig(p, vx, vy, vz)
+    cube.set_pose_and_speed = spy
+    prev_c = None
+    for t in range(260):
+        a = mlp_forward(wts, obs[None].astype(np.float64))[0]
+        n_before = len(calls)
+        obs, rew, done, _ = env.step(a)
+        assert np.isfinite(obs).all() and np.isfinite(rew)
+        c = np.asarray(host._backend.get_state())[0, -13:]
+        if len(calls) > n_before:                      # thrown inside this step's alive_bonus (after the physics)
+            pos, vel = calls[-1]
+            assert np.allclose(c[0:3], pos, atol=1e-9) and np.allclose(c[10:13], vel.astype(np.float32), atol=0) and np.all(c[7:10] == 0)
+            body = np.array(env.body_xyz)
+            d = pos - body
+            assert 3.0 < np.hypot(d[0], d[1]) < 5.0 and abs(d[2] - 1.0) < 0.2      # 4 m away (plus the aim prediction), 1 m above
+            assert 19.0 < np.linalg.norm(vel) < 32.0
+            throws.append(t)
+        elif prev_c is not None and throws and t == throws[-1] + 1:
+            # the first step after a throw is free flight: x(t + dt) = x + v dt up to gravity and 0.04 (1 + |v|) drag over 0.0165 s
+            dt = 0.0165
+            assert np.abs(c[0:3] - (prev_c[0:3] + prev_c[10:13] * dt)).max() < 0.02 * np.linalg.norm(prev_c[10:13]) * dt + 5e-3
+            flights += 1
+        prev_c = c
+        if done:
+            break
+    assert len(throws) >= 3 and flights >= 3, (throws, flights)
+    assert throws[0] == 120 and all(b - a == 30 for a, b in zip(throws, throws[1:])), throws     # alive_bonus runs before the frame counter is advanced: frames 120, 150, ...

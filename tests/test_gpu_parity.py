@@ -189,6 +189,60 @@ def test_cube_throw_flight_and_hits(oracle_lib):
     assert np.median(errs) <= 1e-5 and (errs <= STEP_RTOL).mean() >= 0.95 and errs.max() < 0.5, (np.median(errs), (errs <= STEP_RTOL).mean(), errs.max())
 
 
+def test_cube_world_physics_only_substeps_match_oracle(oracle_lib):
+    """rs_world_substeps on a world with the cube (the drop-in shim's World.step when the reference's own FlagrunHarder class
+    drives it, tests/test_cpp_household_shim.py::test_flagrun_harder_with_thrown_cube_on_shim): physics-only sub-steps on the
+    static-topology code (k_substeps_static), raw joint torques, no epilogue.  Teacher-forced against oracle_substeps through a
+    throw placed by hand (Robot.set_pose_and_speed = 13 state words), the flight, hits on the robot and the floor."""
+    from roboschool_b200.policy import load_zoo_weights
+    env_id = "RoboschoolHumanoidFlagrunHarder-v1"
+    n = 96
+    m, w, o = _worlds(env_id, n, 4)
+    wts = load_zoo_weights(env_id)
+    obs = o.obs()[0]
+    for t in range(60):
+        obs, _, _ = o.step(oracle_lib.mlp_forward(wts, obs), auto_reset=True, seed=4, threads=8)
+    S, nman = m.state_dim, m.n_geoms + m.n_pairs
+    rng = np.random.RandomState(3)
+    errs, n_match, n_samples, cube_floor, cube_hits = [], 0, 0, 0, 0
+    for t in range(36):
+        so = o.get_state()
+        if t == 2:      # throw: 4 m from the torso, 1 m above it, 25 m/s at it
+            for i in range(n):
+                ang = rng.uniform(-3.14, 3.14)
+                cp = so[i, 0:3] + np.array([4 * np.cos(ang), 4 * np.sin(ang), 1.0])
+                v = so[i, 0:3] - cp
+                so[i, S - 13:S - 10] = cp
+                so[i, S - 10:S - 6] = [0, 0, 0, 1]
+                so[i, S - 6:S - 3] = 0
+                so[i, S - 3:S] = 25.0 * v / np.linalg.norm(v)
+        so32 = so.astype(np.float32)
+        w.set_state(so32, clear_contacts=False)
+        w.set_contacts(*o.contact_cache(max_pts=16))
+        tau = rng.uniform(-15, 15, (n, m.n_dof)).astype(np.float32)
+        for i in range(n):
+            o.set_state(i, so32[i].astype(np.float64), clear_contacts=False)
+            o.set_tau(i, tau[i].astype(np.float64))
+            o.substeps(i, 4)
+        w.substeps(4, tau)
+        sg, so2 = w.get_state(), o.get_state()
+        cnt_o, keys_o, _ = o.contact_cache(max_pts=16)
+        for i in range(n):
+            kg, _ = w.contacts(i)
+            n_samples += 1
+            if not (len(kg) == cnt_o[i] and np.array_equal(kg, keys_o[i, :cnt_o[i]])):
+                continue
+            n_match += 1
+            cube_floor += int((kg == nman).sum()); cube_hits += int((kg > nman).sum())
+            errs.append(np.abs(sg[i] - so2[i]).max() / max(1.0, np.abs(so2[i]).max()))
+    errs = np.array(errs)
+    print("\n[cube, physics-only sub-steps] cube-floor points %d, cube-robot points %d, manifolds identical %.4f, state err median %.2e p95 %.2e max %.2e"
+          % (cube_floor, cube_hits, n_match / n_samples, np.median(errs), np.percentile(errs, 95), errs.max()))
+    assert cube_floor > 0 and cube_hits > 0, (cube_floor, cube_hits)
+    assert n_match / n_samples >= 0.99
+    assert np.median(errs) <= 1e-5 and (errs <= STEP_RTOL).mean() >= 0.95 and errs.max() < 0.5, (np.median(errs), (errs <= STEP_RTOL).mean(), errs.max())
+
+
 @pytest.mark.parametrize("env_id", STEP_ENVS)
 def test_free_running_bounded_divergence(env_id, oracle_lib):
     """No teacher forcing: fp32 GPU vs fp64 oracle over a short horizon; divergence stays bounded and
