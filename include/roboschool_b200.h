@@ -73,6 +73,9 @@ int rs_world_destroy(rs_world* w);
 int rs_world_n_envs(const rs_world* w);
 /* 0: runtime-topology step kernel; >0: step kernel specialised on a generated compile-time topology */
 int rs_world_kernel_variant(const rs_world* w);
+/* warps per CTA of the step kernel this world runs on (chosen from the batch size at creation, RS_WPC overrides).  Results are
+ * bit-identical between worlds of the same model only when this number agrees (one compiled instantiation per value). */
+int rs_world_cta_warps(const rs_world* w);
 int rs_world_state_dim(const rs_world* w);
 int rs_world_obs_dim(const rs_world* w);
 int rs_world_act_dim(const rs_world* w);

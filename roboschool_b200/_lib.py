@@ -31,7 +31,7 @@ def lib():
     L.rs_world_create.argtypes = [P, I, I, PP]
     L.rs_model_compile.argtypes = [ctypes.c_char_p, ctypes.c_double, ctypes.c_double, I, I, P, P]
     L.rs_world_destroy.argtypes = [P]
-    for f in ("rs_world_kernel_variant", "rs_world_n_envs", "rs_world_state_dim", "rs_world_obs_dim", "rs_world_act_dim"):
+    for f in ("rs_world_kernel_variant", "rs_world_cta_warps", "rs_world_n_envs", "rs_world_state_dim", "rs_world_obs_dim", "rs_world_act_dim"):
         getattr(L, f).argtypes = [P]
     L.rs_world_reset.argtypes = [P, U, U, P, P, P]
     L.rs_world_step.argtypes = [P, P, P, P, P, I, P]
@@ -72,7 +72,7 @@ def check(rc):
 
 
 EXPORTED_SYMBOLS = [
-    "rs_last_error", "rs_device_count", "rs_model_compile", "rs_world_create", "rs_world_destroy", "rs_world_n_envs", "rs_world_kernel_variant",
+    "rs_last_error", "rs_device_count", "rs_model_compile", "rs_world_create", "rs_world_destroy", "rs_world_n_envs", "rs_world_kernel_variant", "rs_world_cta_warps",
     "rs_world_state_dim", "rs_world_obs_dim", "rs_world_act_dim", "rs_world_reset", "rs_world_step",
     "rs_world_step_stats", "rs_world_step_profile", "rs_world_step_host", "rs_world_policy_step_host", "rs_world_substeps", "rs_world_set_joint_motor", "rs_world_set_state", "rs_world_get_state",
     "rs_world_set_episode", "rs_world_get_episode", "rs_world_set_flags", "rs_world_get_flags", "rs_world_set_task_state", "rs_world_get_task_state", "rs_world_link_poses", "rs_world_get_contacts", "rs_world_set_contacts",

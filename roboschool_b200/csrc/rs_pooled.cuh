@@ -198,8 +198,8 @@ RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*
             if constexpr (d >= 0) {
                 float h[6];
 #pragma unroll
-                for (int k = 0; k < 6; k++) h[k] = lc.at(lc_h<T>() + 6 * i + k);
-                const float invD = lc.at(lc_invd<T>() + i);
+                for (int k = 0; k < 6; k++) h[k] = lc.at(lc_h<T>() + 6 * LcSlot<T, i>::v + k);
+                const float invD = lc.at(lc_invd<T>() + LcSlot<T, i>::v);
                 const float jj = (!HASW && body == i + 1) ? jdir : 0.f;
 #pragma unroll
                 for (int rr = 0; rr < NR; rr++) {
@@ -276,8 +276,8 @@ RS_HD void pooled_response(const LinkCache<STRIDE>& lc, int body, const float (*
         float h[6], invD = 0.f;
         if constexpr (d >= 0) {
 #pragma unroll
-            for (int k = 0; k < 6; k++) h[k] = lc.at(lc_h<T>() + 6 * i + k);
-            invD = lc.at(lc_invd<T>() + i);
+            for (int k = 0; k < 6; k++) h[k] = lc.at(lc_h<T>() + 6 * LcSlot<T, i>::v + k);
+            invD = lc.at(lc_invd<T>() + LcSlot<T, i>::v);
         }
 #pragma unroll
         for (int rr = 0; rr < NR; rr++) {

@@ -31,12 +31,14 @@ struct LinkCache {
     float* p;
     RS_HD float& at(int k) const { return p[k * STRIDE]; }
 };
+// slot of link I's joint quantities (cos / sin, h, 1/D): its dof index -- links without a dof (fixed joints) take no room
+template <class T, int I> struct LcSlot { static constexpr int v = T::dof[I]; };
 template <class T> constexpr int lc_cs() { return 0; }
-template <class T> constexpr int lc_h() { return 2 * T::NL; }
-template <class T> constexpr int lc_invd() { return 8 * T::NL; }
-template <class T> constexpr int lc_lb() { return 9 * T::NL; }
-template <class T> constexpr int lc_rb() { return 9 * T::NL + 21; }     // base rotation (world -> base coords), 9 floats
-template <class T> constexpr int lc_size() { return 9 * T::NL + 30; }
+template <class T> constexpr int lc_h() { return 2 * T::ND; }
+template <class T> constexpr int lc_invd() { return 8 * T::ND; }
+template <class T> constexpr int lc_lb() { return 9 * T::ND; }
+template <class T> constexpr int lc_rb() { return 9 * T::ND + 21; }     // base rotation (world -> base coords), 9 floats
+template <class T> constexpr int lc_size() { return 9 * T::ND + 30; }
 
 // S . x for link I with the constant joint subspace
 template <class T, int I>
@@ -271,8 +273,8 @@ template <class T, int I, int STRIDE>
 RS_HD void cached_xform(const LinkCache<STRIDE>& lc, float* R, float* r) {
     float c = 1.0f, s = 0.0f, q = 0.0f;
     constexpr int jt = T::jtype[I];
-    if constexpr (jt == RS_JOINT_REVOLUTE) { c = lc.at(lc_cs<T>() + 2 * I); s = lc.at(lc_cs<T>() + 2 * I + 1); }
-    if constexpr (jt == RS_JOINT_PRISMATIC) q = lc.at(lc_cs<T>() + 2 * I);
+    if constexpr (jt == RS_JOINT_REVOLUTE) { c = lc.at(lc_cs<T>() + 2 * LcSlot<T, I>::v); s = lc.at(lc_cs<T>() + 2 * LcSlot<T, I>::v + 1); }
+    if constexpr (jt == RS_JOINT_PRISMATIC) q = lc.at(lc_cs<T>() + 2 * LcSlot<T, I>::v);
     link_xform<T, I>(c, s, q, R, r);
 }
 
@@ -322,9 +324,9 @@ RS_HD void static_kinematics(Work<NL, MC, SL>& W, const LinkCache<STRIDE>& lc, f
         float c = 1.0f, s = 0.0f, q = 0.0f;
         if constexpr (jt == RS_JOINT_REVOLUTE) {
             rs_sincos(W.q[dI], &s, &c);
-            lc.at(lc_cs<T>() + 2 * i) = c; lc.at(lc_cs<T>() + 2 * i + 1) = s;
+            lc.at(lc_cs<T>() + 2 * LcSlot<T, i>::v) = c; lc.at(lc_cs<T>() + 2 * LcSlot<T, i>::v + 1) = s;
         }
-        if constexpr (jt == RS_JOINT_PRISMATIC) { q = W.q[dI]; lc.at(lc_cs<T>() + 2 * i) = q; }
+        if constexpr (jt == RS_JOINT_PRISMATIC) { q = W.q[dI]; lc.at(lc_cs<T>() + 2 * LcSlot<T, i>::v) = q; }
         float R[9], r[3];
         link_xform<T, i>(c, s, q, R, r);
         rot_mul33<rot_kind<T, i>()>(W.Rwl[i + 1], R, W.Rwl[p + 1]);
@@ -489,9 +491,9 @@ RS_HD void static_aba(const DevModel& M, Work<NL, MC, SL>& W, const LinkCache<ST
             float y = W.tau[dI] - sdot<T, i>(Z[i + 1]) - dot6(c[i], h);
             float invD = 1.0f / D;
             Y[i] = y;
-            lc.at(lc_invd<T>() + i) = invD;
+            lc.at(lc_invd<T>() + LcSlot<T, i>::v) = invD;
 #pragma unroll
-            for (int k = 0; k < 6; k++) lc.at(lc_h<T>() + 6 * i + k) = h[k];
+            for (int k = 0; k < 6; k++) lc.at(lc_h<T>() + 6 * LcSlot<T, i>::v + k) = h[k];
             float Ic[6];
             inertia_mul(Ic, IA[i + 1], c[i]);
             float kk = invD * y;
@@ -543,8 +545,8 @@ RS_HD void static_aba(const DevModel& M, Work<NL, MC, SL>& W, const LinkCache<ST
         if constexpr (dI >= 0) {
             float h[6];
 #pragma unroll
-            for (int k = 0; k < 6; k++) h[k] = lc.at(lc_h<T>() + 6 * i + k);
-            float a = lc.at(lc_invd<T>() + i) * (Y[i] - dot6(acc[i + 1], h));
+            for (int k = 0; k < 6; k++) h[k] = lc.at(lc_h<T>() + 6 * LcSlot<T, i>::v + k);
+            float a = lc.at(lc_invd<T>() + LcSlot<T, i>::v) * (Y[i] - dot6(acc[i + 1], h));
 #pragma unroll
             for (int k = 0; k < 6; k++) acc[i + 1][k] += c[i][k];
             saxpy<T, i>(acc[i + 1], a);

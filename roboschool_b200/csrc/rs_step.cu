@@ -26,9 +26,9 @@ extern "C" const char* rs_last_error(void) { return g_err.c_str(); }
 extern "C" int rs_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 
 // static-topology instantiations register themselves here (rs_static_inst.cu, one object file each)
-static StaticLaunchFn g_static[8][2][9];   // [topology id][profiling][warps per CTA]
+static StaticLaunchFn g_static[8][2][17];   // [topology id][profiling][warps per CTA]
 void rs_register_static(int topo, int prof, int wpc, StaticLaunchFn fn) {
-    if (topo >= 0 && topo < 8 && wpc >= 0 && wpc < 9) g_static[topo][prof ? 1 : 0][wpc] = fn;
+    if (topo >= 0 && topo < 8 && wpc >= 0 && wpc < 17) g_static[topo][prof ? 1 : 0][wpc] = fn;
 }
 static SubstepsLaunchFn g_substeps[8];
 void rs_register_substeps(int topo, SubstepsLaunchFn fn) { if (topo >= 0 && topo < 8) g_substeps[topo] = fn; }
@@ -36,7 +36,7 @@ void rs_register_substeps(int topo, SubstepsLaunchFn fn) { if (topo >= 0 && topo
 static StaticLaunchFn pick_static(int topo, int prof, int def_wpc) {
     int wpc = def_wpc;
     if (const char* e = getenv("RS_WPC")) wpc = atoi(e);
-    if (wpc < 0 || wpc > 8 || !g_static[topo][prof][wpc]) wpc = def_wpc;
+    if (wpc < 0 || wpc > 16 || !g_static[topo][prof][wpc]) wpc = def_wpc;
     if (!g_static[topo][prof][wpc]) wpc = 1;
     return g_static[topo][prof][wpc];
 }
@@ -242,6 +242,18 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
     // measured crossover of 7-warp aligned CTAs over 1-warp CTAs (a 7-warp CTA occupies a whole SM: below ~148 CTAs part of the GPU
     // idles): 24576 envs for Humanoid, Ant and the planar models (16384-20480: 1-warp CTAs +5..25 %), 8192 for the Flagrun tasks
     w->wpc = n_envs >= (model->flag_task ? 8192 : 24576) ? 7 : 1;
+    {
+        // Batches that 7-warp CTAs would run in two waves but wider CTAs still fit in one (a CTA fills an SM; the link cache is
+        // compacted by dof so that shared memory allows it): Ant 65536 envs in 14-warp CTAs at 128 registers, 1.48 -> 1.35 ms per
+        // step (at 32768 envs 14-warp CTAs lose, 0.85 vs 0.70 ms: spills); Humanoid 33153..37888 envs in 8-warp CTAs (0.92 ms for
+        // 37888 envs against 1.49 ms in two waves; 9-warp CTAs spill 2.2 KB at 168 registers and lose: 1.19 ms for 42624 envs).
+        int n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+        if (w->wpc == 7 && n_envs > n_sm * 224) {
+            if (w->topo == 2 && n_envs <= n_sm * 448 && g_static[2][0][14]) w->wpc = 14;
+            else if (w->topo == 1 && n_envs <= n_sm * 256 && g_static[1][0][8]) w->wpc = 8;
+        }
+    }
     // TPC-pair clusters pay on the Humanoid-family kernels (largest instruction stream); measured neutral to -2 % on the Ant.
     // RS_CLUSTER / RS_EXTRA_SYNC override (tuning knobs, like RS_WPC)
     w->cluster = (w->topo == 1 || w->topo == 6) && w->wpc > 1 ? 2 : 0;
@@ -271,7 +283,7 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
     CK(cudaMalloc(&B.hx_d, sizeof(double) * N * 2));
     CK(cudaMemset(B.hx_i, 0, sizeof(int) * N * 7));
     CK(cudaMemset(B.hx_d, 0, sizeof(double) * N * 2));
-    CK(cudaMalloc(&B.rows, sizeof(float) * (size_t)((n_envs + 255) / 256 * 256 + 256) * B.rec * B.maxr));   // one pool per warp of 32 envs, incl. the spare warps of the last CTA (up to 8 warps per CTA)
+    CK(cudaMalloc(&B.rows, sizeof(float) * (size_t)((n_envs + 511) / 512 * 512 + 512) * B.rec * B.maxr));   // one pool per warp of 32 envs, incl. the spare warps of the last CTA (up to 16 warps per CTA)
     CK(cudaMalloc(&B.tau, sizeof(float) * N * (model->n_dof > 0 ? model->n_dof : 1)));
     CK(cudaMalloc(&B.rewards5, sizeof(float) * N * 5));
     CK(cudaMalloc(&B.nrows, sizeof(int) * N));
@@ -335,6 +347,15 @@ extern "C" int rs_world_destroy(rs_world* w) {
 
 extern "C" int rs_world_n_envs(const rs_world* w) { return w->n; }
 extern "C" int rs_world_kernel_variant(const rs_world* w) { return w->topo; }
+extern "C" int rs_world_cta_warps(const rs_world* w) {
+    if (!w->topo) return 2;                                    // runtime-topology kernels: 64-thread CTAs
+    int per = 0;
+    StaticLaunch q{&w->M, &w->B, w->n, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, nullptr, nullptr, nullptr};
+    q.per_out = &per;
+    StaticLaunchFn fn = pick_static(w->topo, 0, w->wpc);
+    if (fn) fn(q);
+    return per / 32;
+}
 extern "C" int rs_world_state_dim(const rs_world* w) { return w->B.S; }
 extern "C" int rs_world_obs_dim(const rs_world* w) { return w->desc.obs_dim; }
 extern "C" int rs_world_act_dim(const rs_world* w) { return w->desc.n_act; }

@@ -553,8 +553,11 @@ def test_baseline_config_sizes_properties(env_id, n, monkeypatch):
     # bit-identity is a property of ONE compiled kernel: a 300-env world would pick 1-warp CTAs, the full-size one 7-warp
     # CTAs from 24576 envs up, and ptxas contracts multiply-adds differently in the two instantiations (measured on the Ant:
     # observations differ by 1-7 ulp, 1e-7 .. 9e-7, between them; identical with the same CTA shape)
+    # (the Ant at 65536 envs runs on 14-warp CTAs: one wave instead of two of 7-warp CTAs)
     if n >= 24576:
-        monkeypatch.setenv("RS_WPC", "7")
+        wpc = env.world.L.rs_world_cta_warps(env.world.h)
+        assert wpc == (14 if env_id == "RoboschoolAnt-v1" else 7), wpc
+        monkeypatch.setenv("RS_WPC", str(wpc))
     env3 = VecEnv(env_id, 300, 0, env_id0=off)
     assert torch.equal(env3.reset(seed=2), obs0[off:])
     for a, (o, r, d) in zip(acts, outs):
