@@ -201,7 +201,7 @@ def short_run(env_id, n, device, stream, settle=200, steps=50):
     W.rollout(pol, settle, stats=stats, stream=stream)
     torch.cuda.synchronize()
     W.set_episode(frame=np.random.RandomState(7).randint(0, max(m.max_episode_steps - 1, 1), size=n).astype(np.int32))
-    W.rollout(pol, 10, stats=stats, stream=stream)
+    W.rollout(pol, m.max_episode_steps, stats=stats, stream=stream)      # every env reset once, at its own time (decorrelated gaits)
     torch.cuda.synchronize()
     stats.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -213,7 +213,7 @@ def short_run(env_id, n, device, stream, settle=200, steps=50):
     st = stats.cpu().numpy()
     W.close(); pol.close()
     return {"env": env_id, "envs": n, "value": n * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
-            "settle_steps": settle, "mean_rows": st[4] / max(st[6], 1), "mean_contacts": st[5] / max(st[6], 1),
+            "settle_steps": settle + m.max_episode_steps, "mean_rows": st[4] / max(st[6], 1), "mean_contacts": st[5] / max(st[6], 1),
             "algorithmic_bytes_per_env_step": algorithmic_bytes(m)}
 
 
@@ -271,6 +271,11 @@ def main():
     rng = np.random.RandomState(1234 + rank)
     if not os.environ.get("RS_BENCH_NO_STAGGER"):       # diagnosis only: synchronised episodes (no resets inside the timed region)
         W.set_episode(frame=rng.randint(0, max(m.max_episode_steps - 1, 1), size=n).astype(np.int32))
+        # ... and one more time limit of untimed steps, so that every env has gone through a reset at its own time: the envs of
+        # a synchronously reset batch walk in step (the step time swings 0.75 <-> 0.97 ms with the gait, period ~25 steps) and a
+        # short timed window would sample one phase of that swing; after this the batch is decorrelated (0.84-0.88 ms)
+        W.rollout(pol, m.max_episode_steps, stats=stats, stream=stream)
+        torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -397,7 +402,7 @@ def main():
         "dtype": "f32", "dtype_policy": "f16xf16->f32 (tcgen05 kind::f16, fp32 accumulate; tolerance 5e-3 of the action scale, tests/test_gpu_parity.py)",
         "data": "synthetic",
         "config": {"workload": "%s, %d envs/GPU (%d total), agent_zoo v1 MLP policy on tensor cores, frame_skip 4, on-device auto-reset; steady state: "
-                               "%d untimed settle steps after reset + episode clocks staggered over the time limit, then --warmup" % (args.env, n, total_envs, SETTLE),
+                               "%d untimed settle steps after reset + episode clocks staggered over the time limit + %d untimed steps (every env reset once, at its own time), then --warmup" % (args.env, n, total_envs, SETTLE, m.max_episode_steps),
                    "l2": l2_note,
                    "parallelism": "env-sharded, %d process(es), no step-path collective" % world_size},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -23,7 +23,7 @@ for e in RoboschoolHumanoid-v1 RoboschoolHumanoidFlagrunHarder-v1; do
 done
 # ncu: launch list of the bench command (shares), then one --set full capture of a steady-state step launch and of the policy
 B="python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extra"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 604 -c 44 --csv --log-file $out/launches.csv $B > $out/ncu_launches.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_step_static --launch-skip 310 -c 1 -o $out/k_step_full -f $B > $out/ncu_full_step.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_mlp_tc5 --launch-skip 310 -c 1 -o $out/k_mlp_full -f $B > $out/ncu_full_mlp.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 2604 -c 44 --csv --log-file $out/launches.csv $B > $out/ncu_launches.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_step_static --launch-skip 1310 -c 1 -o $out/k_step_full -f $B > $out/ncu_full_step.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_mlp_tc5 --launch-skip 1310 -c 1 -o $out/k_mlp_full -f $B > $out/ncu_full_mlp.log 2>&1
 ls -la $out

@@ -23,7 +23,7 @@ for arg in sys.argv[1:]:
     W.rollout(pol, 300, stream=st)
     torch.cuda.synchronize()
     W.set_episode(frame=np.random.RandomState(7).randint(0, m.max_episode_steps - 1, size=n).astype(np.int32))
-    W.rollout(pol, 100, stream=st)
+    W.rollout(pol, int(os.environ.get("STEP_TIME_WARM", "1000")), stream=st)     # steps between staggering the episode clocks and timing
     torch.cuda.synchronize()
     T = 100
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(T)]
@@ -39,6 +39,6 @@ for arg in sys.argv[1:]:
     ts = [a.elapsed_time(b) for a, b in ev]
     ms = float(np.median(ts))
     r, c = W.counts()
-    print(json.dumps({"env": env_id, "envs": n, "k_step_ms": ms, "env_steps_per_s": n / ms * 1e3, "k_step_ms_mean": float(np.mean(ts)), "k_step_ms_max": float(np.max(ts)), "stats": stats is not None, "mean_rows": float(r.mean()),
+    print(json.dumps({"env": env_id, "envs": n, "k_step_ms": ms, "env_steps_per_s": n / ms * 1e3, "k_step_ms_mean": float(np.mean(ts)), "k_step_ms_max": float(np.max(ts)), "stats": stats is not None, "first_steps_ms": [round(x, 3) for x in ts[:24]], "mean_rows": float(r.mean()),
                       "variant": W.L.rs_world_kernel_variant(W.h)}), flush=True)
     del W
