@@ -56,10 +56,29 @@ struct PoolRef {
     RS_HD const PoolRef& operator=(const PoolRef& o) const { put(o.get()); return *this; }
     RS_HD const PoolRef& operator+=(float v) const { put(get() + v); return *this; }
 };
+// The rows of a sub-step are dead once its Gauss-Seidel sweeps are through, but they sit in the L2 as dirty lines and would be
+// written back to DRAM when the next sub-step's rows (or another warp's local frame) evict them: ~100 MB per step of writes
+// nobody reads.  discard.global.L2 drops a line without the write-back and makes it the preferred victim (RS_POOL_DISCARD=0: off).
+#ifndef RS_POOL_DISCARD
+#define RS_POOL_DISCARD 1
+#endif
 template <int CAP>
 struct RowPool {
     float* p;
     RS_HD PoolRef at(int slot, int k) const { return PoolRef{p + (k * CAP + slot)}; }
+    // drop the 128-byte lines that hold slots [slot0, slot0 + nslots) of words [0, nwords): one line per lane and step (CAP is a multiple of 32
+    // floats and the pool of a warp starts on a 128-byte boundary, so no line is shared with live data of anybody else)
+    RS_HD void discard(int lane, int width, int slot0, int nslots, int nwords) const {      // slot0: a multiple of 32
+#if defined(__CUDA_ARCH__) && RS_POOL_DISCARD
+        const int lpw = (nslots + 31) >> 5;                 // lines per word
+        const int total = lpw * nwords;
+        for (int i = lane; i < total; i += width) {
+            const int k = i / lpw, l = i - k * lpw;
+            const float* a = p + ((size_t)k * CAP + slot0 + 32 * l);
+            asm volatile("discard.global.L2 [%0], 128;" :: "l"(a) : "memory");
+        }
+#endif
+    }
 };
 // Slot map of a warp's pool (WIDTH = lanes = envs of the warp), two forms chosen per topology (pool_columns<T>):
 //   dense    rows of the warp packed in owner order: non-contact row j of an env at lbase + j, contact ci direction w at
@@ -89,6 +108,7 @@ struct WarpHost {
     static constexpr int WIDTH = 1;
     RS_HD int lane() const { return 0; }
     RS_HD int excl_scan(int v, int& total) const { total = v; return 0; }
+    RS_HD int max_all(int v) const { return v; }
     RS_HD void sync() const {}
     RS_HD void cta_sync() const {}
     RS_HD void extra_sync() const {}
@@ -132,6 +152,13 @@ struct WarpDev {
         return x - v;
 #else
         total = v; return 0;
+#endif
+    }
+    RS_HD int max_all(int v) const {
+#ifdef __CUDA_ARCH__
+        return __reduce_max_sync(0xffffffffu, v);
+#else
+        return v;
 #endif
     }
     RS_HD void sync() const {
@@ -342,7 +369,7 @@ RS_HD void resolve_span(int span, const Pool& pool, int slot, float* dv, float r
 //   lc_lane0: link cache of lane 0 of this warp; the cache of lane o is lc_lane0 + o (host: o == 0)
 // ---------------------------------------------------------------------------------------------
 template <class T, class Warp, int NL, int MC, bool SL, int STRIDE, class Pool>
-RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL, MC, SL>& W, float dt, const Pool& pool, float* lc_lane0, PhaseClock* pc = nullptr) {
+RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL, MC, SL>& W, float dt, const Pool& pool, float* lc_lane0, int* used, PhaseClock* pc = nullptr) {
     long long q0 = 0, q1 = 0;
     if (pc) q0 = RS_CLOCK();
     static_assert(pool_rec<T>() >= POOL_DESC_WORDS, "row record too small to hold a task descriptor");
@@ -401,6 +428,12 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
     auto slot_nc = [&](int j) { return COL ? j * Wd + lane : lbase + j; };                       // this lane's rows
     auto slot_c = [&](int ci) { return COL ? (NNC + 3 * ci) * Wd + lane : LT + 3 * (cbase + ci); };  // direction w: + w * RST
     W.n_rows = n_nc + 3 * nc; W.n_contacts = nc;
+    // row slots this warp touches in this sub-step (warp-uniform; the caller drops their lines once every lane is through)
+    if constexpr (COL) {
+        used[0] = 0; used[1] = warp.max_all(n_nc) * Wd; used[2] = NNC * Wd; used[3] = 3 * warp.max_all(nc) * Wd;
+    } else {
+        used[0] = 0; used[1] = LT + 3 * CT; used[2] = 0; used[3] = 0;
+    }
     // The helpers' task lists are compact directories filled by the owners: one entry per limit / motor row, one per contact
     // that has a robot side (a cube-floor point needs no helper: the owner writes its rows, and a resting cube has four of them
     // in every env).
@@ -741,8 +774,12 @@ RS_HD void substep_pooled(const Warp& warp, bool valid, const DevModel& M, Work<
     if (pc) { c1 = RS_CLOCK(); pc->t[2] += c1 - c0; c0 = c1; }
     warp.cta_sync();
     warp.sync();   // link caches complete before other lanes read them
-    solve_pooled<T, Warp, NL, MC, SL, STRIDE, Pool>(warp, valid, M, W, dt, pool, lc_lane0, pc);
+    int used[4];
+    solve_pooled<T, Warp, NL, MC, SL, STRIDE, Pool>(warp, valid, M, W, dt, pool, lc_lane0, used, pc);
     warp.sync();   // all helpers done with this sub-step's caches before kinematics overwrites them
+    // the rows are dead: drop their L2 lines instead of letting them be written back (RowPool::discard)
+    if (used[1] > 0) pool.discard(warp.lane(), Warp::WIDTH, used[0], used[1], pool_rec<T>());
+    if (used[3] > 0) pool.discard(warp.lane(), Warp::WIDTH, used[2], used[3], pool_rec<T>());
     if (pc) { c1 = RS_CLOCK(); pc->t[3] += c1 - c0; c0 = c1; }
     if (valid) {
         integrate(M, W, dt);
