@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(32 * WPC) k_step_static(const __grid_constant_
     constexpr int CAP = pool_cap<T, MC, 32>();      // <= 32 * B.maxr: the allocation covers it
     const RowPool<CAP> pool{B.rows + (size_t)(cta * WPC + wic) * ((size_t)CAP * pool_rec<T>())};
     WarpDev<WPC> warp;
-    warp.cluster = (cluster & 1) != 0; warp.extra = (cluster & 2) != 0;
+    warp.cluster = (cluster & 1) != 0; warp.extra = (cluster & 2) != 0; warp.drop = (cluster & 4) != 0;
     PhaseClock pc;
     if (PROF) { for (int k = 0; k < 12; k++) pc.t[k] = 0; t1 = clock64(); }
     for (int s = 0; s < M.frame_skip; s++) substep_pooled<T>(warp, valid, M, W, pool, lc, lc0, PROF ? &pc : nullptr);
@@ -257,6 +257,7 @@ struct StaticLaunch {
     int cta0 = 0, ncta = 0;      // slice of the grid to launch (ncta == 0: all CTAs)
     int cluster = 0;             // > 1: launch as thread-block clusters of that many CTAs, phase barriers span the cluster
     int extra_sync = 0;          // 1: two more re-alignment points inside the solve phase (heterogeneous batches)
+    int drop_rows = 0;           // 1: dead constraint rows are dropped from the L2 after every sub-step (large batches)
     int* per_out = nullptr;      // query: receives envs per CTA, nothing is launched
 };
 
@@ -302,7 +303,7 @@ static int launch_static(const StaticLaunch& a) {
     // barriers both SMs walk the same lines of the (instruction-fetch bound) stream.  Measured on a steady-state batch of 32768
     // Humanoid envs: 0.996 -> 0.933 ms per step; clusters of 3..8 CTAs cannot all be resident (one CTA fills an SM) and run
     // 1.4 ms.  The grid is padded with CTAs that own no env (cta >= cta_end) up to a multiple of the cluster size.
-    const int extra = a.extra_sync ? 2 : 0;
+    const int extra = (a.extra_sync ? 2 : 0) | (a.drop_rows ? 4 : 0);
     if (a.cluster > 1 && WPC > 1) {
         grid = (grid + a.cluster - 1) / a.cluster * a.cluster;
         cudaLaunchConfig_t cfg = {};

@@ -112,6 +112,7 @@ struct WarpHost {
     RS_HD void sync() const {}
     RS_HD void cta_sync() const {}
     RS_HD void extra_sync() const {}
+    RS_HD bool drop_rows() const { return false; }
     RS_HD unsigned ballot(bool p) const { return p ? 1u : 0u; }
     RS_HD float shfl(float v, int) const { return v; }
     RS_HD int shfl(int v, int) const { return v; }
@@ -126,6 +127,9 @@ struct WarpDev {
     bool extra = false;        // two more re-alignment points inside the solve phase (before the row tasks, before the PGS): pays
                                // when the envs of a batch differ a lot in row count (FlagrunHarder: 6.0 -> 5.0 ms per step), costs ~5 %
                                // on homogeneous batches
+    bool drop = false;         // drop the dead rows of a sub-step from the L2 (RowPool::discard): pays once the batch's working set
+                               // competes for the L2 (Humanoid 32768: -4 %), costs 2 % on batches that fit it anyway (Hopper 4096)
+    RS_HD bool drop_rows() const { return drop; }
     RS_HD void extra_sync() const { if (extra) cta_sync(); }
     RS_HD void cta_sync() const {
 #ifdef __CUDA_ARCH__
@@ -778,8 +782,10 @@ RS_HD void substep_pooled(const Warp& warp, bool valid, const DevModel& M, Work<
     solve_pooled<T, Warp, NL, MC, SL, STRIDE, Pool>(warp, valid, M, W, dt, pool, lc_lane0, used, pc);
     warp.sync();   // all helpers done with this sub-step's caches before kinematics overwrites them
     // the rows are dead: drop their L2 lines instead of letting them be written back (RowPool::discard)
-    if (used[1] > 0) pool.discard(warp.lane(), Warp::WIDTH, used[0], used[1], pool_rec<T>());
-    if (used[3] > 0) pool.discard(warp.lane(), Warp::WIDTH, used[2], used[3], pool_rec<T>());
+    if (warp.drop_rows()) {
+        if (used[1] > 0) pool.discard(warp.lane(), Warp::WIDTH, used[0], used[1], pool_rec<T>());
+        if (used[3] > 0) pool.discard(warp.lane(), Warp::WIDTH, used[2], used[3], pool_rec<T>());
+    }
     if (pc) { c1 = RS_CLOCK(); pc->t[3] += c1 - c0; c0 = c1; }
     if (valid) {
         integrate(M, W, dt);
