@@ -159,7 +159,10 @@ def reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    cpu = CpuStepper(args.env, cores)
+    # world sized so that the K timed steps cover ~10 s of CPU work at ~17 k env-steps/s per thread (a 20-step run over 64 envs
+    # per thread lasted 70 ms and read anything between 144 k and 276 k env-steps/s on the same kind of box)
+    ept = int(min(1024, max(64, -(-12 * 17000 // max(args.steps, 1)))))
+    cpu = CpuStepper(args.env, cores, envs_per_thread=ept, settle_steps=30, settle_seconds=3.0)
     for _ in range(min(max(args.warmup, 3), 50)):
         cpu.step()
     # a bench step = one env.step of every env of the settled CPU world; bounded so that the run ends within ~1.5 minutes
