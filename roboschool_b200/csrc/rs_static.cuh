@@ -4,7 +4,7 @@
 // every loop over links is unrolled against constexpr parent/dof tables: accumulators of the
 // leaves->root and root->leaves sweeps live in registers, joint-subspace dot products collapse to the
 // non-zero terms, and the per-link cache that the response passes re-read for every constraint row
-// (cos q, sin q, h = I^A S, 1/D, Cholesky factor of the base inertia: 9*NL+21 floats per env) is staged
+// (cos q, sin q, h = I^A S, 1/D, Cholesky factor of the base inertia, base rotation: 9*ND+30 floats per env, slots by dof index) is staged
 // in SHARED memory, laid out [slot][lane] so a warp's accesses are conflict-free.
 #pragma once
 #include <utility>
