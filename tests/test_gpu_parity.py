@@ -634,19 +634,20 @@ def test_throughput_floor_on_b200():
     assert rate > 2.5e7, "%.1f M env-steps/s" % (rate / 1e6)
 
 
-def test_seven_warp_world_oracle_spot_check(oracle_lib):
-    """Direct oracle check of the 7-warp-CTA step kernel: a 32768-env Humanoid world (the bench
-    operating point: `k_step_static<TopoHumanoid,16,0,7>`) free-runs 6 steps of random actions; 8 blocks of 32 envs
-    spread over the batch (first / interior / last CTA, CTA-straddling offsets) are compared with oracle worlds that
-    were reset with the matching global env ids."""
+@pytest.mark.parametrize("env_id,n,wpc", [("RoboschoolHumanoid-v1", 32768, 7), ("RoboschoolHumanoid-v1", 37888, 8), ("RoboschoolAnt-v1", 65536, 14)])
+def test_wide_cta_world_oracle_spot_check(env_id, n, wpc, oracle_lib):
+    """Direct oracle check of the wide-CTA step kernels: a 32768-env Humanoid world (the bench
+    operating point: `k_step_static<TopoHumanoid,16,0,7>`), a 37888-env one (8-warp CTAs) and a 65536-env Ant world (one wave of
+    14-warp CTAs, row discard on) free-run 6 steps of random actions; 8 blocks of 32 envs spread over the batch (first / interior /
+    last CTA, CTA-straddling offsets) are compared with oracle worlds that were reset with the matching global env ids."""
     from roboschool_b200.world import BatchedWorld
     from oracle.oracle import OracleWorld
-    env_id = "RoboschoolHumanoid-v1"
     m = load_env_model(env_id)
-    n = 32768
     w = BatchedWorld(m, n, 0)
+    assert w.L.rs_world_cta_warps(w.h) == wpc
     w.reset(seed=13)
-    offs = [0, 200, 224 * 3 - 16, 9999, 16384, 20000, 32768 - 224, 32768 - 32]
+    per = 32 * wpc
+    offs = [0, 200, per * 3 - 16, 9999, 16384, 20000, n - per, n - 32]
     orc = []
     for off in offs:
         o = OracleWorld(m, 32)
