@@ -258,7 +258,7 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
     // TPC-pair clusters pay on the Humanoid-family kernels (largest instruction stream); measured neutral to -2 % on the Ant.
     // RS_CLUSTER / RS_EXTRA_SYNC override (tuning knobs, like RS_WPC)
     w->cluster = (w->topo == 1 || w->topo == 6) && w->wpc > 1 ? 2 : 0;
-    w->extra_sync = model->flag_task == 2 ? 1 : 0;
+    w->extra_sync = model->flag_task ? 1 : 0;      // Flagrun 32768: 1.23 -> 1.19 ms, FlagrunHarder 3.29 -> 2.83 ms; Humanoid 0.82 -> 0.85 ms (off)
     if (const char* e = getenv("RS_CLUSTER")) w->cluster = atoi(e);
     if (const char* e = getenv("RS_EXTRA_SYNC")) w->extra_sync = atoi(e) != 0;
     // measured: Humanoid 32768 0.85 -> 0.81 ms, Walker2d 65536 0.99 -> 0.95 ms, Hopper 4096 (everything fits the L2) 0.103 -> 0.106 ms
