@@ -243,17 +243,20 @@ extern "C" int rs_world_create(const rs_model_desc* model, int n_envs, int devic
     // measured crossover of 7-warp aligned CTAs over 1-warp CTAs (a 7-warp CTA occupies a whole SM: below ~148 CTAs part of the GPU
     // idles): 24576 envs for Humanoid, Ant and the planar models (16384-20480: 1-warp CTAs +5..25 %), 8192 for the Flagrun tasks
     w->wpc = n_envs >= (model->flag_task ? 8192 : 24576) ? 7 : 1;
-    {
-        // Batches that 7-warp CTAs would run in two waves but wider CTAs still fit in one (a CTA fills an SM; the link cache is
-        // compacted by dof so that shared memory allows it): Ant 65536 envs in 14-warp CTAs at 128 registers, 1.48 -> 1.35 ms per
-        // step (at 32768 envs 14-warp CTAs lose, 0.85 vs 0.70 ms: spills); Humanoid 33153..37888 envs in 8-warp CTAs (0.92 ms for
-        // 37888 envs against 1.49 ms in two waves; 9-warp CTAs spill 2.2 KB at 168 registers and lose: 1.19 ms for 42624 envs).
+    if (w->topo && !model->flag_task) {
+        // One wave of aligned CTAs: the narrowest instantiation whose CTAs (one per SM -- 255 registers fill it) hold the whole
+        // batch, so that the warps of an SM walk the instruction stream together and no SM runs a second wave.  Measured
+        // (profiles/r02_v4_cta_width.txt): Humanoid 16384 envs 1.15 ms (1-warp CTAs) -> 0.65 (4-warp, TPC pairs), 8192 envs 0.75 ->
+        // 0.58 (2-warp); Ant 16384 0.58 -> 0.44, 8192 0.39 -> 0.36; Ant 65536 in 14-warp CTAs at 128 registers 1.48 -> 1.35 ms (at
+        // 32768 envs they lose to 7-warp CTAs, 0.85 vs 0.70 ms: spills); Humanoid 37888 envs in 8-warp CTAs 0.92 ms against 1.49 ms
+        // in two waves (9-warp CTAs spill 2.2 KB at 168 registers and lose).  Batches beyond one wave of the widest instantiation
+        // run as several waves of 7-warp CTAs.
         int n_sm = 148;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
-        if (w->wpc == 7 && n_envs > n_sm * 224) {
-            if (w->topo == 2 && n_envs <= n_sm * 448 && g_static[2][0][14]) w->wpc = 14;
-            else if (w->topo == 1 && n_envs <= n_sm * 256 && g_static[1][0][8]) w->wpc = 8;
-        }
+        const int need = (n_envs + 32 * n_sm - 1) / (32 * n_sm);
+        int pick = 0;
+        for (int k = need; k <= 16 && !pick; k++) if (g_static[w->topo][0][k]) pick = k;
+        w->wpc = pick ? pick : 7;
     }
     // TPC-pair clusters pay on the Humanoid-family kernels (largest instruction stream); measured neutral to -2 % on the Ant.
     // RS_CLUSTER / RS_EXTRA_SYNC override (tuning knobs, like RS_WPC)
