@@ -5,6 +5,7 @@
 tag=${1:-r02x}
 out=gpurun_out/$tag
 mkdir -p $out
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke.log 2>&1; tail -1 $out/smoke.log
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > $out/gpu.txt 2>&1
 if [ "${2:-tests}" = "tests" ]; then
   timeout 1500 python -m pytest tests -m gpu -x -q > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $out/pytest_gpu.log
