@@ -566,6 +566,7 @@ void compile(const char* path, double gravity, double timestep, int frame_skip, 
     mat_to_quat_xyzw(base_rot, m->reset_base_quat);
     m->alive_rule = RS_ALIVE_ALWAYS;
     m->body_link = -1;
+    m->task_link = m->task_link2 = -1;       // no task link until a task spec names one (a link-less body has no link 0)
     m->initial_z = -1.0;
     m->max_episode_steps = 1000;
     m->max_contacts = 16;                               // live contact points per env (envspec.py's default; Hopper-size models may use 8)

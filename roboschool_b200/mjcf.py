@@ -516,6 +516,7 @@ def compile_mjcf(xml_path, honour_density=False, honour_damping=False, has_floor
     m.reset_set_base = 0
     m.alive_rule = 2
     m.body_link = -1
+    m.task_link = m.task_link2 = -1       # no task link until a task spec names one (a link-less body has no link 0)
     m.initial_z = -1.0
     m.max_episode_steps = 1000
     m.dt_env = timestep * frame_skip   # python double, scene_abstract.py:22
