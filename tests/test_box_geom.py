@@ -227,3 +227,66 @@ def test_sliding_brick_on_cuda(tmp_path):
             x += h * max(v, 0.0)
         dist = np.hypot(*(se[i, 0:2] - x0[i]))
         assert abs(dist - x) < (0.02 if i < 2 else 0.04) * x, (i, dist, x)
+
+
+BALL_XML = """<mujoco model="ball">
+  <compiler angle="radian" coordinate="local"/>
+  <default><geom conaffinity="0" contype="1" friction="0.5 .1 .1"/></default>
+  <worldbody>
+    <body name="ball" pos="0 0 0.1">
+      <geom name="ball_geom" type="sphere" size="0.1"/>
+    </body>
+  </worldbody>
+</mujoco>
+"""
+
+
+@pytest.mark.parametrize("world", ["oracle", "emulated-kernel"])
+def test_sliding_ball_starts_to_roll(world, tmp_path, oracle_lib):
+    """Friction coupled to rotation, in closed form: a ball set sliding at v0 without spin is braked by mu m g at the contact
+    point, which also spins it up with torque mu m g r; slipping ends when v = omega r, at v = v0 / (1 + I / (m r^2)) for ANY mu
+    (angular momentum about the contact point is conserved) -- here with the link damping terms integrated alongside.  I is the
+    descriptor's inertia (the importer's box-of-the-AABB rule gives 2/3 m r^2, so 0.6 v0 instead of the solid sphere's 5/7 v0)."""
+    p = tmp_path / "ball.xml"
+    p.write_text(BALL_XML)
+    m = mjcf.compile_mjcf(str(p))
+    m.max_contacts = 8
+    if world == "oracle":
+        w = oracle_lib.OracleWorld(m, 1)
+    else:
+        from tests.host_emul import emul
+        emul.build()
+        w = emul.EmulWorld(m, 1)
+    r, mass, I = 0.1, float(m.base_mass), float(m.base_inertia[1])
+    assert abs(I - 2.0 / 3.0 * mass * r * r) < 1e-9 * I + 1e-12
+    s = np.zeros(13)
+    s[0:3] = [0.0, 0.0, r]
+    s[6] = 1.0
+    w.set_state(0, s)
+    for _ in range(300):
+        w.substeps(0, 1)
+    s = np.array(w.get_state(0), dtype=np.float64)
+    assert np.abs(s[7:13]).max() < 1e-3
+    v0 = 2.0
+    s[10] = v0
+    w.set_state(0, s, clear_contacts=False)
+    mu, g, dt = float(m.g_friction[0]) * float(m.floor_friction), float(m.gravity), float(m.timestep)
+    kl, ka = float(m.lin_damping), float(m.ang_damping)
+    # reference: integrate v and omega (about +y) with friction and damping until the contact point stops slipping
+    v, om, t, h = v0, 0.0, 0.0, dt / 64
+    while v - om * r > 0:
+        v -= h * (mu * g + kl * (1 + abs(v)) * v)
+        om += h * (mu * mass * g * r / I - ka * (1 + abs(om)) * om)
+        t += h
+    assert abs(v - v0 / (1 + I / (mass * r * r))) < 0.03 * v0          # damping moves the textbook value by < 3 %
+    n = int(round(t / dt))
+    slip = []
+    for k in range(n + 40):
+        w.substeps(0, 1)
+        sk = np.array(w.get_state(0), dtype=np.float64)
+        slip.append(sk[10] - sk[8] * r)
+        if k == n + 5:
+            v_sim, om_sim = sk[10], sk[8]
+    slip = np.array(slip)
+    assert slip[: n - 10].min() > 0.02 * v0 and np.abs(slip[n + 10:]).max() < 0.01 * v0, (slip[n - 12:n + 12])   # slipping ends on time
+    assert abs(v_sim - v) < 0.02 * v0 and abs(om_sim * r - v) < 0.02 * v0, (v_sim, om_sim * r, v)
