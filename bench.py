@@ -190,15 +190,17 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
-def short_run(env_id, n, device, stream, settle=200, steps=50):
-    """Device-resident env-steps/s of another BASELINE config: settle, stagger the episode clocks, time `steps` steps."""
+def short_run(env_id, n, device, stream, settle=200, steps=50, random_actions=False):
+    """Device-resident env-steps/s of another BASELINE config: settle, stagger the episode clocks, time `steps` steps.
+    random_actions: i.i.d. U(-1, 1) actions from the counter-based RNG on the device instead of the zoo policy (the north star's
+    'synthetic random-action rollouts': the robots fall within ~20 steps, so this is a reset-heavy workload)."""
     import torch
     from roboschool_b200.envspec import load_env_model
     from roboschool_b200.world import BatchedWorld
     from roboschool_b200.policy import ZooPolicy, load_zoo_weights
     m = load_env_model(env_id)
     W = BatchedWorld(m, n, device)
-    pol = ZooPolicy(load_zoo_weights(env_id), device)
+    pol = None if random_actions else ZooPolicy(load_zoo_weights(env_id), device)
     stats = torch.zeros(8, dtype=torch.float64, device="cuda:%d" % device)
     W.rollout_reset(seed=0, env_id0=0, stream=stream)
     W.rollout(pol, settle, stats=stats, stream=stream)
@@ -214,8 +216,10 @@ def short_run(env_id, n, device, stream, settle=200, steps=50):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     st = stats.cpu().numpy()
-    W.close(); pol.close()
-    return {"env": env_id, "envs": n, "value": n * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+    W.close()
+    if pol is not None:
+        pol.close()
+    return {"env": env_id, "envs": n, "actions": "uniform random (device RNG)" if random_actions else "agent_zoo policy", "value": n * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
             "settle_steps": settle + m.max_episode_steps, "mean_rows": st[4] / max(st[6], 1), "mean_contacts": st[5] / max(st[6], 1),
             "algorithmic_bytes_per_env_step": algorithmic_bytes(m)}
 
@@ -378,6 +382,8 @@ def main():
         for cfg, eid, ne in (("configs[1]", "RoboschoolHopper-v1", 4096), ("configs[2]", "RoboschoolAnt-v1", 65536),
                              ("configs[4]", "RoboschoolHumanoidFlagrunHarder-v1", 32768)):
             extra[cfg] = short_run(eid, ne, local_rank, stream)
+        # the headline workload under uniform random actions instead of the policy (north star: random-action rollouts)
+        extra["random_actions"] = short_run(ENV_ID, n, local_rank, stream, random_actions=True)
 
     # the policy forward is the one contraction of the path: reported against the tensor peak
     wshape = [w.shape for w in load_zoo_weights(args.env)]
