@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libroboschool_b200.so")
+LIB_PATH = os.environ.get("RS_B200_LIB") or os.path.join(_HERE, "libroboschool_b200.so")     # RS_B200_LIB: A/B builds (tools/_ab)
 _LIB = None
 
 

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(32 * WPC) k_step_static(const __grid_constant_
         apply_action(M, W, a, 1);
     }
     constexpr int CAP = pool_cap<T, MC, 32>();      // <= 32 * B.maxr: the allocation covers it
-    const RowPool<CAP> pool{B.rows + (size_t)(cta * WPC + wic) * ((size_t)CAP * pool_rec<T>())};
+    const RowPool<CAP, pool_layout_rec<T>()> pool{B.rows + (size_t)(cta * WPC + wic) * ((size_t)CAP * pool_rec<T>())};
     WarpDev<WPC> warp;
     warp.cluster = (cluster & 1) != 0; warp.extra = (cluster & 2) != 0; warp.drop = (cluster & 4) != 0;
     PhaseClock pc;
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(32) k_substeps_static(const __grid_constant__ 
         for (int d = 0; d < M.n_dof; d++) W.tau[d] = B.tau[(size_t)d * B.N + e];
     }
     constexpr int CAP = pool_cap<T, MC, 32>();
-    const RowPool<CAP> pool{B.rows + (size_t)blockIdx.x * ((size_t)CAP * pool_rec<T>())};
+    const RowPool<CAP, pool_layout_rec<T>()> pool{B.rows + (size_t)blockIdx.x * ((size_t)CAP * pool_rec<T>())};
     WarpDev<1> warp;
     for (int s = 0; s < nsub; s++) substep_pooled<T>(warp, valid, M, W, pool, lc, s_lc, nullptr);
     if (valid) store_env(M, B, e, W, E);

@@ -62,14 +62,25 @@ struct PoolRef {
 #ifndef RS_POOL_DISCARD
 #define RS_POOL_DISCARD 1
 #endif
-template <int CAP>
+// REC > 0: record-major layout -- the REC words of a slot are contiguous (word k of slot s at p[s * REC + k]): a Gauss-Seidel sweep
+// then reads a row as 6 full sectors instead of one word out of each of 2 nd + 1 sectors (the builders' stores lose their
+// coalescing across lanes instead).  REC == 0: word-major, word k of slot s at p[k * CAP + s] (slot-contiguous, coalesced stores).
+template <int CAP, int REC = 0>
 struct RowPool {
     float* p;
-    RS_HD PoolRef at(int slot, int k) const { return PoolRef{p + (k * CAP + slot)}; }
+    RS_HD PoolRef at(int slot, int k) const { return PoolRef{REC > 0 ? p + (slot * REC + k) : p + (k * CAP + slot)}; }
     // drop the 128-byte lines that hold slots [slot0, slot0 + nslots) of words [0, nwords): one line per lane and step (CAP is a multiple of 32
     // floats and the pool of a warp starts on a 128-byte boundary, so no line is shared with live data of anybody else)
     RS_HD void discard(int lane, int width, int slot0, int nslots, int nwords) const {      // slot0: a multiple of 32
 #if defined(__CUDA_ARCH__) && RS_POOL_DISCARD
+        if (REC > 0) {
+            const int total = (nslots * REC + 31) >> 5;       // lines of the contiguous record range (rounded up: the tail line holds dead slots only)
+            for (int i = lane; i < total; i += width) {
+                const float* a = p + ((size_t)slot0 * REC + 32 * i);
+                asm volatile("discard.global.L2 [%0], 128;" :: "l"(a) : "memory");
+            }
+            return;
+        }
         const int lpw = (nslots + 31) >> 5;                 // lines per word
         const int total = lpw * nwords;
         for (int i = lane; i < total; i += width) {
@@ -80,6 +91,10 @@ struct RowPool {
 #endif
     }
 };
+#ifndef RS_POOL_ROWMAJOR
+#define RS_POOL_ROWMAJOR 0
+#endif
+template <class T> constexpr int pool_layout_rec() { return RS_POOL_ROWMAJOR ? 2 * (6 + T::ND + (T::CUBE ? 6 : 0)) + 1 : 0; }
 // Slot map of a warp's pool (WIDTH = lanes = envs of the warp), two forms chosen per topology (pool_columns<T>):
 //   dense    rows of the warp packed in owner order: non-contact row j of an env at lbase + j, contact ci direction w at
 //            LT + 3 (cbase + ci) + w (lbase / cbase: warp prefix sums).  Touches the fewest cache lines when the envs of a warp
