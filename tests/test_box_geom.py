@@ -290,3 +290,58 @@ def test_sliding_ball_starts_to_roll(world, tmp_path, oracle_lib):
     slip = np.array(slip)
     assert slip[: n - 10].min() > 0.02 * v0 and np.abs(slip[n + 10:]).max() < 0.01 * v0, (slip[n - 12:n + 12])   # slipping ends on time
     assert abs(v_sim - v) < 0.02 * v0 and abs(om_sim * r - v) < 0.02 * v0, (v_sim, om_sim * r, v)
+
+
+PENDULUM_XML = """<mujoco model="limitpend">
+  <compiler angle="radian" coordinate="local"/>
+  <default><geom conaffinity="0" contype="0"/></default>
+  <worldbody>
+    <body name="arm" pos="0 0 2">
+      <joint name="hinge" type="hinge" axis="0 1 0" pos="0 0 0" range="-0.6 0.6" limited="true"/>
+      <geom type="capsule" fromto="0 0 0 0.5 0 0" size="0.04"/>
+    </body>
+  </worldbody>
+</mujoco>
+"""
+
+
+@pytest.mark.parametrize("world", ["oracle", "emulated-kernel"])
+def test_joint_limit_is_an_inelastic_one_sided_stop(world, tmp_path, oracle_lib):
+    """btMultiBodyJointLimitConstraint as the reference uses it, in closed-form terms: a horizontal arm released at q = 0 swings
+    freely (energy conserved to first order) until it reaches its limit, where the row takes away ALL of the approach velocity in
+    one sub-step (no restitution), never lets the joint pass the limit by more than one sub-step of travel, does not pull back
+    (one-sided: the arm may leave the limit freely), and holds the arm at the limit against gravity afterwards."""
+    p = tmp_path / "pend.xml"
+    p.write_text(PENDULUM_XML)
+    m = mjcf.compile_mjcf(str(p), has_floor=False)
+    m.max_contacts = 8
+    assert m.fixed_base == 1 and m.n_dof == 1
+    if world == "oracle":
+        w = oracle_lib.OracleWorld(m, 1)
+    else:
+        from tests.host_emul import emul
+        emul.build()
+        w = emul.EmulWorld(m, 1)
+    w.set_state(0, np.zeros(2))
+    dt, lim = float(m.timestep), 0.6
+    q_prev, qd_prev, hit = 0.0, 0.0, None
+    for k in range(2000):
+        w.substeps(0, 1)
+        q, qd = [float(x) for x in np.array(w.get_state(0), dtype=np.float64)]
+        if hit is None and abs(q) >= lim - 1e-9:
+            hit = k
+            sign = 1.0 if q > 0 else -1.0
+            assert abs(qd_prev) > 1.0                                   # it arrived swinging
+            assert abs(q) - lim < abs(qd_prev) * dt + 1e-6              # overshoot bounded by one sub-step of travel
+        elif hit is not None and k == hit + 1:
+            assert sign * qd < 1e-3 * abs(qd_prev) + 1e-6, (qd, qd_prev)   # approach velocity gone within one sub-step (inelastic)
+        q_prev, qd_prev = q, qd
+    assert hit is not None
+    assert abs(abs(q) - lim) < 2e-3 and abs(qd) < 1e-3, (q, qd)         # held at the limit against gravity
+    # one-sided: a kick away from the limit is not resisted by the row
+    s = np.array(w.get_state(0), dtype=np.float64)
+    s[1] = -sign * 2.0
+    w.set_state(0, s, clear_contacts=False)
+    w.substeps(0, 1)
+    q2, qd2 = [float(x) for x in np.array(w.get_state(0), dtype=np.float64)]
+    assert sign * qd2 < -1.5 and sign * (q2 - s[0]) < 0
