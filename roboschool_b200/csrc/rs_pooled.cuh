@@ -94,6 +94,9 @@ struct RowPool {
 #ifndef RS_POOL_ROWMAJOR
 #define RS_POOL_ROWMAJOR 0
 #endif
+#ifndef RS_PGS_PAIR
+#define RS_PGS_PAIR 0
+#endif
 template <class T> constexpr int pool_layout_rec() { return RS_POOL_ROWMAJOR ? 2 * (6 + T::ND + (T::CUBE ? 6 : 0)) + 1 : 0; }
 // Slot map of a warp's pool (WIDTH = lanes = envs of the warp), two forms chosen per topology (pool_columns<T>):
 //   dense    rows of the warp packed in owner order: non-contact row j of an env at lbase + j, contact ci direction w at
@@ -364,6 +367,41 @@ RS_HD void resolve_pooled(const Pool& pool, int slot, float* dv, float rhs, floa
     else applied = sum;
 #pragma unroll
     for (int k = K0; k < K1; k++) dv[k] += u[k - K0] * dimp;
+}
+// The two friction rows of a contact point, resolved one after the other like resolve_pooled does, but with the loads of BOTH rows
+// issued before the first is resolved: a row's J / M^-1 J^T words do not depend on dv, so the second row's L2 round trip runs
+// under the first row's arithmetic (the Gauss-Seidel sweeps are bound by that latency).  Same operations in the same order per row.
+template <int K0, int K1, int ND, class Pool>
+RS_HD void resolve_pair_pooled(const Pool& pool, int slotA, int slotB, float* dv, const float* rhs, const float* invd, float lim, float* applied) {
+    float jA[K1 - K0], uA[K1 - K0], jB[K1 - K0], uB[K1 - K0];
+#pragma unroll
+    for (int k = K0; k < K1; k++) { jA[k - K0] = pool.at(slotA, k); uA[k - K0] = pool.at(slotA, ND + k); }
+#pragma unroll
+    for (int k = K0; k < K1; k++) { jB[k - K0] = pool.at(slotB, k); uB[k - K0] = pool.at(slotB, ND + k); }
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const float* j = r ? jB : jA;
+        const float* u = r ? uB : uA;
+        float dot = 0.f;
+#pragma unroll
+        for (int k = K0; k < K1; k++) dot += j[k - K0] * dv[k];
+        float dimp = rhs[r] - dot * invd[r];
+        float sum = applied[r] + dimp;
+        if (sum < -lim) { dimp = -lim - applied[r]; applied[r] = -lim; }
+        else if (sum > lim) { dimp = lim - applied[r]; applied[r] = lim; }
+        else applied[r] = sum;
+#pragma unroll
+        for (int k = K0; k < K1; k++) dv[k] += u[k - K0] * dimp;
+    }
+}
+template <class T, class Pool>
+RS_HD void resolve_pair_span(int span, const Pool& pool, int slotA, int slotB, float* dv, const float* rhs, const float* invd, float lim, float* applied) {
+    constexpr int nd = nd_of<T>(), ndr = 6 + T::ND;
+    if constexpr (T::CUBE != 0) {
+        if (span == 1) { resolve_pair_pooled<ndr, nd, nd>(pool, slotA, slotB, dv, rhs, invd, lim, applied); return; }
+        if (span == 2) { resolve_pair_pooled<0, nd, nd>(pool, slotA, slotB, dv, rhs, invd, lim, applied); return; }
+    }
+    resolve_pair_pooled<0, ndr, nd>(pool, slotA, slotB, dv, rhs, invd, lim, applied);
 }
 // dofs of a contact row by manifold id: 0 robot only, 1 cube only (cube-floor), 2 both (robot geom vs cube)
 template <class T>
@@ -747,10 +785,17 @@ RS_HD void solve_pooled(const Warp& warp, bool valid, const DevModel& M, Work<NL
                 if (key < M.n_geoms) fr = M.g_fric_floor[key];
                 else if (!T::CUBE || key < M.n_geoms + M.n_pairs) fr = M.pair_friction[key - M.n_geoms];
                 else fr = key == M.n_geoms + M.n_pairs ? M.cube_fric_floor : M.cube_fric_geom[key - M.n_geoms - M.n_pairs - 1];
+                // measured (profiles/r02_v5_pgs_pair_ab.txt): loading both friction rows before resolving the first pays on the
+                // row-heavy cube topology (FlagrunHarder 2.83 -> 2.77 ms per step), nothing on the others, +2 % on Hopper 4096
+                if constexpr (RS_PGS_PAIR != 0 || T::CUBE != 0) {
+                    const int row = n_nc + 3 * ci + 1;      // rows + 1 and + 2 are adjacent in r_rhs / r_invd / r_applied
+                    resolve_pair_span<T>(row_span<T>(M, key), pool, slot_c(ci) + RST, slot_c(ci) + 2 * RST, dv, r_rhs + row, r_invd + row, fr * tot, r_applied + row);
+                } else {
 #pragma unroll
-                for (int w = 1; w < 3; w++) {
-                    const int row = n_nc + 3 * ci + w;
-                    resolve_span<T>(row_span<T>(M, key), pool, slot_c(ci) + w * RST, dv, r_rhs[row], r_invd[row], -fr * tot, fr * tot, r_applied[row]);
+                    for (int w = 1; w < 3; w++) {
+                        const int row = n_nc + 3 * ci + w;
+                        resolve_span<T>(row_span<T>(M, key), pool, slot_c(ci) + w * RST, dv, r_rhs[row], r_invd[row], -fr * tot, fr * tot, r_applied[row]);
+                    }
                 }
             }
         }
